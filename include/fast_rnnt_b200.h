@@ -1,0 +1,195 @@
+/*
+ * fast_rnnt_b200 — C ABI of the B200 (sm_100a) pruned RNN-T loss hot path.
+ *
+ * Drop-in boundary for Samsung/tf-fast-rnnt: these entry points are what a
+ * TensorFlow custom-op shim (tf.load_op_library), a ctypes binding or any other
+ * FFI binds instead of the reference's native entry points
+ *   MutualInformationCuda / MutualInformationBackwardCuda / CumminCuda
+ *   (tf_fast_rnnt/csrc/mutual_information.h:134-168)
+ * and instead of the TensorFlow-graph math of
+ *   tf_fast_rnnt/python/tf_fast_rnnt/rnnt_loss.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with host_;
+ *     tensors are dense row-major, last axis unit-stride;
+ *   - float tensors are float32; index tensors int32;
+ *   - `boundary` is [B][4] = {s_begin, t_begin, s_end, t_end} per utterance
+ *     (tf_fast_rnnt/python/tf_fast_rnnt/__init__.py:98-106) and is mandatory
+ *     (README.md:5);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises the host, nothing is allocated or freed by the
+ *     library: the caller supplies `workspace` of at least the size the matching
+ *     *_workspace_bytes() query returns (256-byte aligned);
+ *   - return value: FRN_OK (0) or a negative FRN_E* code; CUDA launch errors are
+ *     returned as FRN_ECUDA with the cudaError_t available from
+ *     frn_last_cuda_error().  (The reference returns 1 unconditionally,
+ *     mutual_information_cuda.cu:810,873,1011.)
+ *   - re-entrant: no global mutable state apart from the per-thread last error.
+ */
+#ifndef FAST_RNNT_B200_H_
+#define FAST_RNNT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRN_VERSION 100 /* 1.0.0 */
+
+enum frn_status {
+  FRN_OK = 0,
+  FRN_EINVAL = -1,     /* bad shape / argument */
+  FRN_EWORKSPACE = -2, /* workspace too small or misaligned */
+  FRN_ECUDA = -3,      /* CUDA runtime error, see frn_last_cuda_error() */
+  FRN_EUNSUPPORTED = -4
+};
+
+/* rnnt_type of the reference API (rnnt_loss.py:110-122) */
+enum frn_rnnt_type { FRN_REGULAR = 0, FRN_MODIFIED = 1, FRN_CONSTRAINED = 2 };
+
+/* element type of the joiner logits handed to the pruned loss */
+enum frn_dtype { FRN_F32 = 0, FRN_BF16 = 1 };
+
+/* reduction of the reference API (rnnt_loss.py:327-338) */
+enum frn_reduction { FRN_NONE = 0, FRN_MEAN = 1, FRN_SUM = 2 };
+
+int frn_version(void);
+const char *frn_status_string(int status);
+int frn_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------
+ * A4. Lattice recursion, forward + occupation counts in one call.
+ * Replaces op "FastRNNTLoss" (tf_fast_rnnt_op.cc:27-34,48-117) =
+ * MutualInformationCuda + 2 memsets + H2D copy + MutualInformationBackwardCuda.
+ *   px [B][S][T1] with T1 == T+1 (regular) or T1 == T (modified recursion)
+ *   py [B][S+1][T]
+ *   ans [B]; px_grad [B][S][T1] (shape of px — reference defect D2 fixed);
+ *   py_grad [B][S+1][T].  If calc_gradients == 0 the grad pointers may be NULL.
+ * ---------------------------------------------------------------------- */
+size_t frn_mi_workspace_bytes(int B, int S, int T, int T1);
+int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary,
+                   int B, int S, int T, int T1, int calc_gradients, float *ans,
+                   float *px_grad, float *py_grad, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* Replaces op "Cummin" (tf_fast_rnnt_op.cc:36-38,135-165; CumminCuda):
+ * inclusive running minimum along the last axis of an int32 [rows][n] matrix. */
+int frn_cummin(const int32_t *in, int32_t *out, int rows, int n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * A1/A2. get_rnnt_logprobs / get_rnnt_logprobs_smoothed
+ * (rnnt_loss.py:63-223, 1132-1367): px [B][S][T1], py [B][S+1][T] in the
+ * reference's layout.  smoothed != 0 selects the smoothed variant with the two
+ * scales.  T1 = T+1 for FRN_REGULAR, T otherwise.
+ * ---------------------------------------------------------------------- */
+size_t frn_simple_logprobs_workspace_bytes(int B, int S, int T, int C);
+int frn_simple_logprobs(const float *lm, const float *am, const int32_t *symbols,
+                        const int32_t *boundary, int B, int S, int T, int C,
+                        int termination_symbol, int rnnt_type, int smoothed,
+                        float lm_only_scale, float am_only_scale, float *px,
+                        float *py, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* ------------------------------------------------------------------------
+ * A1/A2 + A3 + A4 fused: rnnt_loss_simple / rnnt_loss_smoothed
+ * (rnnt_loss.py:225-338, 1369-1494) with reduction "none":
+ *   scores[b] = p[b, s_end, t_end]  (loss = -scores; reduce with frn_reduce)
+ *   px_grad [B][S][T1], py_grad [B][S+1][T] occupation counts (may be NULL when
+ *   calc_gradients == 0).  The log-probs never leave the workspace.
+ * ---------------------------------------------------------------------- */
+size_t frn_simple_loss_workspace_bytes(int B, int S, int T, int C);
+int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols,
+                    const int32_t *boundary, int B, int S, int T, int C,
+                    int termination_symbol, int rnnt_type, int smoothed,
+                    float lm_only_scale, float am_only_scale,
+                    float delay_penalty, int calc_gradients, float *scores,
+                    float *px_grad, float *py_grad, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* A9. Gradient of sum_b scores_grad[b]*scores[b] w.r.t. am and lm given the
+ * occupation counts (what TensorFlow autodiff + _RNNTLossGrad,
+ * __init__.py:154-162, produce for rnnt_loss_simple; smoothed not covered). */
+size_t frn_simple_loss_bwd_workspace_bytes(int B, int S, int T, int C);
+int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols,
+                        const int32_t *boundary, const float *px_grad,
+                        const float *py_grad, const float *scores_grad, int B,
+                        int S, int T, int C, int termination_symbol,
+                        int rnnt_type, float *am_grad, float *lm_grad,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * A5. get_rnnt_prune_ranges (rnnt_loss.py:647-761): ranges [B][T][R_out],
+ * R_out = (s_range > S ? S+1 : s_range), see frn_prune_ranges_width().
+ * ---------------------------------------------------------------------- */
+int frn_prune_ranges_width(int S, int s_range);
+size_t frn_prune_ranges_workspace_bytes(int B, int T);
+int frn_prune_ranges(const float *px_grad, const float *py_grad,
+                     const int32_t *boundary, int B, int S, int T, int T1,
+                     int s_range, int32_t *ranges, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * A6. do_rnnt_pruning (rnnt_loss.py:763-812) and its gradient.
+ *   am [B][T][C], lm [B][S+1][C], ranges [B][T][R]
+ *   am_pruned, lm_pruned [B][T][R][C]
+ * ---------------------------------------------------------------------- */
+int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B,
+                   int S, int T, int R, int C, float *am_pruned,
+                   float *lm_pruned, void *stream);
+int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad,
+                       const int32_t *ranges, int B, int S, int T, int R, int C,
+                       float *am_grad, float *lm_grad, void *stream);
+/* (f2) fused additive joiner: logits[b,t,i,:] = am[b,t,:] + lm[b,ranges[b,t,i],:]
+ * without materialising am_pruned / lm_pruned. out_dtype: frn_dtype. */
+int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges,
+                          int B, int S, int T, int R, int C, int out_dtype,
+                          void *logits, void *stream);
+
+/* ------------------------------------------------------------------------
+ * A7. get_rnnt_logprobs_pruned (rnnt_loss.py:853-1020): dense px [B][S][T1],
+ * py [B][S+1][T] from joiner logits [B][T][R][C] (float32 or bf16).
+ * ---------------------------------------------------------------------- */
+size_t frn_pruned_logprobs_workspace_bytes(int B, int S, int T, int R);
+int frn_pruned_logprobs(const void *logits, int logits_dtype,
+                        const int32_t *symbols, const int32_t *ranges,
+                        const int32_t *boundary, int B, int S, int T, int R,
+                        int C, int termination_symbol, int rnnt_type, float *px,
+                        float *py, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* ------------------------------------------------------------------------
+ * A7 + A3 + A8 fused: rnnt_loss_pruned (rnnt_loss.py:1022-1130), reduction
+ * "none", on the band only.  scores [B].  If logits_grad != NULL it receives
+ * d(sum_b scores_grad[b]*scores[b])/d logits, same dtype/shape as logits
+ * (scores_grad == NULL means all ones) — the backward TensorFlow autodiff runs
+ * through rnnt_loss.py:942-1018.
+ * ---------------------------------------------------------------------- */
+size_t frn_pruned_loss_workspace_bytes(int B, int S, int T, int R);
+int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols,
+                    const int32_t *ranges, const int32_t *boundary, int B, int S,
+                    int T, int R, int C, int termination_symbol, int rnnt_type,
+                    float delay_penalty, const float *scores_grad, float *scores,
+                    void *logits_grad, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+/* (f1) rnnt_loss on the full joiner, logits [B][T][S+1][C]
+ * (rnnt_loss.py:340-551): the pruned loss with the identity band. */
+size_t frn_joint_loss_workspace_bytes(int B, int S, int T);
+int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
+                   const int32_t *boundary, int B, int S, int T, int C,
+                   int termination_symbol, int rnnt_type, float delay_penalty,
+                   const float *scores_grad, float *scores, void *logits_grad,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* A3. out[0] = -sum(scores) (FRN_SUM) or -mean (FRN_MEAN); FRN_NONE writes
+ * out[b] = -scores[b].  `denominator` <= 0 means B (pass the global batch size
+ * when the sum is completed by an all-reduce across ranks). */
+int frn_reduce(const float *scores, int B, int reduction, float denominator,
+               float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAST_RNNT_B200_H_ */

@@ -1,0 +1,1 @@
+// empty stand-in: the reference's kernels only need TTypes<> (see framework/tensor.h)

@@ -1,0 +1,107 @@
+"""GPU parity of the lattice recursion (A4) and cummin: CUDA path through the
+C ABI vs the float64 oracle, and the oracle vs the reference's own CUDA kernels
+(oracle/_ref) — the run that pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import rnnt_oracle as orc
+from tests.helpers import (GRAD_ATOL, GRAD_RTOL, LOSS_RTOL, RefKernels, assert_close,
+                           load_golden, random_pxpy)
+
+pytestmark = pytest.mark.gpu
+
+
+def _boundaries(rng, B, S, T, kind):
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 2], bd[:, 3] = S, T
+    if kind in ("ragged", "begin"):
+        bd[:, 3] = rng.integers(max(1, T // 2), T + 1, B)
+        bd[:, 2] = np.minimum(rng.integers(0, S + 1, B), bd[:, 3])
+        bd[0, 2], bd[0, 3] = S, T
+    if kind == "begin":
+        bd[:, 0] = np.minimum(rng.integers(0, 3, B), bd[:, 2])
+        bd[:, 1] = np.minimum(rng.integers(0, 4, B), bd[:, 3])
+    return bd
+
+
+@pytest.mark.parametrize("modified", [False, True])
+@pytest.mark.parametrize("shape", [(2, 10, 50), (3, 1, 1), (4, 33, 70), (2, 127, 129), (2, 130, 300),
+                                   (1, 300, 40), (5, 64, 64)])
+@pytest.mark.parametrize("kind", ["full", "ragged", "begin"])
+def test_mi_against_float64_oracle(modified, shape, kind):
+    import tf_fast_rnnt
+    B, S, T = shape
+    rng = np.random.default_rng(hash((modified, shape, kind)) % (2 ** 31))
+    px, py = random_pxpy(rng.integers(1 << 30), B, S, T, modified)
+    bd = _boundaries(rng, B, S, T, kind)
+    ans, (gx, gy) = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
+    ans64, (gx64, gy64) = orc.mutual_information_recursion(px, py, bd, True, np.float64)
+    assert_close(ans, ans64, LOSS_RTOL, 1e-6, "ans")
+    assert_close(gx, gx64, GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy, gy64, GRAD_RTOL, GRAD_ATOL, "py_grad")
+    only = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=False)
+    assert np.array_equal(only, ans)
+
+
+def test_mi_with_minus_inf_inputs():
+    """px/py holding -inf (what get_rnnt_logprobs produces at t_end) and an
+    unreachable end state."""
+    import tf_fast_rnnt
+    B, S, T = 3, 6, 9
+    px, py = random_pxpy(7, B, S, T, False)
+    px[:, :, T] = -np.inf
+    px[1, 2, :] = -np.inf          # utterance 1 cannot pass symbol 2: score = -inf
+    py[2, 3, 4] = -np.inf
+    bd = np.tile(np.array([0, 0, S, T], np.int32), (B, 1))
+    ans, (gx, gy) = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
+    ans64, (gx64, gy64) = orc.mutual_information_recursion(px, py, bd, True, np.float64)
+    assert np.isneginf(ans[1]) and np.isneginf(ans64[1])
+    assert_close(ans[[0, 2]], ans64[[0, 2]], LOSS_RTOL, 1e-6, "ans")
+    assert_close(gx[[0, 2]], gx64[[0, 2]], GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy[[0, 2]], gy64[[0, 2]], GRAD_RTOL, GRAD_ATOL, "py_grad")
+    assert not np.isnan(gx).any() and not np.isnan(gy).any()
+
+
+@pytest.mark.parametrize("modified", [False, True])
+def test_oracle_pinned_by_reference_kernels(modified):
+    """The plain-C oracle (float32) against the REFERENCE's CUDA kernels."""
+    ref = RefKernels()
+    rng = np.random.default_rng(11 + modified)
+    for (B, S, T) in [(2, 10, 50), (4, 33, 70), (2, 100, 200)]:
+        px, py = random_pxpy(rng.integers(1 << 30), B, S, T, modified)
+        bd = _boundaries(rng, B, S, T, "ragged")
+        if modified:
+            bd[:, 2] = np.minimum(bd[:, 2], bd[:, 3])
+        r_ans, r_gx, r_gy, r_ag = ref.fast_rnnt_loss(px, py, bd)
+        o_ans, (o_gx, o_gy) = orc.mutual_information_recursion(px, py, bd, True, np.float32)
+        assert_close(o_ans, r_ans, 2e-6, 1e-5, "oracle ans vs reference kernel")
+        assert_close(o_gx, r_gx, 2e-4, 1e-6, "oracle px_grad vs reference kernel")
+        assert_close(o_gy, r_gy, 2e-4, 1e-6, "oracle py_grad vs reference kernel")
+        # the reference's built-in self check: p_grad[s_begin,t_begin] == ans_grad == 1
+        np.testing.assert_allclose(r_ag, 1.0, rtol=1e-3)
+
+
+def test_cuda_path_against_reference_kernels():
+    import tf_fast_rnnt
+    ref = RefKernels()
+    g = load_golden("stress_b2_t200_s50_c50")
+    px, py, bd = g["simple_px"], g["simple_py"], g["boundary"]
+    r_ans, r_gx, r_gy, _ = ref.fast_rnnt_loss(px, py, bd)
+    ans, (gx, gy) = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
+    assert_close(ans, r_ans, LOSS_RTOL, 0, "ans vs reference kernel")
+    # the reference itself is float32 on |p| ~ 1e3 here: 1e-3 is its own accuracy
+    assert_close(gx, r_gx, 2e-3, 1e-6, "px_grad vs reference kernel")
+    assert_close(gy, r_gy, 2e-3, 1e-6, "py_grad vs reference kernel")
+
+
+def test_cummin_bit_exact():
+    import tf_fast_rnnt
+    ref = RefKernels()
+    rng = np.random.default_rng(5)
+    for rows, n in [(1, 1), (2, 31), (3, 32), (5, 33), (32, 500), (7, 1500)]:
+        x = rng.integers(-1000, 1000, (rows, n)).astype(np.int32)
+        out = tf_fast_rnnt.cummin(x)
+        assert out.dtype == np.int32
+        assert np.array_equal(out, np.minimum.accumulate(x, axis=1))
+        assert np.array_equal(out, orc.cummin(x))
+        assert np.array_equal(out, ref.cummin(x))

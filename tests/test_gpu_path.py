@@ -1,0 +1,215 @@
+"""GPU parity of the rest of the hot path through the public API / C ABI:
+simple & smoothed log-probs and losses (A1-A3), prune ranges (A5), pruning
+(A6), pruned log-probs, loss and logits gradient (A7, A8), full joiner (f1)."""
+import numpy as np
+import pytest
+
+from oracle import rnnt_oracle as orc
+from tests.helpers import (GRAD_ATOL, GRAD_RTOL, LOSS_RTOL, assert_close, load_golden, make_inputs)
+
+pytestmark = pytest.mark.gpu
+LOGP_RTOL, LOGP_ATOL = 2e-6, 2e-5     # log-probs: float32 vs float64 oracle
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", ["c1_readme", "stress_b2_t200_s50_c50"])
+def test_golden_simple_and_smoothed(name):
+    import tf_fast_rnnt as frn
+    g = load_golden(name)
+    term = int(g["termination_symbol"])
+    px, py = frn.get_rnnt_logprobs(g["lm"], g["am"], g["symbols"], term, "regular", g["boundary"])
+    assert_close(px, g["simple_px"], LOGP_RTOL, LOGP_ATOL, "px")
+    assert_close(py, g["simple_py"], LOGP_RTOL, LOGP_ATOL, "py")
+    for dp, tag in ((0.0, "dp0"), (0.2, "dp2")):
+        loss, (gx, gy) = frn.rnnt_loss_simple(g["lm"], g["am"], g["symbols"], term, g["boundary"],
+                                              "regular", dp, "none", True)
+        assert_close(loss, g[f"simple_loss_{tag}"], LOSS_RTOL, 0, "loss")
+        # the golden grads are the reference's float32 recursion: 1e-3 is its own accuracy
+        assert_close(gx, g[f"simple_px_grad_{tag}"], 2e-3, 1e-6, "px_grad")
+        assert_close(gy, g[f"simple_py_grad_{tag}"], 2e-3, 1e-6, "py_grad")
+    s = frn.rnnt_loss_simple(g["lm"], g["am"], g["symbols"], term, g["boundary"], reduction="sum")
+    assert_close(s, g["simple_loss_sum"], LOSS_RTOL, 0, "sum")
+    for lms, ams in ((0.1, 0.2), (0.25, 0.0)):
+        tag = f"l{int(lms * 100)}_a{int(ams * 100)}"
+        spx, spy = frn.get_rnnt_logprobs_smoothed(g["lm"], g["am"], g["symbols"], term, lms, ams,
+                                                  g["boundary"], "regular")
+        assert_close(spx, g[f"smoothed_px_{tag}"], LOGP_RTOL, LOGP_ATOL, "smoothed px")
+        assert_close(spy, g[f"smoothed_py_{tag}"], LOGP_RTOL, LOGP_ATOL, "smoothed py")
+        loss = frn.rnnt_loss_smoothed(g["lm"], g["am"], g["symbols"], term, lms, ams, g["boundary"],
+                                      "regular", 0.2, "none")
+        assert_close(loss, g[f"smoothed_loss_{tag}"], LOSS_RTOL, 0, "smoothed loss")
+
+
+@pytest.mark.parametrize("name", ["c1_readme", "stress_b2_t200_s50_c50"])
+def test_golden_prune_and_pruned(name):
+    import tf_fast_rnnt as frn
+    g = load_golden(name)
+    term = int(g["termination_symbol"])
+    for r in g["s_ranges"]:
+        ranges = frn.get_rnnt_prune_ranges(g["simple_px_grad_dp2"], g["simple_py_grad_dp2"],
+                                           g["boundary"], int(r))
+        assert ranges.dtype == np.int32
+        assert np.array_equal(ranges, g[f"ranges_r{r}"]), f"s_range={r}"          # bit-exact
+        am_p, lm_p = frn.do_rnnt_pruning(g["am"], g["lm"], ranges)
+        o_am_p, o_lm_p = orc.do_rnnt_pruning(g["am"], g["lm"], ranges)
+        assert np.array_equal(am_p, o_am_p) and np.array_equal(lm_p, o_lm_p)      # bit-exact copy
+        logits = (1.0 / (1.0 + np.exp(-(am_p + lm_p)))).astype(np.float32)
+        for rt in ("regular", "modified", "constrained"):
+            px, py = frn.get_rnnt_logprobs_pruned(logits, g["symbols"], ranges, term, g["boundary"], rt)
+            assert_close(px, g[f"pruned_px_r{r}_{rt}"], LOGP_RTOL, 5e-6, f"pruned px {rt}")
+            assert_close(py, g[f"pruned_py_r{r}_{rt}"], LOGP_RTOL, 5e-6, f"pruned py {rt}")
+            for dp in (0.0, 0.2):
+                loss = frn.rnnt_loss_pruned(logits, g["symbols"], ranges, term, g["boundary"], rt, dp, "none")
+                assert_close(loss, g[f"pruned_loss_r{r}_{rt}_dp{int(dp * 10)}"], LOSS_RTOL, 0,
+                             f"pruned loss r={r} {rt} dp={dp}")
+    r0 = int(g["s_ranges"][0])
+    am_p, lm_p = frn.do_rnnt_pruning(g["am"], g["lm"], g[f"ranges_r{r0}"])
+    assert np.array_equal(am_p, g[f"am_pruned_r{r0}"]) and np.array_equal(lm_p, g[f"lm_pruned_r{r0}"])
+
+
+@pytest.mark.parametrize("name", ["c1_readme", "stress_b2_t200_s50_c50"])
+def test_golden_joint(name):
+    import tf_fast_rnnt as frn
+    g = load_golden(name)
+    term = int(g["termination_symbol"])
+    full = (1.0 / (1.0 + np.exp(-(g["am"][:, :, None, :] + g["lm"][:, None, :, :])))).astype(np.float32)
+    px, py = frn.get_rnnt_logprobs_joint(full, g["symbols"], term, g["boundary"])
+    assert_close(px, g["joint_px"], LOGP_RTOL, 5e-6, "joint px")
+    assert_close(py, g["joint_py"], LOGP_RTOL, 5e-6, "joint py")
+    loss = frn.rnnt_loss(full, g["symbols"], term, g["boundary"], "regular", 0.2, "none")
+    assert_close(loss, g["joint_loss_dp2"], LOSS_RTOL, 0, "joint loss")
+
+
+# ------------------------------------------------------------------ seeded inputs vs float64 oracle
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+@pytest.mark.parametrize("shape", [(2, 50, 10, 16), (3, 70, 33, 37), (2, 200, 130, 50)])
+@pytest.mark.parametrize("dp", [0.0, 0.2])
+def test_simple_loss_types(rnnt_type, shape, dp):
+    import tf_fast_rnnt as frn
+    B, T, S, C = shape
+    am, lm, sym, term, bd = make_inputs(100 + S, B, T, S, C, ragged=True)
+    loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, "none", True)
+    o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, "none", True,
+                                                dtype=np.float64)
+    assert_close(loss, o_loss, LOSS_RTOL, 0, "loss")
+    assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, "py_grad")
+    for red in ("mean", "sum"):
+        v = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, red)
+        o = orc.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, red, dtype=np.float64)
+        assert_close(v, o, LOSS_RTOL, 0, red)
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_smoothed_loss_types(rnnt_type):
+    import tf_fast_rnnt as frn
+    B, T, S, C = 3, 60, 20, 30
+    am, lm, sym, term, bd = make_inputs(7, B, T, S, C, ragged=True)
+    for lms, ams in ((0.25, 0.0), (0.1, 0.2)):
+        px, py = frn.get_rnnt_logprobs_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type)
+        o_px, o_py = orc.get_rnnt_logprobs_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, np.float64)
+        assert_close(px, o_px, LOGP_RTOL, LOGP_ATOL, "px")
+        assert_close(py, o_py, LOGP_RTOL, LOGP_ATOL, "py")
+        loss, (gx, gy) = frn.rnnt_loss_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, 0.2, "none", True)
+        o_loss, (o_gx, o_gy) = orc.rnnt_loss_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, 0.2,
+                                                      "none", True, dtype=np.float64)
+        assert_close(loss, o_loss, LOSS_RTOL, 0, "loss")
+        assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, "px_grad")
+        assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, "py_grad")
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+@pytest.mark.parametrize("s_range", [2, 5, 9, 100])
+def test_pipeline_vs_oracle(rnnt_type, s_range):
+    """simple -> prune ranges -> pruning -> pruned loss (+ logits gradient)."""
+    import torch
+    import tf_fast_rnnt as frn
+    if rnnt_type == "regular" and s_range < 2:
+        pytest.skip("regular needs s_range >= 2")
+    B, T, S, C = 3, 80, 24, 20
+    am, lm, sym, term, bd = make_inputs(31, B, T, S, C, ragged=True)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, s_range)
+    assert np.array_equal(ranges, orc.get_rnnt_prune_ranges(gx, gy, bd, s_range))
+    am_p, lm_p = frn.do_rnnt_pruning(am, lm, ranges)
+    logits = np.tanh(am_p + lm_p).astype(np.float32) * 3
+    for dp in (0.0, 0.2):
+        loss = frn.rnnt_loss_pruned(logits, sym, ranges, term, bd, rnnt_type, dp, "none")
+        o_loss = orc.rnnt_loss_pruned(logits, sym, ranges, term, bd, rnnt_type, dp, "none", dtype=np.float64)
+        assert_close(loss, o_loss, LOSS_RTOL, 0, f"pruned loss dp={dp}")
+    # logits gradient of sum_b w_b * loss_b
+    w = np.array([1.0, -0.5, 2.0], np.float32)
+    scores, grad = frn.pruned_loss_fwd_bwd(torch.from_numpy(logits).cuda(), sym, ranges, term, bd, rnnt_type,
+                                           0.2, -w)
+    o_grad = orc.pruned_logits_grad(logits, sym, ranges, term, bd, rnnt_type, 0.2, w, np.float64)
+    assert_close(grad.cpu().numpy(), o_grad, GRAD_RTOL, 2e-6, "logits grad")
+    # autograd wrapper
+    lg = torch.from_numpy(logits).cuda().requires_grad_(True)
+    l = frn.rnnt_loss_pruned(lg, sym, ranges, term, bd, rnnt_type, 0.2, "sum")
+    l.backward()
+    o_grad1 = orc.pruned_logits_grad(logits, sym, ranges, term, bd, rnnt_type, 0.2, None, np.float64)
+    assert_close(lg.grad.cpu().numpy(), o_grad1, GRAD_RTOL, 2e-6, "autograd logits grad")
+
+
+def test_pruned_full_band_equals_unpruned():
+    import tf_fast_rnnt as frn
+    B, T, S, C = 2, 40, 12, 18
+    am, lm, sym, term, bd = make_inputs(3, B, T, S, C, ragged=True)
+    full = am[:, :, None, :] + lm[:, None, :, :]
+    simple = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none")
+    joint = frn.rnnt_loss(full, sym, term, bd, "regular", 0.0, "none")
+    assert_close(joint, simple, LOSS_RTOL, 0, "joint == simple for an additive joiner")
+    try:
+        import torchaudio
+        import torch
+        ta = torchaudio.functional.rnnt_loss(
+            torch.from_numpy(full), torch.from_numpy(sym), torch.from_numpy(bd[:, 3].copy()),
+            torch.from_numpy(bd[:, 2].copy()), blank=term, reduction="none", fused_log_softmax=True)
+        assert_close(joint, ta.numpy(), LOSS_RTOL, 0, "torchaudio cross-check")
+    except ImportError:
+        pass
+
+
+def test_bf16_logits():
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 2, 60, 20, 64, 5
+    am, lm, sym, term, bd = make_inputs(9, B, T, S, C, ragged=True)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+    lg = frn.pruned_add_joiner(torch.from_numpy(am).cuda(), torch.from_numpy(lm).cuda(),
+                               torch.from_numpy(ranges).cuda(), dtype=torch.bfloat16)
+    assert lg.dtype == torch.bfloat16
+    up = lg.float().cpu().numpy()        # oracle: upcast then reference math
+    scores, grad = frn.pruned_loss_fwd_bwd(lg, sym, ranges, term, bd, "regular", 0.0, None)
+    o_loss = orc.rnnt_loss_pruned(up, sym, ranges, term, bd, "regular", 0.0, "none", dtype=np.float64)
+    assert_close(-scores.cpu().numpy(), o_loss, LOSS_RTOL, 0, "bf16 loss")
+    o_grad = orc.pruned_logits_grad(up, sym, ranges, term, bd, "regular", 0.0, -np.ones(B), np.float64)
+    assert grad.dtype == torch.bfloat16
+    assert_close(grad.float().cpu().numpy(), o_grad, 1e-2, 1e-4, "bf16 logits grad (bf16 rounding)")
+
+
+def test_pruning_backward():
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 2, 30, 9, 12, 4
+    am, lm, sym, term, bd = make_inputs(4, B, T, S, C, ragged=True)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+    rng = np.random.default_rng(1)
+    ga = rng.standard_normal((B, T, R, C), dtype=np.float32)
+    gl = rng.standard_normal((B, T, R, C), dtype=np.float32)
+    am_g, lm_g = frn.do_rnnt_pruning_backward(ga, gl, ranges, S)
+    o_am, o_lm = orc.do_rnnt_pruning_bwd(ga, gl, ranges, S + 1)
+    assert_close(am_g, o_am, 1e-5, 1e-5, "am grad")
+    assert_close(lm_g, o_lm, 1e-5, 1e-5, "lm grad")
+
+
+def test_argument_errors():
+    import tf_fast_rnnt as frn
+    am, lm, sym, term, bd = make_inputs(1, 2, 20, 5, 8)
+    with pytest.raises(ValueError):
+        frn.rnnt_loss_simple(lm, am, sym, term, bd, reduction="bogus")
+    with pytest.raises(ValueError):
+        frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type="bogus")
+    with pytest.raises(ValueError):
+        frn.mutual_information_recursion(np.zeros((2, 3, 9), np.float32), np.zeros((2, 4, 5), np.float32), None)

@@ -1,0 +1,319 @@
+// extern "C" entry points of libfast_rnnt_b200.so (see include/fast_rnnt_b200.h).
+// Argument validation, workspace carve-up and kernel sequencing only; all
+// kernels live in the other translation units.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace frn {
+static thread_local int g_last_cuda_error = 0;
+int note_cuda_error(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return e == cudaSuccess ? FRN_OK : FRN_ECUDA;
+}
+int check_launch() { return note_cuda_error(cudaPeekAtLastError()); }
+
+static inline bool aligned256(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
+static inline int type_t1(int T, int rnnt_type) { return rnnt_type == FRN_REGULAR ? T + 1 : T; }
+}  // namespace frn
+
+using namespace frn;
+
+#define FRN_REQUIRE(cond) \
+  do {                    \
+    if (!(cond)) return FRN_EINVAL; \
+  } while (0)
+#define FRN_TRY(expr)      \
+  do {                     \
+    int rc__ = (expr);     \
+    if (rc__) return rc__; \
+  } while (0)
+
+extern "C" {
+
+int frn_version(void) { return FRN_VERSION; }
+
+const char *frn_status_string(int status) {
+  switch (status) {
+    case FRN_OK: return "ok";
+    case FRN_EINVAL: return "invalid argument";
+    case FRN_EWORKSPACE: return "workspace too small or misaligned";
+    case FRN_ECUDA: return "CUDA error";
+    case FRN_EUNSUPPORTED: return "unsupported size";
+    default: return "unknown status";
+  }
+}
+
+int frn_last_cuda_error(void) { return g_last_cuda_error; }
+
+// ------------------------------------------------------------------ A4
+size_t frn_mi_workspace_bytes(int B, int S, int T, int T1) {
+  if (B <= 0 || S < 0 || T < 0) return 0;
+  DpGeom g = make_geom(B, S, T, T1);
+  return carve_dp(nullptr, g).bytes;
+}
+
+int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, int B, int S, int T, int T1,
+                   int calc_gradients, float *ans, float *px_grad, float *py_grad, void *workspace,
+                   size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FRN_REQUIRE(B > 0 && S >= 0 && T >= 0 && (T1 == T || T1 == T + 1));
+  FRN_REQUIRE(px && py && boundary && ans);
+  FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
+  DpGeom g = make_geom(B, S, T, T1);
+  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  if (!workspace || !aligned256(workspace) || workspace_bytes < carve_dp(nullptr, g).bytes) return FRN_EWORKSPACE;
+  DpWorkspace w = carve_dp(workspace, g);
+  FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
+  FRN_TRY(launch_chain(boundary, g, w, calc_gradients != 0, stream));
+  FRN_TRY(launch_finalize_dense(boundary, g, w, ans, calc_gradients ? px_grad : nullptr,
+                                calc_gradients ? py_grad : nullptr, stream));
+  return FRN_OK;
+}
+
+int frn_cummin(const int32_t *in, int32_t *out, int rows, int n, void *stream) {
+  FRN_REQUIRE(rows >= 0 && n >= 0 && (rows == 0 || n == 0 || (in && out)));
+  return launch_cummin(in, out, rows, n, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ A5
+int frn_prune_ranges_width(int S, int s_range) { return s_range > S ? S + 1 : s_range; }
+
+size_t frn_prune_ranges_workspace_bytes(int B, int T) {
+  return round_up_sz((size_t)(B > 0 ? B : 0) * (T > 0 ? T : 0) * sizeof(int32_t), 256);
+}
+
+int frn_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
+                     int T1, int s_range, int32_t *ranges, void *workspace, size_t workspace_bytes,
+                     void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && (T1 == T || T1 == T + 1) && s_range >= 1);
+  FRN_REQUIRE(px_grad && py_grad && boundary && ranges);
+  if (!workspace || workspace_bytes < frn_prune_ranges_workspace_bytes(B, T)) return FRN_EWORKSPACE;
+  const int R = frn_prune_ranges_width(S, s_range);
+  return launch_prune_ranges(px_grad, py_grad, boundary, B, S, T, T1, R, ranges,
+                             static_cast<int32_t *>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ A6
+int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
+                   float *am_pruned, float *lm_pruned, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
+  FRN_REQUIRE(am && lm && ranges && am_pruned && lm_pruned);
+  return launch_do_pruning(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, static_cast<cudaStream_t>(stream));
+}
+
+int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad, const int32_t *ranges, int B,
+                       int S, int T, int R, int C, float *am_grad, float *lm_grad, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0 && ranges);
+  FRN_REQUIRE((!am_grad || am_pruned_grad) && (!lm_grad || lm_pruned_grad));
+  return launch_do_pruning_bwd(am_pruned_grad, lm_pruned_grad, ranges, B, S, T, R, C, am_grad, lm_grad,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
+                          int C, int out_dtype, void *logits, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0 && am && lm && ranges && logits);
+  return launch_pruned_add_joiner(am, lm, ranges, B, S, T, R, C, out_dtype, logits,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+
+// ------------------------------------------------------------------ A1 / A2
+size_t frn_simple_logprobs_workspace_bytes(int B, int S, int T, int C) {
+  if (B <= 0 || S < 0 || T <= 0 || C <= 0) return 0;
+  return simple_stats_bytes(B, S, T, C);
+}
+
+int frn_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary, int B,
+                        int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
+                        float lm_only_scale, float am_only_scale, float *px, float *py, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
+  FRN_REQUIRE(lm && am && symbols && boundary && px && py);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < simple_stats_bytes(B, S, T, C)) return FRN_EWORKSPACE;
+  return launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                lm_only_scale, am_only_scale, px, py, workspace, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ A1/A2 + A3 + A4
+namespace {
+struct SimpleLossWs {
+  float *px, *py;
+  void *stats;
+  void *dp;
+  size_t bytes;
+};
+SimpleLossWs carve_simple_loss(void *base, int B, int S, int T, int T1, int C) {
+  SimpleLossWs w;
+  char *p = static_cast<char *>(base);
+  w.px = reinterpret_cast<float *>(p); p += round_up_sz((size_t)B * S * T1 * sizeof(float), 256);
+  w.py = reinterpret_cast<float *>(p); p += round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256);
+  w.stats = p; p += simple_stats_bytes(B, S, T, C);
+  w.dp = p; p += carve_dp(nullptr, make_geom(B, S, T, T1)).bytes;
+  w.bytes = (size_t)(p - static_cast<char *>(base));
+  return w;
+}
+}  // namespace
+
+size_t frn_simple_loss_workspace_bytes(int B, int S, int T, int C) {
+  if (B <= 0 || S < 0 || T <= 0 || C <= 0) return 0;
+  return carve_simple_loss(nullptr, B, S, T, T + 1, C).bytes;  // T1 = T+1 is the larger case
+}
+
+int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary, int B,
+                    int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
+                    float lm_only_scale, float am_only_scale, float delay_penalty, int calc_gradients,
+                    float *scores, float *px_grad, float *py_grad, void *workspace, size_t workspace_bytes,
+                    void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
+  FRN_REQUIRE(lm && am && symbols && boundary && scores);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
+  const int T1 = type_t1(T, rnnt_type);
+  DpGeom g = make_geom(B, S, T, T1);
+  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  if (!workspace || !aligned256(workspace) || workspace_bytes < carve_simple_loss(nullptr, B, S, T, T1, C).bytes)
+    return FRN_EWORKSPACE;
+  SimpleLossWs w = carve_simple_loss(workspace, B, S, T, T1, C);
+  DpWorkspace dw = carve_dp(w.dp, g);
+  FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                 lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream));
+  FRN_TRY(launch_skew_dense(w.px, w.py, boundary, g, dw, delay_penalty > 0.f ? delay_penalty : 0.f, stream));
+  FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
+  FRN_TRY(launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
+                                calc_gradients ? py_grad : nullptr, stream));
+  return FRN_OK;
+}
+
+size_t frn_simple_loss_bwd_workspace_bytes(int, int, int, int) { return 256; }
+int frn_simple_loss_bwd(const float *, const float *, const int32_t *, const int32_t *, const float *,
+                        const float *, const float *, int, int, int, int, int, int, float *, float *, void *,
+                        size_t, void *) {
+  return FRN_EUNSUPPORTED;  // A9: scheduled after the forward path
+}
+
+// ------------------------------------------------------------------ A7 / A8
+namespace {
+struct PrunedWs {
+  float *pxc, *pyc, *lse, *gxc, *gyc;
+  int32_t *ranges;  // only for the full joiner
+  void *dp;
+  size_t bytes;
+};
+PrunedWs carve_pruned(void *base, int B, int S, int T, int T1, int R, bool with_dp, bool with_ranges) {
+  PrunedWs w;
+  char *p = static_cast<char *>(base);
+  const size_t n = round_up_sz((size_t)B * T * R * sizeof(float), 256);
+  w.pxc = reinterpret_cast<float *>(p); p += n;
+  w.pyc = reinterpret_cast<float *>(p); p += n;
+  w.lse = reinterpret_cast<float *>(p); p += n;
+  w.gxc = reinterpret_cast<float *>(p); p += n;
+  w.gyc = reinterpret_cast<float *>(p); p += n;
+  w.ranges = reinterpret_cast<int32_t *>(p);
+  if (with_ranges) p += n;
+  w.dp = p;
+  if (with_dp) p += carve_dp(nullptr, make_geom(B, S, T, T1)).bytes;
+  w.bytes = (size_t)(p - static_cast<char *>(base));
+  return w;
+}
+
+int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges,
+                     const int32_t *boundary, int B, int S, int T, int R, int C, int term, int rnnt_type,
+                     float delay_penalty, const float *scores_grad, float *scores, void *logits_grad,
+                     const PrunedWs &w, cudaStream_t stream) {
+  const int T1 = type_t1(T, rnnt_type);
+  DpGeom g = make_geom(B, S, T, T1);
+  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  DpWorkspace dw = carve_dp(w.dp, g);
+  FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
+  FRN_TRY(launch_skew_band(w.pxc, w.pyc, ranges, boundary, g, dw, R, rnnt_type,
+                           delay_penalty > 0.f ? delay_penalty : 0.f, stream));
+  const bool want_grad = logits_grad != nullptr;
+  FRN_TRY(launch_chain(boundary, g, dw, want_grad, stream));
+  FRN_TRY(launch_finalize_band(ranges, boundary, g, dw, R, rnnt_type, want_grad ? w.gxc : nullptr,
+                               want_grad ? w.gyc : nullptr, scores, stream));
+  if (want_grad)
+    FRN_TRY(launch_pruned_logits_grad(logits, dtype, symbols, ranges, w.lse, w.gxc, w.gyc, scores_grad, B, S, T,
+                                      R, C, term, logits_grad, stream));
+  return FRN_OK;
+}
+}  // namespace
+
+size_t frn_pruned_logprobs_workspace_bytes(int B, int S, int T, int R) {
+  if (B <= 0 || S < 0 || T <= 0 || R <= 0) return 0;
+  return carve_pruned(nullptr, B, S, T, T + 1, R, false, false).bytes;
+}
+
+int frn_pruned_logprobs(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *ranges,
+                        const int32_t *boundary, int B, int S, int T, int R, int C, int termination_symbol,
+                        int rnnt_type, float *px, float *py, void *workspace, size_t workspace_bytes,
+                        void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
+  FRN_REQUIRE(logits && symbols && ranges && boundary && px && py);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_pruned_logprobs_workspace_bytes(B, S, T, R))
+    return FRN_EWORKSPACE;
+  const int T1 = type_t1(T, rnnt_type);
+  PrunedWs w = carve_pruned(workspace, B, S, T, T1, R, false, false);
+  FRN_TRY(launch_pruned_lse(logits, logits_dtype, symbols, ranges, B, S, T, R, C, termination_symbol, w.pxc,
+                            w.pyc, w.lse, stream));
+  return launch_band_to_dense(w.pxc, w.pyc, ranges, boundary, B, S, T, T1, R, rnnt_type, px, py, stream);
+}
+
+size_t frn_pruned_loss_workspace_bytes(int B, int S, int T, int R) {
+  if (B <= 0 || S < 0 || T <= 0 || R <= 0) return 0;
+  return carve_pruned(nullptr, B, S, T, T + 1, R, true, false).bytes;
+}
+
+int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *ranges,
+                    const int32_t *boundary, int B, int S, int T, int R, int C, int termination_symbol,
+                    int rnnt_type, float delay_penalty, const float *scores_grad, float *scores,
+                    void *logits_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
+  FRN_REQUIRE(logits && symbols && ranges && boundary && scores);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_pruned_loss_workspace_bytes(B, S, T, R))
+    return FRN_EWORKSPACE;
+  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, true, false);
+  return pruned_loss_impl(logits, logits_dtype, symbols, ranges, boundary, B, S, T, R, C, termination_symbol,
+                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w,
+                          static_cast<cudaStream_t>(stream));
+}
+
+size_t frn_joint_loss_workspace_bytes(int B, int S, int T) {
+  if (B <= 0 || S < 0 || T <= 0) return 0;
+  return carve_pruned(nullptr, B, S, T, T + 1, S + 1, true, true).bytes;
+}
+
+int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *boundary, int B,
+                   int S, int T, int C, int termination_symbol, int rnnt_type, float delay_penalty,
+                   const float *scores_grad, float *scores, void *logits_grad, void *workspace,
+                   size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
+  FRN_REQUIRE(logits && symbols && boundary && scores);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_joint_loss_workspace_bytes(B, S, T))
+    return FRN_EWORKSPACE;
+  const int R = S + 1;
+  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, true, true);
+  FRN_TRY(launch_iota_ranges(w.ranges, (size_t)B * T * R, R, stream));
+  return pruned_loss_impl(logits, logits_dtype, symbols, w.ranges, boundary, B, S, T, R, C, termination_symbol,
+                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w, stream);
+}
+
+// ------------------------------------------------------------------ A3
+int frn_reduce(const float *scores, int B, int reduction, float denominator, float *out, void *stream) {
+  FRN_REQUIRE(B > 0 && scores && out && reduction >= FRN_NONE && reduction <= FRN_SUM);
+  return launch_reduce(scores, B, reduction, denominator > 0.f ? denominator : (float)B, out,
+                       static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Host-side launchers implemented next to their kernels; called from api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace frn {
+// mi_dp.cu
+int launch_skew_dense(const float *px, const float *py, const int32_t *boundary, const DpGeom &g,
+                      const DpWorkspace &w, float delay_penalty, cudaStream_t stream);
+int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, bool both_directions,
+                 cudaStream_t stream);
+int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, float *ans,
+                          float *px_grad, float *py_grad, cudaStream_t stream);
+// prune.cu
+int launch_cummin(const int32_t *in, int32_t *out, int rows, int n, cudaStream_t stream);
+int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
+                        int T1, int R, int32_t *ranges, int32_t *s_begin_ws, cudaStream_t stream);
+int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
+                      float *am_p, float *lm_p, cudaStream_t stream);
+int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const int32_t *ranges, int B, int S,
+                          int T, int R, int C, float *am_grad, float *lm_grad, cudaStream_t stream);
+int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
+                             int C, int out_dtype, void *logits, cudaStream_t stream);
+}  // namespace frn
+
+namespace frn {
+// logprobs_simple.cu
+size_t simple_stats_bytes(int B, int S, int T, int C);
+int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                           int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
+                           float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
+                           cudaStream_t stream);
+// logprobs_pruned.cu
+int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges, int B, int S,
+                      int T, int R, int C, int term, float *pxc, float *pyc, float *lse, cudaStream_t stream);
+int launch_skew_band(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary,
+                     const DpGeom &g, const DpWorkspace &w, int R, int rnnt_type, float delay_penalty,
+                     cudaStream_t stream);
+int launch_finalize_band(const int32_t *ranges, const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
+                         int R, int rnnt_type, float *gxc, float *gyc, float *scores, cudaStream_t stream);
+int launch_pruned_logits_grad(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges,
+                              const float *lse, const float *gxc, const float *gyc, const float *scores_grad,
+                              int B, int S, int T, int R, int C, int term, void *dlogits, cudaStream_t stream);
+int launch_band_to_dense(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary,
+                         int B, int S, int T, int T1, int R, int rnnt_type, float *px, float *py,
+                         cudaStream_t stream);
+// misc.cu
+int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream);
+int launch_iota_ranges(int32_t *ranges, size_t n, int R, cudaStream_t stream);
+}  // namespace frn

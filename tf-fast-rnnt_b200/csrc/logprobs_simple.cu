@@ -1,0 +1,256 @@
+// Simple / smoothed log-probs (A1, A2): the am+lm normaliser
+//   norm[b,s,t] = log( sum_c exp(lm[b,s,c]-lmmax[b,s]) * exp(am[b,t,c]-ammax[b,t]) + tiny )
+//                 + lmmax[b,s] + ammax[b,t]
+// fused with the max-shift, the log and the px/py symbol gather
+// (rnnt_loss.py:175-221, 1266-1365: ~10 TF kernels and 3 lattice-sized
+// temporaries in the reference).
+//
+// This translation unit holds the float32 SIMT implementation (exact float32
+// products, the parity baseline).  The tcgen05/TMA split-precision version of
+// the contraction lives in logprobs_simple_tc.cu when enabled; both share the
+// row-statistics kernels and the epilogue below.
+#include "common.cuh"
+
+namespace frn {
+
+// tf.math.nextafter(0., 1.) in float32 (rnnt_loss.py:181)
+__device__ __forceinline__ float tiny_f32() { return __int_as_float(1); }
+
+// ---------------------------------------------------------------------------
+// row statistics: max (and sum of exp(x-max)) over C, one warp per row
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowstats_kernel(const float *x, int rows, int C, float *rmax,
+                                                       float *rsum) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float *src = x + (size_t)row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
+  m = warp_max(m);
+  if (rsum) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(src[c] - m);
+    s = warp_sum(s);
+    if (lane == 0) rsum[row] = s;
+  }
+  if (lane == 0) rmax[row] = m;
+}
+
+// unigram[c] = mean_rows( exp(lm-lmmax)/lmsum ) + tiny  (rnnt_loss.py:1279-1280),
+// deterministic column reduction: block = 32 columns x 8 row-striding warps.
+__global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const float *lmmax, const float *lmsum,
+                                                      int rows, int C, float *unigram, float *log_unigram) {
+  __shared__ float part[8][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = w; r < rows; r += 8) acc += expf(lm[(size_t)r * C + c] - lmmax[r]) / lmsum[r];
+  part[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][lane];
+    const float u = s / (float)rows + tiny_f32();
+    unigram[c] = u;
+    log_unigram[c] = logf(u);
+  }
+}
+
+// amonly[b,t] = log( sum_c exp(am-ammax) * unigram[c] ) + ammax  (rnnt_loss.py:1281-1286)
+__global__ void __launch_bounds__(256) amonly_kernel(const float *am, const float *ammax, const float *unigram,
+                                                     int rows, int C, float *amonly) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float *src = am + (size_t)row * C;
+  const float m = ammax[row];
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(src[c] - m) * unigram[c];
+  s = warp_sum(s);
+  if (lane == 0) amonly[row] = logf(s) + m;
+}
+
+// ---------------------------------------------------------------------------
+// contraction + epilogue.  Block: 64 (s) x 64 (t) tile of one utterance,
+// 256 threads, 4x4 micro-tile per thread, K chunks of 32.
+// ---------------------------------------------------------------------------
+struct SimpleParams {
+  const float *lm, *am;
+  const int32_t *symbols, *boundary;
+  const float *lmmax, *ammax;           // row maxima
+  const float *lmsum, *amonly, *logu;   // smoothed only (may be null)
+  float *px, *py;                       // reference layout
+  int B, S, T, T1, C, term, rnnt_type, smoothed;
+  float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
+};
+
+constexpr int kTile = 64, kBK = 32, kPitchG = 68;
+
+__global__ void __launch_bounds__(256) simple_logprobs_kernel(SimpleParams p) {
+  __shared__ __align__(16) float As[kBK * kPitchG];  // lm probs, [k][s]
+  __shared__ __align__(16) float Bs[kBK * kPitchG];  // am probs, [k][t]
+  __shared__ float s_lmmax[kTile], s_ammax[kTile];
+  const int b = blockIdx.z, s0 = blockIdx.y * kTile, t0 = blockIdx.x * kTile;
+  const int tid = threadIdx.x;
+  const int S1 = p.S + 1, C = p.C;
+  const float *lmb = p.lm + (size_t)b * S1 * C;
+  const float *amb = p.am + (size_t)b * p.T * C;
+  if (tid < kTile) {
+    const int s = s0 + tid, t = t0 + tid;
+    s_lmmax[tid] = (s < S1) ? p.lmmax[(size_t)b * S1 + s] : 0.f;
+    s_ammax[tid] = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int lr = tid >> 3, lk = (tid & 7) * 4;  // loader: row (0..31), k offset
+  for (int k0 = 0; k0 < C; k0 += kBK) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = lr + half * 32;
+      const int s = s0 + r, t = t0 + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = k0 + lk + j;
+        float a = 0.f, bb = 0.f;
+        if (c < C) {
+          if (s < S1) a = expf(lmb[(size_t)s * C + c] - s_lmmax[r]);
+          if (t < p.T) bb = expf(amb[(size_t)t * C + c] - s_ammax[r]);
+        }
+        As[(lk + j) * kPitchG + r] = a;
+        Bs[(lk + j) * kPitchG + r] = bb;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      const float4 a = *reinterpret_cast<const float4 *>(&As[k * kPitchG + ty * 4]);
+      const float4 c = *reinterpret_cast<const float4 *>(&Bs[k * kPitchG + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], cv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue: log, un-shift, symbol / blank gather (rnnt_loss.py:186-216) ----
+  const int t_end = p.boundary[4 * b + 3];
+  const int32_t *symb = p.symbols + (size_t)b * p.S;
+  float *pxb = p.px + (size_t)b * p.S * p.T1;
+  float *pyb = p.py + (size_t)b * S1 * p.T;
+  float py_am[4], amonly[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = t0 + tx * 4 + j;
+    py_am[j] = (t < p.T) ? amb[(size_t)t * C + p.term] : 0.f;
+    amonly[j] = (p.smoothed && t < p.T) ? p.amonly[(size_t)b * p.T + t] : 0.f;
+  }
+  const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int s = s0 + ty * 4 + i;
+    if (s >= S1) continue;
+    const float lmmax = s_lmmax[ty * 4 + i];
+    const float py_lm = lmb[(size_t)s * C + p.term];
+    const int sym = (s < p.S) ? symb[s] : 0;
+    const float px_lm = (s < p.S) ? lmb[(size_t)s * C + sym] : 0.f;
+    float lmonly = 0.f, logu_sym = 0.f;
+    if (p.smoothed) {
+      lmonly = logf(p.lmsum[(size_t)b * S1 + s]) + lmmax;
+      logu_sym = p.logu[sym];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx * 4 + j;
+      if (t < p.T) {
+        const float norm = logf(acc[i][j] + tiny_f32()) + lmmax + s_ammax[tx * 4 + j];
+        float py = py_am[j] + py_lm - norm;
+        if (p.smoothed)
+          py = py * p.comb + (py_lm - lmonly) * p.lm_scale + (py_am[j] + logu_term - amonly[j]) * p.am_scale;
+        pyb[(size_t)s * p.T + t] = py;
+        if (s < p.S) {
+          const float px_am = amb[(size_t)t * C + sym];
+          float px = px_am + px_lm - norm;
+          if (p.smoothed)
+            px = px * p.comb + (px_lm - lmonly) * p.lm_scale + (px_am + logu_sym - amonly[j]) * p.am_scale;
+          if (p.rnnt_type == FRN_REGULAR && t == t_end) px = -INFINITY;  // fix_for_boundary, :28-61
+          pxb[(size_t)s * p.T1 + t] = px;
+        }
+      } else if (t == p.T && p.T1 == p.T + 1 && s < p.S) {
+        pxb[(size_t)s * p.T1 + t] = -INFINITY;  // regular: one-past-the-last frame, :193-203
+      }
+    }
+  }
+}
+
+// constrained: px[b,s,t] += py[b,s+1,t]  (rnnt_loss.py:221, 1365)
+__global__ void __launch_bounds__(256) constrained_fix_kernel(float *px, const float *py, int B, int S, int T) {
+  const size_t n = (size_t)B * S * T;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / ((size_t)S * T));
+  const size_t rem = i - (size_t)b * S * T;
+  px[i] += py[(size_t)b * (S + 1) * T + T + rem];
+}
+
+// ---------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------
+size_t simple_stats_bytes(int B, int S, int T, int C) {
+  size_t n = 2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256) +
+             2 * round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)C * sizeof(float), 256);
+  return n;
+}
+
+int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                           int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
+                           float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
+                           cudaStream_t stream) {
+  const int S1 = S + 1;
+  char *w = static_cast<char *>(stats_ws);
+  float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *lmsum = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *ammax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+  float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+  float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
+  float *logu = reinterpret_cast<float *>(w);
+  rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, C, lmmax, smoothed ? lmsum : nullptr);
+  rowstats_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, B * T, C, ammax, nullptr);
+  if (smoothed) {
+    unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
+    amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
+  }
+  int rc = check_launch();
+  if (rc) return rc;
+  SimpleParams sp;
+  sp.lm = lm; sp.am = am; sp.symbols = symbols; sp.boundary = boundary;
+  sp.lmmax = lmmax; sp.ammax = ammax; sp.lmsum = lmsum; sp.amonly = amonly; sp.logu = logu;
+  sp.px = px; sp.py = py;
+  sp.B = B; sp.S = S; sp.T = T; sp.T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T; sp.C = C; sp.term = term;
+  sp.rnnt_type = rnnt_type; sp.smoothed = smoothed;
+  // Python-float arithmetic of rnnt_loss.py:1342-1349, then cast to float32
+  const double lms = (double)lm_only_scale, ams = (double)am_only_scale;
+  sp.comb = (float)(1.0 - lms - ams);
+  sp.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
+  sp.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
+  dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
+  simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
+  rc = check_launch();
+  if (rc) return rc;
+  if (rnnt_type == FRN_CONSTRAINED) {
+    const size_t n = (size_t)B * S * T;
+    constrained_fix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(px, py, B, S, T);
+    rc = check_launch();
+  }
+  return rc;
+}
+
+}  // namespace frn

@@ -1,0 +1,41 @@
+// Small utility kernels: loss reduction (A3) and identity band for the full joiner.
+#include "common.cuh"
+
+namespace frn {
+
+// out = -scores (none) | -sum | -sum/denominator; one block, deterministic order.
+__global__ void __launch_bounds__(256) reduce_kernel(const float *scores, int B, int reduction, float denom,
+                                                     float *out) {
+  if (reduction == FRN_NONE) {
+    for (int i = threadIdx.x; i < B; i += blockDim.x) out[i] = -scores[i];
+    return;
+  }
+  __shared__ float part[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) acc += scores[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) s += part[j];
+    out[0] = (reduction == FRN_MEAN) ? -(s / denom) : -s;
+  }
+}
+
+__global__ void iota_ranges_kernel(int32_t *ranges, size_t n, int R) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ranges[i] = (int32_t)(i % (size_t)R);
+}
+
+int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream) {
+  reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out);
+  return check_launch();
+}
+
+int launch_iota_ranges(int32_t *ranges, size_t n, int R, cudaStream_t stream) {
+  iota_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ranges, n, R);
+  return check_launch();
+}
+
+}  // namespace frn

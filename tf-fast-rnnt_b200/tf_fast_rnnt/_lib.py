@@ -1,0 +1,82 @@
+"""ctypes binding of libfast_rnnt_b200.so (C ABI: include/fast_rnnt_b200.h).
+
+This is the TensorFlow-free twin of the ``tf.load_op_library`` call of the
+reference (tf_fast_rnnt/python/tf_fast_rnnt/__init__.py:38-40).  There is no CPU
+fallback: if the shared library is missing or does not load, importing the
+package fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_size_t, c_void_p
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get(
+    "FAST_RNNT_B200_LIB",
+    os.path.join(os.path.dirname(_PKG_DIR), "lib", "libfast_rnnt_b200.so"))
+
+FRN_OK = 0
+REGULAR, MODIFIED, CONSTRAINED = 0, 1, 2
+F32, BF16 = 0, 1
+NONE, MEAN, SUM = 0, 1, 2
+RNNT_TYPES = {"regular": REGULAR, "modified": MODIFIED, "constrained": CONSTRAINED}
+REDUCTIONS = {"none": NONE, "mean": MEAN, "sum": SUM}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"fast_rnnt_b200: {LIB_PATH} not found. Build it with "
+        "`make -C tf-fast-rnnt_b200/csrc` (or __graft_entry__.build()); "
+        "there is no CPU fallback.")
+lib = ctypes.CDLL(LIB_PATH)
+
+_P = c_void_p
+_SIGS = {
+    "frn_version": (c_int, []),
+    "frn_status_string": (ctypes.c_char_p, [c_int]),
+    "frn_last_cuda_error": (c_int, []),
+    "frn_mi_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_mi_fwd_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_cummin": (c_int, [_P, _P, c_int, c_int, _P]),
+    "frn_simple_logprobs_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_simple_logprobs": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_loss_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_simple_loss": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_float, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_loss_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_simple_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    _P, _P, _P, c_size_t, _P]),
+    "frn_prune_ranges_width": (c_int, [c_int, c_int]),
+    "frn_prune_ranges_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "frn_prune_ranges": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "frn_do_pruning": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "frn_do_pruning_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "frn_pruned_add_joiner": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "frn_pruned_logprobs_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_pruned_logprobs": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    _P, _P, _P, c_size_t, _P]),
+    "frn_pruned_loss_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_pruned_loss": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_joint_loss_workspace_bytes": (c_size_t, [c_int] * 3),
+    "frn_joint_loss": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                               _P, _P, _P, _P, c_size_t, _P]),
+    "frn_reduce": (c_int, [_P, c_int, c_int, c_float, _P, _P]),
+}
+EXPORTS = tuple(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)      # AttributeError here = header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class FastRnntError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status != FRN_OK:
+        msg = lib.frn_status_string(status).decode()
+        extra = f" (cudaError {lib.frn_last_cuda_error()})" if status == -3 else ""
+        raise FastRnntError(f"{what}: {msg}{extra}")

@@ -1,0 +1,455 @@
+"""Host-side mirror of the reference's ``tf_fast_rnnt/rnnt_loss.py`` API.
+
+Same function names, argument names, defaults and return conventions as
+/root/reference/tf_fast_rnnt/python/tf_fast_rnnt/rnnt_loss.py; every function is
+a thin call into the C ABI (include/fast_rnnt_b200.h) of hand-written sm_100a
+kernels.  No math is done here and nothing falls back to the CPU.
+
+Tensors: CUDA ``torch.Tensor`` in -> CUDA ``torch.Tensor`` out (zero copies;
+torch is used for device memory and streams only).  ``numpy.ndarray`` (host
+buffers) in -> copied to the current device, result copied back, ``numpy`` out;
+that is the path a host-resident caller such as a TensorFlow-free harness uses.
+
+Differences from the reference, all decisions of SURVEY.md §9:
+  * ``modified`` / ``constrained`` work in the simple/smoothed losses (the
+    reference raises a shape error there, rnnt_loss.py:211);
+  * ``px_grad`` has the shape of ``px`` (tf_fast_rnnt_op.cc:84 always made it
+    [B,S,T+1]);
+  * ``reduction="mean"`` of ``rnnt_loss_simple`` works (rnnt_loss.py:331 is a
+    NameError);
+  * ``boundary=None`` means ``[0, 0, S, T]`` for every utterance.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+Tensor = Union[torch.Tensor, np.ndarray]
+
+
+# ---------------------------------------------------------------- plumbing
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.FastRnntError(
+            "fast_rnnt_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Io:
+    """Remembers whether the caller handed host (numpy) or device buffers."""
+
+    def __init__(self, *xs):
+        self.host = any(isinstance(x, np.ndarray) for x in xs if x is not None) or not any(
+            isinstance(x, torch.Tensor) and x.is_cuda for x in xs if x is not None)
+        devs = [x.device for x in xs if isinstance(x, torch.Tensor) and x.is_cuda]
+        self.dev = devs[0] if devs else _device()
+
+    def dev_tensor(self, x, dtype) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            t = x
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(x))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        if not t.is_cuda:
+            t = t.to(self.dev, non_blocking=True)
+        return t.contiguous()
+
+    def out(self, t: torch.Tensor):
+        return t.cpu().numpy() if self.host else t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _workspace(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def _boundary(io: _Io, boundary, B: int, S: int, T: int) -> torch.Tensor:
+    if boundary is None:
+        b = torch.tensor([0, 0, S, T], dtype=torch.int32).repeat(B, 1)
+        return b.to(io.dev)
+    b = io.dev_tensor(boundary, torch.int32)
+    if tuple(b.shape) != (B, 4):
+        raise ValueError(f"boundary must have shape ({B}, 4), got {tuple(b.shape)}")
+    return b
+
+
+def _rnnt_type(rnnt_type: str) -> int:
+    if rnnt_type not in _lib.RNNT_TYPES:
+        raise ValueError(f"rnnt_type must be one of {list(_lib.RNNT_TYPES)}, given {rnnt_type}")
+    return _lib.RNNT_TYPES[rnnt_type]
+
+
+def _logits_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError(f"logits must be float32 or bfloat16, got {t.dtype}")
+
+
+def _reduce(scores: torch.Tensor, reduction: str, group=None) -> torch.Tensor:
+    """loss = -scores with the reference's reductions (rnnt_loss.py:327-338).
+    With a ``torch.distributed`` group the sum/mean is completed across ranks by
+    one scalar all-reduce (the only collective on this path)."""
+    if reduction not in _lib.REDUCTIONS:
+        raise ValueError(
+            f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    B = scores.shape[0]
+    red = _lib.REDUCTIONS[reduction]
+    out = torch.empty(B if red == _lib.NONE else 1, dtype=torch.float32, device=scores.device)
+    denom = 0.0
+    if group is not None and red == _lib.MEAN:
+        import torch.distributed as dist
+        n = torch.tensor([B], dtype=torch.int64, device=scores.device)
+        dist.all_reduce(n, group=group)
+        denom = float(n.item())
+    check(lib.frn_reduce(_ptr(scores), B, red, denom, _ptr(out), _stream(scores.device)), "frn_reduce")
+    if red == _lib.NONE:
+        return out
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(out, group=group)
+    return out.reshape(())
+
+
+# ---------------------------------------------------------------- A4 / cummin
+def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tensor] = None,
+                                 calc_gradients: bool = False):
+    """Reference: tf_fast_rnnt/__init__.py:42-149 (op FastRNNTLoss)."""
+    io = _Io(px, py)
+    px_d = io.dev_tensor(px, torch.float32)
+    py_d = io.dev_tensor(py, torch.float32)
+    if px_d.dim() != 3 or py_d.dim() != 3:
+        raise ValueError("px and py must be 3-dimensional")
+    B, S, T1 = px_d.shape
+    T = py_d.shape[2]
+    if T1 not in (T, T + 1) or tuple(py_d.shape) != (B, S + 1, T):
+        raise ValueError(f"bad shapes px {tuple(px_d.shape)} py {tuple(py_d.shape)}")
+    bd = _boundary(io, boundary, B, S, T)
+    ans = torch.empty(B, dtype=torch.float32, device=io.dev)
+    gx = torch.empty_like(px_d) if calc_gradients else None
+    gy = torch.empty_like(py_d) if calc_gradients else None
+    nbytes = lib.frn_mi_workspace_bytes(B, S, T, T1)
+    ws = _workspace(nbytes, io.dev)
+    check(lib.frn_mi_fwd_bwd(_ptr(px_d), _ptr(py_d), _ptr(bd), B, S, T, T1, int(calc_gradients),
+                             _ptr(ans), _ptr(gx), _ptr(gy), _ptr(ws), ws.numel(), _stream(io.dev)),
+          "frn_mi_fwd_bwd")
+    if calc_gradients:
+        return io.out(ans), (io.out(gx), io.out(gy))
+    return io.out(ans)
+
+
+def cummin(x: Tensor):
+    """Reference: tf_fast_rnnt/__init__.py:151-152 (op Cummin)."""
+    io = _Io(x)
+    x_d = io.dev_tensor(x, torch.int32)
+    if x_d.dim() != 2:
+        raise ValueError("cummin expects a 2-D int32 tensor")
+    out = torch.empty_like(x_d)
+    check(lib.frn_cummin(_ptr(x_d), _ptr(out), x_d.shape[0], x_d.shape[1], _stream(io.dev)), "frn_cummin")
+    return io.out(out)
+
+
+# ---------------------------------------------------------------- A1 / A2
+def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed,
+                     lm_only_scale, am_only_scale):
+    io = _Io(lm, am)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    am_d = io.dev_tensor(am, torch.float32)
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    if tuple(lm_d.shape) != (B, S + 1, C) or tuple(sym_d.shape) != (B, S):
+        raise ValueError("lm must be [B,S+1,C], am [B,T,C], symbols [B,S]")
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    T1 = T + 1 if rt == _lib.REGULAR else T
+    px = torch.empty((B, S, T1), dtype=torch.float32, device=io.dev)
+    py = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev)
+    ws = _workspace(lib.frn_simple_logprobs_workspace_bytes(B, S, T, C), io.dev)
+    check(lib.frn_simple_logprobs(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                                  int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                                  float(am_only_scale), _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
+                                  _stream(io.dev)), "frn_simple_logprobs")
+    return io.out(px), io.out(py)
+
+
+def get_rnnt_logprobs(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
+                      rnnt_type: str = "regular", boundary: Optional[Tensor] = None):
+    """Reference: rnnt_loss.py:63-223."""
+    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, False, 0.0, 0.0)
+
+
+def get_rnnt_logprobs_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
+                               lm_only_scale: float = 0.1, am_only_scale: float = 0.1,
+                               boundary: Optional[Tensor] = None, rnnt_type: str = "regular"):
+    """Reference: rnnt_loss.py:1132-1367."""
+    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, True,
+                            lm_only_scale, am_only_scale)
+
+
+def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
+                 calc_gradients, smoothed, lm_only_scale, am_only_scale, group=None):
+    if reduction not in _lib.REDUCTIONS:
+        raise ValueError(
+            f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    io = _Io(lm, am)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    am_d = io.dev_tensor(am, torch.float32)
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    if tuple(lm_d.shape) != (B, S + 1, C) or tuple(sym_d.shape) != (B, S):
+        raise ValueError("lm must be [B,S+1,C], am [B,T,C], symbols [B,S]")
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    T1 = T + 1 if rt == _lib.REGULAR else T
+    scores = torch.empty(B, dtype=torch.float32, device=io.dev)
+    gx = torch.empty((B, S, T1), dtype=torch.float32, device=io.dev) if calc_gradients else None
+    gy = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev) if calc_gradients else None
+    ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), io.dev)
+    dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    check(lib.frn_simple_loss(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                              int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                              float(am_only_scale), dp, int(calc_gradients), _ptr(scores), _ptr(gx), _ptr(gy),
+                              _ptr(ws), ws.numel(), _stream(io.dev)), "frn_simple_loss")
+    loss = io.out(_reduce(scores, reduction, group))
+    return (loss, (io.out(gx), io.out(gy))) if calc_gradients else loss
+
+
+def rnnt_loss_simple(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
+                     boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
+                     delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
+                     calc_gradients: bool = False, group=None):
+    """Reference: rnnt_loss.py:225-338.  ``group``: optional torch.distributed
+    process group over which 'sum'/'mean' are completed (batch sharded by
+    utterance)."""
+    return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
+                        reduction, calc_gradients, False, 0.0, 0.0, group)
+
+
+def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
+                       lm_only_scale: float = 0.1, am_only_scale: float = 0.1,
+                       boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
+                       delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
+                       calc_gradients: bool = False, group=None):
+    """Reference: rnnt_loss.py:1369-1494."""
+    return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
+                        reduction, calc_gradients, True, lm_only_scale, am_only_scale, group)
+
+
+# ---------------------------------------------------------------- A5 / A6
+def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_range: int):
+    """Reference: rnnt_loss.py:647-761."""
+    io = _Io(px_grad, py_grad)
+    gx = io.dev_tensor(px_grad, torch.float32)
+    gy = io.dev_tensor(py_grad, torch.float32)
+    B, S, T1 = gx.shape
+    T = gy.shape[2]
+    if T1 not in (T, T + 1) or tuple(gy.shape) != (B, S + 1, T):
+        raise ValueError(f"bad shapes px_grad {tuple(gx.shape)} py_grad {tuple(gy.shape)}")
+    bd = _boundary(io, boundary, B, S, T)
+    R = lib.frn_prune_ranges_width(S, int(s_range))
+    ranges = torch.empty((B, T, R), dtype=torch.int32, device=io.dev)
+    ws = _workspace(lib.frn_prune_ranges_workspace_bytes(B, T), io.dev)
+    check(lib.frn_prune_ranges(_ptr(gx), _ptr(gy), _ptr(bd), B, S, T, T1, int(s_range), _ptr(ranges),
+                               _ptr(ws), ws.numel(), _stream(io.dev)), "frn_prune_ranges")
+    return io.out(ranges)
+
+
+def do_rnnt_pruning(am: Tensor, lm: Tensor, ranges: Tensor):
+    """Reference: rnnt_loss.py:763-812."""
+    io = _Io(am, lm)
+    am_d = io.dev_tensor(am, torch.float32)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    R = rg.shape[2]
+    if tuple(rg.shape) != (B, T, R) or tuple(lm_d.shape) != (B, S + 1, C):
+        raise ValueError("am [B,T,C], lm [B,S+1,C], ranges [B,T,s_range] expected")
+    am_p = torch.empty((B, T, R, C), dtype=torch.float32, device=io.dev)
+    lm_p = torch.empty((B, T, R, C), dtype=torch.float32, device=io.dev)
+    check(lib.frn_do_pruning(_ptr(am_d), _ptr(lm_d), _ptr(rg), B, S, T, R, C, _ptr(am_p), _ptr(lm_p),
+                             _stream(io.dev)), "frn_do_pruning")
+    return io.out(am_p), io.out(lm_p)
+
+
+def do_rnnt_pruning_backward(am_pruned_grad: Tensor, lm_pruned_grad: Tensor, ranges: Tensor, S: int):
+    """Gradient of do_rnnt_pruning (what TF autodiff derives for rnnt_loss.py:802-811)."""
+    io = _Io(am_pruned_grad, lm_pruned_grad)
+    ga = io.dev_tensor(am_pruned_grad, torch.float32)
+    gl = io.dev_tensor(lm_pruned_grad, torch.float32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, R, C = ga.shape
+    am_g = torch.empty((B, T, C), dtype=torch.float32, device=io.dev)
+    lm_g = torch.empty((B, S + 1, C), dtype=torch.float32, device=io.dev)
+    check(lib.frn_do_pruning_bwd(_ptr(ga), _ptr(gl), _ptr(rg), B, S, T, R, C, _ptr(am_g), _ptr(lm_g),
+                                 _stream(io.dev)), "frn_do_pruning_bwd")
+    return io.out(am_g), io.out(lm_g)
+
+
+def pruned_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor, dtype=torch.float32):
+    """(extension) logits = am_pruned + lm_pruned without
+    materialising either."""
+    io = _Io(am, lm)
+    am_d = io.dev_tensor(am, torch.float32)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    R = rg.shape[2]
+    out = torch.empty((B, T, R, C), dtype=dtype, device=io.dev)
+    check(lib.frn_pruned_add_joiner(_ptr(am_d), _ptr(lm_d), _ptr(rg), B, S, T, R, C, _logits_dtype(out),
+                                    _ptr(out), _stream(io.dev)), "frn_pruned_add_joiner")
+    return io.out(out) if dtype == torch.float32 else out
+
+
+# ---------------------------------------------------------------- A7 / A8
+def get_rnnt_logprobs_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, termination_symbol: int,
+                             boundary: Tensor, rnnt_type: str = "regular"):
+    """Reference: rnnt_loss.py:853-1020."""
+    io = _Io(logits)
+    lg = logits if isinstance(logits, torch.Tensor) and logits.is_cuda else io.dev_tensor(logits, torch.float32)
+    lg = lg.contiguous()
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, R, C = lg.shape
+    S = sym_d.shape[1]
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    T1 = T + 1 if rt == _lib.REGULAR else T
+    px = torch.empty((B, S, T1), dtype=torch.float32, device=io.dev)
+    py = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev)
+    ws = _workspace(lib.frn_pruned_logprobs_workspace_bytes(B, S, T, R), io.dev)
+    check(lib.frn_pruned_logprobs(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(rg), _ptr(bd), B, S, T, R, C,
+                                  int(termination_symbol), rt, _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
+                                  _stream(io.dev)), "frn_pruned_logprobs")
+    return io.out(px), io.out(py)
+
+
+def pruned_loss_fwd_bwd(logits, symbols, ranges, termination_symbol, boundary, rnnt_type="regular",
+                        delay_penalty=0.0, scores_grad=None, want_logits_grad=True):
+    """One fused call: scores [B] and d(sum_b scores_grad[b]*scores[b])/d logits
+    (scores_grad None = ones).  Device tensors only."""
+    dev = logits.device
+    io = _Io(logits)
+    lg = logits.contiguous()
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, R, C = lg.shape
+    S = sym_d.shape[1]
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    scores = torch.empty(B, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(lg) if want_logits_grad else None
+    sg = None if scores_grad is None else io.dev_tensor(scores_grad, torch.float32)
+    ws = _workspace(lib.frn_pruned_loss_workspace_bytes(B, S, T, R), dev)
+    dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    check(lib.frn_pruned_loss(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(rg), _ptr(bd), B, S, T, R, C,
+                              int(termination_symbol), rt, dp, _ptr(sg), _ptr(scores), _ptr(grad), _ptr(ws),
+                              ws.numel(), _stream(dev)), "frn_pruned_loss")
+    return scores, grad
+
+
+class _PrunedLossFn(torch.autograd.Function):
+    """Autograd node standing where TF's GradientTape + _RNNTLossGrad
+    (__init__.py:154-162) stand in the reference."""
+
+    @staticmethod
+    def forward(ctx, logits, symbols, ranges, termination_symbol, boundary, rnnt_type, delay_penalty):
+        scores, _ = pruned_loss_fwd_bwd(logits, symbols, ranges, termination_symbol, boundary, rnnt_type,
+                                        delay_penalty, None, want_logits_grad=False)
+        ctx.save_for_backward(logits, symbols, ranges, boundary)
+        ctx.args = (termination_symbol, rnnt_type, delay_penalty)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, symbols, ranges, boundary = ctx.saved_tensors
+        term, rnnt_type, dp = ctx.args
+        _, grad = pruned_loss_fwd_bwd(logits, symbols, ranges, term, boundary, rnnt_type, dp,
+                                      g.contiguous(), want_logits_grad=True)
+        return grad, None, None, None, None, None, None
+
+
+def rnnt_loss_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, termination_symbol: int,
+                     boundary: Tensor = None, rnnt_type: str = "regular", delay_penalty: float = 0.0,
+                     reduction: Optional[str] = "mean", calc_gradients: bool = False, group=None):
+    """Reference: rnnt_loss.py:1022-1130 (returns only the loss, like the
+    reference, whatever ``calc_gradients`` is)."""
+    if reduction not in _lib.REDUCTIONS:
+        raise ValueError(
+            f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    io = _Io(logits)
+    if isinstance(logits, torch.Tensor) and logits.is_cuda:
+        lg = logits
+    else:
+        lg = io.dev_tensor(logits, torch.float32)
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, R, C = lg.shape
+    S = sym_d.shape[1]
+    bd = _boundary(io, boundary, B, S, T)
+    if lg.requires_grad and torch.is_grad_enabled():
+        scores = _PrunedLossFn.apply(lg, sym_d, rg, int(termination_symbol), bd, rnnt_type,
+                                     float(delay_penalty))
+        if reduction == "none":
+            return -scores
+        loss = -scores.sum() if reduction == "sum" else -scores.mean()
+        return loss
+    scores, _ = pruned_loss_fwd_bwd(lg, sym_d, rg, termination_symbol, bd, rnnt_type, delay_penalty, None,
+                                    want_logits_grad=False)
+    return io.out(_reduce(scores, reduction, group))
+
+
+# ---------------------------------------------------------------- (f1) full joiner
+def get_rnnt_logprobs_joint(logits: Tensor, symbols: Tensor, termination_symbol: int,
+                            boundary: Optional[Tensor] = None, rnnt_type: str = "regular"):
+    """Reference: rnnt_loss.py:340-452.  The full joiner is the pruned case with
+    the identity band ranges[b,t,i] = i."""
+    io = _Io(logits)
+    lg = logits if isinstance(logits, torch.Tensor) and logits.is_cuda else io.dev_tensor(logits, torch.float32)
+    B, T, S1, C = lg.shape
+    ranges = torch.arange(S1, dtype=torch.int32, device=io.dev).expand(B, T, S1).contiguous()
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    bd = _boundary(io, boundary, B, S1 - 1, T)
+    px, py = get_rnnt_logprobs_pruned(lg, sym_d, ranges, termination_symbol, bd, rnnt_type)
+    return io.out(px), io.out(py)
+
+
+def rnnt_loss(logits: Tensor, symbols: Tensor, termination_symbol: int, boundary: Optional[Tensor] = None,
+              rnnt_type: str = "regular", delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
+              calc_gradients: bool = False, group=None):
+    """Reference: rnnt_loss.py:454-551."""
+    if reduction not in _lib.REDUCTIONS:
+        raise ValueError(
+            f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+    io = _Io(logits)
+    lg = logits if isinstance(logits, torch.Tensor) and logits.is_cuda else io.dev_tensor(logits, torch.float32)
+    lg = lg.contiguous()
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    B, T, S1, C = lg.shape
+    S = S1 - 1
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    scores = torch.empty(B, dtype=torch.float32, device=io.dev)
+    ws = _workspace(lib.frn_joint_loss_workspace_bytes(B, S, T), io.dev)
+    dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    check(lib.frn_joint_loss(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                             int(termination_symbol), rt, dp, None, _ptr(scores), None, _ptr(ws), ws.numel(),
+                             _stream(io.dev)), "frn_joint_loss")
+    return io.out(_reduce(scores, reduction, group))
