@@ -31,14 +31,18 @@ def _boundaries(rng, B, S, T, kind):
 def test_mi_against_float64_oracle(modified, shape, kind):
     import tf_fast_rnnt
     B, S, T = shape
-    rng = np.random.default_rng(hash((modified, shape, kind)) % (2 ** 31))
+    rng = np.random.default_rng([int(modified), *shape, len(kind)])
     px, py = random_pxpy(rng.integers(1 << 30), B, S, T, modified)
     bd = _boundaries(rng, B, S, T, kind)
     ans, (gx, gy) = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
     ans64, (gx64, gy64) = orc.mutual_information_recursion(px, py, bd, True, np.float64)
-    assert_close(ans, ans64, LOSS_RTOL, 1e-6, "ans")
-    assert_close(gx, gx64, GRAD_RTOL, GRAD_ATOL, "px_grad")
-    assert_close(gy, gy64, GRAD_RTOL, GRAD_ATOL, "py_grad")
+    # scores here are sums of ~(S+T) O(1) terms of both signs that may cancel to ~0,
+    # hence the absolute term (1e-5 in log-probability)
+    assert_close(ans, ans64, LOSS_RTOL, 1e-5, "ans")
+    ok = np.isfinite(ans64)      # no path (score -inf): the reference's grads are meaningless there
+    assert_close(gx[ok], gx64[ok], GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy[ok], gy64[ok], GRAD_RTOL, GRAD_ATOL, "py_grad")
+    assert not np.isnan(gx).any() and not np.isnan(gy).any()
     only = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=False)
     assert np.array_equal(only, ans)
 

@@ -42,7 +42,11 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // log2(2^a + 2^b) for finite a, b (kNeg stands in for -inf).
 __device__ __forceinline__ float logadd2(float a, float b) {
   float mx = fmaxf(a, b), mn = fminf(a, b);
+#ifdef FRN_ACCURATE_LOGADD
+  return mx + log2f(1.0f + exp2f(mn - mx));
+#else
   return mx + lg2_approx(1.0f + ex2_approx(mn - mx));
+#endif
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -122,7 +126,7 @@ struct DpGeom {
   int P;            // padded row count, multiple of 128
   int Dn;           // allocated diagonals, multiple of kChunk
 };
-constexpr int kChunk = 16;  // diagonals per bulk copy
+constexpr int kChunk = 16;    // diagonals per bulk copy
 
 inline DpGeom make_geom(int B, int S, int T, int T1) {
   DpGeom g;
@@ -136,23 +140,23 @@ inline DpGeom make_geom(int B, int S, int T, int T1) {
 // Workspace carve-up of one DP invocation.
 struct DpWorkspace {
   float *X, *Y;        // [B][Dn][P] skewed log2-domain arc scores
-  float *alpha;        // [B][Dn][P] renormalised forward scores
-  float *bx, *by;      // [B][Dn][P] backward-side operands (arc score + beta of the arc's head)
-  double *offA, *offB; // [B][Dn]    cumulative renormalisation offsets
+  // every lattice value is held as (exact integer offset o) + (small float32 residual r)
+  float *ar, *ao;      // [B][Dn][P] forward scores: residual, offset
+  float *bx, *by;      // [B][Dn][P] backward-side operands (arc score + beta of the arc's head), residuals
+  float *bo;           // [B][Dn][P] offset of the frame bx/by are expressed in
   size_t bytes;
 };
 inline DpWorkspace carve_dp(void *base, const DpGeom &g) {
   DpWorkspace w;
   char *p = static_cast<char *>(base);
   size_t plane = round_up_sz((size_t)g.B * g.Dn * g.P * sizeof(float), 256);
-  size_t offs = round_up_sz((size_t)g.B * g.Dn * sizeof(double), 256);
   w.X = reinterpret_cast<float *>(p); p += plane;
   w.Y = reinterpret_cast<float *>(p); p += plane;
-  w.alpha = reinterpret_cast<float *>(p); p += plane;
+  w.ar = reinterpret_cast<float *>(p); p += plane;
+  w.ao = reinterpret_cast<float *>(p); p += plane;
   w.bx = reinterpret_cast<float *>(p); p += plane;
   w.by = reinterpret_cast<float *>(p); p += plane;
-  w.offA = reinterpret_cast<double *>(p); p += offs;
-  w.offB = reinterpret_cast<double *>(p); p += offs;
+  w.bo = reinterpret_cast<float *>(p); p += plane;
   w.bytes = (size_t)(p - static_cast<char *>(base));
   return w;
 }

@@ -62,23 +62,23 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
       const float mn = fmaxf(m, mx);
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc += ex2_approx((x[j] - mn) * kLog2e);
-      ssum = ssum * ex2_approx((m - mn) * kLog2e) + acc;
+      for (int j = 0; j < V; ++j) acc += expf(x[j] - mn);
+      ssum = ssum * expf(m - mn) + acc;
       m = mn;
     }
   } else {
     for (int c = lane; c < C; c += 32) {
       const float x = to_f(src[c]);
       const float mn = fmaxf(m, x);
-      ssum = ssum * ex2_approx((m - mn) * kLog2e) + ex2_approx((x - mn) * kLog2e);
+      ssum = ssum * expf(m - mn) + expf(x - mn);
       m = mn;
     }
   }
   // combine lanes
   const float M = warp_max(m);
-  const float scaled = (m == -INFINITY) ? 0.f : ssum * ex2_approx((m - M) * kLog2e);
+  const float scaled = (m == -INFINITY) ? 0.f : ssum * expf(m - M);
   const float tot = warp_sum(scaled);
-  const float lse = (M == -INFINITY) ? -INFINITY : M + lg2_approx(tot) * kLn2;
+  const float lse = (M == -INFINITY) ? -INFINITY : M + logf(tot);
   if (lane == 0) {
     const int b = row / TR;
     const int s = ranges[row];  // symbol context of this band entry (rnnt_loss.py:954-958)
@@ -144,8 +144,7 @@ __global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float *X, 
 // (constrained: the px arc's count is folded into the py entry it borrowed).
 // ---------------------------------------------------------------------------
 struct BandFinalizeParams {
-  const float *alpha, *bx, *by;
-  const double *offA, *offB;
+  const float *ar, *ao, *bx, *by, *bo;
   const int32_t *ranges, *boundary;
   int S, T, R, P, Dn, k, rnnt_type;
 };
@@ -163,8 +162,9 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
     float v = 0.f;
     if (bd_ok(bd, p.S, p.T)) {
       const int Sb = bd.z - bd.x, Tb = bd.w - bd.y, Db = Tb + p.k * Sb;
-      const double tot = (double)p.alpha[((size_t)idx * p.Dn + Db) * p.P + Sb] + p.offA[(size_t)idx * p.Dn + Db];
-      v = (tot < (double)kNegThresh) ? -INFINITY : (float)(tot * 0.6931471805599453);
+      const size_t at = ((size_t)idx * p.Dn + Db) * p.P + Sb;
+      const float tr = p.ar[at], to = p.ao[at];
+      v = (tr < kNegThresh) ? -INFINITY : (float)(((double)tr + (double)to) * 0.6931471805599453);
     }
     scores[idx] = v;
   }
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
   if (bd_ok(bd, p.S, p.T) && t >= bd.y && t < bd.w) {
     const int Sb = bd.z - bd.x, Tb = bd.w - bd.y, Db = Tb + p.k * Sb;
     const size_t plane = (size_t)b * p.Dn * p.P;
-    const double tot = (double)p.alpha[plane + (size_t)Db * p.P + Sb] + p.offA[(size_t)b * p.Dn + Db];
-    if (!(tot < (double)kNegThresh)) {
+    const float tot_r = p.ar[plane + (size_t)Db * p.P + Sb], tot_o = p.ao[plane + (size_t)Db * p.P + Sb];
+    if (!(tot_r < kNegThresh)) {
       const int r0 = p.ranges[(size_t)(b * p.T + t) * p.R];
       const int s = band_row(r0, i, p.S + 1);
       auto occ = [&](int sa, bool px_arc) -> float {
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
         if (px_arc && !(sa < p.S && sp < Sb)) return 0.f;
         const int d = tp + p.k * sp;
         const size_t at = plane + (size_t)d * p.P + sp;
-        const float c = (float)(p.offA[(size_t)b * p.Dn + d] + p.offB[(size_t)b * p.Dn + d] - tot);
-        return ex2_approx(p.alpha[at] + (px_arc ? p.bx[at] : p.by[at]) + c);
+        const float base = (p.ar[at] - tot_r) + ((p.ao[at] + p.bo[at]) - tot_o);
+        return ex2_approx((px_arc ? p.bx[at] : p.by[at]) + base);
       };
       vx = occ(s, true);
       vy = occ(s, false);
@@ -328,7 +328,7 @@ int launch_skew_band(const float *pxc, const float *pyc, const int32_t *ranges, 
 
 int launch_finalize_band(const int32_t *ranges, const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
                          int R, int rnnt_type, float *gxc, float *gyc, float *scores, cudaStream_t stream) {
-  BandFinalizeParams fp{w.alpha, w.bx, w.by, w.offA, w.offB, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type};
+  BandFinalizeParams fp{w.ar, w.ao, w.bx, w.by, w.bo, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type};
   const int n = gxc ? max(g.B * g.T * R, g.B) : g.B;
   finalize_band_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fp, gxc, gyc, scores, g.B);
   return check_launch();
