@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the pruned RNN-T loss hot path (BASELINE.json metric).
+
+One "step" = one pass of the full pruned pipeline over one batch of synthetic
+utterances, through the C ABI (include/fast_rnnt_b200.h):
+
+    frn_simple_loss (fwd + occupation counts)  ->  frn_prune_ranges
+    -> frn_do_pruning -> frn_add_joiner (additive joiner of the reference's
+    tests, standing in for the user's joiner network) -> frn_pruned_loss
+    (fwd + logits gradient) -> frn_reduce x2 (+ one 2-float NCCL all-reduce
+    when N > 1)
+
+Workload: BASELINE.json configs[1] — B=32 T=500 S=100 C=500 s_range=5 fp32,
+rnnt_type=regular, reduction=sum.  `value` is utterances/s with inputs resident
+in HBM; `e2e` is the same step driven from pinned HOST buffers (H2D of
+am/lm/symbols/boundary and D2H of the two losses inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the CPU restatement of the reference's path (the
+oracle; the reference has no CPU implementation and its TensorFlow half cannot
+run here) on the host cores.  Under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "tf-fast-rnnt_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (B, T, S, C, R)
+    "c1": (2, 50, 10, 16, 5),
+    "c2": (32, 500, 100, 500, 5),
+    "c4": (16, 1500, 400, 5000, 5),
+}
+METRIC = "utterances/sec (pruned loss fwd+bwd) at B32 T500 S100 C500; lattice cells/s; HBM %"
+UNIT = "utterances/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth(B, T, S, C, seed):
+    """N(0,1) am/lm, uniform symbols, blank = C-1, full-length boundary."""
+    rng = np.random.default_rng(seed)
+    am = rng.standard_normal((B, T, C), dtype=np.float32)
+    lm = rng.standard_normal((B, S + 1, C), dtype=np.float32)
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    bd = np.tile(np.array([0, 0, S, T], np.int32), (B, 1))
+    return am, lm, sym, bd
+
+
+# ----------------------------------------------------------------------------
+# CPU arm (oracle port) — also the cpu_baseline leg of the GPU arm
+# ----------------------------------------------------------------------------
+def cpu_step(am, lm, sym, bd, C, R):
+    from oracle import rnnt_oracle as orc
+    term = C - 1
+    loss, (gx, gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "sum", True)
+    ranges = orc.get_rnnt_prune_ranges(gx, gy, bd, R)
+    am_p, lm_p = orc.do_rnnt_pruning(am, lm, ranges)
+    logits = am_p + lm_p
+    grad, scores = orc.pruned_logits_grad(logits, sym, ranges, term, bd, "regular", 0.0, None, np.float32,
+                                          return_scores=True)      # pruned loss fwd + bwd in one pass
+    return float(loss), float(-scores.sum()), grad
+
+
+def cpu_bench(workload, steps, warmup, sample_B=None):
+    B, T, S, C, R = WORKLOADS[workload]
+    Bs = sample_B or B
+    am, lm, sym, bd = synth(Bs, T, S, C, 1234)
+    for _ in range(warmup):
+        cpu_step(am, lm, sym, bd, C, R)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(am, lm, sym, bd, C, R)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    cores = os.cpu_count() or 1
+    return {"value": Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} full steps of {workload} with B={Bs} (numpy/BLAS + OpenMP C recursion, "
+                      f"all {cores} host threads), {dt * 1e3:.0f} ms per step"}, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload
+    B = WORKLOADS[workload][0]
+    steps = max(1, min(args.steps, 5))
+    base, dt = cpu_bench(workload, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: full pruned pipeline B={B} T/S/C/R={WORKLOADS[workload][1:]} fp32 "
+                               "regular sum; CPU restatement of the reference path (no CPU kernel exists in "
+                               "the reference; TensorFlow absent)"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+class Pipeline:
+    """Pre-allocated device buffers + the C-ABI call sequence of one step."""
+
+    KERNELS_PER_STEP = 17  # 6 simple loss + 2 prune + 1 pruning + 1 joiner + 5 pruned loss + 2 reduce
+
+    def __init__(self, B, T, S, C, R, dev):
+        import torch
+        from tf_fast_rnnt import _lib
+        self.torch, self.lib, self._lib = torch, _lib.lib, _lib
+        self.B, self.T, self.S, self.C, self.R, self.dev = B, T, S, C, R, dev
+        f32, i32 = torch.float32, torch.int32
+        e = lambda *shape, dtype=f32: torch.empty(shape, dtype=dtype, device=dev)
+        self.scores, self.pscores = e(B), e(B)
+        self.gx, self.gy = e(B, S, T + 1), e(B, S + 1, T)
+        self.ranges = e(B, T, R, dtype=i32)
+        self.am_p, self.lm_p = e(B, T, R, C), e(B, T, R, C)
+        self.logits, self.dlogits = e(B, T, R, C), e(B, T, R, C)
+        self.losses = e(2)
+        self.sgrad = torch.full((B,), -1.0, dtype=f32, device=dev)  # d(sum loss)/d scores
+        lib = self.lib
+        self.ws_simple = torch.empty(lib.frn_simple_loss_workspace_bytes(B, S, T, C), dtype=torch.uint8, device=dev)
+        self.ws_prune = torch.empty(lib.frn_prune_ranges_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+        self.ws_pruned = torch.empty(lib.frn_pruned_loss_workspace_bytes(B, S, T, R), dtype=torch.uint8, device=dev)
+
+    def stages(self, am, lm, sym, bd):
+        """List of (name, algorithmic bytes, callable) — SURVEY.md §8(d) byte counts."""
+        lib, B, T, S, C, R = self.lib, self.B, self.T, self.S, self.C, self.R
+        p = lambda t: t.data_ptr()
+        term = C - 1
+        st = lambda: self.torch.cuda.current_stream(self.dev).cuda_stream
+        chk = self._lib.check
+        n_logits = B * T * R * C
+        return [
+            ("simple_loss", 4 * B * ((T + S + 1) * C + 2 * (S * (T + 1) + (S + 1) * T)),
+             lambda: chk(lib.frn_simple_loss(p(lm), p(am), p(sym), p(bd), B, S, T, C, term, 0, 0, 0.0, 0.0, 0.0, 1,
+                                             p(self.scores), p(self.gx), p(self.gy), p(self.ws_simple),
+                                             self.ws_simple.numel(), st()), "simple_loss")),
+            ("prune_ranges", 4 * B * (S * (T + 1) + (S + 1) * T) + 4 * B * T * R,
+             lambda: chk(lib.frn_prune_ranges(p(self.gx), p(self.gy), p(bd), B, S, T, T + 1, R, p(self.ranges),
+                                              p(self.ws_prune), self.ws_prune.numel(), st()), "prune_ranges")),
+            ("do_pruning", 4 * B * (T * C + (S + 1) * C + T * R) + 8 * n_logits,
+             lambda: chk(lib.frn_do_pruning(p(am), p(lm), p(self.ranges), B, S, T, R, C, p(self.am_p),
+                                            p(self.lm_p), st()), "do_pruning")),
+            ("add_joiner", 12 * n_logits,
+             lambda: chk(lib.frn_add_joiner(p(self.am_p), p(self.lm_p), p(self.logits), n_logits, st()),
+                         "add_joiner")),
+            ("pruned_loss", 4 * n_logits + 8 * B * T * R + 8 * n_logits + 16 * B * T * R,
+             lambda: chk(lib.frn_pruned_loss(p(self.logits), 0, p(sym), p(self.ranges), p(bd), B, S, T, R, C, term,
+                                             0, 0.0, p(self.sgrad), p(self.pscores), p(self.dlogits),
+                                             p(self.ws_pruned), self.ws_pruned.numel(), st()), "pruned_loss")),
+            ("reduce", 8 * B,
+             lambda: (chk(lib.frn_reduce(p(self.scores), B, 2, 0.0, p(self.losses), st()), "reduce"),
+                      chk(lib.frn_reduce(p(self.pscores), B, 2, 0.0, p(self.losses) + 4, st()), "reduce"))),
+        ]
+
+    def step(self, am, lm, sym, bd):
+        for _, _, fn in self.stages(am, lm, sym, bd):
+            fn()
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, S, C, R = WORKLOADS[args.workload]
+    pipe = Pipeline(B, T, S, C, R, dev)
+
+    # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
+    # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
+    NSETS = 4
+    host_sets, dev_sets = [], []
+    for i in range(NSETS):
+        arrs = synth(B, T, S, C, 1234 + 17 * rank + i)
+        host_sets.append([torch.from_numpy(a).pin_memory() for a in arrs])
+        dev_sets.append([h.to(dev) for h in host_sets[-1]])
+    stage_buf = [torch.empty_like(d) for d in dev_sets[0]]  # e2e landing buffers
+    host_out = torch.empty(2, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def allreduce_losses():
+        if world > 1:
+            dist.all_reduce(pipe.losses)
+
+    # ---- CUDA graphs of one step per input set (launch-bound inner loop) ----
+    use_graph = not args.no_graph
+    graphs = []
+    side = torch.cuda.Stream(dev)
+    if use_graph:
+        try:
+            with torch.cuda.stream(side):
+                pipe.step(*dev_sets[0])      # warm the lazily-set function attributes outside capture
+                side.synchronize()
+                for i in range(NSETS):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        pipe.step(*dev_sets[i])
+                    graphs.append(g)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({e}); direct launches", file=sys.stderr)
+            graphs, use_graph = [], False
+
+    def run_step(i):
+        if use_graph:
+            graphs[i % NSETS].replay()
+        else:
+            pipe.step(*dev_sets[i % NSETS])
+        allreduce_losses()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for i in range(args.warmup):
+        run_step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    loss_check = pipe.losses.cpu().tolist()
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses ----
+    def e2e_step(i):
+        for dst, src in zip(stage_buf, host_sets[i % NSETS]):
+            dst.copy_(src, non_blocking=True)
+        pipe.step(*stage_buf)
+        allreduce_losses()
+        host_out.copy_(pipe.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the loss
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(t.item()) / args.steps
+    h2d = sum(h.numel() * h.element_size() for h in host_sets[0])
+
+    # ---- per-stage device times (outside the timed region) -> roofline of the dominant kernel ----
+    stage_ms = {}
+    for name, nbytes, fn in pipe.stages(*dev_sets[0]):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        stage_ms[name] = (a.elapsed_time(b) / reps, nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    # the HBM-bound kernels of the step and their algorithmic bytes
+    hbm_stages = {k: v for k, v in stage_ms.items() if k in ("do_pruning", "add_joiner", "pruned_loss")}
+    dom = max(hbm_stages, key=lambda k: hbm_stages[k][0])
+    dom_ms, dom_bytes = hbm_stages[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    cells = B * (S + 1) * (T + 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning -> additive "
+                        f"joiner -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
+            "launch": "cuda_graph" if use_graph else "direct",
+            "l2": f"{NSETS} rotating input sets ({NSETS * h2d / 1e6:.0f} MB) + ~1.1 GB of streamed intermediates per step (> 126 MB L2)",
+            "sharding": "utterances sharded across ranks, one 2-float NCCL all-reduce per step" if world > 1 else "single GPU",
+            "loss_check": loss_check,
+        },
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * B / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms_per_step, "wall_ms_per_step": wall / args.steps * 1e3},
+        "gpu_launches": Pipeline.KERNELS_PER_STEP * args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
+        "stages_ms": {k: round(v[0], 4) for k, v in stage_ms.items()},
+        "stages_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in stage_ms.items()},
+        "lattice_cells_per_s": cells / (stage_ms["simple_loss"][0] * 1e-3),
+    }
+    if world == 1 and not args.no_cpu:
+        sample_B = 8 if args.workload == "c2" else None
+        base, _ = cpu_bench(args.workload, 2, 1, sample_B)
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -141,6 +141,11 @@ int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int 
 int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad,
                        const int32_t *ranges, int B, int S, int T, int R, int C,
                        float *am_grad, float *lm_grad, void *stream);
+/* The additive joiner of the reference's tests/README (logits = am_pruned +
+ * lm_pruned, simple_rnnt_loss_test.py:120-125) as an element-wise kernel over n
+ * floats; stands in for the user's joiner network in the benchmark. */
+int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits, size_t n,
+                   void *stream);
 /* (f2) fused additive joiner: logits[b,t,i,:] = am[b,t,:] + lm[b,ranges[b,t,i],:]
  * without materialising am_pruned / lm_pruned. out_dtype: frn_dtype. */
 int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges,

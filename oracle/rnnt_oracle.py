@@ -439,7 +439,7 @@ def rnnt_loss(logits, symbols, termination_symbol, boundary, rnnt_type="regular"
 # --------------------------------------------------------------------------
 def pruned_logits_grad(logits, symbols, ranges, termination_symbol, boundary,
                        rnnt_type="regular", delay_penalty=0.0, loss_grad=None,
-                       dtype=np.float64):
+                       dtype=np.float64, return_scores=False):
     """d(sum_b loss_grad[b] * loss[b]) / d logits for rnnt_loss_pruned with
     reduction='none' (loss = -score): chain of _RNNTLossGrad (__init__.py:154-162)
     through the gathers of rnnt_loss.py:942-1018.
@@ -453,7 +453,7 @@ def pruned_logits_grad(logits, symbols, ranges, termination_symbol, boundary,
     px, py = get_rnnt_logprobs_pruned(logits64, symbols, ranges,
                                       termination_symbol, boundary, rnnt_type, dtype)
     px = apply_delay_penalty(px, boundary, delay_penalty)
-    _, (gpx, gpy) = mutual_information_recursion(px, py, boundary, True, dtype)
+    scores, (gpx, gpy) = mutual_information_recursion(px, py, boundary, True, dtype)
     if rnnt_type == "constrained":
         gpy = gpy.copy()
         gpy[:, 1:, :] += gpx
@@ -473,7 +473,8 @@ def pruned_logits_grad(logits, symbols, ranges, termination_symbol, boundary,
                       np.take_along_axis(d, psym[..., None].astype(np.int64), axis=3) + gx[..., None], axis=3)
     d[:, :, :, termination_symbol] += gy
     g = np.ones((B,), dtype=dtype) if loss_grad is None else np.asarray(loss_grad, dtype=dtype)
-    return (-g[:, None, None, None]) * d
+    grad = (-g[:, None, None, None]) * d
+    return (grad, scores) if return_scores else grad
 
 
 def simple_am_lm_grad(lm, am, symbols, termination_symbol, boundary,

@@ -60,7 +60,7 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, in
   FRN_REQUIRE(px && py && boundary && ans);
   FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   if (!workspace || !aligned256(workspace) || workspace_bytes < carve_dp(nullptr, g).bytes) return FRN_EWORKSPACE;
   DpWorkspace w = carve_dp(workspace, g);
   FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
@@ -174,7 +174,7 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
   FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
   const int T1 = type_t1(T, rnnt_type);
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   if (!workspace || !aligned256(workspace) || workspace_bytes < carve_simple_loss(nullptr, B, S, T, T1, C).bytes)
     return FRN_EWORKSPACE;
   SimpleLossWs w = carve_simple_loss(workspace, B, S, T, T1, C);
@@ -226,7 +226,7 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
                      const PrunedWs &w, cudaStream_t stream) {
   const int T1 = type_t1(T, rnnt_type);
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
   FRN_TRY(launch_skew_band(w.pxc, w.pyc, ranges, boundary, g, dw, R, rnnt_type,
@@ -307,6 +307,11 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
   FRN_TRY(launch_iota_ranges(w.ranges, (size_t)B * T * R, R, stream));
   return pruned_loss_impl(logits, logits_dtype, symbols, w.ranges, boundary, B, S, T, R, C, termination_symbol,
                           rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w, stream);
+}
+
+int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits, size_t n, void *stream) {
+  FRN_REQUIRE(am_pruned && lm_pruned && logits);
+  return launch_add(am_pruned, lm_pruned, logits, n, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ A3

@@ -18,9 +18,7 @@ constexpr float kNeg = -1.0e30f;
 constexpr float kNegThresh = -1.0e29f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kRowsPerLane = 4;                 // lattice rows held by one lane
-constexpr int kRowsPerWarp = 32 * kRowsPerLane; // 128
-constexpr int kMaxWarpsDp = 8;                  // S + 1 <= 1024
+constexpr int kMaxRowsDp = 1024;                // S + 1 <= 1024 (8 warps x 32 lanes x 4 rows)
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
@@ -64,6 +62,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
@@ -123,7 +124,8 @@ __host__ __device__ inline float delay_penalty_value(int t_end, int t, float del
 struct DpGeom {
   int B, S, T, T1;  // T1 = T+1 regular recursion, T modified recursion
   int k;            // diagonal index d = t' + k*s'   (k = 1 regular, 0 modified)
-  int P;            // padded row count, multiple of 128
+  int P;            // padded row count: multiple of 32 * rpl
+  int rpl;          // lattice rows per lane in the chain kernel (1, 2 or 4)
   int Dn;           // allocated diagonals, multiple of kChunk
 };
 constexpr int kChunk = 16;    // diagonals per bulk copy
@@ -132,7 +134,8 @@ inline DpGeom make_geom(int B, int S, int T, int T1) {
   DpGeom g;
   g.B = B; g.S = S; g.T = T; g.T1 = T1;
   g.k = (T1 == T) ? 0 : 1;
-  g.P = round_up(S + 1, kRowsPerWarp);
+  g.rpl = (S + 1 <= 256) ? 1 : ((S + 1 <= 512) ? 2 : 4);
+  g.P = round_up(S + 1, 32 * g.rpl);
   g.Dn = round_up(T + 1 + g.k * S, kChunk);
   return g;
 }

@@ -45,5 +45,6 @@ int launch_band_to_dense(const float *pxc, const float *pyc, const int32_t *rang
                          cudaStream_t stream);
 // misc.cu
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream);
+int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
 int launch_iota_ranges(int32_t *ranges, size_t n, int R, cudaStream_t stream);
 }  // namespace frn

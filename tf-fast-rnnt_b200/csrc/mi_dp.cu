@@ -7,9 +7,9 @@
 //   skew     px/py [B][S][T1] / [B][S+1][T]  ->  X/Y [B][d][s'] (diagonal-major,
 //            log2 domain, boundary masks applied, -inf replaced by a finite
 //            sentinel).  Fully parallel, HBM/L2 bound.
-//   chain    one CTA per (utterance, direction).  Each lane owns 4 consecutive
-//            lattice rows; one step = one anti-diagonal (d = t' + k s', k = 1
-//            regular / 0 modified), neighbours exchanged by warp shuffle, the
+//   chain    one CTA per (utterance, direction), a software pipeline of warps
+//            (see dp_chain_kernel); one step = one anti-diagonal (d = t' + k s',
+//            k = 1 regular / 0 modified), neighbours exchanged by warp shuffle, the
 //            diagonal-major arc scores streamed into a shared-memory ring by
 //            1-D bulk async copies (TMA engine) behind mbarriers.  Forward
 //            (alpha) and backward (beta) chains run concurrently in different
@@ -105,20 +105,31 @@ struct ChainParams {
   float *ar, *ao;      // [B][Dn][P]  forward residual / offset (dir 0)
   float *bx, *by, *bo; // [B][Dn][P]  backward-side operands and their frame offset (dir 1)
   const int32_t *boundary;
-  int k, P, Dn, S, T, CH;  // CH: diagonals per bulk copy (divides kChunk)
+  int k, P, Dn, S, T;
+  int CH, NST;         // diagonals per bulk copy (divides kChunk); ring stages (>= warps + 2)
 };
 
-template <bool MULTI>
-__global__ void __launch_bounds__(256, 1) dp_chain_kernel(ChainParams p) {
+// Execution.  One CTA per (utterance, direction); RPL consecutive lattice rows
+// per lane, 32*RPL rows per warp, W = P / (32*RPL) warps.  The warps form a
+// software pipeline: warp w runs one chunk (CH diagonals) behind the warp that
+// owns the rows feeding it and picks the boundary row's (residual, offset) of
+// every step out of a shared-memory ring that warp filled; one mbarrier per
+// (warp, ring slot) says "chunk published".  There is no per-step block barrier
+// and every warp sits alone on its SM sub-partition, so a step costs one
+// dependent log-add (shuffle + ex2 + lg2 + a few adds) rather than the issue
+// time of four interleaved rows.  X/Y chunks are shared by all warps: NST >= W+2
+// stages of 1-D bulk copies; the tail warp of the pipeline recycles a stage.
+template <int RPL, int DIR>
+__device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int b = blockIdx.x, dir = blockIdx.y;
+  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5;
-  const int P = p.P, CH = p.CH;
+  const int P = p.P, CH = p.CH, NST = p.NST;
   const int stage_floats = 2 * CH * P;
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(ring + kStages * stage_floats);
-  float *edge_r = reinterpret_cast<float *>(mbar + kStages);  // [2][8] residual hand-off between warps
-  float *edge_o = edge_r + 16;                                // [2][8] offset hand-off
+  uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + NST * stage_floats);
+  uint64_t *mbar_edge = mbar_xy + NST;                               // [W][NST], indexed by consumer warp
+  float2 *edge = reinterpret_cast<float2 *>(mbar_edge + W * NST);    // [W][NST][CH], indexed by consumer warp
 
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int Sb = bd.z - bd.x, Tb = bd.w - bd.y;
@@ -127,141 +138,160 @@ __global__ void __launch_bounds__(256, 1) dp_chain_kernel(ChainParams p) {
   const int nchunk = Db / CH + 1;
   const size_t plane = (size_t)b * p.Dn * P;
   const float *Xg = p.X + plane, *Yg = p.Y + plane;
-  float *outAr = p.ar + plane, *outAo = p.ao + plane;
-  float *outBx = p.bx + plane, *outBy = p.by + plane, *outBo = p.bo + plane;
   const uint32_t chunk_bytes = (uint32_t)(CH * P * sizeof(float));
 
   auto issue = [&](int seq, int st) {
-    const int ci = dir ? nchunk - 1 - seq : seq;
-    mbar_arrive_expect_tx(&mbar[st], 2 * chunk_bytes);
-    bulk_g2s(ring + st * stage_floats, Xg + (size_t)ci * CH * P, chunk_bytes, &mbar[st]);
-    bulk_g2s(ring + st * stage_floats + CH * P, Yg + (size_t)ci * CH * P, chunk_bytes, &mbar[st]);
+    const int ci = DIR ? nchunk - 1 - seq : seq;
+    mbar_arrive_expect_tx(&mbar_xy[st], 2 * chunk_bytes);
+    bulk_g2s(ring + st * stage_floats, Xg + (size_t)ci * CH * P, chunk_bytes, &mbar_xy[st]);
+    bulk_g2s(ring + st * stage_floats + CH * P, Yg + (size_t)ci * CH * P, chunk_bytes, &mbar_xy[st]);
   };
 
   if (tid == 0) {
-    for (int st = 0; st < kStages; ++st) mbar_init(&mbar[st], 1);
+    for (int i = 0; i < NST + W * NST; ++i) mbar_init(&mbar_xy[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (tid == 0)
-    for (int i = 0; i < kStages && i < nchunk; ++i) issue(i, i);
+    for (int i = 0; i < NST && i < nchunk; ++i) issue(i, i);
 
-  const int r0 = kRowsPerLane * tid;  // first lattice row of this lane
-  const bool first_row_lane = (tid == 0), last_row_lane = (tid == (int)blockDim.x - 1);
-  float r[4], o[4];
+  const int pos = DIR ? (W - 1 - w) : w;        // position in the warp pipeline, 0 = head
+  const bool is_tail = (pos == W - 1), fed = (pos > 0), feeds = (pos < W - 1);
+  const int wc = DIR ? w - 1 : w + 1;           // the warp this one feeds
+  const int r0 = RPL * tid;                     // first lattice row of this lane
+  const bool lane_in = DIR ? (lane == 31) : (lane == 0);    // lane fed across the warp boundary
+  const bool lane_out = DIR ? (lane == 0) : (lane == 31);   // lane feeding the next warp
+  const bool global_edge = DIR ? (tid == (int)blockDim.x - 1) : (tid == 0);  // row with no neighbour at all
+  const bool take_edge = lane_in && fed, publish = lane_out && feeds;
+  constexpr int step_sign = DIR ? -1 : 1;
+
+  float r[RPL], o[RPL];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    r[j] = ((r0 + j) == (dir ? Sb : 0)) ? 0.f : kNeg;
+  for (int j = 0; j < RPL; ++j) {
+    r[j] = ((r0 + j) == (DIR ? Sb : 0)) ? 0.f : kNeg;
     o[j] = 0.f;
   }
-  if (!dir) {
-    *reinterpret_cast<float4 *>(outAr + r0) = make_float4(r[0], r[1], r[2], r[3]);
-    *reinterpret_cast<float4 *>(outAo + r0) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float *const out0 = (DIR ? p.bx : p.ar) + plane + r0;   // alpha: residual | beta: px-arc operand
+  float *const out1 = (DIR ? p.bo : p.ao) + plane + r0;   // frame offset
+  float *const out2 = p.by + plane + r0;                  // beta only: py-arc operand
+  if (!DIR) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { out0[j] = r[j]; out1[j] = 0.f; }
   }
-  if (MULTI) {
-    if (lane == (dir ? 0 : 31)) {
-      edge_r[8 + w] = dir ? r[0] : r[3];
-      edge_o[8 + w] = 0.f;
-    }
-    __syncthreads();
-  }
+  // state of the row feeding lane_in before the first step (initial condition)
+  float2 carry = make_float2(kNeg, 0.f);
+  if (DIR && (r0 + RPL) == Sb) carry.x = 0.f;
 
-  int step = 0;
   for (int i = 0; i < nchunk; ++i) {
-    const int st = i % kStages;
-    const int ci = dir ? nchunk - 1 - i : i;
-    mbar_wait(&mbar[st], (uint32_t)((i / kStages) & 1));
-    const float *xs = ring + st * stage_floats, *ys = xs + CH * P;
+    const int st = i % NST;
+    const uint32_t par = (uint32_t)((i / NST) & 1);
+    const int ci = DIR ? nchunk - 1 - i : i;
+    mbar_wait(&mbar_xy[st], par);
+    if (fed) mbar_wait(&mbar_edge[w * NST + st], par);   // the feeding warp has published this chunk
+    const float *xs = ring + st * stage_floats + r0, *ys = xs + CH * P;
+    const float2 *ein = edge + (size_t)(w * NST + st) * CH;
+    float2 *eout = edge + (size_t)((feeds ? wc : w) * NST + st) * CH;
     const int e_lo = max(ci * CH, 1), e_hi = min(ci * CH + CH - 1, Db);
     const int n = e_hi - e_lo + 1;
-    float4 x = make_float4(kNeg, kNeg, kNeg, kNeg), y = x;
-    float xn = kNeg;
+    int e = DIR ? e_hi : e_lo;
+    int el = e - ci * CH;
+    // operands of the first step of the chunk
+    float x[RPL], y[RPL], xnext = kNeg;
+    float2 ev = carry;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { x[j] = kNeg; y[j] = kNeg; }
     if (n > 0) {
-      const int el = (dir ? e_hi : e_lo) - ci * CH;
-      x = *reinterpret_cast<const float4 *>(xs + el * P + r0);
-      y = *reinterpret_cast<const float4 *>(ys + el * P + r0);
-      if (dir && r0 + 4 < P) xn = xs[el * P + r0 + 4];
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) { x[j] = xs[el * P + j]; y[j] = ys[el * P + j]; }
+      if (DIR && r0 + RPL < P) xnext = xs[el * P + RPL];
     }
     for (int q = 0; q < n; ++q) {
-      const int e = dir ? e_hi - q : e_lo + q;
-      // prefetch the next diagonal's arc scores (off the dependency chain)
-      float4 x2 = x, y2 = y;
-      float xn2 = kNeg;
-      if (q + 1 < n) {
-        const int el2 = (dir ? e - 1 : e + 1) - ci * CH;
-        x2 = *reinterpret_cast<const float4 *>(xs + el2 * P + r0);
-        y2 = *reinterpret_cast<const float4 *>(ys + el2 * P + r0);
-        if (dir && r0 + 4 < P) xn2 = xs[el2 * P + r0 + 4];
-      }
-      // lag-1 re-centring (exact): k = rint(previous residual) moves into the offset
-      bool alive[4];
-      float kk[4], on[4];
+      // ---- prefetch the operands of the next step (off the dependency chain) ----
+      const int eln = (q + 1 < n) ? el + step_sign : el;
+      float x2[RPL], y2[RPL], xnext2 = kNeg;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < RPL; ++j) { x2[j] = xs[eln * P + j]; y2[j] = ys[eln * P + j]; }
+      if (DIR && r0 + RPL < P) xnext2 = xs[eln * P + RPL];
+      const float2 ev2 = ein[el];   // the feeding row's state after ITS step e = input of our next step (broadcast read)
+
+      // ---- neighbour across the lane boundary: raw residual + the frame it is expressed in ----
+      float nb_r = DIR ? __shfl_down_sync(0xffffffffu, r[0], 1) : __shfl_up_sync(0xffffffffu, r[RPL - 1], 1);
+      float nb_o = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
+      nb_r = lane_in ? (fed ? ev.x : kNeg) : nb_r;
+      nb_o = take_edge ? ev.y : nb_o;
+
+      // ---- lag-1 re-centring (exact): k = rint(previous residual) moves into the offset ----
+      bool alive[RPL];
+      float kk[RPL], on[RPL], rc[RPL];
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) {
         alive[j] = r[j] > kNegThresh;
         kk[j] = alive[j] ? rintf(r[j]) : 0.f;
+        rc[j] = r[j] - kk[j];
       }
-      if (!dir) {
+      // A dead row adopts the NEW frame of the row that feeds it (across the lane
+      // boundary that frame is re-derived from the shuffled raw residual and old
+      // offset), so a moving wave-front never inherits a stale frame.
+      const float nb_k = (nb_r > kNegThresh) ? rintf(nb_r) : 0.f;
+      if (!DIR) {
         // alpha_e(s') = logadd(alpha_{e-1}(s'-1) + X[e][s'], alpha_{e-1}(s') + Y[e][s'])
-        float up_r = __shfl_up_sync(0xffffffffu, r[3], 1);
-        float up_o = __shfl_up_sync(0xffffffffu, o[3], 1);
-        if (lane == 0) {
-          up_r = (MULTI && w > 0) ? edge_r[((step + 1) & 1) * 8 + w - 1] : kNeg;
-          up_o = (MULTI && w > 0) ? edge_o[((step + 1) & 1) * 8 + w - 1] : o[0];
+        on[0] = (alive[0] || global_edge) ? o[0] + kk[0] : nb_o + nb_k;
+#pragma unroll
+        for (int j = 1; j < RPL; ++j) on[j] = alive[j] ? o[j] + kk[j] : on[j - 1];
+        float nn[RPL];
+        nn[0] = logadd2((nb_r + x[0]) + (nb_o - on[0]), rc[0] + y[0]);
+#pragma unroll
+        for (int j = 1; j < RPL; ++j) nn[j] = logadd2(rc[j - 1] + (x[j] + (on[j - 1] - on[j])), rc[j] + y[j]);
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          r[j] = nn[j]; o[j] = on[j];
+          out0[(unsigned)(e * P + j)] = r[j];
+          out1[(unsigned)(e * P + j)] = o[j];
         }
-        // New frame of every row.  A dead row adopts the frame of the row that
-        // feeds it: the NEW frame for the three in-lane neighbours (exact, local),
-        // the one-step-old frame across lanes (the shuffled residual is raw).
-        on[0] = (alive[0] || first_row_lane) ? o[0] + kk[0] : up_o;
-        on[1] = alive[1] ? o[1] + kk[1] : on[0];
-        on[2] = alive[2] ? o[2] + kk[2] : on[1];
-        on[3] = alive[3] ? o[3] + kk[3] : on[2];
-        const float rc0 = r[0] - kk[0], rc1 = r[1] - kk[1], rc2 = r[2] - kk[2], rc3 = r[3] - kk[3];
-        const float n0 = logadd2(up_r + (x.x + (up_o - on[0])), rc0 + y.x);
-        const float n1 = logadd2(rc0 + (x.y + (on[0] - on[1])), rc1 + y.y);
-        const float n2 = logadd2(rc1 + (x.z + (on[1] - on[2])), rc2 + y.z);
-        const float n3 = logadd2(rc2 + (x.w + (on[2] - on[3])), rc3 + y.w);
-        r[0] = n0; r[1] = n1; r[2] = n2; r[3] = n3;
-        o[0] = on[0]; o[1] = on[1]; o[2] = on[2]; o[3] = on[3];
-        *reinterpret_cast<float4 *>(outAr + (size_t)e * P + r0) = make_float4(r[0], r[1], r[2], r[3]);
-        *reinterpret_cast<float4 *>(outAo + (size_t)e * P + r0) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
         // beta_{e-1}(s') = logadd(X[e][s'+1] + beta_e(s'+1), Y[e][s'] + beta_e(s'))
-        float dn_r = __shfl_down_sync(0xffffffffu, r[0], 1);
-        float dn_o = __shfl_down_sync(0xffffffffu, o[0], 1);
-        if (lane == 31) {
-          dn_r = (MULTI && w < W - 1) ? edge_r[((step + 1) & 1) * 8 + w + 1] : kNeg;
-          dn_o = (MULTI && w < W - 1) ? edge_o[((step + 1) & 1) * 8 + w + 1] : o[3];
+        on[RPL - 1] = (alive[RPL - 1] || global_edge) ? o[RPL - 1] + kk[RPL - 1] : nb_o + nb_k;
+#pragma unroll
+        for (int j = RPL - 2; j >= 0; --j) on[j] = alive[j] ? o[j] + kk[j] : on[j + 1];
+        float a[RPL], c[RPL];
+        a[RPL - 1] = (nb_r + xnext) + (nb_o - on[RPL - 1]);
+#pragma unroll
+        for (int j = 0; j < RPL - 1; ++j) a[j] = rc[j + 1] + (x[j + 1] + (on[j + 1] - on[j]));
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          c[j] = rc[j] + y[j];
+          // operands of diagonal e-1, expressed in the frame `on`
+          out0[(unsigned)((e - 1) * P + j)] = a[j];
+          out2[(unsigned)((e - 1) * P + j)] = c[j];
+          out1[(unsigned)((e - 1) * P + j)] = on[j];
+          r[j] = logadd2(a[j], c[j]);
+          o[j] = on[j];
         }
-        on[3] = (alive[3] || last_row_lane) ? o[3] + kk[3] : dn_o;
-        on[2] = alive[2] ? o[2] + kk[2] : on[3];
-        on[1] = alive[1] ? o[1] + kk[1] : on[2];
-        on[0] = alive[0] ? o[0] + kk[0] : on[1];
-        const float rc0 = r[0] - kk[0], rc1 = r[1] - kk[1], rc2 = r[2] - kk[2], rc3 = r[3] - kk[3];
-        const float a0 = rc1 + (x.y + (on[1] - on[0])), a1 = rc2 + (x.z + (on[2] - on[1])),
-                    a2 = rc3 + (x.w + (on[3] - on[2])), a3 = dn_r + (xn + (dn_o - on[3]));
-        const float c0 = rc0 + y.x, c1 = rc1 + y.y, c2 = rc2 + y.z, c3 = rc3 + y.w;
-        // operands of diagonal e-1, expressed in the frame `on`
-        *reinterpret_cast<float4 *>(outBx + (size_t)(e - 1) * P + r0) = make_float4(a0, a1, a2, a3);
-        *reinterpret_cast<float4 *>(outBy + (size_t)(e - 1) * P + r0) = make_float4(c0, c1, c2, c3);
-        *reinterpret_cast<float4 *>(outBo + (size_t)(e - 1) * P + r0) = make_float4(on[0], on[1], on[2], on[3]);
-        r[0] = logadd2(a0, c0); r[1] = logadd2(a1, c1);
-        r[2] = logadd2(a2, c2); r[3] = logadd2(a3, c3);
-        o[0] = on[0]; o[1] = on[1]; o[2] = on[2]; o[3] = on[3];
       }
-      ++step;
-      if (MULTI) {
-        if (lane == (dir ? 0 : 31)) {
-          edge_r[((step + 1) & 1) * 8 + w] = dir ? r[0] : r[3];
-          edge_o[((step + 1) & 1) * 8 + w] = dir ? o[0] : o[3];
-        }
-        __syncthreads();
-      }
-      x = x2; y = y2; xn = xn2;
+      if (publish) eout[el] = DIR ? make_float2(r[0], o[0]) : make_float2(r[RPL - 1], o[RPL - 1]);
+      // rotate the prefetched operands in
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) { x[j] = x2[j]; y[j] = y2[j]; }
+      xnext = xnext2;
+      ev = ev2;
+      e += step_sign;
+      el = eln;
     }
-    if (!MULTI) __syncwarp();
-    if (tid == 0 && i + kStages < nchunk) issue(i + kStages, st);
+    carry = ev;   // the feeding row's state after the last step of this chunk
+    if (publish) mbar_arrive(&mbar_edge[wc * NST + st]);
+    if (is_tail) {
+      __syncwarp();
+      if (lane == 0 && i + NST < nchunk) issue(i + NST, st);
+    }
   }
+}
+
+// grid = (B, 2): blockIdx.y selects the direction so that the forward and the
+// backward chain of every utterance run concurrently on different SMs.
+template <int RPL>
+__global__ void __launch_bounds__(256, 1) dp_chain_kernel(ChainParams p) {
+  if (blockIdx.y == 0) dp_chain_body<RPL, 0>(p);
+  else dp_chain_body<RPL, 1>(p);
 }
 
 // ---------------------------------------------------------------------------
@@ -363,30 +393,37 @@ int launch_skew_dense(const float *px, const float *py, const int32_t *boundary,
   return check_launch();
 }
 
-size_t chain_smem_bytes(const DpGeom &g, int *ch_out) {
-  int CH = (g.P <= 512) ? kChunk : kChunk / 2;
-  *ch_out = CH;
-  return (size_t)kStages * 2 * CH * g.P * sizeof(float) + kStages * sizeof(uint64_t) + 32 * sizeof(float) + 64;
+struct ChainConfig { int W, CH, NST; size_t smem; };
+static ChainConfig chain_config(const DpGeom &g) {
+  ChainConfig c;
+  c.W = g.P / (32 * g.rpl);
+  c.NST = c.W + 2;
+  c.CH = kChunk;
+  auto bytes = [&](int ch) {
+    return (size_t)c.NST * 2 * ch * g.P * sizeof(float) + (size_t)(c.NST + c.W * c.NST) * sizeof(uint64_t) +
+           (size_t)c.W * c.NST * ch * sizeof(float2) + 128;
+  };
+  while (c.CH > 1 && bytes(c.CH) > 200 * 1024) c.CH >>= 1;
+  c.smem = bytes(c.CH);
+  return c;
 }
 
 int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, bool both_directions,
                  cudaStream_t stream) {
-  if (g.P > kRowsPerWarp * kMaxWarpsDp) return FRN_EUNSUPPORTED;
-  int CH;
-  const size_t smem = chain_smem_bytes(g, &CH);
-  ChainParams cp{w.X, w.Y, w.ar, w.ao, w.bx, w.by, w.bo, boundary, g.k, g.P, g.Dn, g.S, g.T, CH};
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
+  const ChainConfig c = chain_config(g);
+  ChainParams cp{w.X, w.Y, w.ar, w.ao, w.bx, w.by, w.bo, boundary, g.k, g.P, g.Dn, g.S, g.T, c.CH, c.NST};
   dim3 grid(g.B, both_directions ? 2 : 1);
-  const int threads = g.P / kRowsPerLane;
+  const int threads = 32 * c.W;
   cudaError_t e;
-  if (threads == 32) {
-    e = cudaFuncSetAttribute(dp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return note_cuda_error(e);
-    dp_chain_kernel<false><<<grid, threads, smem, stream>>>(cp);
-  } else {
-    e = cudaFuncSetAttribute(dp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return note_cuda_error(e);
-    dp_chain_kernel<true><<<grid, threads, smem, stream>>>(cp);
-  }
+#define FRN_LAUNCH_CHAIN(RPL_)                                                                              \
+  e = cudaFuncSetAttribute(dp_chain_kernel<RPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem); \
+  if (e != cudaSuccess) return note_cuda_error(e);                                                          \
+  dp_chain_kernel<RPL_><<<grid, threads, c.smem, stream>>>(cp);
+  if (g.rpl == 1) { FRN_LAUNCH_CHAIN(1) }
+  else if (g.rpl == 2) { FRN_LAUNCH_CHAIN(2) }
+  else { FRN_LAUNCH_CHAIN(4) }
+#undef FRN_LAUNCH_CHAIN
   return check_launch();
 }
 

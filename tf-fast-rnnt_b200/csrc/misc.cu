@@ -28,6 +28,27 @@ __global__ void iota_ranges_kernel(int32_t *ranges, size_t n, int R) {
   if (i < n) ranges[i] = (int32_t)(i % (size_t)R);
 }
 
+// out = a + b, the additive joiner of the reference's tests and README
+// (simple_rnnt_loss_test.py:120-125: logits = pruned_am + pruned_lm)
+__global__ void __launch_bounds__(256) add_kernel(const float *a, const float *b, float *out, size_t n) {
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 x = ld_stream_f4(reinterpret_cast<const float4 *>(a + i4));
+    const float4 y = ld_stream_f4(reinterpret_cast<const float4 *>(b + i4));
+    st_stream_f4(reinterpret_cast<float4 *>(out + i4), make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+  } else {
+    for (size_t i = i4; i < n; ++i) out[i] = a[i] + b[i];
+  }
+}
+
+int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_t stream) {
+  if (n == 0) return FRN_OK;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u)
+    return FRN_EINVAL;
+  add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, stream>>>(a, b, out, n);
+  return check_launch();
+}
+
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream) {
   reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out);
   return check_launch();

@@ -40,69 +40,93 @@ __global__ void cummin_kernel(const int32_t *in, int32_t *out, int rows, int n) 
 }
 
 // ---------------------------------------------------------------------------
-// A5 step 1: s_begin[b,t] = argmax_k ( sum_{k<=s<k+R} py_grad[s,t] - px_grad[k-1,t] )
-// (rnnt_loss.py:722-748), thread per (b,t) column, coalesced along t.
+// A5, one launch, one block per utterance:
+//  (1) s_begin[t] = argmax_k ( sum_{k<=s<k+R} py_grad[s,t] - px_grad[k-1,t] )
+//      (rnnt_loss.py:722-748): thread per column t, coalesced along t, the
+//      window walked sequentially in s (= the sequential-cumsum float order the
+//      oracle defines) in chunks of 8 with all loads of a chunk issued first;
+//  (2) the monotonic fix-ups of _adjust_pruning_lower_bound (:623-641) as two
+//      block-wide reverse running minima on the int32 row held in shared memory;
+//  (3) ranges[t,i] = s_begin[t] + i (:758-759).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) prune_argmax_kernel(const float *px_grad, const float *py_grad,
-                                                           const int32_t *boundary, int S, int T, int T1,
-                                                           int R, int32_t *s_begin) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
+constexpr int kPruneThreads = 512;
+
+// reverse inclusive running minimum of x[0..T) in shared memory, whole block
+__device__ void block_rev_cummin(int32_t *x, int T, int32_t *warp_carry) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int NW = kPruneThreads / 32;
+  int carry = INT32_MAX;  // running minimum of everything to the right of the current tile
+  for (int hi = T - 1; hi >= 0; hi -= kPruneThreads) {
+    const int i = hi - tid;  // thread 0 holds the largest t of the tile
+    int v = (i >= 0) ? x[i] : INT32_MAX;
+    v = warp_incl_min_scan(v, lane);
+    if (lane == 31) warp_carry[w] = v;
+    __syncthreads();
+    int pre = carry;
+    for (int j = 0; j < w; ++j) pre = min(pre, warp_carry[j]);
+    v = min(v, pre);
+    if (i >= 0) x[i] = v;
+    int tile_min = warp_carry[0];
+    for (int j = 1; j < NW; ++j) tile_min = min(tile_min, warp_carry[j]);
+    carry = min(carry, tile_min);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kPruneThreads) prune_ranges_kernel(const float *px_grad, const float *py_grad,
+                                                                     const int32_t *boundary, int S, int T, int T1,
+                                                                     int R, int r_fix, int32_t *ranges) {
+  extern __shared__ int32_t sb[];  // [T] s_begin, then [16] warp carries
+  int32_t *warp_carry = sb + T;
+  const int b = blockIdx.x;
   const int s_end = boundary[4 * b + 2], t_end = boundary[4 * b + 3];
   const int S1 = S + 1;
-  int best_k = 0;
-  if (t < t_end - 1) {
-    const float *py = py_grad + (size_t)b * S1 * T + t;
-    const float *px = px_grad + (size_t)b * S * T1 + t;
-    const int nk = S1 - R + 1;
-    float cs_lo = 0.f, cs_hi = 0.f;
-    for (int s = 0; s < R; ++s) cs_hi = cs_hi + py[(size_t)s * T];  // cs[R], sequential
-    float best = 0.f;
-    for (int k = 0; k < nk; ++k) {
-      float fin = cs_hi - cs_lo;
-      if (k > 0) fin = fin - px[(size_t)(k - 1) * T1];
-      if (k == 0 || fin > best) { best = fin; best_k = k; }
-      cs_lo = cs_lo + py[(size_t)k * T];
-      if (k + R < S1) cs_hi = cs_hi + py[(size_t)(k + R) * T];
+  const int nk = S1 - R + 1;
+  for (int t = threadIdx.x; t < T; t += kPruneThreads) {
+    int best_k = 0;
+    if (t < t_end - 1) {
+      const float *py = py_grad + (size_t)b * S1 * T + t;
+      const float *px = px_grad + (size_t)b * S * T1 + t;
+      float cs_lo = 0.f, cs_hi = 0.f;
+      for (int s = 0; s < R; ++s) cs_hi = cs_hi + py[(size_t)s * T];  // cs[R], sequential
+      float best = 0.f;
+      for (int k0 = 0; k0 < nk; k0 += 8) {
+        float lo[8], hi[8], pxv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // all loads of the chunk first (independent)
+          const int k = k0 + j;
+          lo[j] = (k < nk) ? py[(size_t)k * T] : 0.f;
+          hi[j] = (k < nk && k + R < S1) ? py[(size_t)(k + R) * T] : 0.f;
+          pxv[j] = (k < nk && k > 0) ? px[(size_t)(k - 1) * T1] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + j;
+          if (k < nk) {
+            float fin = cs_hi - cs_lo;
+            if (k > 0) fin = fin - pxv[j];
+            if (k == 0 || fin > best) { best = fin; best_k = k; }
+            cs_lo = cs_lo + lo[j];
+            if (k + R < S1) cs_hi = cs_hi + hi[j];
+          }
+        }
+      }
+    } else {
+      best_k = max(s_end - R + 1, 0);  // padding frames, rnnt_loss.py:744-748
     }
-  } else {
-    best_k = max(s_end - R + 1, 0);  // padding frames, rnnt_loss.py:744-748
+    sb[t] = best_k;
   }
-  s_begin[(size_t)b * T + t] = best_k;
-}
-
-// ---------------------------------------------------------------------------
-// A5 step 2: monotonic fix-ups (rnnt_loss.py:623-641) + range expansion
-// (:758-759).  One warp per utterance; reverse running minima by chunked warp
-// scans walking t from the end.
-// ---------------------------------------------------------------------------
-__device__ void rev_cummin_row(int32_t *x, int T, int lane) {
-  int carry = INT32_MAX;
-  for (int base = T - 1; base >= 0; base -= 32) {
-    const int i = base - lane;  // lane 0 holds the largest t
-    int v = (i >= 0) ? x[i] : INT32_MAX;
-    v = min(warp_incl_min_scan(v, lane), carry);
-    if (i >= 0) x[i] = v;
-    carry = __shfl_sync(0xffffffffu, v, 31);
-  }
-}
-
-__global__ void __launch_bounds__(32) prune_fixup_kernel(int32_t *s_begin, int T, int r, int R, int32_t *ranges) {
-  const int b = blockIdx.x, lane = threadIdx.x;
-  int32_t *x = s_begin + (size_t)b * T;
-  rev_cummin_row(x, T, lane);
-  __syncwarp();
-  for (int t = lane; t < T; t += 32) x[t] = -(x[t] - (r - 1) * t);
-  __syncwarp();
-  rev_cummin_row(x, T, lane);
-  __syncwarp();
-  for (int t = lane; t < T; t += 32) x[t] = -(max(x[t], 0) - (r - 1) * t);
-  __syncwarp();
+  __syncthreads();
+  block_rev_cummin(sb, T, warp_carry);
+  for (int t = threadIdx.x; t < T; t += kPruneThreads) sb[t] = -(sb[t] - (r_fix - 1) * t);
+  __syncthreads();
+  block_rev_cummin(sb, T, warp_carry);
+  for (int t = threadIdx.x; t < T; t += kPruneThreads) sb[t] = -(max(sb[t], 0) - (r_fix - 1) * t);
+  __syncthreads();
   int32_t *out = ranges + (size_t)b * T * R;
-  for (int i = lane; i < T * R; i += 32) {
+  for (int i = threadIdx.x; i < T * R; i += kPruneThreads) {
     const int t = i / R;
-    out[i] = x[t] + (i - t * R);
+    out[i] = sb[t] + (i - t * R);
   }
 }
 
@@ -219,13 +243,15 @@ int launch_cummin(const int32_t *in, int32_t *out, int rows, int n, cudaStream_t
 }
 
 int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
-                        int T1, int R, int32_t *ranges, int32_t *s_begin_ws, cudaStream_t stream) {
-  dim3 grid((T + 127) / 128, B);
-  prune_argmax_kernel<<<grid, 128, 0, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, s_begin_ws);
-  int rc = check_launch();
-  if (rc) return rc;
-  const int r = (T1 == T) ? 2 : R;  // rnnt_loss.py:756
-  prune_fixup_kernel<<<B, 32, 0, stream>>>(s_begin_ws, T, r, R, ranges);
+                        int T1, int R, int32_t *ranges, int32_t * /*unused workspace*/, cudaStream_t stream) {
+  const int r_fix = (T1 == T) ? 2 : R;  // rnnt_loss.py:756
+  const size_t smem = (size_t)(T + 16) * sizeof(int32_t);
+  if (smem > 200 * 1024) return FRN_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(prune_ranges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return note_cuda_error(e);
+  }
+  prune_ranges_kernel<<<B, kPruneThreads, smem, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, r_fix, ranges);
   return check_launch();
 }
 
