@@ -184,32 +184,54 @@ class Pipeline:
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML (same data as the
+    nvidia-smi clocks line of B200_PROFILING.md, but fast enough for a short
+    timed region)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.err = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.05)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                tok = vis.split(",")[self.index]
+                h = nv.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(int(tok))
+            else:
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                                  getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            while not self.stop_flag:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    bits = int(get_reasons(h))
+                    for bit, n in names.items():
+                        if bits & bit:
+                            self.reasons.add(n)
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def run_gpu_arm(args):
@@ -278,8 +300,10 @@ def run_gpu_arm(args):
     for i in range(args.warmup):
         run_step(i)
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    time.sleep(0.05)          # let NVML initialise before the timed region
+    sampler.samples.clear()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -383,7 +407,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

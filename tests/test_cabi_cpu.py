@@ -1,0 +1,110 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/fast_rnnt_b200.h declares, validates arguments before touching
+CUDA, and the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fast_rnnt_b200.h")
+PKG = os.path.join(ROOT, "tf-fast-rnnt_b200")
+LIB = os.path.join(PKG, "lib", "libfast_rnnt_b200.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frn_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(PKG, "csrc")])
+    return ctypes.CDLL(LIB)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+
+
+def test_python_binding_covers_the_header():
+    sys.path.insert(0, PKG)
+    from tf_fast_rnnt import _lib
+    assert sorted(_lib.EXPORTS) == declared_functions()
+
+
+def test_version_and_status_strings(lib):
+    assert lib.frn_version() == 100
+    lib.frn_status_string.restype = ctypes.c_char_p
+    assert lib.frn_status_string(0) == b"ok"
+    assert b"invalid" in lib.frn_status_string(-1)
+    assert b"workspace" in lib.frn_status_string(-2)
+
+
+def test_workspace_queries(lib):
+    for f in ("frn_mi_workspace_bytes", "frn_simple_loss_workspace_bytes", "frn_pruned_loss_workspace_bytes",
+              "frn_simple_logprobs_workspace_bytes", "frn_pruned_logprobs_workspace_bytes"):
+        getattr(lib, f).restype = ctypes.c_size_t
+    B, S, T, C, R = 32, 100, 500, 500, 5
+    mi = lib.frn_mi_workspace_bytes(B, S, T, T + 1)
+    # 7 diagonal-major planes of [B][Dn][P] floats
+    P, Dn = 128, 608
+    assert mi == 7 * B * Dn * P * 4
+    assert lib.frn_simple_loss_workspace_bytes(B, S, T, C) > mi
+    assert lib.frn_pruned_loss_workspace_bytes(B, S, T, R) > mi
+    assert lib.frn_mi_workspace_bytes(0, S, T, T + 1) == 0
+    assert lib.frn_prune_ranges_width(100, 5) == 5
+    assert lib.frn_prune_ranges_width(3, 5) == 4      # s_range > S -> S + 1 (rnnt_loss.py:710-711)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    null = ctypes.c_void_p(0)
+    EINVAL, EWORKSPACE = -1, -2
+    # null tensors / bad shapes are rejected before any CUDA call
+    assert lib.frn_mi_fwd_bwd(null, null, null, 2, 3, 4, 5, 1, null, null, null, null, 0, null) == EINVAL
+    assert lib.frn_mi_fwd_bwd(null, null, null, 2, 3, 4, 7, 1, null, null, null, null, 0, null) == EINVAL
+    one = ctypes.c_void_p(256)
+    assert lib.frn_mi_fwd_bwd(one, one, one, 2, 3, 4, 5, 0, one, null, null, null, 0, null) == EWORKSPACE
+    assert lib.frn_prune_ranges(one, one, one, 1, 0, 4, 5, 2, one, one, ctypes.c_size_t(1 << 20), null) == EINVAL
+    assert lib.frn_reduce(one, 4, 7, ctypes.c_float(0), one, null) == EINVAL
+    assert lib.frn_simple_loss(one, one, one, one, 1, 4, 8, 16, 99, 0, 0, ctypes.c_float(0), ctypes.c_float(0),
+                               ctypes.c_float(0), 0, one, null, null, one, ctypes.c_size_t(1 << 30), null) == EINVAL
+
+
+def test_product_does_not_reach_the_oracle_or_a_cpu_fallback():
+    bad = re.compile(r"^\s*(from|import)\s+oracle\b|rnnt_oracle|liborc", re.M)
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                text = open(os.path.join(base, f)).read()
+                assert not bad.search(text), f"{f} references the oracle"
+    src = open(os.path.join(PKG, "tf_fast_rnnt", "_lib.py")).read()
+    assert "no CPU fallback" in src and "raise ImportError" in src
+
+
+def test_public_api_names_match_the_reference():
+    sys.path.insert(0, PKG)
+    import tf_fast_rnnt
+    # tf_fast_rnnt/python/tf_fast_rnnt/__init__.py:24-36,42,151
+    for n in ("do_rnnt_pruning", "get_rnnt_logprobs", "get_rnnt_logprobs_joint", "get_rnnt_logprobs_pruned",
+              "get_rnnt_logprobs_smoothed", "get_rnnt_prune_ranges", "rnnt_loss", "rnnt_loss_pruned",
+              "rnnt_loss_simple", "rnnt_loss_smoothed", "mutual_information_recursion", "cummin"):
+        assert callable(getattr(tf_fast_rnnt, n)), n
+    assert tf_fast_rnnt.__version__ == "1.2"
+    import inspect
+    sig = inspect.signature(tf_fast_rnnt.rnnt_loss_simple)
+    assert list(sig.parameters)[:9] == ["lm", "am", "symbols", "termination_symbol", "boundary", "rnnt_type",
+                                        "delay_penalty", "reduction", "calc_gradients"]
+    sig = inspect.signature(tf_fast_rnnt.rnnt_loss_pruned)
+    assert list(sig.parameters)[:9] == ["logits", "symbols", "ranges", "termination_symbol", "boundary",
+                                        "rnnt_type", "delay_penalty", "reduction", "calc_gradients"]
+    sig = inspect.signature(tf_fast_rnnt.rnnt_loss_smoothed)
+    assert sig.parameters["lm_only_scale"].default == 0.1 and sig.parameters["am_only_scale"].default == 0.1

@@ -1,0 +1,80 @@
+"""Host-side multi-GPU logic on CPU: utterance sharding + the scalar all-reduce
+of reduction='sum'/'mean', 2 ranks over gloo.  The per-rank compute is the oracle
+here (no GPU); on the B200 the same code path calls the CUDA kernels."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "tf-fast-rnnt_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from tests.helpers import make_inputs  # noqa: E402
+
+
+def test_partition_is_a_balanced_exact_cover():
+    from tf_fast_rnnt.sharding import lattice_cells, partition_batch, shard_max_shapes
+    rng = np.random.default_rng(0)
+    B = 256
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 3] = rng.integers(200, 1501, B)                      # config c5: T 200-1500
+    bd[:, 2] = np.minimum(rng.integers(20, 401, B), bd[:, 3])  # S 20-400
+    for world in (1, 2, 4, 8):
+        parts = partition_batch(bd, world)
+        allidx = np.concatenate(parts)
+        assert sorted(allidx.tolist()) == list(range(B))
+        loads = np.array([lattice_cells(bd[p]).sum() for p in parts], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.05, (world, loads)
+        for p in parts:
+            s, t = shard_max_shapes(bd, p)
+            assert s == bd[p, 2].max() and t == bd[p, 3].max()
+    assert partition_batch(bd, 2)[0].tolist() == partition_batch(bd, 2)[0].tolist()   # deterministic
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, reduction, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import rnnt_oracle as orc
+    from tf_fast_rnnt.sharding import allreduce_loss, partition_batch
+    am, lm, sym, term, bd = make_inputs(11, 6, 30, 8, 12, ragged=True)
+    mine = partition_batch(bd, world)[rank]
+    losses = orc.rnnt_loss_simple(lm[mine], am[mine], sym[mine], term, bd[mine], "regular", 0.0, "none",
+                                  dtype=np.float64)
+    total = allreduce_loss(torch.tensor(float(losses.sum()), dtype=torch.float64), len(mine), reduction)
+    if rank == 0:
+        out.put(float(total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+def test_two_rank_reduction_equals_unsharded(reduction):
+    from oracle import rnnt_oracle as orc
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, reduction, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = out.get()
+    am, lm, sym, term, bd = make_inputs(11, 6, 30, 8, 12, ragged=True)
+    want = orc.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, reduction, dtype=np.float64)
+    np.testing.assert_allclose(got, float(want), rtol=1e-12)

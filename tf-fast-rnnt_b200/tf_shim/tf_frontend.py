@@ -1,0 +1,115 @@
+"""TensorFlow front-end over the shim ops (tf_fast_rnnt_b200_ops.cc).
+
+Drop this in place of the reference's ``tf_fast_rnnt/__init__.py`` + ``rnnt_loss.py``
+on a machine that has TensorFlow: same public names and signatures, the graph
+math replaced by the fused ops.  It cannot be imported in this repository's
+container (TensorFlow is absent); the TensorFlow-free twin with identical
+semantics, which the tests exercise, is ``tf_fast_rnnt/rnnt_loss.py``.
+"""
+import glob
+import os
+
+import tensorflow as tf
+from tensorflow.python.framework import ops
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_so = glob.glob(os.path.join(_here, "_tf_fast_rnnt*.so"))       # reference: imp.find_module (__init__.py:38-40)
+if not _so:
+    raise ImportError("_tf_fast_rnnt*.so not found next to tf_frontend.py; build tf_fast_rnnt_b200_ops.cc")
+_ops = tf.load_op_library(_so[0])
+_TYPES = {"regular": 0, "modified": 1, "constrained": 2}
+__version__ = "1.2"
+
+
+def mutual_information_recursion(px, py, boundary, calc_gradients=False):
+    ans, gx, gy = _ops.fast_rnnt_loss(px, py, boundary, calc_gradients)
+    return (ans, (gx, gy)) if calc_gradients else ans
+
+
+def cummin(x):
+    return _ops.cummin(x)
+
+
+@ops.RegisterGradient("FastRNNTLoss")
+def _rnnt_loss_grad(op, *grads):           # reference: __init__.py:154-162
+    g = tf.reshape(grads[0], (-1, 1, 1))
+    return [g * op.outputs[1], g * op.outputs[2], None, None]
+
+
+@ops.RegisterGradient("FastRnntDoPruning")
+def _do_pruning_grad(op, g_am, g_lm):
+    S = op.inputs[1].shape[1] - 1
+    am_g, lm_g = _ops.fast_rnnt_do_pruning_grad(g_am, g_lm, op.inputs[2], S=S)
+    return [am_g, lm_g, None]
+
+
+def _reduce(scores, reduction):
+    if reduction == "none":
+        return -scores
+    if reduction == "mean":
+        return -tf.reduce_mean(scores)
+    if reduction == "sum":
+        return -tf.reduce_sum(scores)
+    raise ValueError(f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+
+
+def _boundary(boundary, B, S, T):
+    if boundary is None:
+        return tf.tile(tf.constant([[0, 0, S, T]], tf.int32), [B, 1])
+    return tf.cast(boundary, tf.int32)
+
+
+def _simple(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
+            calc_gradients, smoothed, lms, ams):
+    B, T = am.shape[0], am.shape[1]
+    S = lm.shape[1] - 1
+    scores, gx, gy = _ops.fast_rnnt_simple_loss(
+        lm, am, tf.cast(symbols, tf.int32), _boundary(boundary, B, S, T), termination_symbol=termination_symbol,
+        rnnt_type=_TYPES[rnnt_type], smoothed=smoothed, lm_only_scale=lms, am_only_scale=ams,
+        delay_penalty=max(delay_penalty, 0.0), calc_gradients=calc_gradients)
+    loss = _reduce(scores, reduction)
+    return (loss, (gx, gy)) if calc_gradients else loss
+
+
+def rnnt_loss_simple(lm, am, symbols, termination_symbol, boundary=None, rnnt_type="regular",
+                     delay_penalty=0.0, reduction="mean", calc_gradients=False):
+    return _simple(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
+                   calc_gradients, False, 0.0, 0.0)
+
+
+def rnnt_loss_smoothed(lm, am, symbols, termination_symbol, lm_only_scale=0.1, am_only_scale=0.1,
+                       boundary=None, rnnt_type="regular", delay_penalty=0.0, reduction="mean",
+                       calc_gradients=False):
+    return _simple(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
+                   calc_gradients, True, lm_only_scale, am_only_scale)
+
+
+def get_rnnt_prune_ranges(px_grad, py_grad, boundary, s_range):
+    return _ops.fast_rnnt_prune_ranges(px_grad, py_grad, tf.cast(boundary, tf.int32), s_range=s_range)
+
+
+def do_rnnt_pruning(am, lm, ranges):
+    return _ops.fast_rnnt_do_pruning(am, lm, ranges)
+
+
+def rnnt_loss_pruned(logits, symbols, ranges, termination_symbol, boundary=None, rnnt_type="regular",
+                     delay_penalty=0.0, reduction="mean", calc_gradients=False):
+    B, T = logits.shape[0], logits.shape[1]
+    S = symbols.shape[1]
+    bd = _boundary(boundary, B, S, T)
+    sym = tf.cast(symbols, tf.int32)
+
+    @tf.custom_gradient
+    def _scores(lg):
+        s, _ = _ops.fast_rnnt_pruned_loss(lg, sym, ranges, bd, tf.ones([B], tf.float32),
+                                          termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type],
+                                          delay_penalty=max(delay_penalty, 0.0), with_logits_grad=False)
+
+        def grad(upstream):
+            _, g = _ops.fast_rnnt_pruned_loss(lg, sym, ranges, bd, upstream,
+                                              termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type],
+                                              delay_penalty=max(delay_penalty, 0.0), with_logits_grad=True)
+            return g
+        return s, grad
+
+    return _reduce(_scores(logits), reduction)
