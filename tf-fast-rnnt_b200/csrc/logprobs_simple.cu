@@ -9,7 +9,10 @@
 // products, the parity baseline).  The tcgen05/TMA split-precision version of
 // the contraction lives in logprobs_simple_tc.cu when enabled; both share the
 // row-statistics kernels and the epilogue below.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "simple_params.cuh"
 
 namespace frn {
 
@@ -77,16 +80,6 @@ __global__ void __launch_bounds__(256) amonly_kernel(const float *am, const floa
 // contraction + epilogue.  Block: 64 (s) x 64 (t) tile of one utterance,
 // 256 threads, 4x4 micro-tile per thread, K chunks of 32.
 // ---------------------------------------------------------------------------
-struct SimpleParams {
-  const float *lm, *am;
-  const int32_t *symbols, *boundary;
-  const float *lmmax, *ammax;           // row maxima
-  const float *lmsum, *amonly, *logu;   // smoothed only (may be null)
-  float *px, *py;                       // reference layout
-  int B, S, T, T1, C, term, rnnt_type, smoothed;
-  float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
-};
-
 constexpr int kTile = 64, kBK = 32, kPitchG = 68;
 
 __global__ void __launch_bounds__(256) simple_logprobs_kernel(SimpleParams p) {
@@ -241,9 +234,15 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   sp.comb = (float)(1.0 - lms - ams);
   sp.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
   sp.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
-  dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
-  simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
-  rc = check_launch();
+  // tensor-core path (tcgen05 + TMA); the exact-FP32 SIMT kernel serves shapes
+  // TMA cannot address (C % 4 != 0) and FRN_SIMPLE_SIMT=1 forces it for A/B runs
+  static const bool force_simt = [] { const char *e = getenv("FRN_SIMPLE_SIMT"); return e && e[0] == '1'; }();
+  rc = force_simt ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
+  if (rc == FRN_EUNSUPPORTED) {
+    dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
+    simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
+    rc = check_launch();
+  }
   if (rc) return rc;
   if (rnnt_type == FRN_CONSTRAINED) {
     const size_t n = (size_t)B * S * T;
