@@ -108,9 +108,11 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols,
                     float *px_grad, float *py_grad, void *workspace,
                     size_t workspace_bytes, void *stream);
 
-/* A9. Gradient of sum_b scores_grad[b]*scores[b] w.r.t. am and lm given the
- * occupation counts (what TensorFlow autodiff + _RNNTLossGrad,
- * __init__.py:154-162, produce for rnnt_loss_simple; smoothed not covered). */
+/* A9. Gradient of sum_b scores_grad[b]*scores[b] w.r.t. am [B][T][C] and lm
+ * [B][S+1][C] given the occupation counts returned by frn_simple_loss with the
+ * same arguments (what TensorFlow autodiff + _RNNTLossGrad, __init__.py:154-162,
+ * produce for rnnt_loss_simple; the smoothed variant is not covered).
+ * scores_grad == NULL means all ones. */
 size_t frn_simple_loss_bwd_workspace_bytes(int B, int S, int T, int C);
 int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols,
                         const int32_t *boundary, const float *px_grad,

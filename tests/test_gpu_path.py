@@ -213,3 +213,25 @@ def test_argument_errors():
         frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type="bogus")
     with pytest.raises(ValueError):
         frn.mutual_information_recursion(np.zeros((2, 3, 9), np.float32), np.zeros((2, 4, 5), np.float32), None)
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_simple_loss_am_lm_gradients(rnnt_type):
+    """A9: gradients w.r.t. am / lm (C-ABI frn_simple_loss_bwd and the autograd wrapper)."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 3, 70, 21, 28
+    am, lm, sym, term, bd = make_inputs(17, B, T, S, C, ragged=True)
+    w = np.array([1.0, 0.5, -2.0], np.float32)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.2, "none", True)
+    am_g, lm_g = frn.simple_loss_backward(lm, am, sym, term, bd, gx, gy, -w, rnnt_type)
+    o_am, o_lm = orc.simple_am_lm_grad(lm, am, sym, term, bd, rnnt_type, 0.2, w, np.float64)
+    assert_close(am_g, o_am, GRAD_RTOL, 2e-6, "am grad")
+    assert_close(lm_g, o_lm, GRAD_RTOL, 2e-5, "lm grad")       # lm rows sum ~T terms
+    lm_t = torch.from_numpy(lm).cuda().requires_grad_(True)
+    am_t = torch.from_numpy(am).cuda().requires_grad_(True)
+    loss = frn.rnnt_loss_simple(lm_t, am_t, sym, term, bd, rnnt_type, 0.2, "sum")
+    loss.backward()
+    o_am1, o_lm1 = orc.simple_am_lm_grad(lm, am, sym, term, bd, rnnt_type, 0.2, None, np.float64)
+    assert_close(am_t.grad.cpu().numpy(), o_am1, GRAD_RTOL, 2e-6, "autograd am grad")
+    assert_close(lm_t.grad.cpu().numpy(), o_lm1, GRAD_RTOL, 2e-5, "autograd lm grad")

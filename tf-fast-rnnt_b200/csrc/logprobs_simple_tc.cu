@@ -20,6 +20,12 @@
 // float32-accurate by construction (the occupation counts downstream need ~2^-21
 // on the normaliser, which rules out plain bf16/tf32: DESIGN.md "numerics").
 #include <cuda.h>
+#ifdef FRN_TC_TIMING
+#include <cstdio>
+#define TCT(i) do { if (tid == 0 && blockIdx.x == 1 && blockIdx.z == 3) tct[i] = clock64(); } while (0)
+#else
+#define TCT(i) do { } while (0)
+#endif
 
 #include "common.cuh"
 #include "simple_params.cuh"
@@ -110,24 +116,23 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
   __trap();
 }
 
-// probability -> three bf16 terms, packed two at a time
-__device__ __forceinline__ void split3(float p, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l) {
-  h = __float2bfloat16_rn(p);
-  const float r1 = p - __bfloat162float(h);
-  m = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(m);
-  l = __float2bfloat16_rn(r2);
-}
-
 }  // namespace tc
 
 __global__ void __launch_bounds__(tc::kThreads, 1)
 simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __grid_constant__ CUtensorMap map_lm,
                           SimpleParams p) {
   using namespace tc;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B operands need a 1024-byte aligned base; keep the arithmetic on the
+  // __shared__ array so that accesses stay LDS/STS (a pointer rebuilt from an integer
+  // degrades them to generic LD/ST)
+  unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#ifdef FRN_TC_TIMING
+  long long tct[48];
+  for (int i = 0; i < 48; ++i) tct[i] = 0;
+#endif
+  TCT(0);
   const int b = blockIdx.z, t0 = blockIdx.x * TM, s0 = blockIdx.y * TN;
   const int S1 = p.S + 1, C = p.C;
   const int nk = (C + KC - 1) / KC;
@@ -172,6 +177,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *s_tmem;
+  TCT(1);
 
   auto issue_tma = [&](int k, int stage) {
     unsigned char *raw = smem + kOffRaw + stage * kRawStage;
@@ -183,13 +189,30 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     issue_tma(0, 0);
     if (nk > 1) issue_tma(1, 1);
   }
+  // Epilogue operands that do not depend on the contraction are fetched now, so the
+  // scattered am[b,t,sym[s]] gathers (one 32-byte sector each) hide behind the k loop.
+  const int q = w & 3, half = w >> 2;
+  const int erow = q * 32 + lane, et = t0 + erow;
+  const bool t_ok = et < p.T;
+  const float *amrow = amb + (size_t)(t_ok ? et : 0) * C;
+  constexpr int kColsPerHalf = TN / 2;          // 56 columns per thread, 7 batches of 8
+  float pxam[kColsPerHalf];
+#pragma unroll
+  for (int i = 0; i < kColsPerHalf; ++i) pxam[i] = __ldg(amrow + s_sym[half * kColsPerHalf + i]);
+  const float py_am = __ldg(amrow + p.term);
+  const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
+  const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
+
+  TCT(2);
   const uint32_t idesc = umma_idesc(TM, n_rows);
   const uint32_t a_base = smem_u32(smem + kOffA), b_base = smem_u32(smem + kOffB);
 
   for (int k = 0; k < nk; ++k) {
     const int stage = k & 1;
     mbar_wait_bounded(&bars[stage], (uint32_t)((k >> 1) & 1));             // raw tiles landed
+    if (k < 8) TCT(4 + 4 * k);
     if (k > 0) mbar_wait_bounded(&bars[2], (uint32_t)((k - 1) & 1));       // previous MMAs done: operands free
+    if (k < 8) TCT(5 + 4 * k);
     const float *raw_am = reinterpret_cast<const float *>(smem + kOffRaw + stage * kRawStage);
     const float *raw_lm = raw_am + TM * KC;
     const int k0 = k * KC;
@@ -204,28 +227,33 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
       const bool row_ok = isA ? (t0 + row < p.T) : (s0 + row < S1);
       const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
       const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      __nv_bfloat16 h[8], m[8], l[8];
+      // three-term bf16 split by mantissa truncation: h = top 16 bits of p, m = top 16
+      // bits of the (exact) remainder, l likewise -> h+m+l = p to 2^-24; ALU ops only
+      uint32_t hb[8], mb[8], lb[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const bool ok = row_ok && (k0 + j * 8 + e < C);
         const float pr = ok ? ex2_approx((x[e] - mx) * kLog2e) : 0.f;
-        split3(pr, h[e], m[e], l[e]);
+        hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
+        const float r1 = pr - __uint_as_float(hb[e]);
+        mb[e] = __float_as_uint(r1) & 0xFFFF0000u;
+        const float r2 = r1 - __uint_as_float(mb[e]);
+        lb[e] = __float_as_uint(r2) & 0xFFFF0000u;
       }
       const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
       unsigned char *dst = smem + (isA ? kOffA : kOffB) + off;
       const uint32_t stride = isA ? kOpABytes : kOpBBytes;
-      auto pack = [](const __nv_bfloat16 (&v)[8]) {
-        auto two = [](__nv_bfloat16 lo, __nv_bfloat16 hi) {
-          return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
-        };
-        return make_uint4(two(v[0], v[1]), two(v[2], v[3]), two(v[4], v[5]), two(v[6], v[7]));
+      auto pack = [](const uint32_t (&v)[8]) {   // element e in the low half, e+1 in the high half
+        return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
+                          __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
       };
-      *reinterpret_cast<uint4 *>(dst) = pack(h);
-      *reinterpret_cast<uint4 *>(dst + stride) = pack(m);
-      *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(l);
+      *reinterpret_cast<uint4 *>(dst) = pack(hb);
+      *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
+      *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
     }
     fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncthreads();
+    if (k < 8) TCT(6 + 4 * k);
     if (tid == 0) {
       if (k + 2 < nk) issue_tma(k + 2, stage);   // this raw stage has been consumed
       tc_fence_after();
@@ -242,56 +270,67 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
       }
       umma_commit(&bars[2]);
     }
+    if (k < 8) TCT(7 + 4 * k);
   }
   mbar_wait_bounded(&bars[2], (uint32_t)((nk - 1) & 1));
   tc_fence_after();
+  TCT(40);
 
   // ---- epilogue: one frame per thread (TMEM lane), 56 symbol columns per warp half ----
   {
-    const int q = w & 3, half = w >> 2;
-    const int row = q * 32 + lane, t = t0 + row;
+    const int t = et;
     const int t_end = p.boundary[4 * b + 3];
-    const bool t_ok = t < p.T;
-    const float ammax = s_ammax[row];
-    const float *amrow = amb + (size_t)(t_ok ? t : 0) * C;
-    const float py_am = t_ok ? amrow[p.term] : 0.f;
-    const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + t] : 0.f;
-    const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
+    const float ammax = s_ammax[erow];
     float *pxb = p.px + (size_t)b * p.S * p.T1;
     float *pyb = p.py + (size_t)b * S1 * p.T;
     const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
-    for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 8) {
-      if (c0 >= n_rows) break;           // warp-uniform
-      float acc[8];
-      tmem_ld8(lane_addr + (uint32_t)c0, acc);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = c0 + e, s = s0 + j;
-        if (s >= S1) continue;
-        if (t_ok) {
-          const float norm = logf(acc[e] + __int_as_float(1)) + s_lmmax[j] + ammax;
-          const float py_lm = s_pylm[j];
-          float py = py_am + py_lm - norm;
-          if (p.smoothed)
-            py = py * p.comb + (py_lm - s_lmonly[j]) * p.lm_scale + (py_am + logu_term - amonly) * p.am_scale;
-          pyb[(size_t)s * p.T + t] = py;
-          if (s < p.S) {
-            const float px_am = amrow[s_sym[j]];
-            const float px_lm = s_pxlm[j];
-            float px = px_am + px_lm - norm;
-            if (p.smoothed)
-              px = px * p.comb + (px_lm - s_lmonly[j]) * p.lm_scale + (px_am + s_logusym[j] - amonly) * p.am_scale;
-            if (p.rnnt_type == FRN_REGULAR && t == t_end) px = -INFINITY;   // fix_for_boundary
-            pxb[(size_t)s * p.T1 + t] = px;
+    for (int bi = 0; bi < kColsPerHalf / 8; ++bi) {
+      const int c0 = half * kColsPerHalf + bi * 8;
+      if (c0 < n_rows) {                 // warp-uniform
+        float acc[8];
+        tmem_ld8(lane_addr + (uint32_t)c0, acc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = c0 + e, s = s0 + j;
+          if (s < S1) {
+            if (t_ok) {
+              const float norm = logf(acc[e] + __int_as_float(1)) + s_lmmax[j] + ammax;
+              const float py_lm = s_pylm[j];
+              float py = py_am + py_lm - norm;
+              if (p.smoothed)
+                py = py * p.comb + (py_lm - s_lmonly[j]) * p.lm_scale + (py_am + logu_term - amonly) * p.am_scale;
+              pyb[(size_t)s * p.T + t] = py;
+              if (s < p.S) {
+                const float px_am = pxam[bi * 8 + e];
+                const float px_lm = s_pxlm[j];
+                float px = px_am + px_lm - norm;
+                if (p.smoothed)
+                  px = px * p.comb + (px_lm - s_lmonly[j]) * p.lm_scale + (px_am + s_logusym[j] - amonly) * p.am_scale;
+                if (p.rnnt_type == FRN_REGULAR && t == t_end) px = -INFINITY;   // fix_for_boundary
+                pxb[(size_t)s * p.T1 + t] = px;
+              }
+            } else if (t == p.T && p.T1 == p.T + 1 && s < p.S) {
+              pxb[(size_t)s * p.T1 + t] = -INFINITY;                            // regular: one-past-the-last frame
+            }
           }
-        } else if (t == p.T && p.T1 == p.T + 1 && s < p.S) {
-          pxb[(size_t)s * p.T1 + t] = -INFINITY;                            // regular: one-past-the-last frame
         }
       }
     }
   }
+  TCT(41);
   tc_fence_before();
   __syncthreads();
+  TCT(42);
+#ifdef FRN_TC_TIMING
+  if (tid == 0 && blockIdx.x == 1 && blockIdx.z == 3) {
+    printf("TC timing (cycles from start): setup %lld gathers %lld\n", tct[1] - tct[0], tct[2] - tct[0]);
+    for (int k = 0; k < 8 && k < nk; ++k)
+      printf("  k%d raw_wait->%lld mma_wait->%lld convert+sync->%lld issue->%lld\n", k, tct[4 + 4 * k] - tct[0],
+             tct[5 + 4 * k] - tct[0], tct[6 + 4 * k] - tct[0], tct[7 + 4 * k] - tct[0]);
+    printf("  last mma done %lld epilogue end %lld final sync %lld\n", tct[40] - tct[0], tct[41] - tct[0], tct[42] - tct[0]);
+  }
+#endif
   if (w == 0) tmem_dealloc(tmem_d, kTmemCols);
 }
 

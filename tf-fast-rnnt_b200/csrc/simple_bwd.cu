@@ -1,0 +1,189 @@
+// A9: gradient of sum_b g_b * scores_b w.r.t. am and lm for rnnt_loss_simple —
+// what TensorFlow autodiff produces through rnnt_loss.py:175-221 once
+// _RNNTLossGrad (__init__.py:154-162) has supplied the occupation counts.
+//
+//   px[s,t] = am[t,sym_s] + lm[s,sym_s] - norm[s,t]      py[s,t] = am[t,blank] + lm[s,blank] - norm[s,t]
+//   norm[s,t] = log Z[s,t] + lmmax[s] + ammax[t],  Z = sum_c lmp[s,c] amp[t,c] (+tiny)
+//   G[s,t]  = gpy[s,t] + gpx[s,t]                         (total weight on -norm; constrained: gpx also feeds py[s+1,t])
+//   W[s,t]  = G[s,t] / Z[s,t]
+//   am_grad[t,c] = g ( [c=sym_s] sum_s gpx[s,t] + [c=blank] sum_s gpy[s,t] - amp[t,c] sum_s W[s,t] lmp[s,c] )
+//   lm_grad[s,c] = g ( [c=sym_s] sum_t gpx[s,t] + [c=blank] sum_t gpy[s,t] - lmp[s,c] sum_t W[s,t] amp[t,c] )
+//
+// First version: exact-FP32 SIMT tiles for the two contractions ([T x S1].[S1 x C]
+// and [S1 x T].[T x C]); the tcgen05 version follows the forward kernel's scheme.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace frn {
+
+struct BwdParams {
+  const float *lm, *am;
+  const int32_t *symbols, *boundary;
+  const float *gpx, *gpy;       // occupation counts, reference layout ([B,S,T1], [B,S+1,T])
+  const float *py;              // forward py [B,S+1,T] (recomputed), gives Z
+  const float *lmmax, *ammax;   // row maxima
+  const float *scores_grad;     // [B] or null (ones)
+  float *W;                     // [B][S+1][T] workspace
+  float *am_grad, *lm_grad;
+  int B, S, T, T1, C, term, rnnt_type;
+};
+
+// W[b,s,t] = G / Z with Z = exp(norm - lmmax - ammax), norm = am[t,blank] + lm[s,blank] - py[s,t]
+__global__ void __launch_bounds__(256) bwd_weights_kernel(BwdParams p) {
+  const int S1 = p.S + 1;
+  const size_t n = (size_t)p.B * S1 * p.T;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / ((size_t)S1 * p.T));
+  const int rem = (int)(i - (size_t)b * S1 * p.T);
+  const int s = rem / p.T, t = rem - s * p.T;
+  float G = p.gpy[i];
+  if (s < p.S) G += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+  if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) G += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];  // px[s-1,t] += py[s,t]
+  float w = 0.f;
+  if (G != 0.f) {
+    const float norm = p.am[((size_t)b * p.T + t) * p.C + p.term] + p.lm[((size_t)b * S1 + s) * p.C + p.term] - p.py[i];
+    const float logZ = norm - p.lmmax[(size_t)b * S1 + s] - p.ammax[(size_t)b * p.T + t];
+    w = G * expf(-logZ);
+  }
+  p.W[i] = w;
+}
+
+// out[m,n] = -g * probs(x[m,n]) * sum_k Wk[m,k] * probs(y[k,n])   (+ scatter terms added afterwards)
+// AM side: m = t, k = s, x = am, y = lm, Wk[m,k] = W[k][m];  LM side: m = s, k = t, x = lm, y = am, Wk[m,k] = W[m][k].
+template <bool AM_SIDE>
+__global__ void __launch_bounds__(256) bwd_contract_kernel(BwdParams p) {
+  constexpr int TILE = 64, BK = 16;
+  __shared__ float Ws[BK][TILE + 4];   // [k][m]
+  __shared__ float Ys[BK][TILE + 4];   // [k][n] probabilities
+  const int b = blockIdx.z, m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+  const int S1 = p.S + 1, C = p.C, T = p.T;
+  const int M = AM_SIDE ? T : S1, K = AM_SIDE ? S1 : T;
+  const float *x = (AM_SIDE ? p.am + (size_t)b * T * C : p.lm + (size_t)b * S1 * C);
+  const float *y = (AM_SIDE ? p.lm + (size_t)b * S1 * C : p.am + (size_t)b * T * C);
+  const float *xmax = AM_SIDE ? p.ammax + (size_t)b * T : p.lmmax + (size_t)b * S1;
+  const float *ymax = AM_SIDE ? p.lmmax + (size_t)b * S1 : p.ammax + (size_t)b * T;
+  const float *Wb = p.W + (size_t)b * S1 * T;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = tid; i < BK * TILE; i += 256) {
+      const int kk = i / TILE, mm = i - kk * TILE;      // mm fastest
+      const int k = k0 + kk, m = m0 + mm;
+      float w = 0.f;
+      if (k < K && m < M) w = AM_SIDE ? Wb[(size_t)k * T + m] : Wb[(size_t)m * T + k];
+      Ws[kk][mm] = w;
+      const int n = n0 + mm;
+      float pr = 0.f;
+      if (k < K && n < C) pr = expf(y[(size_t)k * C + n] - ymax[k]);
+      Ys[kk][mm] = pr;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4 *>(&Ws[kk][ty * 4]);
+      const float4 c = *reinterpret_cast<const float4 *>(&Ys[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], cv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
+  float *out = AM_SIDE ? p.am_grad + (size_t)b * T * C : p.lm_grad + (size_t)b * S1 * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < C) out[(size_t)m * C + n] = -g * expf(x[(size_t)m * C + n] - xmax[m]) * acc[i][j];
+    }
+  }
+}
+
+// scatter terms; one thread per output row, sequential over the other axis (deterministic, no atomics)
+__global__ void __launch_bounds__(128) bwd_scatter_am_kernel(BwdParams p) {
+  const int S1 = p.S + 1;
+  const int bt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bt >= p.B * p.T) return;
+  const int b = bt / p.T, t = bt - b * p.T;
+  const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
+  float *row = p.am_grad + (size_t)bt * p.C;
+  const int32_t *sym = p.symbols + (size_t)b * p.S;
+  float blank = 0.f;
+  for (int s = 0; s < S1; ++s) {
+    float gy = p.gpy[((size_t)b * S1 + s) * p.T + t];
+    if (s < p.S) {
+      const float gx = p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+      row[sym[s]] += g * gx;
+      if (p.rnnt_type == FRN_CONSTRAINED) blank += gx;   // px[s,t] also contains py[s+1,t]
+    }
+    blank += gy;
+  }
+  row[p.term] += g * blank;
+}
+
+__global__ void __launch_bounds__(256) bwd_scatter_lm_kernel(BwdParams p) {
+  // one warp per (b,s): row sums over t
+  const int S1 = p.S + 1;
+  const int bs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (bs >= p.B * S1) return;
+  const int b = bs / S1, s = bs - b * S1;
+  float sx = 0.f, sy = 0.f;
+  for (int t = lane; t < p.T; t += 32) {
+    sy += p.gpy[(size_t)bs * p.T + t];
+    if (s < p.S) sx += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) {
+    const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
+    float *row = p.lm_grad + (size_t)bs * p.C;
+    if (s < p.S) row[p.symbols[(size_t)b * p.S + s]] += g * sx;
+    row[p.term] += g * sy;
+  }
+}
+
+size_t simple_bwd_workspace_bytes(int B, int S, int T, int C) {
+  const int T1 = T + 1;
+  return round_up_sz((size_t)B * S * T1 * sizeof(float), 256) + 2 * round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256) +
+         simple_stats_bytes(B, S, T, C);
+}
+
+int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                      const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T, int C,
+                      int term, int rnnt_type, float *am_grad, float *lm_grad, void *workspace, cudaStream_t stream) {
+  const int S1 = S + 1, T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T;
+  char *w = static_cast<char *>(workspace);
+  float *px = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S * (T + 1) * sizeof(float), 256);
+  float *py = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
+  float *W = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
+  void *stats = w;
+  // forward log-probs again (py gives Z); non-smoothed, and without the constrained px += py fold
+  int rc = launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, term,
+                                  rnnt_type == FRN_CONSTRAINED ? FRN_MODIFIED : rnnt_type, 0, 0.f, 0.f, px, py, stats,
+                                  stream);
+  if (rc) return rc;
+  char *sw = static_cast<char *>(stats);
+  BwdParams p;
+  p.lm = lm; p.am = am; p.symbols = symbols; p.boundary = boundary; p.gpx = px_grad; p.gpy = py_grad; p.py = py;
+  p.lmmax = reinterpret_cast<float *>(sw);
+  p.ammax = reinterpret_cast<float *>(sw + 2 * round_up_sz((size_t)B * S1 * sizeof(float), 256));
+  p.scores_grad = scores_grad; p.W = W; p.am_grad = am_grad; p.lm_grad = lm_grad;
+  p.B = B; p.S = S; p.T = T; p.T1 = T1; p.C = C; p.term = term; p.rnnt_type = rnnt_type;
+  const size_t n = (size_t)B * S1 * T;
+  bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+  dim3 g_am((C + 63) / 64, (T + 63) / 64, B), g_lm((C + 63) / 64, (S1 + 63) / 64, B);
+  bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
+  bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
+  bwd_scatter_am_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
+  bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
+  return check_launch();
+}
+
+}  // namespace frn

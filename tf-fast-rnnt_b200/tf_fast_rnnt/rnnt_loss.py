@@ -230,13 +230,82 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
     return (loss, (io.out(gx), io.out(gy))) if calc_gradients else loss
 
 
+def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad=None,
+                         rnnt_type: str = "regular"):
+    """d(sum_b scores_grad[b] * scores[b]) / d(am, lm) for rnnt_loss_simple, from the
+    occupation counts (px_grad, py_grad) that ``rnnt_loss_simple(..., calc_gradients=True)``
+    returned — the chain TensorFlow autodiff runs through rnnt_loss.py:175-221."""
+    io = _Io(lm, am)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    am_d = io.dev_tensor(am, torch.float32)
+    sym_d = io.dev_tensor(symbols, torch.int32)
+    gx = io.dev_tensor(px_grad, torch.float32)
+    gy = io.dev_tensor(py_grad, torch.float32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    rt = _rnnt_type(rnnt_type)
+    bd = _boundary(io, boundary, B, S, T)
+    sg = None if scores_grad is None else io.dev_tensor(scores_grad, torch.float32)
+    am_g = torch.empty_like(am_d)
+    lm_g = torch.empty_like(lm_d)
+    ws = _workspace(lib.frn_simple_loss_bwd_workspace_bytes(B, S, T, C), io.dev)
+    check(lib.frn_simple_loss_bwd(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy), _ptr(sg),
+                                  B, S, T, C, int(termination_symbol), rt, _ptr(am_g), _ptr(lm_g), _ptr(ws),
+                                  ws.numel(), _stream(io.dev)), "frn_simple_loss_bwd")
+    return io.out(am_g), io.out(lm_g)
+
+
+class _SimpleLossFn(torch.autograd.Function):
+    """scores(lm, am) with gradients; stands where TF's GradientTape +
+    _RNNTLossGrad (__init__.py:154-162) stand in the reference."""
+
+    @staticmethod
+    def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty):
+        B, T, C = am.shape
+        S = lm.shape[1] - 1
+        rt = _rnnt_type(rnnt_type)
+        T1 = T + 1 if rt == _lib.REGULAR else T
+        scores = torch.empty(B, dtype=torch.float32, device=am.device)
+        gx = torch.empty((B, S, T1), dtype=torch.float32, device=am.device)
+        gy = torch.empty((B, S + 1, T), dtype=torch.float32, device=am.device)
+        ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), am.device)
+        dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+        check(lib.frn_simple_loss(_ptr(lm), _ptr(am), _ptr(symbols), _ptr(boundary), B, S, T, C,
+                                  int(termination_symbol), rt, 0, 0.0, 0.0, dp, 1, _ptr(scores), _ptr(gx), _ptr(gy),
+                                  _ptr(ws), ws.numel(), _stream(am.device)), "frn_simple_loss")
+        ctx.save_for_backward(lm, am, symbols, boundary, gx, gy)
+        ctx.args = (termination_symbol, rnnt_type)
+        ctx.mark_non_differentiable(gx, gy)
+        return scores, gx, gy
+
+    @staticmethod
+    def backward(ctx, g, _gx, _gy):
+        lm, am, symbols, boundary, gx, gy = ctx.saved_tensors
+        term, rnnt_type = ctx.args
+        am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, gx, gy, g.contiguous(), rnnt_type)
+        return lm_g, am_g, None, None, None, None, None
+
+
 def rnnt_loss_simple(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                      boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
                      delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
                      calc_gradients: bool = False, group=None):
     """Reference: rnnt_loss.py:225-338.  ``group``: optional torch.distributed
     process group over which 'sum'/'mean' are completed (batch sharded by
-    utterance)."""
+    utterance).  CUDA tensors that require grad get gradients w.r.t. lm and am."""
+    if (isinstance(lm, torch.Tensor) and isinstance(am, torch.Tensor) and lm.is_cuda and am.is_cuda
+            and (lm.requires_grad or am.requires_grad) and torch.is_grad_enabled()):
+        if reduction not in _lib.REDUCTIONS:
+            raise ValueError(
+                f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+        io = _Io(lm, am)
+        B, T, _ = am.shape
+        S = lm.shape[1] - 1
+        scores, gx, gy = _SimpleLossFn.apply(lm.contiguous().float(), am.contiguous().float(),
+                                             io.dev_tensor(symbols, torch.int32), int(termination_symbol),
+                                             _boundary(io, boundary, B, S, T), rnnt_type, float(delay_penalty))
+        loss = -scores if reduction == "none" else (-scores.sum() if reduction == "sum" else -scores.mean())
+        return (loss, (gx, gy)) if calc_gradients else loss
     return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
                         reduction, calc_gradients, False, 0.0, 0.0, group)
 
