@@ -7,7 +7,7 @@
 //   1. TMA (cp.async.bulk.tensor.3d, tensor maps over am [B][T][C] and
 //      lm [B][S+1][C]) drops the raw float32 tiles into a 2-stage shared-memory
 //      ring behind mbarriers;
-//   2. all 256 threads turn them into probabilities exp(x - rowmax) and split
+//   2. all 512 threads turn them into probabilities exp(x - rowmax) and split
 //      each into three bfloat16 terms h+m+l (24 mantissa bits), written in the
 //      K-major SWIZZLE_128B layout tcgen05 reads;
 //   3. one thread issues 6 tcgen05.mma (hh, hm, mh, mm, hl, lh — everything down
@@ -36,8 +36,9 @@ namespace tc {
 constexpr int TM = 128;   // frames per CTA  (MMA M)
 constexpr int TN = 112;   // symbols per CTA (MMA N, multiple of 16)
 constexpr int KC = 64;    // vocabulary slice per stage = one 128-byte swizzle row of bf16
-constexpr int kThreads = 256;
-constexpr int kTmemCols = 128;
+constexpr int kThreads = 512;   // 16 warps: 4 per TMEM lane quarter, 28 symbol columns each
+constexpr int kTmemCols = 256;  // [0,112) accumulator, [128,240) px_am staging
+constexpr int kPxCol = 128;
 constexpr uint32_t kRawAmBytes = TM * KC * 4, kRawLmBytes = TN * KC * 4;
 constexpr uint32_t kOpABytes = TM * KC * 2, kOpBBytes = TN * KC * 2;
 // shared memory map (byte offsets from a 1024-aligned base)
@@ -46,7 +47,7 @@ constexpr uint32_t kOffB = kOffA + 3 * kOpABytes;              // 3 x B operand
 constexpr uint32_t kOffRaw = kOffB + 3 * kOpBBytes;            // 2 x (am raw, lm raw)
 constexpr uint32_t kRawStage = kRawAmBytes + kRawLmBytes;
 constexpr uint32_t kOffSmall = kOffRaw + 2 * kRawStage;
-constexpr uint32_t kSmallBytes = 4096;
+constexpr uint32_t kSmallBytes = 5120;
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes + 1024;  // + alignment slack
 
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
@@ -93,14 +94,24 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+// log(z + tiny) for z >= 0: exponent taken exactly, lg2.approx only sees the mantissa in
+// [1,2) where its absolute error is 2^-22.6 (better than 1 ulp of the result here);
+// z == 0 gives log(tiny) like the reference's log(0 + nextafter(0,1)) (rnnt_loss.py:181).
+__device__ __forceinline__ float log_plus_tiny(float z) {
+  const uint32_t u = __float_as_uint(z);
+  const float e = (float)((int)(u >> 23) - 127);
+  const float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
+  const float r = (e + lg2_approx(m)) * kLn2;
+  return (z < 1.1754944e-38f) ? -103.27893f : r;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 // bounded mbarrier wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -138,7 +149,9 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   const int nk = (C + KC - 1) / KC;
   const int n_rows = min(TN, round_up(S1 - s0, 16));   // MMA N for this tile (multiple of 16)
 
-  float *s_ammax = reinterpret_cast<float *>(smem + kOffSmall);          // [128]
+  float *s_amneg = reinterpret_cast<float *>(smem + kOffSmall);          // [128] -ammax*log2e (-inf: row masked)
+  float *s_lmneg = s_amneg + TM;                                         // [112] -lmmax*log2e
+  float *s_ammax = s_lmneg + TN;                                         // [128]
   float *s_lmmax = s_ammax + TM;                                         // [112]
   float *s_pxlm = s_lmmax + TN, *s_pylm = s_pxlm + TN, *s_lmonly = s_pylm + TN, *s_logusym = s_lmonly + TN;
   int *s_sym = reinterpret_cast<int *>(s_logusym + TN);                  // [112]
@@ -149,11 +162,13 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   const float *amb = p.am + (size_t)b * p.T * C;
   if (tid < TM) {
     const int t = t0 + tid;
-    s_ammax[tid] = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
+    const float mx = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
+    s_ammax[tid] = mx;
+    s_amneg[tid] = (t < p.T) ? -mx * kLog2e : -INFINITY;   // exp2(x*log2e - inf) = 0 for masked rows
   } else if (tid < TM + TN) {
     const int j = tid - TM, s = s0 + j;
     float lmmax = 0.f, pxlm = 0.f, pylm = 0.f, lmonly = 0.f, logus = 0.f;
-    int sym = 0;
+    int sym = -1;
     if (s < S1) {
       lmmax = p.lmmax[(size_t)b * S1 + s];
       pylm = lmb[(size_t)s * C + p.term];
@@ -163,10 +178,11 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
       }
       if (p.smoothed) {
         lmonly = logf(p.lmsum[(size_t)b * S1 + s]) + lmmax;
-        logus = p.logu[sym];
+        logus = (sym >= 0) ? p.logu[sym] : 0.f;
       }
     }
-    s_lmmax[j] = lmmax; s_pxlm[j] = pxlm; s_pylm[j] = pylm; s_lmonly[j] = lmonly; s_logusym[j] = logus; s_sym[j] = sym;
+    s_lmmax[j] = lmmax; s_lmneg[j] = (s < S1) ? -lmmax * kLog2e : -INFINITY;
+    s_pxlm[j] = pxlm; s_pylm[j] = pylm; s_lmonly[j] = lmonly; s_logusym[j] = logus; s_sym[j] = sym;
   }
   if (tid == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
@@ -189,20 +205,33 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     issue_tma(0, 0);
     if (nk > 1) issue_tma(1, 1);
   }
-  // Epilogue operands that do not depend on the contraction are fetched now, so the
-  // scattered am[b,t,sym[s]] gathers (one 32-byte sector each) hide behind the k loop.
-  const int q = w & 3, half = w >> 2;
+  // epilogue mapping, also used inside the k loop: thread <-> frame (TMEM lane), the four
+  // warps of a lane quarter take 28 symbol columns each
+  const int q = w & 3, half = w >> 2;            // `half` = column part 0..3
   const int erow = q * 32 + lane, et = t0 + erow;
   const bool t_ok = et < p.T;
-  const float *amrow = amb + (size_t)(t_ok ? et : 0) * C;
-  constexpr int kColsPerHalf = TN / 2;          // 56 columns per thread, 7 batches of 8
-  float pxam[kColsPerHalf];
-#pragma unroll
-  for (int i = 0; i < kColsPerHalf; ++i) pxam[i] = __ldg(amrow + s_sym[half * kColsPerHalf + i]);
-  const float py_am = __ldg(amrow + p.term);
+  constexpr int kColsPerHalf = TN / 4;          // 28 columns per thread, 7 batches of 4
+  const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+  const float py_am = __ldg(amb + (size_t)(t_ok ? et : 0) * C + p.term);
   const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
   const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
-
+  // the symbols of this warp's columns, one per lane
+  const int my_sym0 = (lane < kColsPerHalf) ? s_sym[half * kColsPerHalf + lane] : -1;
+  float accr[kColsPerHalf];                     // float32 sum of the per-slice tensor-core partial sums
+#pragma unroll
+  for (int i = 0; i < kColsPerHalf; ++i) accr[i] = 0.f;
+  auto drain_accumulator = [&]() {              // TMEM partial sums of one slice -> registers
+#pragma unroll
+    for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
+      const int c0 = half * kColsPerHalf + bi * 4;
+      if (c0 < n_rows) {                        // warp-uniform
+        float part[4];
+        tmem_ld4(lane_addr + (uint32_t)c0, part);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) accr[bi * 4 + e] += part[e];
+      }
+    }
+  };
   TCT(2);
   const uint32_t idesc = umma_idesc(TM, n_rows);
   const uint32_t a_base = smem_u32(smem + kOffA), b_base = smem_u32(smem + kOffB);
@@ -211,61 +240,86 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     const int stage = k & 1;
     mbar_wait_bounded(&bars[stage], (uint32_t)((k >> 1) & 1));             // raw tiles landed
     if (k < 8) TCT(4 + 4 * k);
-    if (k > 0) mbar_wait_bounded(&bars[2], (uint32_t)((k - 1) & 1));       // previous MMAs done: operands free
+    if (k > 0) {
+      mbar_wait_bounded(&bars[2], (uint32_t)((k - 1) & 1));                // previous slice's MMAs done
+      tc_fence_after();
+      drain_accumulator();                                                 // (operands are free again, too)
+    }
     if (k < 8) TCT(5 + 4 * k);
     const float *raw_am = reinterpret_cast<const float *>(smem + kOffRaw + stage * kRawStage);
     const float *raw_lm = raw_am + TM * KC;
     const int k0 = k * KC;
-    // ---- convert: 16-byte operand chunks (8 probabilities) ----
-#pragma unroll 1
-    for (int idx = tid; idx < (TM + TN) * 8; idx += kThreads) {
-      const bool isA = idx < TM * 8;
-      const int li = isA ? idx : idx - TM * 8;
-      const int row = li >> 3, j = li & 7;
-      const float *src = (isA ? raw_am : raw_lm) + row * KC + j * 8;
-      const float mx = isA ? s_ammax[row] : s_lmmax[row];
-      const bool row_ok = isA ? (t0 + row < p.T) : (s0 + row < S1);
-      const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
-      const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      // three-term bf16 split by mantissa truncation: h = top 16 bits of p, m = top 16
-      // bits of the (exact) remainder, l likewise -> h+m+l = p to 2^-24; ALU ops only
-      uint32_t hb[8], mb[8], lb[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool ok = row_ok && (k0 + j * 8 + e < C);
-        const float pr = ok ? ex2_approx((x[e] - mx) * kLog2e) : 0.f;
-        hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
-        const float r1 = pr - __uint_as_float(hb[e]);
-        mb[e] = __float_as_uint(r1) & 0xFFFF0000u;
-        const float r2 = r1 - __uint_as_float(mb[e]);
-        lb[e] = __float_as_uint(r2) & 0xFFFF0000u;
+    // ---- px_am[t][s] = am[b,t,sym_s]: picked out of the raw tile while it is in shared
+    //      memory and parked in spare tensor-memory columns (no global gather) ----
+    {
+      // lane l watches column l of its warp's part; a ballot gives the hits of this slice
+      uint32_t hit0 = __ballot_sync(0xffffffffu, my_sym0 >= k0 && my_sym0 < k0 + KC);
+      while (hit0) {                                                       // warp-uniform loop
+        const int src_lane = __ffs(hit0) - 1;
+        hit0 &= hit0 - 1;
+        const int sym = __shfl_sync(0xffffffffu, my_sym0, src_lane);
+        const int j = half * kColsPerHalf + src_lane;
+        const uint32_t v = __float_as_uint(raw_am[erow * KC + (sym - k0)]);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_addr + (uint32_t)(kPxCol + j)), "r"(v)
+                     : "memory");
       }
-      const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-      unsigned char *dst = smem + (isA ? kOffA : kOffB) + off;
-      const uint32_t stride = isA ? kOpABytes : kOpBBytes;
-      auto pack = [](const uint32_t (&v)[8]) {   // element e in the low half, e+1 in the high half
-        return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
-                          __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
-      };
-      *reinterpret_cast<uint4 *>(dst) = pack(hb);
-      *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
-      *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    // ---- convert: 16-byte operand chunks (8 probabilities); three-term bf16 split by
+    //      mantissa truncation: h = top 16 bits of p, m = top 16 bits of the (exact)
+    //      remainder, l likewise -> h+m+l = p to 2^-24, plain ALU ops ----
+    const int lim = C - k0;                     // columns of this slice that exist
+    auto convert = [&](const float *raw, const float *negmax, unsigned char *ops, uint32_t stride, int nchunks) {
+#pragma unroll 2
+      for (int li = tid; li < nchunks; li += kThreads) {
+        const int row = li >> 3, j = li & 7;
+        const float *src = raw + row * KC + j * 8;
+        const float nmx = negmax[row];
+        const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
+        const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t hb[8], mb[8], lb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float pr = ex2_approx(fmaf(x[e], kLog2e, nmx));
+          pr = (j * 8 + e < lim) ? pr : 0.f;
+          hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
+          const float r1 = pr - __uint_as_float(hb[e]);
+          mb[e] = __float_as_uint(r1);
+          const float r2 = r1 - __uint_as_float(mb[e] & 0xFFFF0000u);
+          lb[e] = __float_as_uint(r2);
+        }
+        unsigned char *dst = ops + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+        auto pack = [](const uint32_t (&v)[8]) {   // upper halves: element e low, e+1 high
+          return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
+                            __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
+        };
+        *reinterpret_cast<uint4 *>(dst) = pack(hb);
+        *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
+        *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
+      }
+    };
+    convert(raw_am, s_amneg, smem + kOffA, kOpABytes, TM * 8);
+    convert(raw_lm, s_lmneg, smem + kOffB, kOpBBytes, TN * 8);
     fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+    tc_fence_before();
     __syncthreads();
     if (k < 8) TCT(6 + 4 * k);
     if (tid == 0) {
       if (k + 2 < nk) issue_tma(k + 2, stage);   // this raw stage has been consumed
       tc_fence_after();
-      // (A split, B split) pairs kept: everything down to 2^-24 relative
-      const int ia[6] = {0, 0, 1, 1, 0, 2}, ib[6] = {0, 1, 0, 1, 2, 0};
+      // Tensor-core FP32 accumulation truncates, so (i) every slice starts from a zeroed
+      // accumulator and is summed in registers, (ii) the five small products go first and
+      // h*h last: <= 4 truncations at full magnitude per slice.
+      const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+      uint32_t first = 1;
 #pragma unroll
-      for (int ks = 0; ks < KC / 16; ++ks) {
+      for (int c = 0; c < 6; ++c) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
+        for (int ks = 0; ks < KC / 16; ++ks) {
           const uint64_t ad = umma_desc(a_base + ia[c] * kOpABytes + ks * 32);
           const uint64_t bd = umma_desc(b_base + ib[c] * kOpBBytes + ks * 32);
-          umma_bf16(tmem_d, ad, bd, idesc, (k > 0 || ks > 0 || c > 0) ? 1u : 0u);
+          umma_bf16(tmem_d, ad, bd, idesc, first ? 0u : 1u);
+          first = 0;
         }
       }
       umma_commit(&bars[2]);
@@ -274,46 +328,43 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   }
   mbar_wait_bounded(&bars[2], (uint32_t)((nk - 1) & 1));
   tc_fence_after();
+  drain_accumulator();
   TCT(40);
 
-  // ---- epilogue: one frame per thread (TMEM lane), 56 symbol columns per warp half ----
+  // ---- epilogue: one frame per thread (TMEM lane), 56 symbol columns per warp half.
+  //      Straight-line: everything is computed for all 8 columns of a batch, only the
+  //      stores are predicated. ----
   {
     const int t = et;
     const int t_end = p.boundary[4 * b + 3];
     const float ammax = s_ammax[erow];
-    float *pxb = p.px + (size_t)b * p.S * p.T1;
-    float *pyb = p.py + (size_t)b * S1 * p.T;
-    const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+    float *pxb = p.px + (size_t)b * p.S * p.T1 + t;
+    float *pyb = p.py + (size_t)b * S1 * p.T + t;
+    const bool regular = (p.T1 == p.T + 1);
+    const bool px_col_ok = t_ok || (regular && t == p.T);       // regular: column T exists and is -inf
+    const bool px_inf = !t_ok || (p.rnnt_type == FRN_REGULAR && t == t_end);
+    const bool smoothed = p.smoothed != 0;
 #pragma unroll
-    for (int bi = 0; bi < kColsPerHalf / 8; ++bi) {
-      const int c0 = half * kColsPerHalf + bi * 8;
+    for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
+      const int c0 = half * kColsPerHalf + bi * 4;
       if (c0 < n_rows) {                 // warp-uniform
-        float acc[8];
-        tmem_ld8(lane_addr + (uint32_t)c0, acc);
+        float pxam[4];
+        tmem_ld4(lane_addr + (uint32_t)(kPxCol + c0), pxam);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < 4; ++e) {
           const int j = c0 + e, s = s0 + j;
-          if (s < S1) {
-            if (t_ok) {
-              const float norm = logf(acc[e] + __int_as_float(1)) + s_lmmax[j] + ammax;
-              const float py_lm = s_pylm[j];
-              float py = py_am + py_lm - norm;
-              if (p.smoothed)
-                py = py * p.comb + (py_lm - s_lmonly[j]) * p.lm_scale + (py_am + logu_term - amonly) * p.am_scale;
-              pyb[(size_t)s * p.T + t] = py;
-              if (s < p.S) {
-                const float px_am = pxam[bi * 8 + e];
-                const float px_lm = s_pxlm[j];
-                float px = px_am + px_lm - norm;
-                if (p.smoothed)
-                  px = px * p.comb + (px_lm - s_lmonly[j]) * p.lm_scale + (px_am + s_logusym[j] - amonly) * p.am_scale;
-                if (p.rnnt_type == FRN_REGULAR && t == t_end) px = -INFINITY;   // fix_for_boundary
-                pxb[(size_t)s * p.T1 + t] = px;
-              }
-            } else if (t == p.T && p.T1 == p.T + 1 && s < p.S) {
-              pxb[(size_t)s * p.T1 + t] = -INFINITY;                            // regular: one-past-the-last frame
-            }
+          const float norm = log_plus_tiny(accr[bi * 4 + e]) + s_lmmax[j] + ammax;
+          const float py_lm = s_pylm[j], px_lm = s_pxlm[j], px_am = pxam[e];
+          float py = py_am + py_lm - norm;
+          float px = px_am + px_lm - norm;
+          if (smoothed) {                // warp-uniform
+            const float lmonly = s_lmonly[j];
+            py = py * p.comb + (py_lm - lmonly) * p.lm_scale + (py_am + logu_term - amonly) * p.am_scale;
+            px = px * p.comb + (px_lm - lmonly) * p.lm_scale + (px_am + s_logusym[j] - amonly) * p.am_scale;
           }
+          px = px_inf ? -INFINITY : px;
+          if (t_ok && s < S1) pyb[(size_t)s * p.T] = py;
+          if (px_col_ok && s < p.S) pxb[(size_t)s * p.T1] = px;
         }
       }
     }
@@ -324,9 +375,9 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   TCT(42);
 #ifdef FRN_TC_TIMING
   if (tid == 0 && blockIdx.x == 1 && blockIdx.z == 3) {
-    printf("TC timing (cycles from start): setup %lld gathers %lld\n", tct[1] - tct[0], tct[2] - tct[0]);
+    printf("TC timing (cycles from start): setup %lld prologue %lld\n", tct[1] - tct[0], tct[2] - tct[0]);
     for (int k = 0; k < 8 && k < nk; ++k)
-      printf("  k%d raw_wait->%lld mma_wait->%lld convert+sync->%lld issue->%lld\n", k, tct[4 + 4 * k] - tct[0],
+      printf("  k%d raw_wait->%lld mma_wait+drain->%lld stage+convert+sync->%lld issue->%lld\n", k, tct[4 + 4 * k] - tct[0],
              tct[5 + 4 * k] - tct[0], tct[6 + 4 * k] - tct[0], tct[7 + 4 * k] - tct[0]);
     printf("  last mma done %lld epilogue end %lld final sync %lld\n", tct[40] - tct[0], tct[41] - tct[0], tct[42] - tct[0]);
   }
