@@ -48,23 +48,39 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
   if (vec) {
     const int nv = C / V;
     const uint4 *p = reinterpret_cast<const uint4 *>(src);
-    for (int c = lane; c < nv; c += 32) {
-      uint4 raw;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p + c));
-      float x[V];
-      const T *e = reinterpret_cast<const T *>(&raw);
+    constexpr int kU = 4;   // 16-byte loads issued back to back per lane before any arithmetic
+    for (int cb = 0; cb < nv; cb += 32 * kU) {
+      uint4 raw[kU];
 #pragma unroll
-      for (int j = 0; j < V; ++j) x[j] = to_f(e[j]);
-      float mx = x[0];
+      for (int u = 0; u < kU; ++u) {
+        const int c = cb + u * 32 + lane;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (c < nv)
+          asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w) : "l"(p + c));
+      }
+      float x[kU][V];
+      float mx = -INFINITY;
 #pragma unroll
-      for (int j = 1; j < V; ++j) mx = fmaxf(mx, x[j]);
+      for (int u = 0; u < kU; ++u) {
+        const bool ok = cb + u * 32 + lane < nv;
+        const T *e = reinterpret_cast<const T *>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+          mx = fmaxf(mx, x[u][j]);
+        }
+      }
       const float mn = fmaxf(m, mx);
-      float acc = 0.f;
+      if (mn > -INFINITY) {
+        float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc += expf(x[j] - mn);
-      ssum = ssum * expf(m - mn) + acc;
-      m = mn;
+        for (int u = 0; u < kU; ++u)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc += expf(x[u][j] - mn);
+        ssum = ssum * expf(m - mn) + acc;
+        m = mn;
+      }
     }
   } else {
     for (int c = lane; c < C; c += 32) {
