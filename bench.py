@@ -192,6 +192,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.err = None
+        self.ready = threading.Event()      # set once NVML is initialised (or has failed)
 
     def run(self):
         try:
@@ -214,6 +215,7 @@ class ClockSampler(threading.Thread):
             }
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
                                   getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            self.ready.set()
             while not self.stop_flag:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 if get_reasons is not None:
@@ -224,6 +226,8 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
+        finally:
+            self.ready.set()
 
     def summary(self):
         s = sorted(self.samples)
@@ -301,7 +305,7 @@ def run_gpu_arm(args):
         run_step(i)
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.05)          # let NVML initialise before the timed region
+    sampler.ready.wait(30.0)  # NVML initialised before the timed region starts
     sampler.samples.clear()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -2,6 +2,8 @@
 // Argument validation, workspace carve-up and kernel sequencing only; all
 // kernels live in the other translation units.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "launchers.h"
 
 namespace frn {
@@ -241,6 +243,18 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
   if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
+  // narrow bands: transfer-matrix recursion on the band itself (band_dp.cu);
+  // FRN_BAND_DENSE=1 forces the dense-lattice wavefront for A/B runs and cross-checks
+  static const bool force_dense = [] { const char *e = getenv("FRN_BAND_DENSE"); return e && e[0] == '1'; }();
+  if (!force_dense && band_dp_supported(S, T, R) && band_dp_workspace_bytes(B, T) <= dw.bytes) {
+    const bool want = logits_grad != nullptr;
+    FRN_TRY(launch_band_dp(w.pxc, w.pyc, ranges, boundary, B, S, T, R, rnnt_type, delay_penalty > 0.f ? delay_penalty : 0.f,
+                           want, w.dp, w.gxc, w.gyc, scores, stream));
+    if (want)
+      FRN_TRY(launch_pruned_logits_grad(logits, dtype, symbols, ranges, w.lse, w.gxc, w.gyc, scores_grad, B, S, T, R, C,
+                                        term, logits_grad, stream));
+    return FRN_OK;
+  }
   FRN_TRY(launch_skew_band(w.pxc, w.pyc, ranges, boundary, g, dw, R, rnnt_type,
                            delay_penalty > 0.f ? delay_penalty : 0.f, stream));
   const bool want_grad = logits_grad != nullptr;

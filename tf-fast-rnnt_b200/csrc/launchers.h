@@ -48,6 +48,12 @@ int launch_pruned_logits_grad(const void *logits, int dtype, const int32_t *symb
 int launch_band_to_dense(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary,
                          int B, int S, int T, int T1, int R, int rnnt_type, float *px, float *py,
                          cudaStream_t stream);
+// band_dp.cu
+size_t band_dp_workspace_bytes(int B, int T);
+bool band_dp_supported(int S, int T, int R);
+int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary, int B, int S,
+                   int T, int R, int rnnt_type, float delay_penalty, bool want_grad, void *workspace, float *gxc,
+                   float *gyc, float *scores, cudaStream_t stream);
 // misc.cu
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream);
 int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
