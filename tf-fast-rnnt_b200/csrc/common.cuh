@@ -47,6 +47,37 @@ __device__ __forceinline__ float logadd2(float a, float b) {
 #endif
 }
 
+// ---- extended-range linear-domain arithmetic of the lattice kernels ----
+// A lattice value is  m * 2^o : `m` a float32 mantissa kept within a few binades
+// of 1 (0 = "minus infinity"), `o` an exact int32 exponent ("frame").  All
+// re-scalings are by exact powers of two, so the only roundings are those of the
+// multiply-adds themselves.  kNegI is the frame of a dead value / dead arc; sums
+// of up to four of them stay inside int32.
+constexpr int kNegI = -(1 << 28);
+constexpr int kNegIThresh = -(1 << 27);
+// 2^d for d <= 127; anything below 2^-126 flushes to +0
+__device__ __forceinline__ float pow2i(int d) { return __int_as_float((max(d, -127) + 127) << 23); }
+// floor(log2(m)) of a positive normal float; 0 for m == 0
+__device__ __forceinline__ int expo_of(float m) { return m > 0.f ? ((__float_as_int(m) >> 23) - 127) : 0; }
+// log2-domain arc score -> (mantissa in [1,2], exponent); dead arcs -> (0, kNegI)
+__device__ __forceinline__ float2 encode_arc(float v_log2) {
+  if (!(v_log2 > -1.0e8f)) return make_float2(0.f, __int_as_float(kNegI));   // total scores must stay above -2^27
+  const float e = floorf(v_log2);
+  return make_float2(exp2f(v_log2 - e), __int_as_float((int)e));
+}
+
+// natural-log score of a lattice value {mantissa, frame}
+__device__ __forceinline__ float lattice_score(float2 v) {
+  if (!(v.x > 0.f)) return -INFINITY;
+  return (float)(((double)log2f(v.x) + (double)__float_as_int(v.y)) * 0.6931471805599453);
+}
+// alpha * 2^(alpha frame + operand frame - total frame) / total mantissa: multiply by a backward-side
+// operand (arc * beta(head)) to get the arc's occupation count
+__device__ __forceinline__ float occupation_scale(float2 alpha, int operand_frame, int total_frame, float inv_total) {
+  const int d = __float_as_int(alpha.y) + operand_frame - total_frame;
+  return (alpha.x * inv_total) * pow2i(min(d, 96));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -140,26 +171,20 @@ inline DpGeom make_geom(int B, int S, int T, int T1) {
   return g;
 }
 
-// Workspace carve-up of one DP invocation.
+// Workspace carve-up of one DP invocation (diagonal-major planes, [B][Dn][P]).
 struct DpWorkspace {
-  float *X, *Y;        // [B][Dn][P] skewed log2-domain arc scores
-  // every lattice value is held as (exact integer offset o) + (small float32 residual r)
-  float *ar, *ao;      // [B][Dn][P] forward scores: residual, offset
-  float *bx, *by;      // [B][Dn][P] backward-side operands (arc score + beta of the arc's head), residuals
-  float *bo;           // [B][Dn][P] offset of the frame bx/by are expressed in
+  float4 *XY;          // arcs entering cell (d, s'): {px mantissa, px exponent, py mantissa, py exponent}
+  float2 *A;           // forward scores alpha: {mantissa, frame}
+  float4 *Bq;          // backward side: {px-arc operand, py-arc operand, their frame, unused}; operand = arc * beta(head)
   size_t bytes;
 };
 inline DpWorkspace carve_dp(void *base, const DpGeom &g) {
   DpWorkspace w;
   char *p = static_cast<char *>(base);
-  size_t plane = round_up_sz((size_t)g.B * g.Dn * g.P * sizeof(float), 256);
-  w.X = reinterpret_cast<float *>(p); p += plane;
-  w.Y = reinterpret_cast<float *>(p); p += plane;
-  w.ar = reinterpret_cast<float *>(p); p += plane;
-  w.ao = reinterpret_cast<float *>(p); p += plane;
-  w.bx = reinterpret_cast<float *>(p); p += plane;
-  w.by = reinterpret_cast<float *>(p); p += plane;
-  w.bo = reinterpret_cast<float *>(p); p += plane;
+  const size_t cells = (size_t)g.B * g.Dn * g.P;
+  w.XY = reinterpret_cast<float4 *>(p); p += round_up_sz(cells * sizeof(float4), 256);
+  w.A = reinterpret_cast<float2 *>(p); p += round_up_sz(cells * sizeof(float2), 256);
+  w.Bq = reinterpret_cast<float4 *>(p); p += round_up_sz(cells * sizeof(float4), 256);
   w.bytes = (size_t)(p - static_cast<char *>(base));
   return w;
 }

@@ -120,7 +120,13 @@ struct BandParams {
   float delay_penalty;
 };
 
-__global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float *X, float *Y, int BTR) {
+__global__ void __launch_bounds__(256) fill_dead_arcs_kernel(float4 *XY, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float dead = __int_as_float(kNegI);
+  if (i < n) XY[i] = make_float4(0.f, dead, 0.f, dead);
+}
+
+__global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float4 *XY, int BTR) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= BTR) return;
   const int TR = p.T * p.R;
@@ -138,7 +144,8 @@ __global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float *X, 
   // py arc (s,t) -> (s,t+1): destination diagonal (tp+1) + k*sp
   {
     const float v = p.pyc[idx];
-    Y[plane + (size_t)(tp + 1 + p.k * sp) * p.P + sp] = fmaxf(v * kLog2e, kNeg);
+    float2 *cell = reinterpret_cast<float2 *>(XY + plane + (size_t)(tp + 1 + p.k * sp) * p.P + sp);
+    cell[1] = encode_arc(fmaxf(v * kLog2e, kNeg));
   }
   // px arc (s,t) -> (s+1,t+noff)
   if (s < p.S && s < s_end) {
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float *X, 
       v += add;
     }
     if (p.delay_penalty != 0.f) v += delay_penalty_value(t_end, t, p.delay_penalty);
-    X[plane + (size_t)(tp + noff + p.k * (sp + 1)) * p.P + sp + 1] = fmaxf(v * kLog2e, kNeg);
+    float2 *cell = reinterpret_cast<float2 *>(XY + plane + (size_t)(tp + noff + p.k * (sp + 1)) * p.P + sp + 1);
+    cell[0] = encode_arc(fmaxf(v * kLog2e, kNeg));
   }
 }
 
@@ -160,7 +168,8 @@ __global__ void __launch_bounds__(256) skew_band_kernel(BandParams p, float *X, 
 // (constrained: the px arc's count is folded into the py entry it borrowed).
 // ---------------------------------------------------------------------------
 struct BandFinalizeParams {
-  const float *ar, *ao, *bx, *by, *bo;
+  const float2 *A;
+  const float4 *Bq;
   const int32_t *ranges, *boundary;
   int S, T, R, P, Dn, k, rnnt_type;
 };
@@ -178,9 +187,7 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
     float v = 0.f;
     if (bd_ok(bd, p.S, p.T)) {
       const int Sb = bd.z - bd.x, Tb = bd.w - bd.y, Db = Tb + p.k * Sb;
-      const size_t at = ((size_t)idx * p.Dn + Db) * p.P + Sb;
-      const float tr = p.ar[at], to = p.ao[at];
-      v = (tr < kNegThresh) ? -INFINITY : (float)(((double)tr + (double)to) * 0.6931471805599453);
+      v = lattice_score(p.A[((size_t)idx * p.Dn + Db) * p.P + Sb]);
     }
     scores[idx] = v;
   }
@@ -191,8 +198,10 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
   if (bd_ok(bd, p.S, p.T) && t >= bd.y && t < bd.w) {
     const int Sb = bd.z - bd.x, Tb = bd.w - bd.y, Db = Tb + p.k * Sb;
     const size_t plane = (size_t)b * p.Dn * p.P;
-    const float tot_r = p.ar[plane + (size_t)Db * p.P + Sb], tot_o = p.ao[plane + (size_t)Db * p.P + Sb];
-    if (!(tot_r < kNegThresh)) {
+    const float2 tot = p.A[plane + (size_t)Db * p.P + Sb];
+    if (tot.x > 0.f) {
+      const float inv_tot = 1.0f / tot.x;
+      const int tot_o = __float_as_int(tot.y);
       const int r0 = p.ranges[(size_t)(b * p.T + t) * p.R];
       const int s = band_row(r0, i, p.S + 1);
       auto occ = [&](int sa, bool px_arc) -> float {
@@ -202,8 +211,8 @@ __global__ void __launch_bounds__(256) finalize_band_kernel(BandFinalizeParams p
         if (px_arc && !(sa < p.S && sp < Sb)) return 0.f;
         const int d = tp + p.k * sp;
         const size_t at = plane + (size_t)d * p.P + sp;
-        const float base = (p.ar[at] - tot_r) + ((p.ao[at] + p.bo[at]) - tot_o);
-        return ex2_approx((px_arc ? p.bx[at] : p.by[at]) + base);
+        const float4 bq = p.Bq[at];
+        return (px_arc ? bq.x : bq.y) * occupation_scale(p.A[at], __float_as_int(bq.z), tot_o, inv_tot);
       };
       vx = occ(s, true);
       vy = occ(s, false);
@@ -332,19 +341,18 @@ int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, con
 int launch_skew_band(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary,
                      const DpGeom &g, const DpWorkspace &w, int R, int rnnt_type, float delay_penalty,
                      cudaStream_t stream) {
-  // fill X and Y (adjacent planes) with the 0xF0F0F0F0 sentinel (-5.96e29)
-  const size_t plane = round_up_sz((size_t)g.B * g.Dn * g.P * sizeof(float), 256);
-  cudaError_t e = cudaMemsetAsync(w.X, 0xF0, 2 * plane, stream);
-  if (e != cudaSuccess) return note_cuda_error(e);
+  // every arc of the lattice is dead except the band's
+  const size_t cells = (size_t)g.B * g.Dn * g.P;
+  fill_dead_arcs_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(w.XY, cells);
   BandParams bp{pxc, pyc, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type, delay_penalty};
   const int BTR = g.B * g.T * R;
-  skew_band_kernel<<<(BTR + 255) / 256, 256, 0, stream>>>(bp, w.X, w.Y, BTR);
+  skew_band_kernel<<<(BTR + 255) / 256, 256, 0, stream>>>(bp, w.XY, BTR);
   return check_launch();
 }
 
 int launch_finalize_band(const int32_t *ranges, const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
                          int R, int rnnt_type, float *gxc, float *gyc, float *scores, cudaStream_t stream) {
-  BandFinalizeParams fp{w.ar, w.ao, w.bx, w.by, w.bo, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type};
+  BandFinalizeParams fp{w.A, w.Bq, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type};
   const int n = gxc ? max(g.B * g.T * R, g.B) : g.B;
   finalize_band_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fp, gxc, gyc, scores, g.B);
   return check_launch();

@@ -4,22 +4,22 @@
 // 174-422 forward, 490-760 backward, launched 2*(S/32+T/32+1) times from host
 // loops at :799-808 and :860-872) with three launches:
 //
-//   skew     px/py [B][S][T1] / [B][S+1][T]  ->  X/Y [B][d][s'] (diagonal-major,
-//            log2 domain, boundary masks applied, -inf replaced by a finite
-//            sentinel).  Fully parallel, HBM/L2 bound.
+//   skew     px/py [B][S][T1] / [B][S+1][T]  ->  XY [B][d][s'] (diagonal-major,
+//            boundary masks and delay penalty applied).  Every arc probability
+//            is stored as (mantissa in [1,2], integer exponent), so the chain
+//            never evaluates a transcendental.  Fully parallel, HBM/L2 bound.
 //   chain    one CTA per (utterance, direction), a software pipeline of warps
 //            (see dp_chain_kernel); one step = one anti-diagonal (d = t' + k s',
 //            k = 1 regular / 0 modified), neighbours exchanged by warp shuffle, the
-//            diagonal-major arc scores streamed into a shared-memory ring by
-//            1-D bulk async copies (TMA engine) behind mbarriers.  Forward
-//            (alpha) and backward (beta) chains run concurrently in different
-//            CTAs.  Each row keeps an exact integer offset plus a small float32
-//            residual, re-centred every step off the dependency chain (see the
-//            comment above ChainParams), which makes the float32 result two
-//            orders of magnitude closer to float64 truth than the reference's
-//            plain float32 p[].
-//            Latency bound: (S_b + T_b) dependent log-adds.
-//   finalize occupation counts  px_grad = exp(alpha + px + beta' - total),
+//            diagonal-major arcs streamed into a shared-memory ring by 1-D bulk
+//            async copies (TMA engine) behind mbarriers.  Forward (alpha) and
+//            backward (beta) chains run concurrently in different CTAs.
+//            The recursion runs in the LINEAR domain with an extended exponent:
+//            value = m * 2^o (float32 mantissa, exact int32 frame per row), one
+//            dependent shuffle + FMA per step instead of a log-add (shuffle +
+//            ex2 + lg2); see the comment above ChainParams.
+//            Latency bound: (S_b + T_b) dependent multiply-adds.
+//   finalize occupation counts  px_grad = alpha * (px * beta') / total,
 //            py_grad likewise (equal to the reference's p_grad recursion,
 //            cu:472-481, in exact arithmetic), written in the reference layout.
 //
@@ -27,15 +27,13 @@
 
 namespace frn {
 
-constexpr int kStages = 3;
-
 // ---------------------------------------------------------------------------
 // skew (dense input)
 // ---------------------------------------------------------------------------
 struct SkewDenseParams {
   const float *px, *py;     // reference layout
   const int32_t *boundary;  // [B][4]
-  float *X, *Y;             // [B][Dn][P]
+  float4 *XY;               // [B][Dn][P]
   int S, T, T1, P, Dn;
   float delay_penalty;      // added to px (rnnt_loss.py:316-321); 0 = none
 };
@@ -74,60 +72,62 @@ __global__ void __launch_bounds__(256) skew_dense_kernel(SkewDenseParams p) {
     sy[row * kPitch + col] = vy;
   }
   __syncthreads();
-  // store: s' fastest (coalesced along the row axis of X/Y)
-  float *Xb = p.X + (size_t)b * p.Dn * p.P, *Yb = p.Y + (size_t)b * p.Dn * p.P;
+  // store: s' fastest (one 16-byte arc pair per thread, 512 contiguous bytes per warp)
+  float4 *XYb = p.XY + (size_t)b * p.Dn * p.P;
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
     const int dd = i >> 5, ss = i & 31;
     const int d = d0 + dd;
     if (d >= p.Dn) continue;
     const int col = dd + K * (31 - ss);
-    Xb[(size_t)d * p.P + s0 + ss] = sx[ss * kPitch + col];
-    Yb[(size_t)d * p.P + s0 + ss] = sy[ss * kPitch + col];
+    const float2 ax = encode_arc(sx[ss * kPitch + col]), ay = encode_arc(sy[ss * kPitch + col]);
+    XYb[(size_t)d * p.P + s0 + ss] = make_float4(ax.x, ax.y, ay.x, ay.y);
   }
 }
 
 // ---------------------------------------------------------------------------
 // chain
 // ---------------------------------------------------------------------------
-// Numerics.  Every lattice value is carried as  o + r : `o` an exact integer
-// (held in a float, |o| < 2^24) and `r` a small float32 residual.  At every
-// step each row first moves k = rint(r_previous) from its residual into its
-// offset (both operations are exact in float32; k depends on the previous
-// step only, so none of this is on the dependency chain), a row that is still
-// "minus infinity" adopts the offset of the row that feeds it, and the exact
-// offset difference between neighbouring rows is folded into the arc score.
-// All float32 roundings therefore happen at magnitude ~10 instead of |p| ~ 10^3
-// as in the reference's plain float32 p[]: measured 4e-6 max relative error on
-// the occupation counts at the c2 shape against 1.3e-3 for the reference's
-// arithmetic ("numerics").
+// Numerics.  Every lattice value is carried as  m * 2^o : `o` an exact int32
+// frame, `m` a float32 mantissa normalised to [1,2) after every step (0 = dead).
+// One step of a row is
+//     EA = o_feeder + e_x,  EB = o_own + e_y            (exact integer frames of the two terms)
+//     o' = max(EA, EB)
+//     raw = m_feeder * (x_m * 2^(EA-o')) + m_own * (y_m * 2^(EB-o'))      in [1, 8)
+//     k = exponent field of raw;  m' = raw / 2^k (a bit operation);  o' += k
+// Every re-scaling is by an exact power of two built with integer ops, the step
+// has no transcendental and its only roundings are the two products and the
+// FMA.  Magnitudes are bounded by construction (the dominant term is a
+// normalised mantissa times an arc mantissa in [1,2]), so nothing can under- or
+// overflow whatever the arc scores are.  Against float64 the occupation counts
+// come out ~1e-6 relative at the c2 shape; the reference's plain float32
+// log-domain p[] is at 1.3e-3 there ("numerics").
 struct ChainParams {
-  const float *X, *Y;
-  float *ar, *ao;      // [B][Dn][P]  forward residual / offset (dir 0)
-  float *bx, *by, *bo; // [B][Dn][P]  backward-side operands and their frame offset (dir 1)
+  const float4 *XY;
+  float2 *A;           // [B][Dn][P]  forward {mantissa, frame} (dir 0)
+  float4 *Bq;          // [B][Dn][P]  backward-side operands and their frame (dir 1)
   const int32_t *boundary;
   int k, P, Dn, S, T;
-  int CH, NST;         // diagonals per bulk copy (divides kChunk); ring stages (>= warps + 2)
+  int CH, NST;         // diagonals per bulk copy; ring stages (> warps)
 };
 
 // Execution.  One CTA per (utterance, direction); RPL consecutive lattice rows
 // per lane, 32*RPL rows per warp, W = P / (32*RPL) warps.  The warps form a
 // software pipeline: warp w runs one chunk (CH diagonals) behind the warp that
-// owns the rows feeding it and picks the boundary row's (residual, offset) of
+// owns the rows feeding it and picks the boundary row's (mantissa, frame) of
 // every step out of a shared-memory ring that warp filled; one mbarrier per
 // (warp, ring slot) says "chunk published".  There is no per-step block barrier
-// and every warp sits alone on its SM sub-partition, so a step costs one
-// dependent log-add (shuffle + ex2 + lg2 + a few adds) rather than the issue
-// time of four interleaved rows.  X/Y chunks are shared by all warps: NST >= W+2
-// stages of 1-D bulk copies; the tail warp of the pipeline recycles a stage.
+// and every warp sits alone on its SM sub-partition.  XY chunks are shared by
+// all warps: NST > W stages of 1-D bulk copies; the tail warp of the pipeline
+// recycles a stage.
 template <int RPL, int DIR>
 __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5;
   const int P = p.P, CH = p.CH, NST = p.NST;
-  const int stage_floats = 2 * CH * P;
-  float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + NST * stage_floats);
+  const int stage_elems = CH * P;
+  float4 *ring = reinterpret_cast<float4 *>(smem_raw);
+  uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_elems);
   uint64_t *mbar_edge = mbar_xy + NST;                               // [W][NST], indexed by consumer warp
   float2 *edge = reinterpret_cast<float2 *>(mbar_edge + W * NST);    // [W][NST][CH], indexed by consumer warp
 
@@ -137,14 +137,13 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   const int Db = Tb + p.k * Sb;
   const int nchunk = Db / CH + 1;
   const size_t plane = (size_t)b * p.Dn * P;
-  const float *Xg = p.X + plane, *Yg = p.Y + plane;
-  const uint32_t chunk_bytes = (uint32_t)(CH * P * sizeof(float));
+  const float4 *XYg = p.XY + plane;
+  const uint32_t chunk_bytes = (uint32_t)(stage_elems * sizeof(float4));
 
   auto issue = [&](int seq, int st) {
     const int ci = DIR ? nchunk - 1 - seq : seq;
-    mbar_arrive_expect_tx(&mbar_xy[st], 2 * chunk_bytes);
-    bulk_g2s(ring + st * stage_floats, Xg + (size_t)ci * CH * P, chunk_bytes, &mbar_xy[st]);
-    bulk_g2s(ring + st * stage_floats + CH * P, Yg + (size_t)ci * CH * P, chunk_bytes, &mbar_xy[st]);
+    mbar_arrive_expect_tx(&mbar_xy[st], chunk_bytes);
+    bulk_g2s(ring + (size_t)st * stage_elems, XYg + (size_t)ci * stage_elems, chunk_bytes, &mbar_xy[st]);
   };
 
   if (tid == 0) {
@@ -161,26 +160,27 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   const int r0 = RPL * tid;                     // first lattice row of this lane
   const bool lane_in = DIR ? (lane == 31) : (lane == 0);    // lane fed across the warp boundary
   const bool lane_out = DIR ? (lane == 0) : (lane == 31);   // lane feeding the next warp
-  const bool global_edge = DIR ? (tid == (int)blockDim.x - 1) : (tid == 0);  // row with no neighbour at all
-  const bool take_edge = lane_in && fed, publish = lane_out && feeds;
+  const bool publish = lane_out && feeds;
   constexpr int step_sign = DIR ? -1 : 1;
+  const float2 dead2 = make_float2(0.f, __int_as_float(kNegI));
 
-  float r[RPL], o[RPL];
+  float m[RPL];
+  int o[RPL];
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    r[j] = ((r0 + j) == (DIR ? Sb : 0)) ? 0.f : kNeg;
-    o[j] = 0.f;
+    const bool src = (r0 + j) == (DIR ? Sb : 0);
+    m[j] = src ? 1.f : 0.f;
+    o[j] = src ? 0 : kNegI;
   }
-  float *const out0 = (DIR ? p.bx : p.ar) + plane + r0;   // alpha: residual | beta: px-arc operand
-  float *const out1 = (DIR ? p.bo : p.ao) + plane + r0;   // frame offset
-  float *const out2 = p.by + plane + r0;                  // beta only: py-arc operand
+  float2 *const outA = p.A + plane + r0;
+  float4 *const outB = p.Bq + plane + r0;
   if (!DIR) {
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) { out0[j] = r[j]; out1[j] = 0.f; }
+    for (int j = 0; j < RPL; ++j) outA[j] = make_float2(m[j], __int_as_float(o[j]));
   }
   // state of the row feeding lane_in before the first step (initial condition)
-  float2 carry = make_float2(kNeg, 0.f);
-  if (DIR && (r0 + RPL) == Sb) carry.x = 0.f;
+  float2 carry = dead2;
+  if (DIR && fed && (r0 + RPL) == Sb) carry = make_float2(1.f, 0.f);
 
   for (int i = 0; i < nchunk; ++i) {
     const int st = i % NST;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     const int ci = DIR ? nchunk - 1 - i : i;
     mbar_wait(&mbar_xy[st], par);
     if (fed) mbar_wait(&mbar_edge[w * NST + st], par);   // the feeding warp has published this chunk
-    const float *xs = ring + st * stage_floats + r0, *ys = xs + CH * P;
+    const float4 *xs = ring + (size_t)st * stage_elems + r0;
     const float2 *ein = edge + (size_t)(w * NST + st) * CH;
     float2 *eout = edge + (size_t)((feeds ? wc : w) * NST + st) * CH;
     const int e_lo = max(ci * CH, 1), e_hi = min(ci * CH + CH - 1, Db);
@@ -196,82 +196,77 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     int e = DIR ? e_hi : e_lo;
     int el = e - ci * CH;
     // operands of the first step of the chunk
-    float x[RPL], y[RPL], xnext = kNeg;
+    float4 a4[RPL];
+    float2 xnext = dead2;
     float2 ev = carry;
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) { x[j] = kNeg; y[j] = kNeg; }
+    for (int j = 0; j < RPL; ++j) a4[j] = make_float4(0.f, dead2.y, 0.f, dead2.y);
     if (n > 0) {
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) { x[j] = xs[el * P + j]; y[j] = ys[el * P + j]; }
-      if (DIR && r0 + RPL < P) xnext = xs[el * P + RPL];
+      for (int j = 0; j < RPL; ++j) a4[j] = xs[el * P + j];
+      if (DIR && r0 + RPL < P) xnext = *reinterpret_cast<const float2 *>(xs + el * P + RPL);
     }
     for (int q = 0; q < n; ++q) {
       // ---- prefetch the operands of the next step (off the dependency chain) ----
       const int eln = (q + 1 < n) ? el + step_sign : el;
-      float x2[RPL], y2[RPL], xnext2 = kNeg;
+      float4 b4[RPL];
+      float2 xnext2 = dead2;
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) { x2[j] = xs[eln * P + j]; y2[j] = ys[eln * P + j]; }
-      if (DIR && r0 + RPL < P) xnext2 = xs[eln * P + RPL];
-      const float2 ev2 = ein[el];   // the feeding row's state after ITS step e = input of our next step (broadcast read)
+      for (int j = 0; j < RPL; ++j) b4[j] = xs[eln * P + j];
+      if (DIR && r0 + RPL < P) xnext2 = *reinterpret_cast<const float2 *>(xs + eln * P + RPL);
+      float2 ev2 = ein[el];   // the feeding row's state after ITS step e = input of our next step (broadcast read)
+      if (!fed) ev2 = dead2;
 
-      // ---- neighbour across the lane boundary: raw residual + the frame it is expressed in ----
-      float nb_r = DIR ? __shfl_down_sync(0xffffffffu, r[0], 1) : __shfl_up_sync(0xffffffffu, r[RPL - 1], 1);
-      float nb_o = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
-      nb_r = lane_in ? (fed ? ev.x : kNeg) : nb_r;
-      nb_o = take_edge ? ev.y : nb_o;
+      // ---- neighbour across the lane boundary ----
+      float nb_m = DIR ? __shfl_down_sync(0xffffffffu, m[0], 1) : __shfl_up_sync(0xffffffffu, m[RPL - 1], 1);
+      int nb_o = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
+      nb_m = lane_in ? ev.x : nb_m;
+      nb_o = lane_in ? __float_as_int(ev.y) : nb_o;
 
-      // ---- lag-1 re-centring (exact): k = rint(previous residual) moves into the offset ----
-      bool alive[RPL];
-      float kk[RPL], on[RPL], rc[RPL];
-#pragma unroll
-      for (int j = 0; j < RPL; ++j) {
-        alive[j] = r[j] > kNegThresh;
-        kk[j] = alive[j] ? rintf(r[j]) : 0.f;
-        rc[j] = r[j] - kk[j];
-      }
-      // A dead row adopts the NEW frame of the row that feeds it (across the lane
-      // boundary that frame is re-derived from the shuffled raw residual and old
-      // offset), so a moving wave-front never inherits a stale frame.
-      const float nb_k = (nb_r > kNegThresh) ? rintf(nb_r) : 0.f;
+      float raw[RPL];
+      int on[RPL];
       if (!DIR) {
-        // alpha_e(s') = logadd(alpha_{e-1}(s'-1) + X[e][s'], alpha_{e-1}(s') + Y[e][s'])
-        on[0] = (alive[0] || global_edge) ? o[0] + kk[0] : nb_o + nb_k;
-#pragma unroll
-        for (int j = 1; j < RPL; ++j) on[j] = alive[j] ? o[j] + kk[j] : on[j - 1];
-        float nn[RPL];
-        nn[0] = logadd2((nb_r + x[0]) + (nb_o - on[0]), rc[0] + y[0]);
-#pragma unroll
-        for (int j = 1; j < RPL; ++j) nn[j] = logadd2(rc[j - 1] + (x[j] + (on[j - 1] - on[j])), rc[j] + y[j]);
+        // alpha_e(s') = alpha_{e-1}(s'-1) * X[e][s'] + alpha_{e-1}(s') * Y[e][s']
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
-          r[j] = nn[j]; o[j] = on[j];
-          out0[(unsigned)(e * P + j)] = r[j];
-          out1[(unsigned)(e * P + j)] = o[j];
+          const float fm = j ? m[j ? j - 1 : 0] : nb_m;
+          const int fo = j ? o[j ? j - 1 : 0] : nb_o;
+          const int EA = fo + __float_as_int(a4[j].y), EB = o[j] + __float_as_int(a4[j].w);
+          on[j] = max(max(EA, EB), kNegI);
+          const float gx = a4[j].x * pow2i(EA - on[j]);
+          raw[j] = fmaf(fm, gx, (m[j] * a4[j].z) * pow2i(EB - on[j]));
+          outA[(unsigned)(e * P + j)] = make_float2(raw[j], __int_as_float(on[j]));
         }
       } else {
-        // beta_{e-1}(s') = logadd(X[e][s'+1] + beta_e(s'+1), Y[e][s'] + beta_e(s'))
-        on[RPL - 1] = (alive[RPL - 1] || global_edge) ? o[RPL - 1] + kk[RPL - 1] : nb_o + nb_k;
-#pragma unroll
-        for (int j = RPL - 2; j >= 0; --j) on[j] = alive[j] ? o[j] + kk[j] : on[j + 1];
-        float a[RPL], c[RPL];
-        a[RPL - 1] = (nb_r + xnext) + (nb_o - on[RPL - 1]);
-#pragma unroll
-        for (int j = 0; j < RPL - 1; ++j) a[j] = rc[j + 1] + (x[j + 1] + (on[j + 1] - on[j]));
+        // beta_{e-1}(s') = X[e][s'+1] * beta_e(s'+1) + Y[e][s'] * beta_e(s')
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
-          c[j] = rc[j] + y[j];
+          const bool last = (j == RPL - 1);
+          const float fm = last ? nb_m : m[last ? j : j + 1];
+          const int fo = last ? nb_o : o[last ? j : j + 1];
+          const float xm = last ? xnext.x : a4[last ? j : j + 1].x;
+          const int xe = __float_as_int(last ? xnext.y : a4[last ? j : j + 1].y);
+          const int EA = fo + xe, EB = o[j] + __float_as_int(a4[j].w);
+          on[j] = max(max(EA, EB), kNegI);
+          const float gx = xm * pow2i(EA - on[j]);
+          const float c = (m[j] * a4[j].z) * pow2i(EB - on[j]);
+          raw[j] = fmaf(fm, gx, c);
           // operands of diagonal e-1, expressed in the frame `on`
-          out0[(unsigned)((e - 1) * P + j)] = a[j];
-          out2[(unsigned)((e - 1) * P + j)] = c[j];
-          out1[(unsigned)((e - 1) * P + j)] = on[j];
-          r[j] = logadd2(a[j], c[j]);
-          o[j] = on[j];
+          outB[(unsigned)((e - 1) * P + j)] = make_float4(fm * gx, c, __int_as_float(on[j]), 0.f);
         }
       }
-      if (publish) eout[el] = DIR ? make_float2(r[0], o[0]) : make_float2(r[RPL - 1], o[RPL - 1]);
+      // normalise: raw in [1,8) -> mantissa in [1,2), exponent into the frame (dead rows stay (0, ~kNegI))
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) {
+        const int bits = __float_as_int(raw[j]);
+        m[j] = raw[j] > 0.f ? __int_as_float((bits & 0x007fffff) | 0x3f800000) : 0.f;
+        o[j] = on[j] + ((bits >> 23) - 127);
+      }
+      if (publish)
+        eout[el] = DIR ? make_float2(m[0], __int_as_float(o[0])) : make_float2(m[RPL - 1], __int_as_float(o[RPL - 1]));
       // rotate the prefetched operands in
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) { x[j] = x2[j]; y[j] = y2[j]; }
+      for (int j = 0; j < RPL; ++j) a4[j] = b4[j];
       xnext = xnext2;
       ev = ev2;
       e += step_sign;
@@ -298,7 +293,8 @@ __global__ void __launch_bounds__(256, 1) dp_chain_kernel(ChainParams p) {
 // finalize (dense output)
 // ---------------------------------------------------------------------------
 struct FinalizeDenseParams {
-  const float *ar, *ao, *bx, *by, *bo;
+  const float2 *A;
+  const float4 *Bq;
   const int32_t *boundary;
   float *ans;               // [B]
   float *px_grad, *py_grad; // reference layout, may be null
@@ -315,9 +311,7 @@ __global__ void dp_ans_kernel(FinalizeDenseParams p, int B) {
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   if (!boundary_ok(bd, p.S, p.T)) { p.ans[b] = 0.f; return; }
   const int Sb = bd.z - bd.x, Tb = bd.w - bd.y;
-  const size_t at = ((size_t)b * p.Dn + Tb + p.k * Sb) * p.P + Sb;
-  const float tr = p.ar[at], to = p.ao[at];
-  p.ans[b] = (tr < kNegThresh) ? -INFINITY : (float)(((double)tr + (double)to) * 0.6931471805599453);
+  p.ans[b] = lattice_score(p.A[((size_t)b * p.Dn + Tb + p.k * Sb) * p.P + Sb]);
 }
 
 // One block: 32 absolute diagonals (dabs = t + K s) x 32 rows (s) of one
@@ -337,13 +331,11 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
   const int noff = K ? 0 : 1;
   const int Db = Tb + K * Sb;
   const size_t plane = (size_t)b * p.Dn * p.P;
-  float tot_r = 0.f, tot_o = 0.f;
-  bool dead = !ok;
-  if (ok) {
-    tot_r = p.ar[plane + (size_t)Db * p.P + Sb];
-    tot_o = p.ao[plane + (size_t)Db * p.P + Sb];
-    dead = tot_r < kNegThresh;
-  }
+  float2 tot = make_float2(0.f, 0.f);
+  if (ok) tot = p.A[plane + (size_t)Db * p.P + Sb];
+  const bool dead = !ok || !(tot.x > 0.f);
+  const float inv_tot = dead ? 0.f : 1.0f / tot.x;
+  const int tot_o = __float_as_int(tot.y);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   // phase 1: lane <-> s (coalesced plane reads), 8 warps stride the diagonals
   for (int dd = wrp; dd < 32; dd += 8) {
@@ -355,10 +347,12 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
         const int d = tp + K * sp;
         if (d < Db) {  // arcs leave diagonals 0..Db-1
           const size_t at = plane + (size_t)d * p.P + sp;
-          const float base = (p.ar[at] - tot_r) + ((p.ao[at] + p.bo[at]) - tot_o);
+          const float2 a = p.A[at];
+          const float4 bq = p.Bq[at];
+          const float sc = occupation_scale(a, __float_as_int(bq.z), tot_o, inv_tot);
           // arc (s,t)->(s+1,t+noff): cu:727-746; arc (s,t)->(s,t+1): cu:747-753
-          if (sp < Sb && tp + noff <= Tb) vx = ex2_approx(p.bx[at] + base);
-          if (tp < Tb) vy = ex2_approx(p.by[at] + base);
+          if (sp < Sb && tp + noff <= Tb) vx = bq.x * sc;
+          if (tp < Tb) vy = bq.y * sc;
         }
       }
     }
@@ -377,8 +371,7 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
     if (s < p.S && t < p.T1) gx[(size_t)s * p.T1 + t] = sgx[ss][lane];
     if (t < p.T) gy[(size_t)s * p.T + t] = sgy[ss][lane];
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-    p.ans[b] = !ok ? 0.f : (dead ? -INFINITY : (float)(((double)tot_r + (double)tot_o) * 0.6931471805599453));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.ans[b] = !ok ? 0.f : lattice_score(tot);
 }
 
 // ---------------------------------------------------------------------------
@@ -386,7 +379,7 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
 // ---------------------------------------------------------------------------
 int launch_skew_dense(const float *px, const float *py, const int32_t *boundary, const DpGeom &g,
                       const DpWorkspace &w, float delay_penalty, cudaStream_t stream) {
-  SkewDenseParams sp{px, py, boundary, w.X, w.Y, g.S, g.T, g.T1, g.P, g.Dn, delay_penalty};
+  SkewDenseParams sp{px, py, boundary, w.XY, g.S, g.T, g.T1, g.P, g.Dn, delay_penalty};
   dim3 grid((g.Dn + 31) / 32, g.P / 32, g.B);
   if (g.k) skew_dense_kernel<1><<<grid, 256, 0, stream>>>(sp);
   else skew_dense_kernel<0><<<grid, 256, 0, stream>>>(sp);
@@ -397,14 +390,22 @@ struct ChainConfig { int W, CH, NST; size_t smem; };
 static ChainConfig chain_config(const DpGeom &g) {
   ChainConfig c;
   c.W = g.P / (32 * g.rpl);
-  c.NST = c.W + 2;
-  c.CH = kChunk;
-  auto bytes = [&](int ch) {
-    return (size_t)c.NST * 2 * ch * g.P * sizeof(float) + (size_t)(c.NST + c.W * c.NST) * sizeof(uint64_t) +
-           (size_t)c.W * c.NST * ch * sizeof(float2) + 128;
+  auto bytes = [&](int nst, int ch) {
+    return (size_t)nst * ch * g.P * sizeof(float4) + (size_t)(nst + c.W * nst) * sizeof(uint64_t) +
+           (size_t)c.W * nst * ch * sizeof(float2) + 128;
   };
-  while (c.CH > 1 && bytes(c.CH) > 200 * 1024) c.CH >>= 1;
-  c.smem = bytes(c.CH);
+  const size_t budget = 200 * 1024;
+  // ring = one stage per warp of the pipeline + look-ahead; prefer 32 diagonals of look-ahead (a bulk
+  // copy takes ~1.5k cycles, a step ~50) and long chunks (fewer mbarrier round trips)
+  for (int la = 32; la >= 8; la >>= 1)
+    for (int ch = kChunk; ch >= 4; ch >>= 1) {
+      const int nst = c.W + max(2, (la + ch - 1) / ch);
+      if (bytes(nst, ch) <= budget) { c.CH = ch; c.NST = nst; c.smem = bytes(nst, ch); return c; }
+    }
+  for (int ch = 2; ch >= 1; --ch)
+    for (int extra = 16; extra >= 2; --extra)
+      if (bytes(c.W + extra, ch) <= budget) { c.CH = ch; c.NST = c.W + extra; c.smem = bytes(c.NST, ch); return c; }
+  c.CH = 1; c.NST = c.W + 2; c.smem = bytes(c.NST, 1);
   return c;
 }
 
@@ -412,7 +413,7 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
                  cudaStream_t stream) {
   if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   const ChainConfig c = chain_config(g);
-  ChainParams cp{w.X, w.Y, w.ar, w.ao, w.bx, w.by, w.bo, boundary, g.k, g.P, g.Dn, g.S, g.T, c.CH, c.NST};
+  ChainParams cp{w.XY, w.A, w.Bq, boundary, g.k, g.P, g.Dn, g.S, g.T, c.CH, c.NST};
   dim3 grid(g.B, both_directions ? 2 : 1);
   const int threads = 32 * c.W;
   cudaError_t e;
@@ -429,8 +430,7 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
 
 int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, float *ans,
                           float *px_grad, float *py_grad, cudaStream_t stream) {
-  FinalizeDenseParams fp{w.ar, w.ao, w.bx, w.by, w.bo, boundary, ans, px_grad, py_grad,
-                         g.S, g.T, g.T1, g.P, g.Dn, g.k};
+  FinalizeDenseParams fp{w.A, w.Bq, boundary, ans, px_grad, py_grad, g.S, g.T, g.T1, g.P, g.Dn, g.k};
   if (px_grad == nullptr || py_grad == nullptr) {
     dp_ans_kernel<<<(g.B + 127) / 128, 128, 0, stream>>>(fp, g.B);
     return check_launch();
