@@ -58,6 +58,9 @@ enum frn_reduction { FRN_NONE = 0, FRN_MEAN = 1, FRN_SUM = 2 };
 int frn_version(void);
 const char *frn_status_string(int status);
 int frn_last_cuda_error(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph
+ * under stream capture) in this process so far; diagnostics / benchmarks. */
+unsigned long long frn_kernel_launches(void);
 
 /* ------------------------------------------------------------------------
  * A4. Lattice recursion, forward + occupation counts in one call.

@@ -55,9 +55,9 @@ def test_workspace_queries(lib):
         getattr(lib, f).restype = ctypes.c_size_t
     B, S, T, C, R = 32, 100, 500, 500, 5
     mi = lib.frn_mi_workspace_bytes(B, S, T, T + 1)
-    # 7 diagonal-major planes of [B][Dn][P] floats
+    # diagonal-major planes of [B][Dn][P] cells: arcs (16 B), alpha (8 B), backward operands (16 B)
     P, Dn = 128, 608
-    assert mi == 7 * B * Dn * P * 4
+    assert mi == (16 + 8 + 16) * B * Dn * P
     assert lib.frn_simple_loss_workspace_bytes(B, S, T, C) > mi
     assert lib.frn_pruned_loss_workspace_bytes(B, S, T, R) > mi
     assert lib.frn_mi_workspace_bytes(0, S, T, T + 1) == 0

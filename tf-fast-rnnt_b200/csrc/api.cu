@@ -2,16 +2,19 @@
 // Argument validation, workspace carve-up and kernel sequencing only; all
 // kernels live in the other translation units.
 #include "common.cuh"
+#include <atomic>
 #include <cstdlib>
 
 #include "launchers.h"
 
 namespace frn {
 static thread_local int g_last_cuda_error = 0;
+static std::atomic<unsigned long long> g_kernel_launches{0};
 int note_cuda_error(cudaError_t e) {
   g_last_cuda_error = (int)e;
   return e == cudaSuccess ? FRN_OK : FRN_ECUDA;
 }
+void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 int check_launch() { return note_cuda_error(cudaPeekAtLastError()); }
 
 static inline bool aligned256(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
@@ -46,6 +49,8 @@ const char *frn_status_string(int status) {
 }
 
 int frn_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long frn_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ A4
 size_t frn_mi_workspace_bytes(int B, int S, int T, int T1) {

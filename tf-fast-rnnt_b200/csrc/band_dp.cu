@@ -4,201 +4,181 @@
 // ranges[b,t,0] .. ranges[b,t,0]+R-1 alive (rnnt_loss.py:968-1013 builds a dense
 // [B,S,T+1] lattice that is -inf everywhere else and the reference then runs its
 // dense kernels over it).  Here the recursion is expressed on the band itself as a
-// product of R x R transfer matrices in the (logadd, +) semiring, one per frame:
+// product of 8 x 8 transfer matrices, one per frame,
 //
-//      alpha_{t+1} = M_t (x) alpha_t ,     beta_t = N_t (x) beta_{t+1}
+//      alpha_{t+1} = M_t alpha_t ,     beta_t = N_t beta_{t+1}
 //
-// and evaluated in three short phases instead of S+T dependent steps:
-//   1. every chunk of L = 16 frames propagates the R unit vectors -> chunk matrix
-//      (R threads per chunk, 16 dependent frame steps);
-//   2. one warp walks the chunk matrices (T/16 matrix-vector products) and leaves
+// in the LINEAR domain: a band column is 8 float64 mantissas sharing one exact
+// int32 frame (value = m * 2^frame, re-normalised by an exact power of two after
+// every frame), so a frame costs a handful of FMAs and no transcendental.
+//
+// Slots.  Lattice row s always lives in slot s & 7.  As the band moves up with t
+// a row keeps its slot, rows that leave the band are killed by a zero arc and
+// rows that enter start at zero, so nothing is ever shifted: all band geometry
+// (ranges, boundary, rnnt_type, delay penalty) is folded into two per-frame arc
+// tables in shared memory, PY[t][k] (blank arc of the row in slot k) and
+// PX[t][k] (symbol arc), built once per utterance.  The within-frame closure of
+// the regular recursion (several symbols on one frame) is a cyclic first-order
+// recurrence over the slots with at least one zero link; it is solved exactly by
+// three doubling steps.
+//
+// Evaluation in three short phases instead of S+T dependent steps:
+//   1. every chunk of L frames propagates the 8 unit vectors -> chunk matrix
+//      (8 threads per chunk, L dependent frame steps);
+//   2. one thread walks the chunk matrices (T/L matrix-vector products) and leaves
 //      the state at every chunk boundary;
-//   3. every chunk replays its 16 frames from its boundary state and writes the
-//      per-frame states.
-// Dependent work: ~2*16 frame steps + T/16 matrix-vector products (~12k cycles at
-// T=500) versus 600 wavefront steps.  Forward and backward directions run in
-// different CTAs.  Numerics: every state vector is (exact integer offset, float32
-// residuals), re-centred after each step, as in the dense chain kernel.
+//   3. every chunk replays its L frames from its boundary state and writes the
+//      per-frame states (log2 of the mantissas + frame) for the finalize kernel.
+// Forward and backward directions run in different CTAs.
+//
+// Limits: band entries whose row index wraps around S+1 (only possible with
+// ranges the reference never produces) are treated as outside the band; entries
+// of one column that are more than 2^1000 apart flush to zero.
 #include "common.cuh"
 #include "launchers.h"
 
 namespace frn {
 
-constexpr int kBandR = 8;        // maximum band width handled here
-constexpr int kBandChunk = 16;   // frames per chunk
-constexpr int kBandThreads = 256;
+constexpr int kBandR = 8;          // maximum band width handled here = number of slots
+constexpr int kBandThreads = 512;
+constexpr int kDeadFrame = -(1 << 29);
 
 struct BandDpParams {
   const float *pxc, *pyc;      // [B][T][R] natural-log band log-probs
   const int32_t *ranges;       // [B][T][R]
   const int32_t *boundary;     // [B][4]
-  float *va, *ub;              // [B][T+1][kBandR] forward / backward residual states (log2 domain)
-  float *oa, *ob;              // [B][T+1]          their integer offsets
-  int S, T, R, modified, rnnt_type;
+  float *va, *ub;              // [B][T+1][8] forward / backward states by slot: log2 of the mantissa
+  float *oa, *ob;              // [B][T+1]    their frames
+  int S, T, R, L, modified, rnnt_type;
   float delay_penalty;
 };
 
-__device__ __forceinline__ int band_row_of(int r0, int i, int S1) {
-  int s = (r0 + i) % S1;
-  return s < 0 ? s + S1 : s;
+// 2^e as a double for e in [-1022, 1023]; +0 below
+__device__ __forceinline__ double pow2d(int e) { return __hiloint2double((max(e, -1023) + 1023) << 20, 0); }
+
+// probability of an arc from its natural-log score: mantissa by exp2f (float accuracy, as in the
+// dense chain), exponent exact.  Scores below -1000 (log2) count as -inf.
+__device__ __forceinline__ double arc_prob(float v) {
+  const float x = v * kLog2e;
+  if (!(x > -1000.f)) return 0.0;
+  const float e = floorf(x);
+  return (double)exp2f(x - e) * pow2d((int)e);
 }
 
-// out[i] = (0 <= i + d < R) ? v[i + d] : kNeg      (d may be negative); entries >= R stay kNeg
-template <int R>
-__device__ __forceinline__ void shift_vec(const float (&v)[kBandR], int d, float (&out)[kBandR]) {
+// v *= 2^-k with k = exponent of the largest entry; returns k (kDeadFrame for the zero vector)
+__device__ __forceinline__ int normalise8(double (&v)[8]) {
+  int hi = __double2hiint(v[0]);
 #pragma unroll
-  for (int i = 0; i < kBandR; ++i) out[i] = kNeg;
-  if (d == 0) {
+  for (int k = 1; k < 8; ++k) hi = max(hi, __double2hiint(v[k]));   // entries are >= 0: integer order = magnitude order
+  if ((hi >> 20) == 0) {                                           // zero (or denormal): dead
 #pragma unroll
-    for (int i = 0; i < R; ++i) out[i] = v[i];
-  } else {
-#pragma unroll
-    for (int dd = -(R - 1); dd < R; ++dd) {
-      if (dd != 0 && d == dd) {
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-          if (i + dd >= 0 && i + dd < R) out[i] = v[i + dd];
-      }
-    }
+    for (int k = 0; k < 8; ++k) v[k] = 0.0;
+    return kDeadFrame;
   }
+  const int e = (hi >> 20) - 1023;
+  const double sc = pow2d(-e);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] *= sc;
+  return e;
 }
 
-// exact re-centring: move rint(max) into the offset
-template <int R>
-__device__ __forceinline__ void recentre(float (&v)[kBandR], float &off) {
-  float m = v[0];
+// x[k] <- sum_{j>=0} x[k -/+ j] * prod of the j links leading to k : cyclic first-order recurrence
+// x[k] = b[k] + a[k] * x[k - DIRN] with at least one zero link, by doubling.  a[k] is the link INTO k.
+template <int DIRN>
+__device__ __forceinline__ void closure8(double (&x)[8], const double (&a1)[8]) {
+  double a2[8], a4[8], y[8];
 #pragma unroll
-  for (int i = 1; i < R; ++i) m = fmaxf(m, v[i]);
-  if (m > kNegThresh) {
-    const float k = rintf(m);
-    off += k;
+  for (int k = 0; k < 8; ++k) a2[k] = a1[k] * a1[(k - DIRN) & 7];
 #pragma unroll
-    for (int i = 0; i < R; ++i) v[i] = (v[i] > kNegThresh) ? v[i] - k : kNeg;
-  }
+  for (int k = 0; k < 8; ++k) y[k] = fma(a1[k], x[(k - DIRN) & 7], x[k]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a4[k] = a2[k] * a2[(k - 2 * DIRN) & 7];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = fma(a2[k], y[(k - 2 * DIRN) & 7], y[k]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = fma(a4[k], x[(k - 4 * DIRN) & 7], x[k]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = y[k];
 }
 
-// log2( sum_j 2^z_j ) over n <= R finite terms (kNeg stands for -inf)
-template <int N>
-__device__ __forceinline__ float logsum2(const float (&z)[kBandR]) {
-  float m = z[0];
-#pragma unroll
-  for (int j = 1; j < N; ++j) m = fmaxf(m, z[j]);
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < N; ++j) s += ex2_approx(z[j] - m);
-  return m + lg2_approx(s);
-}
-
-// Per-utterance tables in shared memory (log2 domain, masks applied):
-//   PX[t][i], PY[t][i] for t < Tb (arcs leaving column t), D[t] = r0[t+1] - r0[t]
-//   (0 for the last transition: column Tb keeps the band of column Tb-1).
 struct BandTables {
-  const float *PX, *PY;
-  const int *D;
-  int Tb, modified;
+  const double *PX, *PY;   // [Tb+1][8]
+  int modified;
 };
 
-// forward transition: state of column t -> state of column t+1
-template <int R>
-__device__ __forceinline__ void fwd_step(const BandTables &tb, int t, float (&v)[kBandR]) {
-  const int d = tb.D[t];
-  const float *py = tb.PY + t * kBandR, *px = tb.PX + t * kBandR;
-  float a[kBandR], sh[kBandR];
+__device__ __forceinline__ void load8(const double *src, double (&d)[8]) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) a[i] = v[i] + py[i];               // blank arcs (s,t)->(s,t+1)
-  shift_vec<R>(a, d, sh);
+  for (int k = 0; k < 8; k += 2) {
+    const double2 t = *reinterpret_cast<const double2 *>(src + k);
+    d[k] = t.x; d[k + 1] = t.y;
+  }
+}
+
+// forward transition: closed state of column t -> closed state of column t+1
+__device__ __forceinline__ void fwd_step(const BandTables &tb, int t, double (&v)[8]) {
+  double py[8], px[8];
+  load8(tb.PY + t * 8, py);
   if (tb.modified) {
-    // symbol arcs (s,t)->(s+1,t+1): destination index i' = i + 1 - d
-    float bsrc[kBandR], b[kBandR];
+    load8(tb.PX + t * 8, px);
+    double n[8];
 #pragma unroll
-    for (int i = 0; i < R; ++i) bsrc[i] = v[i] + px[i];
-    shift_vec<R>(bsrc, d - 1, b);
+    for (int k = 0; k < 8; ++k) n[k] = fma(v[(k - 1) & 7], px[(k - 1) & 7], v[k] * py[k]);   // (s,t)->(s+1,t+1) and blank
 #pragma unroll
-    for (int i = 0; i < R; ++i) v[i] = logadd2(sh[i], b[i]);
-  } else if (t + 1 < tb.Tb) {
-    // symbol arcs stay in the column: closure along s with the px of column t+1, written
-    // as R independent log-sum-exps  v[i'] = logsum_{j<=i'} ( sh[j] + px[j] + .. + px[i'-1] )
-    const float *pxn = tb.PX + (t + 1) * kBandR;
-    float pn[kBandR];
-#pragma unroll
-    for (int i = 0; i < R; ++i) pn[i] = pxn[i];
-    float out[kBandR];
-    out[0] = sh[0];
-#pragma unroll
-    for (int ip = 1; ip < R; ++ip) {
-      float z[kBandR];
-      float acc = 0.f;
-      z[ip] = sh[ip];
-#pragma unroll
-      for (int j = ip - 1; j >= 0; --j) {
-        acc += pn[j];
-        z[j] = sh[j] + acc;
-      }
-      // terms z[0..ip]
-      float m = z[0];
-#pragma unroll
-      for (int j = 1; j <= ip; ++j) m = fmaxf(m, z[j]);
-      float ssum = 0.f;
-#pragma unroll
-      for (int j = 0; j <= ip; ++j) ssum += ex2_approx(z[j] - m);
-      out[ip] = m + lg2_approx(ssum);
-    }
-#pragma unroll
-    for (int i = 0; i < R; ++i) v[i] = out[i];
+    for (int k = 0; k < 8; ++k) v[k] = n[k];
   } else {
+    load8(tb.PX + (t + 1) * 8, px);
+    double a1[8];
 #pragma unroll
-    for (int i = 0; i < R; ++i) v[i] = sh[i];
+    for (int k = 0; k < 8; ++k) { v[k] *= py[k]; a1[k] = px[(k - 1) & 7]; }   // link into slot k: symbol arc of slot k-1
+    closure8<1>(v, a1);
   }
 }
 
 // backward transition: state of column t+1 -> state of column t
-template <int R>
-__device__ __forceinline__ void bwd_step(const BandTables &tb, int t, float (&u)[kBandR]) {
-  const int d = tb.D[t];
-  const float *py = tb.PY + t * kBandR, *px = tb.PX + t * kBandR;
-  float sh[kBandR], w[kBandR];
-  shift_vec<R>(u, -d, sh);                                       // u_{t+1}[i - d]
-#pragma unroll
-  for (int i = 0; i < R; ++i) w[i] = py[i] + sh[i];
+__device__ __forceinline__ void bwd_step(const BandTables &tb, int t, double (&u)[8]) {
+  double py[8], px[8];
+  load8(tb.PY + t * 8, py);
+  load8(tb.PX + t * 8, px);
   if (tb.modified) {
-    float sh1[kBandR];
-    shift_vec<R>(u, 1 - d, sh1);                                 // u_{t+1}[i + 1 - d]
+    double n[8];
 #pragma unroll
-    for (int i = 0; i < R; ++i) u[i] = logadd2(w[i], px[i] + sh1[i]);
+    for (int k = 0; k < 8; ++k) n[k] = fma(px[k], u[(k + 1) & 7], py[k] * u[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = n[k];
   } else {
-    // u_t[i] = logsum_{i'>=i} ( px[i] + .. + px[i'-1] + w[i'] ), R independent log-sum-exps
-    float pn[kBandR];
 #pragma unroll
-    for (int i = 0; i < R; ++i) pn[i] = px[i];
-    float out[kBandR];
-    out[R - 1] = w[R - 1];
-#pragma unroll
-    for (int i = 0; i < R - 1; ++i) {
-      float acc = 0.f;
-      float m = w[i];
-      float z[kBandR];
-      z[i] = w[i];
-#pragma unroll
-      for (int ip = i + 1; ip < R; ++ip) {
-        acc += pn[ip - 1];
-        z[ip] = w[ip] + acc;
-        m = fmaxf(m, z[ip]);
-      }
-      float ssum = 0.f;
-#pragma unroll
-      for (int ip = i; ip < R; ++ip) ssum += ex2_approx(z[ip] - m);
-      out[i] = m + lg2_approx(ssum);
-    }
-#pragma unroll
-    for (int i = 0; i < R; ++i) u[i] = out[i];
+    for (int k = 0; k < 8; ++k) u[k] *= py[k];
+    closure8<-1>(u, px);                                                       // link into slot k from slot k+1
   }
 }
 
-template <int R>
+__device__ __forceinline__ void store_state(const double (&v)[8], int frame, float *out_v, float *out_o) {
+  float l[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int hi = __double2hiint(v[k]);
+    if ((hi >> 20) == 0) { l[k] = kNeg; continue; }
+    const int e = (hi >> 20) - 1023;
+    l[k] = log2f((float)(v[k] * pow2d(-e))) + (float)e;
+  }
+  *reinterpret_cast<float4 *>(out_v) = make_float4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<float4 *>(out_v + 4) = make_float4(l[4], l[5], l[6], l[7]);
+  *out_o = (float)(frame <= kDeadFrame / 2 ? 0 : frame);
+}
+
+__host__ __device__ inline size_t band_smem_bytes(int T, int L) {
+  const size_t nC = (size_t)(T + L - 1) / L;
+  return (size_t)(T + 1) * 16 * sizeof(double)        // PX, PY
+         + (size_t)(T + 2) * sizeof(int)               // R0
+         + nC * 64 * sizeof(double)                    // chunk matrices
+         + nC * 8 * sizeof(int) + nC * sizeof(int)     // per-vector frames, chunk frames
+         + (nC + 1) * 8 * sizeof(double) + (nC + 1) * sizeof(int) + 64;   // boundary states
+}
+
 __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p) {
   extern __shared__ __align__(16) unsigned char bsm[];
-  const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const int T = p.T, S1 = p.S + 1;
+  const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x;
+  const int T = p.T, R = p.R, L = p.L;
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int s_begin = bd.x, t_begin = bd.y, s_end = bd.z, t_end = bd.w;
   float *out_v = (dir ? p.ub : p.va) + (size_t)b * (T + 1) * kBandR;
@@ -206,40 +186,48 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   const int Tb = t_end - t_begin;
   if (s_end < s_begin || Tb < 0 || s_begin < 0 || t_begin < 0 || s_end > p.S || t_end > T) return;
 
-  const int nC = (Tb + kBandChunk - 1) / kBandChunk;             // chunks of transitions
-  float *PX = reinterpret_cast<float *>(bsm);                    // [Tb+1][8]
-  float *PY = PX + (size_t)(Tb + 1) * kBandR;                    // [Tb+1][8]
-  int *D = reinterpret_cast<int *>(PY + (size_t)(Tb + 1) * kBandR);   // [Tb+1]
-  int *R0 = D + (Tb + 1);                                        // [Tb+1]
-  float *Pm = reinterpret_cast<float *>(R0 + (Tb + 1));          // [nC][8][8] chunk matrices (basis j -> row j)
-  float *Poff = Pm + (size_t)nC * 64;                            // [nC][8]
-  float *VB = Poff + (size_t)nC * kBandR;                        // [nC+1][8] boundary states
-  float *VBo = VB + (size_t)(nC + 1) * kBandR;                   // [nC+1]
+  const int nC = (Tb + L - 1) / L;                                   // chunks of transitions
+  double *PX = reinterpret_cast<double *>(bsm);                      // [Tb+1][8]
+  double *PY = PX + (size_t)(Tb + 1) * 8;                            // [Tb+1][8]
+  double *Pm = PY + (size_t)(Tb + 1) * 8;                            // [nC][8][8] chunk matrices (basis j -> row j)
+  double *VB = Pm + (size_t)nC * 64;                                 // [nC+1][8] boundary states
+  int *R0 = reinterpret_cast<int *>(VB + (size_t)(nC + 1) * 8);      // [Tb+2]
+  int *Fv = R0 + (Tb + 2);                                           // [nC][8] frame of each propagated unit vector
+  int *Poff = Fv + (size_t)nC * 8;                                   // [nC]    common frame of a chunk matrix
+  int *VBo = Poff + nC;                                              // [nC+1]
 
-  // ---- phase 0: tables ----
-  const float *pxc = p.pxc + (size_t)b * T * R, *pyc = p.pyc + (size_t)b * T * R;
-  const int32_t *rg = p.ranges + (size_t)b * T * R;
-  for (int t = tid; t <= Tb; t += kBandThreads) {
-    const int ta = min(t_begin + (t < Tb ? t : max(Tb - 1, 0)), T - 1);   // column Tb keeps the band of Tb-1
+  // ---- phase 0: arc tables in slot order ----
+  const float *__restrict__ pxc = p.pxc + (size_t)b * T * R;
+  const float *__restrict__ pyc = p.pyc + (size_t)b * T * R;
+  const int32_t *__restrict__ rg = p.ranges + (size_t)b * T * R;
+  for (int t = tid; t <= Tb + 1; t += kBandThreads) {
+    const int ta = min(t_begin + (t < Tb ? t : max(Tb - 1, 0)), T - 1);   // columns >= Tb keep the band of Tb-1
     R0[t] = rg[(size_t)ta * R];
   }
   __syncthreads();
-  for (int t = tid; t <= Tb; t += kBandThreads) D[t] = (t + 1 < Tb) ? R0[t + 1] - R0[t] : 0;
-  for (int idx = tid; idx < (Tb + 1) * kBandR; idx += kBandThreads) {
-    const int t = idx / kBandR, i = idx - t * kBandR;
-    float vx = kNeg, vy = kNeg;
-    if (t < Tb && i < R) {
-      const int ta = t_begin + t;
-      const int r0 = R0[t];
-      const int s = band_row_of(r0, i, S1);
-      if (s >= s_begin && s <= s_end) {
-        vy = fmaxf(pyc[(size_t)ta * R + i] * kLog2e, kNeg);
-        const bool next_in_band = (i + 1 < R) && band_row_of(r0, i + 1, S1) == s + 1;
-        if (s < p.S && s < s_end && (p.modified || next_in_band)) {
-          float v = pxc[(size_t)ta * R + i];
-          if (p.rnnt_type == FRN_CONSTRAINED) v += next_in_band ? pyc[(size_t)ta * R + i + 1] : -INFINITY;
-          if (p.delay_penalty != 0.f) v += delay_penalty_value(t_end, ta, p.delay_penalty);
-          vx = fmaxf(v * kLog2e, kNeg);
+#pragma unroll 4
+  for (int idx = tid; idx < (Tb + 1) * 8; idx += kBandThreads) {
+    const int t = idx >> 3, k = idx & 7;
+    double vx = 0.0, vy = 0.0;
+    if (t < Tb) {
+      const int r0 = R0[t], r1 = R0[t + 1];
+      const int i = (k - r0) & 7, s = r0 + i;
+      if (i < R && s >= s_begin && s <= s_end) {                      // (s <= s_end <= S: no wrap-around)
+        const int ta = t_begin + t;
+        const float fy = pyc[(size_t)ta * R + i];
+        const bool next_in_band = (i + 1 < R);
+        float fx = -INFINITY;
+        if (s < p.S && s < s_end) {
+          fx = pxc[(size_t)ta * R + i];
+          if (p.rnnt_type == FRN_CONSTRAINED) fx += next_in_band ? pyc[(size_t)ta * R + i + 1] : -INFINITY;
+          if (p.delay_penalty != 0.f) fx += delay_penalty_value(t_end, ta, p.delay_penalty);
+        }
+        const unsigned i1 = (unsigned)(s - r1);                       // band index of the same row in column t+1
+        if (i1 < (unsigned)R) vy = arc_prob(fy);
+        if (p.modified) {
+          if ((unsigned)(s + 1 - r1) < (unsigned)R) vx = arc_prob(fx);   // row s+1 inside the band of column t+1
+        } else if (next_in_band) {
+          vx = arc_prob(fx);
         }
       }
     }
@@ -247,120 +235,131 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
     PY[idx] = vy;
   }
   __syncthreads();
-  BandTables tb{PX, PY, D, Tb, p.modified};
+  const BandTables tb{PX, PY, p.modified};
 
   // chunk c (in processing order of this direction) covers transitions
   //   forward : t in [c*L, min((c+1)*L, Tb))         column c*L   -> column min((c+1)L, Tb)
   //   backward: t in [max(Tb-(c+1)L,0), Tb - c*L)    column Tb-cL -> column max(Tb-(c+1)L, 0)
   // ---- phase 1: chunk matrices by propagating the unit vectors ----
-  for (int w = tid; w < nC * R; w += kBandThreads) {
-    const int c = w / R, j = w - c * R;
-    float v[kBandR];
+  {
+    const int w = tid, c = w >> 3, j = w & 7;
+    double v[8];
+    int frame = kDeadFrame;
+    if (w < nC * 8) {
 #pragma unroll
-    for (int i = 0; i < kBandR; ++i) v[i] = (i == j) ? 0.f : kNeg;
-    float off = 0.f;
-    if (!dir) {
-      const int t_lo = c * kBandChunk, t_hi = min(t_lo + kBandChunk, Tb);
-      for (int t = t_lo; t < t_hi; ++t) { fwd_step<R>(tb, t, v); recentre<R>(v, off); }
-    } else {
-      const int t_hi = Tb - c * kBandChunk, t_lo = max(t_hi - kBandChunk, 0);
-      for (int t = t_hi - 1; t >= t_lo; --t) { bwd_step<R>(tb, t, v); recentre<R>(v, off); }
+      for (int k = 0; k < 8; ++k) v[k] = (k == j) ? 1.0 : 0.0;
+      frame = 0;
+      if (!dir) {
+        const int t_lo = c * L, t_hi = min(t_lo + L, Tb);
+        for (int t = t_lo; t < t_hi && frame > kDeadFrame / 2; ++t) {
+          fwd_step(tb, t, v);
+          const int e = normalise8(v);
+          frame = (e == kDeadFrame) ? kDeadFrame : frame + e;
+        }
+      } else {
+        const int t_hi = Tb - c * L, t_lo = max(t_hi - L, 0);
+        for (int t = t_hi - 1; t >= t_lo && frame > kDeadFrame / 2; --t) {
+          bwd_step(tb, t, v);
+          const int e = normalise8(v);
+          frame = (e == kDeadFrame) ? kDeadFrame : frame + e;
+        }
+      }
+      Fv[w] = frame;
     }
+    __syncthreads();
+    if (w < nC * 8) {
+      int F = Fv[c * 8];
 #pragma unroll
-    for (int i = 0; i < kBandR; ++i) Pm[(size_t)c * 64 + j * kBandR + i] = v[i];
-    Poff[c * kBandR + j] = off;
+      for (int q = 1; q < 8; ++q) F = max(F, Fv[c * 8 + q]);
+      const double sc = (frame > kDeadFrame / 2) ? pow2d(frame - F) : 0.0;   // all eight images in one frame
+#pragma unroll
+      for (int k = 0; k < 8; ++k) Pm[(size_t)c * 64 + j * 8 + k] = v[k] * sc;
+      if (j == 0) Poff[c] = F;
+    }
   }
   __syncthreads();
 
-  // ---- phase 2: boundary states, one warp, lane i' <-> component ----
-  if (tid < 32) {
-    // initial state
-    float x = kNeg;      // component `lane` of the current boundary state
-    float off = 0.f;
+  // ---- phase 2: boundary states, one thread ----
+  if (tid == 0) {
+    double x[8];
+    int frame = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 0.0;
     if (!dir) {
-      const int i0 = s_begin - R0[0];
-      float v0[kBandR];
+      const unsigned i0 = (unsigned)(s_begin - R0[0]);
+      if (i0 < (unsigned)R) {
 #pragma unroll
-      for (int i = 0; i < kBandR; ++i) v0[i] = (i == i0 && i0 >= 0 && i0 < R) ? 0.f : kNeg;
+        for (int k = 0; k < 8; ++k) x[k] = (k == (s_begin & 7)) ? 1.0 : 0.0;
+      }
       if (!p.modified && Tb > 0) {               // symbols emitted on the first frame: closure in column 0
+        double px[8], a1[8];
+        load8(PX, px);
 #pragma unroll
-        for (int i = 1; i < kBandR; ++i) v0[i] = logadd2(v0[i - 1] + PX[i - 1], v0[i]);
+        for (int k = 0; k < 8; ++k) a1[k] = px[(k - 1) & 7];
+        closure8<1>(x, a1);
       }
-#pragma unroll
-      for (int i = 0; i < kBandR; ++i) if (lane == i) x = v0[i];
     } else {
-      const int iE = s_end - R0[Tb];
-      x = (lane == iE && iE >= 0 && iE < R) ? 0.f : kNeg;
+      const unsigned iE = (unsigned)(s_end - R0[Tb]);
+      if (iE < (unsigned)R) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (k == (s_end & 7)) ? 1.0 : 0.0;
+      }
     }
-    if (lane < kBandR) VB[lane] = x;
-    if (lane == 0) VBo[0] = 0.f;
+    {
+      const int e = normalise8(x);
+      frame = (e == kDeadFrame) ? kDeadFrame : e;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) VB[k] = x[k];
+    VBo[0] = frame;
     for (int c = 0; c < nC; ++c) {
-      // y[i'] = logsum_j ( x[j] + Pm[c][j][i'] + Poff[c][j] )
-      float z[kBandR], m = kNeg;
+      double y[8];
 #pragma unroll
-      for (int j = 0; j < kBandR; ++j) {
-        const float xj = __shfl_sync(0xffffffffu, x, j);
-        z[j] = (j < R && lane < kBandR) ? xj + (Pm[(size_t)c * 64 + j * kBandR + lane] + Poff[c * kBandR + j]) : kNeg;
-        m = fmaxf(m, z[j]);
-      }
-      float y = kNeg;
-      if (m > kNegThresh) {
-        float ssum = 0.f;
+      for (int k = 0; k < 8; ++k) y[k] = 0.0;
+      const double *M = Pm + (size_t)c * 64;
 #pragma unroll
-        for (int j = 0; j < kBandR; ++j) ssum += ex2_approx(z[j] - m);
-        y = m + lg2_approx(ssum);
-      }
-      // exact re-centring by rint(max over components)
-      float mm = y;
+      for (int j = 0; j < 8; ++j) {
+        double row[8];
+        load8(M + j * 8, row);
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-      if (mm > kNegThresh) {
-        const float k = rintf(mm);
-        off += k;
-        y = (y > kNegThresh) ? y - k : kNeg;
+        for (int k = 0; k < 8; ++k) y[k] = fma(x[j], row[k], y[k]);
       }
-      x = y;
-      if (lane < kBandR) VB[(c + 1) * kBandR + lane] = x;
-      if (lane == 0) VBo[c + 1] = off;
+      const int F = Poff[c];
+      const int e = normalise8(y);
+      frame = (e == kDeadFrame || F <= kDeadFrame / 2 || frame <= kDeadFrame / 2) ? kDeadFrame : frame + F + e;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { x[k] = y[k]; VB[(size_t)(c + 1) * 8 + k] = y[k]; }
+      VBo[c + 1] = frame;
     }
   }
   __syncthreads();
 
   // ---- phase 3: replay every chunk from its boundary state, write per-column states ----
   for (int c = tid; c < nC + 1; c += kBandThreads) {
-    float v[kBandR];
-#pragma unroll
-    for (int i = 0; i < kBandR; ++i) v[i] = VB[c * kBandR + i];
-    float off = VBo[c];
+    double v[8];
+    load8(VB + (size_t)c * 8, v);
+    int frame = VBo[c];
     if (!dir) {
-      const int t_lo = min(c * kBandChunk, Tb);    // column of this boundary state
-      const int t_hi = min(t_lo + kBandChunk, Tb);
-      int col = t_lo;
-      *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      out_o[col] = off;
+      const int t_lo = min(c * L, Tb);    // column of this boundary state
+      const int t_hi = min(t_lo + L, Tb);
+      store_state(v, frame, out_v + (size_t)t_lo * kBandR, out_o + t_lo);
       if (c == nC) continue;
       for (int t = t_lo; t < t_hi - 1; ++t) {      // the last column of the chunk belongs to the next boundary
-        fwd_step<R>(tb, t, v); recentre<R>(v, off);
-        col = t + 1;
-        *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        out_o[col] = off;
+        fwd_step(tb, t, v);
+        const int e = normalise8(v);
+        frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
+        store_state(v, frame, out_v + (size_t)(t + 1) * kBandR, out_o + t + 1);
       }
     } else {
-      const int t_hi = max(Tb - c * kBandChunk, 0);   // column of this boundary state
-      const int t_lo = max(t_hi - kBandChunk, 0);
-      int col = t_hi;
-      *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      out_o[col] = off;
+      const int t_hi = max(Tb - c * L, 0);   // column of this boundary state
+      const int t_lo = max(t_hi - L, 0);
+      store_state(v, frame, out_v + (size_t)t_hi * kBandR, out_o + t_hi);
       if (c == nC) continue;
       for (int t = t_hi - 1; t > t_lo; --t) {
-        bwd_step<R>(tb, t, v); recentre<R>(v, off);
-        col = t;
-        *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(out_v + (size_t)col * kBandR + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        out_o[col] = off;
+        bwd_step(tb, t, v);
+        const int e = normalise8(v);
+        frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
+        store_state(v, frame, out_v + (size_t)t * kBandR, out_o + t);
       }
     }
   }
@@ -371,7 +370,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, float *gxc, float *gyc, float *scores,
                                                             int B) {
-  const int T = p.T, R = p.R, S1 = p.S + 1, TR = T * R;
+  const int T = p.T, R = p.R, TR = T * R;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   auto ok_bd = [&](const int4 &bd) {
     return bd.z >= bd.x && bd.w >= bd.y && bd.x >= 0 && bd.y >= 0 && bd.z <= p.S && bd.w <= T;
@@ -379,9 +378,8 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
   auto total_of = [&](int b, const int4 &bd, float &tr, float &to) -> bool {
     const int Tb = bd.w - bd.y;
     const int r0e = p.ranges[(size_t)(b * T + min(bd.y + max(Tb - 1, 0), T - 1)) * R];
-    const int iE = bd.z - r0e;
-    if (iE < 0 || iE >= R) return false;
-    tr = p.va[((size_t)b * (T + 1) + Tb) * kBandR + iE];
+    if ((unsigned)(bd.z - r0e) >= (unsigned)R) return false;
+    tr = p.va[((size_t)b * (T + 1) + Tb) * kBandR + (bd.z & 7)];
     to = p.oa[(size_t)b * (T + 1) + Tb];
     return tr > kNegThresh;
   };
@@ -407,28 +405,26 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
     const float *va = p.va + (base + t) * kBandR, *un = p.ub + (base + t + 1) * kBandR, *uc = p.ub + (base + t) * kBandR;
     const float oa = p.oa[base + t], obn = p.ob[base + t + 1], obc = p.ob[base + t];
     auto arc = [&](int ii, bool px_arc) -> float {
-      const int s = band_row_of(r0, ii, S1);
+      const int s = r0 + ii;                       // rows that would wrap around S+1 are outside the band
       if (s < bd.x || s > bd.z) return 0.f;
-      const float a = va[ii];
+      const float a = va[s & 7];
       if (!(a > kNegThresh)) return 0.f;
       float score, head, ohead;
       if (!px_arc) {
-        const int ih = ii - d;
-        if (ih < 0 || ih >= R) return 0.f;
+        if ((unsigned)(ii - d) >= (unsigned)R) return 0.f;
         score = p.pyc[(size_t)(b * T + ta) * R + ii];
-        head = un[ih]; ohead = obn;
+        head = un[s & 7]; ohead = obn;
       } else {
-        const bool next_in_band = (ii + 1 < R) && band_row_of(r0, ii + 1, S1) == s + 1;
+        const bool next_in_band = (ii + 1 < R);
         if (!(s < p.S && s < bd.z && (p.modified || next_in_band))) return 0.f;
         score = p.pxc[(size_t)(b * T + ta) * R + ii];
         if (p.rnnt_type == FRN_CONSTRAINED) score += next_in_band ? p.pyc[(size_t)(b * T + ta) * R + ii + 1] : -INFINITY;
         if (p.delay_penalty != 0.f) score += delay_penalty_value(bd.w, ta, p.delay_penalty);
         if (p.modified) {
-          const int ih = ii + 1 - d;
-          if (ih < 0 || ih >= R) return 0.f;
-          head = un[ih]; ohead = obn;
+          if ((unsigned)(ii + 1 - d) >= (unsigned)R) return 0.f;
+          head = un[(s + 1) & 7]; ohead = obn;
         } else {
-          head = uc[ii + 1]; ohead = obc;
+          head = uc[(s + 1) & 7]; ohead = obc;
         }
       }
       if (!(head > kNegThresh) || !(score > -INFINITY)) return 0.f;
@@ -437,8 +433,7 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
     };
     vx = arc(i, true);
     vy = arc(i, false);
-    if (p.rnnt_type == FRN_CONSTRAINED && i >= 1 && band_row_of(r0, i - 1, S1) == band_row_of(r0, i, S1) - 1)
-      vy += arc(i - 1, true);      // the px arc of row s-1 borrowed py[s,t]
+    if (p.rnnt_type == FRN_CONSTRAINED && i >= 1) vy += arc(i - 1, true);      // the px arc of row s-1 borrowed py[s,t]
   }
   gxc[idx] = vx;
   gyc[idx] = vy;
@@ -450,12 +445,13 @@ size_t band_dp_workspace_bytes(int B, int T) {
          2 * round_up_sz((size_t)B * (T + 1) * sizeof(float), 256);
 }
 
-bool band_dp_supported(int S, int T, int R) {
-  if (R > kBandR) return false;
-  const int nC = (T + kBandChunk - 1) / kBandChunk;
-  const size_t smem = (size_t)(T + 1) * (2 * kBandR * 4 + 8) + (size_t)nC * (64 + kBandR) * 4 + (size_t)(nC + 1) * (kBandR + 1) * 4 + 64;
-  return smem <= 200 * 1024;
+static int band_chunk_len(int T) {
+  for (int L = 16; L <= 256; L <<= 1)
+    if ((T + L - 1) / L * 8 <= kBandThreads && band_smem_bytes(T, L) <= 220 * 1024) return L;
+  return 0;
 }
+
+bool band_dp_supported(int S, int T, int R) { return R <= kBandR && band_chunk_len(T) != 0; }
 
 int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary, int B, int S,
                    int T, int R, int rnnt_type, float delay_penalty, bool want_grad, void *workspace, float *gxc,
@@ -469,26 +465,17 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
   p.oa = reinterpret_cast<float *>(w + 2 * nv); p.ob = reinterpret_cast<float *>(w + 2 * nv + no);
   p.S = S; p.T = T; p.R = R; p.modified = (rnnt_type != FRN_REGULAR); p.rnnt_type = rnnt_type;
   p.delay_penalty = delay_penalty;
-  const int nC = (T + kBandChunk - 1) / kBandChunk;
-  const size_t smem = (size_t)(T + 1) * (2 * kBandR * 4 + 8) + (size_t)nC * (64 + kBandR) * 4 +
-                      (size_t)(nC + 1) * (kBandR + 1) * 4 + 64;
-  cudaError_t e = cudaSuccess;
-#define FRN_BAND(R_)                                                                                       \
-  case R_:                                                                                                 \
-    e = cudaFuncSetAttribute(band_dp_kernel<R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return note_cuda_error(e);                                                       \
-    band_dp_kernel<R_><<<dim3(B, want_grad ? 2 : 1), kBandThreads, smem, stream>>>(p);                     \
-    break;
-  switch (R) {
-    FRN_BAND(1) FRN_BAND(2) FRN_BAND(3) FRN_BAND(4) FRN_BAND(5) FRN_BAND(6) FRN_BAND(7) FRN_BAND(8)
-    default: return FRN_EUNSUPPORTED;
-  }
-#undef FRN_BAND
+  p.L = band_chunk_len(T);
+  if (R > kBandR || p.L == 0) return FRN_EUNSUPPORTED;
+  const size_t smem = band_smem_bytes(T, p.L);
+  cudaError_t e = cudaFuncSetAttribute(band_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return note_cuda_error(e);
+  count_launch(), band_dp_kernel<<<dim3(B, want_grad ? 2 : 1), kBandThreads, smem, stream>>>(p);
   int rc = check_launch();
   if (rc) return rc;
   const int n = want_grad ? max(B * T * R, B) : B;
-  band_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, want_grad ? gxc : nullptr, want_grad ? gyc : nullptr,
-                                                            scores, B);
+  count_launch(), band_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, want_grad ? gxc : nullptr,
+                                                                           want_grad ? gyc : nullptr, scores, B);
   return check_launch();
 }
 

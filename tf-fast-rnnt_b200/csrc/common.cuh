@@ -26,6 +26,7 @@ __host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + 
 // thread-local last CUDA error for frn_last_cuda_error()
 int note_cuda_error(cudaError_t e);
 int check_launch();
+void count_launch();   // every launch of the library is written  count_launch(), kernel<<<...>>>(...);
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -59,6 +60,13 @@ constexpr int kNegIThresh = -(1 << 27);
 __device__ __forceinline__ float pow2i(int d) { return __int_as_float((max(d, -127) + 127) << 23); }
 // floor(log2(m)) of a positive normal float; 0 for m == 0
 __device__ __forceinline__ int expo_of(float m) { return m > 0.f ? ((__float_as_int(m) >> 23) - 127) : 0; }
+// (m, o) -> same value with m in [1,2); dead values (m == 0) are left alone
+__device__ __forceinline__ void normalise_pair(float &m, int &o) {
+  const int bits = __float_as_int(m);
+  const bool alive = m > 0.f;
+  o = alive ? o + ((bits >> 23) - 127) : o;
+  m = alive ? __int_as_float((bits & 0x007fffff) | 0x3f800000) : m;
+}
 // log2-domain arc score -> (mantissa in [1,2], exponent); dead arcs -> (0, kNegI)
 __device__ __forceinline__ float2 encode_arc(float v_log2) {
   if (!(v_log2 > -1.0e8f)) return make_float2(0.f, __int_as_float(kNegI));   // total scores must stay above -2^27

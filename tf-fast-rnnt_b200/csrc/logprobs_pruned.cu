@@ -328,10 +328,10 @@ int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, con
   const int BTR = B * T * R;
   const int grid = (BTR + 7) / 8;
   if (dtype == FRN_F32)
-    pruned_lse_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols, ranges, BTR,
+    count_launch(), pruned_lse_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols, ranges, BTR,
                                                       T * R, S, R, C, term, pxc, pyc, lse);
   else if (dtype == FRN_BF16)
-    pruned_lse_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(logits),
+    count_launch(), pruned_lse_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(logits),
                                                               symbols, ranges, BTR, T * R, S, R, C, term, pxc,
                                                               pyc, lse);
   else return FRN_EINVAL;
@@ -343,10 +343,10 @@ int launch_skew_band(const float *pxc, const float *pyc, const int32_t *ranges, 
                      cudaStream_t stream) {
   // every arc of the lattice is dead except the band's
   const size_t cells = (size_t)g.B * g.Dn * g.P;
-  fill_dead_arcs_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(w.XY, cells);
+  count_launch(), fill_dead_arcs_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(w.XY, cells);
   BandParams bp{pxc, pyc, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type, delay_penalty};
   const int BTR = g.B * g.T * R;
-  skew_band_kernel<<<(BTR + 255) / 256, 256, 0, stream>>>(bp, w.XY, BTR);
+  count_launch(), skew_band_kernel<<<(BTR + 255) / 256, 256, 0, stream>>>(bp, w.XY, BTR);
   return check_launch();
 }
 
@@ -354,7 +354,7 @@ int launch_finalize_band(const int32_t *ranges, const int32_t *boundary, const D
                          int R, int rnnt_type, float *gxc, float *gyc, float *scores, cudaStream_t stream) {
   BandFinalizeParams fp{w.A, w.Bq, ranges, boundary, g.S, g.T, R, g.P, g.Dn, g.k, rnnt_type};
   const int n = gxc ? max(g.B * g.T * R, g.B) : g.B;
-  finalize_band_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fp, gxc, gyc, scores, g.B);
+  count_launch(), finalize_band_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fp, gxc, gyc, scores, g.B);
   return check_launch();
 }
 
@@ -364,11 +364,11 @@ int launch_pruned_logits_grad(const void *logits, int dtype, const int32_t *symb
   const int BTR = B * T * R;
   const int grid = (BTR + 7) / 8;
   if (dtype == FRN_F32)
-    pruned_logits_grad_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols,
+    count_launch(), pruned_logits_grad_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols,
                                                               ranges, lse, gxc, gyc, scores_grad, BTR, T * R, S,
                                                               C, term, static_cast<float *>(dlogits));
   else if (dtype == FRN_BF16)
-    pruned_logits_grad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+    count_launch(), pruned_logits_grad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
         static_cast<const __nv_bfloat16 *>(logits), symbols, ranges, lse, gxc, gyc, scores_grad, BTR, T * R, S,
         C, term, static_cast<__nv_bfloat16 *>(dlogits));
   else return FRN_EINVAL;
@@ -379,7 +379,7 @@ int launch_band_to_dense(const float *pxc, const float *pyc, const int32_t *rang
                          int B, int S, int T, int T1, int R, int rnnt_type, float *px, float *py,
                          cudaStream_t stream) {
   const size_t n = (size_t)B * S * T1 + (size_t)B * (S + 1) * T;
-  band_to_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pxc, pyc, ranges, boundary, B, S, T, T1,
+  count_launch(), band_to_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pxc, pyc, ranges, boundary, B, S, T, T1,
                                                                         R, rnnt_type, px, py);
   return check_launch();
 }

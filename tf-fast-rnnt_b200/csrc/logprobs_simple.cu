@@ -215,11 +215,11 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w);
-  rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, C, lmmax, smoothed ? lmsum : nullptr);
-  rowstats_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, B * T, C, ammax, nullptr);
+  count_launch(), rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, C, lmmax, smoothed ? lmsum : nullptr);
+  count_launch(), rowstats_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, B * T, C, ammax, nullptr);
   if (smoothed) {
-    unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
-    amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
+    count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
+    count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
   }
   int rc = check_launch();
   if (rc) return rc;
@@ -240,13 +240,13 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   rc = force_simt ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
   if (rc == FRN_EUNSUPPORTED) {
     dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
-    simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
+    count_launch(), simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
     rc = check_launch();
   }
   if (rc) return rc;
   if (rnnt_type == FRN_CONSTRAINED) {
     const size_t n = (size_t)B * S * T;
-    constrained_fix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(px, py, B, S, T);
+    count_launch(), constrained_fix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(px, py, B, S, T);
     rc = check_launch();
   }
   return rc;

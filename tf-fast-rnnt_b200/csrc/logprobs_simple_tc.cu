@@ -432,7 +432,7 @@ int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
                                        (int)tc::kSmemBytes);
   if (e != cudaSuccess) return note_cuda_error(e);
   dim3 grid((sp.T1 + tc::TM - 1) / tc::TM, (sp.S + 1 + tc::TN - 1) / tc::TN, sp.B);
-  simple_logprobs_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_am, map_lm, sp);
+  count_launch(), simple_logprobs_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_am, map_lm, sp);
   return check_launch();
 }
 

@@ -88,19 +88,21 @@ __global__ void __launch_bounds__(256) skew_dense_kernel(SkewDenseParams p) {
 // chain
 // ---------------------------------------------------------------------------
 // Numerics.  Every lattice value is carried as  m * 2^o : `o` an exact int32
-// frame, `m` a float32 mantissa normalised to [1,2) after every step (0 = dead).
-// One step of a row is
+// frame, `m` a float32 mantissa (0 = dead).  One step of a row is
 //     EA = o_feeder + e_x,  EB = o_own + e_y            (exact integer frames of the two terms)
 //     o' = max(EA, EB)
-//     raw = m_feeder * (x_m * 2^(EA-o')) + m_own * (y_m * 2^(EB-o'))      in [1, 8)
-//     k = exponent field of raw;  m' = raw / 2^k (a bit operation);  o' += k
+//     m' = m_feeder * (x_m * 2^(EA-o')) + m_own * (y_m * 2^(EB-o'))
 // Every re-scaling is by an exact power of two built with integer ops, the step
-// has no transcendental and its only roundings are the two products and the
-// FMA.  Magnitudes are bounded by construction (the dominant term is a
-// normalised mantissa times an arc mantissa in [1,2]), so nothing can under- or
-// overflow whatever the arc scores are.  Against float64 the occupation counts
-// come out ~1e-6 relative at the c2 shape; the reference's plain float32
-// log-domain p[] is at 1.3e-3 there ("numerics").
+// has no transcendental and its only roundings are the products and the FMA.
+// The frames depend on integers only, so a step consists of two short independent
+// dependency chains: (shuffle, add, max) for the frame and (shuffle, FMA) for the
+// mantissa.  The dominant term keeps its mantissa (times an arc mantissa in
+// [1,2]), so m never shrinks below 1 and grows by at most x4 per step; it is
+// re-normalised to [1,2) (a bit operation, exponent moved into the frame) at
+// every chunk boundary (<= 16 steps) and whenever it is handed to another warp.
+// Nothing can under- or overflow whatever the arc scores are.  Against float64
+// the occupation counts come out ~1e-6 relative at the c2 shape; the reference's
+// plain float32 log-domain p[] is at 1.3e-3 there ("numerics").
 struct ChainParams {
   const float4 *XY;
   float2 *A;           // [B][Dn][P]  forward {mantissa, frame} (dir 0)
@@ -126,10 +128,13 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5;
   const int P = p.P, CH = p.CH, NST = p.NST;
   const int stage_elems = CH * P;
-  float4 *ring = reinterpret_cast<float4 *>(smem_raw);
-  uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_elems);
+  // one diagonal of padding on either side of the ring: the operand prefetch of the last step of a
+  // chunk reads one diagonal past it
+  float4 *ring = reinterpret_cast<float4 *>(smem_raw) + P;
+  uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_elems + P);
   uint64_t *mbar_edge = mbar_xy + NST;                               // [W][NST], indexed by consumer warp
   float2 *edge = reinterpret_cast<float2 *>(mbar_edge + W * NST);    // [W][NST][CH], indexed by consumer warp
+  float2 *dead_edge = edge + (size_t)W * NST * CH;                   // one entry: what an unfed warp reads
 
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int Sb = bd.z - bd.x, Tb = bd.w - bd.y;
@@ -149,6 +154,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   if (tid == 0) {
     for (int i = 0; i < NST + W * NST; ++i) mbar_init(&mbar_xy[i], 1);
     mbar_fence_init();
+    *dead_edge = make_float2(0.f, __int_as_float(kNegI));
   }
   __syncthreads();
   if (tid == 0)
@@ -162,6 +168,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   const bool lane_out = DIR ? (lane == 0) : (lane == 31);   // lane feeding the next warp
   const bool publish = lane_out && feeds;
   constexpr int step_sign = DIR ? -1 : 1;
+  const int pe_step = fed ? step_sign : 0;
   const float2 dead2 = make_float2(0.f, __int_as_float(kNegI));
 
   float m[RPL];
@@ -188,13 +195,16 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     const int ci = DIR ? nchunk - 1 - i : i;
     mbar_wait(&mbar_xy[st], par);
     if (fed) mbar_wait(&mbar_edge[w * NST + st], par);   // the feeding warp has published this chunk
-    const float4 *xs = ring + (size_t)st * stage_elems + r0;
-    const float2 *ein = edge + (size_t)(w * NST + st) * CH;
-    float2 *eout = edge + (size_t)((feeds ? wc : w) * NST + st) * CH;
     const int e_lo = max(ci * CH, 1), e_hi = min(ci * CH + CH - 1, Db);
     const int n = e_hi - e_lo + 1;
-    int e = DIR ? e_hi : e_lo;
-    int el = e - ci * CH;
+    const int e0 = DIR ? e_hi : e_lo;
+    const int el0 = e0 - ci * CH;
+    // running pointers, all advanced by one diagonal per step
+    const float4 *xp = ring + (size_t)st * stage_elems + r0 + el0 * P;          // arcs of the current step
+    const float2 *pe = fed ? edge + (size_t)(w * NST + st) * CH + el0 : dead_edge;   // feeding row's state
+    float2 *po = edge + (size_t)((feeds ? wc : w) * NST + st) * CH + el0;        // our state for the fed warp
+    float2 *pa = outA + (size_t)e0 * P;
+    float4 *pb = outB + (size_t)(e0 - 1) * P;
     // operands of the first step of the chunk
     float4 a4[RPL];
     float2 xnext = dead2;
@@ -203,25 +213,25 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     for (int j = 0; j < RPL; ++j) a4[j] = make_float4(0.f, dead2.y, 0.f, dead2.y);
     if (n > 0) {
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) a4[j] = xs[el * P + j];
-      if (DIR && r0 + RPL < P) xnext = *reinterpret_cast<const float2 *>(xs + el * P + RPL);
+      for (int j = 0; j < RPL; ++j) a4[j] = xp[j];
+      if (DIR) xnext = *reinterpret_cast<const float2 *>(xp + RPL);
     }
+    int nb_o_sh = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
+#pragma unroll 2
     for (int q = 0; q < n; ++q) {
-      // ---- prefetch the operands of the next step (off the dependency chain) ----
-      const int eln = (q + 1 < n) ? el + step_sign : el;
+      // ---- prefetch the operands of the next step (off the dependency chain).  After the last
+      // step of a chunk this reads one diagonal past the chunk (the ring is padded); unused. ----
       float4 b4[RPL];
       float2 xnext2 = dead2;
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) b4[j] = xs[eln * P + j];
-      if (DIR && r0 + RPL < P) xnext2 = *reinterpret_cast<const float2 *>(xs + eln * P + RPL);
-      float2 ev2 = ein[el];   // the feeding row's state after ITS step e = input of our next step (broadcast read)
-      if (!fed) ev2 = dead2;
+      for (int j = 0; j < RPL; ++j) b4[j] = xp[step_sign * P + j];
+      if (DIR) xnext2 = *reinterpret_cast<const float2 *>(xp + step_sign * P + RPL);
+      const float2 ev2 = *pe;   // the feeding row's state after ITS step e = input of our next step (broadcast read)
 
-      // ---- neighbour across the lane boundary ----
+      // ---- neighbour across the lane boundary (its frame was shuffled as soon as it was known) ----
       float nb_m = DIR ? __shfl_down_sync(0xffffffffu, m[0], 1) : __shfl_up_sync(0xffffffffu, m[RPL - 1], 1);
-      int nb_o = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
       nb_m = lane_in ? ev.x : nb_m;
-      nb_o = lane_in ? __float_as_int(ev.y) : nb_o;
+      const int nb_o = lane_in ? __float_as_int(ev.y) : nb_o_sh;
 
       float raw[RPL];
       int on[RPL];
@@ -233,14 +243,15 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
           const int fo = j ? o[j ? j - 1 : 0] : nb_o;
           const int EA = fo + __float_as_int(a4[j].y), EB = o[j] + __float_as_int(a4[j].w);
           on[j] = max(max(EA, EB), kNegI);
+          if (j == RPL - 1) nb_o_sh = __shfl_up_sync(0xffffffffu, on[j], 1);     // frame chain runs ahead
           const float gx = a4[j].x * pow2i(EA - on[j]);
-          raw[j] = fmaf(fm, gx, (m[j] * a4[j].z) * pow2i(EB - on[j]));
-          outA[(unsigned)(e * P + j)] = make_float2(raw[j], __int_as_float(on[j]));
+          raw[j] = fmaf(fm, gx, m[j] * (a4[j].z * pow2i(EB - on[j])));
+          pa[j] = make_float2(raw[j], __int_as_float(on[j]));
         }
       } else {
         // beta_{e-1}(s') = X[e][s'+1] * beta_e(s'+1) + Y[e][s'] * beta_e(s')
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) {
+        for (int j = RPL - 1; j >= 0; --j) {
           const bool last = (j == RPL - 1);
           const float fm = last ? nb_m : m[last ? j : j + 1];
           const int fo = last ? nb_o : o[last ? j : j + 1];
@@ -248,30 +259,38 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
           const int xe = __float_as_int(last ? xnext.y : a4[last ? j : j + 1].y);
           const int EA = fo + xe, EB = o[j] + __float_as_int(a4[j].w);
           on[j] = max(max(EA, EB), kNegI);
+          if (j == 0) nb_o_sh = __shfl_down_sync(0xffffffffu, on[j], 1);
           const float gx = xm * pow2i(EA - on[j]);
-          const float c = (m[j] * a4[j].z) * pow2i(EB - on[j]);
+          const float c = m[j] * (a4[j].z * pow2i(EB - on[j]));
           raw[j] = fmaf(fm, gx, c);
           // operands of diagonal e-1, expressed in the frame `on`
-          outB[(unsigned)((e - 1) * P + j)] = make_float4(fm * gx, c, __int_as_float(on[j]), 0.f);
+          pb[j] = make_float4(fm * gx, c, __int_as_float(on[j]), 0.f);
         }
       }
-      // normalise: raw in [1,8) -> mantissa in [1,2), exponent into the frame (dead rows stay (0, ~kNegI))
+      // The frames evolve by integer ops only and the mantissas by one FMA: two short, independent
+      // dependency chains per step.  Mantissas are left un-normalised inside a chunk (they grow by
+      // at most x4 per step) and are re-normalised at the chunk boundary.
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) {
-        const int bits = __float_as_int(raw[j]);
-        m[j] = raw[j] > 0.f ? __int_as_float((bits & 0x007fffff) | 0x3f800000) : 0.f;
-        o[j] = on[j] + ((bits >> 23) - 127);
+      for (int j = 0; j < RPL; ++j) { m[j] = raw[j]; o[j] = on[j]; }
+      {                           // what the fed warp reads is always normalised (bounds do not compound)
+        float pm = DIR ? m[0] : m[RPL - 1];
+        int po_frame = DIR ? o[0] : o[RPL - 1];
+        normalise_pair(pm, po_frame);
+        if (publish) *po = make_float2(pm, __int_as_float(po_frame));
       }
-      if (publish)
-        eout[el] = DIR ? make_float2(m[0], __int_as_float(o[0])) : make_float2(m[RPL - 1], __int_as_float(o[RPL - 1]));
-      // rotate the prefetched operands in
+      // rotate the prefetched operands in, advance the running pointers
 #pragma unroll
       for (int j = 0; j < RPL; ++j) a4[j] = b4[j];
       xnext = xnext2;
       ev = ev2;
-      e += step_sign;
-      el = eln;
+      xp += step_sign * P;
+      pe += pe_step;
+      po += step_sign;
+      pa += step_sign * P;
+      pb += step_sign * P;
     }
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) normalise_pair(m[j], o[j]);
     carry = ev;   // the feeding row's state after the last step of this chunk
     if (publish) mbar_arrive(&mbar_edge[wc * NST + st]);
     if (is_tail) {
@@ -381,8 +400,8 @@ int launch_skew_dense(const float *px, const float *py, const int32_t *boundary,
                       const DpWorkspace &w, float delay_penalty, cudaStream_t stream) {
   SkewDenseParams sp{px, py, boundary, w.XY, g.S, g.T, g.T1, g.P, g.Dn, delay_penalty};
   dim3 grid((g.Dn + 31) / 32, g.P / 32, g.B);
-  if (g.k) skew_dense_kernel<1><<<grid, 256, 0, stream>>>(sp);
-  else skew_dense_kernel<0><<<grid, 256, 0, stream>>>(sp);
+  if (g.k) count_launch(), skew_dense_kernel<1><<<grid, 256, 0, stream>>>(sp);
+  else count_launch(), skew_dense_kernel<0><<<grid, 256, 0, stream>>>(sp);
   return check_launch();
 }
 
@@ -391,8 +410,8 @@ static ChainConfig chain_config(const DpGeom &g) {
   ChainConfig c;
   c.W = g.P / (32 * g.rpl);
   auto bytes = [&](int nst, int ch) {
-    return (size_t)nst * ch * g.P * sizeof(float4) + (size_t)(nst + c.W * nst) * sizeof(uint64_t) +
-           (size_t)c.W * nst * ch * sizeof(float2) + 128;
+    return (size_t)(nst * ch + 2) * g.P * sizeof(float4) + (size_t)(nst + c.W * nst) * sizeof(uint64_t) +
+           (size_t)(c.W * nst * ch + 1) * sizeof(float2) + 128;
   };
   const size_t budget = 200 * 1024;
   // ring = one stage per warp of the pipeline + look-ahead; prefer 32 diagonals of look-ahead (a bulk
@@ -420,7 +439,7 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
 #define FRN_LAUNCH_CHAIN(RPL_)                                                                              \
   e = cudaFuncSetAttribute(dp_chain_kernel<RPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem); \
   if (e != cudaSuccess) return note_cuda_error(e);                                                          \
-  dp_chain_kernel<RPL_><<<grid, threads, c.smem, stream>>>(cp);
+  count_launch(), dp_chain_kernel<RPL_><<<grid, threads, c.smem, stream>>>(cp);
   if (g.rpl == 1) { FRN_LAUNCH_CHAIN(1) }
   else if (g.rpl == 2) { FRN_LAUNCH_CHAIN(2) }
   else { FRN_LAUNCH_CHAIN(4) }
@@ -432,13 +451,13 @@ int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWork
                           float *px_grad, float *py_grad, cudaStream_t stream) {
   FinalizeDenseParams fp{w.A, w.Bq, boundary, ans, px_grad, py_grad, g.S, g.T, g.T1, g.P, g.Dn, g.k};
   if (px_grad == nullptr || py_grad == nullptr) {
-    dp_ans_kernel<<<(g.B + 127) / 128, 128, 0, stream>>>(fp, g.B);
+    count_launch(), dp_ans_kernel<<<(g.B + 127) / 128, 128, 0, stream>>>(fp, g.B);
     return check_launch();
   }
   // absolute diagonals dabs = t + k*s for t in [0, T], s in [0, S]
   dim3 grid((g.T + 1 + g.k * g.S + 31) / 32, (g.S + 1 + 31) / 32, g.B);
-  if (g.k) finalize_dense_kernel<1><<<grid, 256, 0, stream>>>(fp);
-  else finalize_dense_kernel<0><<<grid, 256, 0, stream>>>(fp);
+  if (g.k) count_launch(), finalize_dense_kernel<1><<<grid, 256, 0, stream>>>(fp);
+  else count_launch(), finalize_dense_kernel<0><<<grid, 256, 0, stream>>>(fp);
   return check_launch();
 }
 

@@ -45,17 +45,17 @@ int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_
   if (n == 0) return FRN_OK;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u)
     return FRN_EINVAL;
-  add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, stream>>>(a, b, out, n);
+  count_launch(), add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, stream>>>(a, b, out, n);
   return check_launch();
 }
 
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream) {
-  reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out);
+  count_launch(), reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out);
   return check_launch();
 }
 
 int launch_iota_ranges(int32_t *ranges, size_t n, int R, cudaStream_t stream) {
-  iota_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ranges, n, R);
+  count_launch(), iota_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ranges, n, R);
   return check_launch();
 }
 

@@ -40,14 +40,16 @@ __global__ void cummin_kernel(const int32_t *in, int32_t *out, int rows, int n) 
 }
 
 // ---------------------------------------------------------------------------
-// A5, one launch, one block per utterance:
-//  (1) s_begin[t] = argmax_k ( sum_{k<=s<k+R} py_grad[s,t] - px_grad[k-1,t] )
-//      (rnnt_loss.py:722-748): thread per column t, coalesced along t, the
-//      window walked sequentially in s (= the sequential-cumsum float order the
-//      oracle defines) in chunks of 8 with all loads of a chunk issued first;
-//  (2) the monotonic fix-ups of _adjust_pruning_lower_bound (:623-641) as two
-//      block-wide reverse running minima on the int32 row held in shared memory;
-//  (3) ranges[t,i] = s_begin[t] + i (:758-759).
+// A5 in two launches:
+//  (1) prune_argmax_kernel, thread per (b,t) column, 128 columns per block:
+//      s_begin[t] = argmax_k ( sum_{k<=s<k+R} py_grad[s,t] - px_grad[k-1,t] )
+//      (rnnt_loss.py:722-748), coalesced along t, the window walked sequentially
+//      in s (= the sequential-cumsum float order the oracle defines) in chunks of
+//      16 with all loads of a chunk issued first;
+//  (2) prune_fixup_kernel, one block per utterance: the monotonic fix-ups of
+//      _adjust_pruning_lower_bound (:623-641) as two block-wide reverse running
+//      minima on the int32 row held in shared memory, then
+//      ranges[t,i] = s_begin[t] + i (:758-759).
 // ---------------------------------------------------------------------------
 constexpr int kPruneThreads = 512;
 
@@ -73,49 +75,61 @@ __device__ void block_rev_cummin(int32_t *x, int T, int32_t *warp_carry) {
   }
 }
 
-__global__ void __launch_bounds__(kPruneThreads) prune_ranges_kernel(const float *px_grad, const float *py_grad,
-                                                                     const int32_t *boundary, int S, int T, int T1,
-                                                                     int R, int r_fix, int32_t *ranges) {
-  extern __shared__ int32_t sb[];  // [T] s_begin, then [16] warp carries
-  int32_t *warp_carry = sb + T;
-  const int b = blockIdx.x;
+constexpr int kArgmaxThreads = 128, kArgmaxChunk = 16;
+
+__global__ void __launch_bounds__(kArgmaxThreads) prune_argmax_kernel(const float *px_grad, const float *py_grad,
+                                                                      const int32_t *boundary, int S, int T, int T1,
+                                                                      int R, int32_t *s_begin) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * kArgmaxThreads + threadIdx.x;
+  if (t >= T) return;
   const int s_end = boundary[4 * b + 2], t_end = boundary[4 * b + 3];
   const int S1 = S + 1;
   const int nk = S1 - R + 1;
-  for (int t = threadIdx.x; t < T; t += kPruneThreads) {
-    int best_k = 0;
-    if (t < t_end - 1) {
-      const float *py = py_grad + (size_t)b * S1 * T + t;
-      const float *px = px_grad + (size_t)b * S * T1 + t;
-      float cs_lo = 0.f, cs_hi = 0.f;
-      for (int s = 0; s < R; ++s) cs_hi = cs_hi + py[(size_t)s * T];  // cs[R], sequential
-      float best = 0.f;
-      for (int k0 = 0; k0 < nk; k0 += 8) {
-        float lo[8], hi[8], pxv[8];
+  int best_k = 0;
+  if (t < t_end - 1) {
+    const float *__restrict__ py = py_grad + (size_t)b * S1 * T + t;
+    const float *__restrict__ px = px_grad + (size_t)b * S * T1 + t;
+    float cs_lo = 0.f, cs_hi = 0.f;
+    for (int s = 0; s < R; ++s) cs_hi = cs_hi + py[(size_t)s * T];  // cs[R], sequential
+    float best = 0.f;
+    for (int k0 = 0; k0 < nk; k0 += kArgmaxChunk) {
+      // All loads of the chunk are unconditional (indices clamped into the arrays) so that they are
+      // issued back to back; out-of-range terms are replaced by +0.f, which leaves the sums
+      // bit-identical to the sequential cumsum.
+      float lo[kArgmaxChunk], hi[kArgmaxChunk], pxv[kArgmaxChunk];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // all loads of the chunk first (independent)
-          const int k = k0 + j;
-          lo[j] = (k < nk) ? py[(size_t)k * T] : 0.f;
-          hi[j] = (k < nk && k + R < S1) ? py[(size_t)(k + R) * T] : 0.f;
-          pxv[j] = (k < nk && k > 0) ? px[(size_t)(k - 1) * T1] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = k0 + j;
-          if (k < nk) {
-            float fin = cs_hi - cs_lo;
-            if (k > 0) fin = fin - pxv[j];
-            if (k == 0 || fin > best) { best = fin; best_k = k; }
-            cs_lo = cs_lo + lo[j];
-            if (k + R < S1) cs_hi = cs_hi + hi[j];
-          }
-        }
+      for (int j = 0; j < kArgmaxChunk; ++j) {
+        const int k = k0 + j;
+        lo[j] = py[(size_t)min(k, S) * T];
+        hi[j] = py[(size_t)min(k + R, S) * T];
+        pxv[j] = px[(size_t)min(max(k - 1, 0), S - 1) * T1];
       }
-    } else {
-      best_k = max(s_end - R + 1, 0);  // padding frames, rnnt_loss.py:744-748
+#pragma unroll
+      for (int j = 0; j < kArgmaxChunk; ++j) {
+        const int k = k0 + j;
+        const bool valid = k < nk;
+        float fin = cs_hi - cs_lo;
+        fin = fin - (k > 0 ? pxv[j] : 0.f);
+        const bool take = valid && (k == 0 || fin > best);
+        best = take ? fin : best;
+        best_k = take ? k : best_k;
+        cs_lo = cs_lo + (valid ? lo[j] : 0.f);
+        cs_hi = cs_hi + ((valid && k + R < S1) ? hi[j] : 0.f);
+      }
     }
-    sb[t] = best_k;
+  } else {
+    best_k = max(s_end - R + 1, 0);  // padding frames, rnnt_loss.py:744-748
   }
+  s_begin[(size_t)b * T + t] = best_k;
+}
+
+__global__ void __launch_bounds__(kPruneThreads) prune_fixup_kernel(const int32_t *s_begin, int T, int R, int r_fix,
+                                                                    int32_t *ranges) {
+  extern __shared__ int32_t sb[];  // [T] s_begin, then [16] warp carries
+  int32_t *warp_carry = sb + T;
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < T; t += kPruneThreads) sb[t] = s_begin[(size_t)b * T + t];
   __syncthreads();
   block_rev_cummin(sb, T, warp_carry);
   for (int t = threadIdx.x; t < T; t += kPruneThreads) sb[t] = -(sb[t] - (r_fix - 1) * t);
@@ -270,20 +284,24 @@ __global__ void __launch_bounds__(256) pruned_add_joiner_kernel(const float *am,
 // ---------------------------------------------------------------------------
 int launch_cummin(const int32_t *in, int32_t *out, int rows, int n, cudaStream_t stream) {
   if (rows <= 0 || n <= 0) return FRN_OK;
-  cummin_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(in, out, rows, n);
+  count_launch(), cummin_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(in, out, rows, n);
   return check_launch();
 }
 
 int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
-                        int T1, int R, int32_t *ranges, int32_t * /*unused workspace*/, cudaStream_t stream) {
+                        int T1, int R, int32_t *ranges, int32_t *s_begin_ws, cudaStream_t stream) {
   const int r_fix = (T1 == T) ? 2 : R;  // rnnt_loss.py:756
   const size_t smem = (size_t)(T + 16) * sizeof(int32_t);
   if (smem > 200 * 1024) return FRN_EUNSUPPORTED;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(prune_ranges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(prune_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return note_cuda_error(e);
   }
-  prune_ranges_kernel<<<B, kPruneThreads, smem, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, r_fix, ranges);
+  dim3 grid((T + kArgmaxThreads - 1) / kArgmaxThreads, B);
+  count_launch(), prune_argmax_kernel<<<grid, kArgmaxThreads, 0, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, s_begin_ws);
+  int rc = check_launch();
+  if (rc) return rc;
+  count_launch(), prune_fixup_kernel<<<B, kPruneThreads, smem, stream>>>(s_begin_ws, T, R, r_fix, ranges);
   return check_launch();
 }
 
@@ -292,9 +310,9 @@ int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, i
   const int BT = B * T;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) |
                                      reinterpret_cast<uintptr_t>(am_p) | reinterpret_cast<uintptr_t>(lm_p)) % 16 == 0);
-  if (vec && R <= 8) do_pruning_vec_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
-  else if (vec) do_pruning_kernel<true><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
-  else do_pruning_kernel<false><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
+  if (vec && R <= 8) count_launch(), do_pruning_vec_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
+  else if (vec) count_launch(), do_pruning_kernel<true><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
+  else count_launch(), do_pruning_kernel<false><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
   return check_launch();
 }
 
@@ -302,12 +320,12 @@ int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const 
                           int T, int R, int C, float *am_grad, float *lm_grad, cudaStream_t stream) {
   const int BT = B * T;
   if (am_grad) {
-    do_pruning_bwd_am_kernel<<<(BT + 7) / 8, 256, 0, stream>>>(am_p_grad, BT, R, C, am_grad);
+    count_launch(), do_pruning_bwd_am_kernel<<<(BT + 7) / 8, 256, 0, stream>>>(am_p_grad, BT, R, C, am_grad);
     int rc = check_launch();
     if (rc) return rc;
   }
   if (lm_grad) {
-    do_pruning_bwd_lm_kernel<<<B * (S + 1), 256, 0, stream>>>(lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
+    count_launch(), do_pruning_bwd_lm_kernel<<<B * (S + 1), 256, 0, stream>>>(lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
     return check_launch();
   }
   return FRN_OK;
@@ -317,10 +335,10 @@ int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ra
                              int C, int out_dtype, void *logits, cudaStream_t stream) {
   const int BT = B * T;
   if (out_dtype == FRN_F32)
-    pruned_add_joiner_kernel<float><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C,
+    count_launch(), pruned_add_joiner_kernel<float><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C,
                                                                       static_cast<float *>(logits));
   else if (out_dtype == FRN_BF16)
-    pruned_add_joiner_kernel<__nv_bfloat16><<<(BT + 7) / 8, 256, 0, stream>>>(
+    count_launch(), pruned_add_joiner_kernel<__nv_bfloat16><<<(BT + 7) / 8, 256, 0, stream>>>(
         am, lm, ranges, BT, T, S + 1, R, C, static_cast<__nv_bfloat16 *>(logits));
   else return FRN_EINVAL;
   return check_launch();

@@ -177,12 +177,12 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
   p.scores_grad = scores_grad; p.W = W; p.am_grad = am_grad; p.lm_grad = lm_grad;
   p.B = B; p.S = S; p.T = T; p.T1 = T1; p.C = C; p.term = term; p.rnnt_type = rnnt_type;
   const size_t n = (size_t)B * S1 * T;
-  bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+  count_launch(), bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
   dim3 g_am((C + 63) / 64, (T + 63) / 64, B), g_lm((C + 63) / 64, (S1 + 63) / 64, B);
-  bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
-  bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
-  bwd_scatter_am_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
-  bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
+  count_launch(), bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
+  count_launch(), bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
+  count_launch(), bwd_scatter_am_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
+  count_launch(), bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
   return check_launch();
 }
 

@@ -35,6 +35,7 @@ _SIGS = {
     "frn_version": (c_int, []),
     "frn_status_string": (ctypes.c_char_p, [c_int]),
     "frn_last_cuda_error": (c_int, []),
+    "frn_kernel_launches": (ctypes.c_ulonglong, []),
     "frn_mi_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_mi_fwd_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "frn_cummin": (c_int, [_P, _P, c_int, c_int, _P]),
