@@ -182,6 +182,89 @@ class Pipeline:
             fn()
 
 
+def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=5):
+    """The reference's OWN CUDA op (oracle/_ref/libref_mi.so = mutual_information_cuda.cu compiled
+    unmodified for sm_100, driven like tf_fast_rnnt_op.cc:66-113 incl. its memsets, H2D copy and
+    stream sync) timed on this GPU beside frn_mi_fwd_bwd on the SAME px/py — a reported baseline
+    (BASELINE.json north_star), not part of the product path.  Returns None if the .so is absent."""
+    import ctypes
+    import torch
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_mi.so")
+    if not os.path.exists(path):
+        return None
+    ref = ctypes.CDLL(path)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    ref.ref_fast_rnnt_loss.restype = I
+    ref.ref_fast_rnnt_loss.argtypes = [P, P, P, I, I, I, I, I, P, P, P, P, P, P, I, P]
+    ref.ref_cummin.restype = I
+    ref.ref_cummin.argtypes = [P, P, I, I, P]
+    lib, chk = pipe.lib, pipe._lib.check
+    B, T, S, C, R, dev = pipe.B, pipe.T, pipe.S, pipe.C, pipe.R, pipe.dev
+    f32 = torch.float32
+    e = lambda *shape, dtype=f32: torch.empty(shape, dtype=dtype, device=dev)
+    ptr = lambda t: t.data_ptr()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    px, py = e(B, S, T + 1), e(B, S + 1, T)
+    ws = torch.empty(max(lib.frn_simple_logprobs_workspace_bytes(B, S, T, C),
+                         lib.frn_pruned_logprobs_workspace_bytes(B, S, T, R),
+                         lib.frn_mi_workspace_bytes(B, S, T, T + 1)), dtype=torch.uint8, device=dev)
+    p_, pg = e(B, S + 1, T + 1), e(B, S + 1, T + 1)
+    ans, ag, gx, gy = e(B), e(B), e(B, S, T + 1), e(B, S + 1, T)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    def ref_op():
+        assert ref.ref_fast_rnnt_loss(ptr(px), ptr(py), ptr(bd), B, S, T, T + 1, 1, ptr(p_), ptr(ans), ptr(pg),
+                                      ptr(gx), ptr(gy), ptr(ag), T + 1, st) == 1
+
+    def our_op():
+        chk(lib.frn_mi_fwd_bwd(ptr(px), ptr(py), ptr(bd), B, S, T, T + 1, 1, ptr(ans), ptr(gx), ptr(gy), ptr(ws),
+                               ws.numel(), st), "mi_fwd_bwd")
+
+    out = {"what": "reference FastRNNTLoss op (its own kernels, sm_100 build, op.cc launch sequence incl. sync) vs "
+                   "frn_mi_fwd_bwd on the same dense px/py; host wall clock per call, ms"}
+    # lattice of the simple loss
+    chk(lib.frn_simple_logprobs(ptr(lm), ptr(am), ptr(sym), ptr(bd), B, S, T, C, C - 1, 0, 0, 0.0, 0.0, ptr(px),
+                                ptr(py), ptr(ws), ws.numel(), st), "simple_logprobs")
+    out["simple_lattice"] = {"reference_ms": timed(ref_op), "ours_ms": timed(our_op)}
+    # dense lattice of the pruned loss, as the reference runs it (rnnt_loss.py:968-1018, 1116-1119)
+    chk(lib.frn_pruned_logprobs(ptr(pipe.logits), 0, ptr(sym), ptr(pipe.ranges), ptr(bd), B, S, T, R, C, C - 1, 0,
+                                ptr(px), ptr(py), ptr(ws), ws.numel(), st), "pruned_logprobs")
+    # ... against the product path for that lattice: the recursion on the band itself.  pxc/pyc are the
+    # first two [B][T][R] float32 segments of frn_pruned_loss's workspace (left there by pipe.step)
+    seg = (B * T * R * 4 + 255) // 256 * 256
+    pxc, pyc = pipe.ws_pruned.data_ptr(), pipe.ws_pruned.data_ptr() + seg
+    gxc, gyc = e(B, T, R), e(B, T, R)
+    bws = torch.empty(max(lib.frn_band_mi_workspace_bytes(B, S, T, R), 256), dtype=torch.uint8, device=dev)
+
+    def our_band():
+        chk(lib.frn_band_mi_fwd_bwd(pxc, pyc, ptr(pipe.ranges), ptr(bd), B, S, T, R, 0, 0.0, 1, ptr(ans), ptr(gxc),
+                                    ptr(gyc), ptr(bws), bws.numel(), st), "band_mi_fwd_bwd")
+
+    out["pruned_lattice"] = {"reference_ms": timed(ref_op), "ours_ms": timed(our_band),
+                             "ours_dense_kernels_ms": timed(our_op),
+                             "note": "reference: its dense kernels on the [B,S,T+1] lattice it builds from the band; "
+                                     "ours: frn_band_mi_fwd_bwd on the band (what frn_pruned_loss runs)"}
+    # the two Cummin op calls of _adjust_pruning_lower_bound (rnnt_loss.py:628,634)
+    x = torch.randint(0, S, (B, T), dtype=torch.int32, device=dev)
+    y = torch.empty_like(x)
+    out["cummin_x2"] = {"reference_ms": 2 * timed(lambda: ref.ref_cummin(ptr(x), ptr(y), B, T, st)),
+                        "ours_ms": 2 * timed(lambda: chk(lib.frn_cummin(ptr(x), ptr(y), B, T, st), "cummin"))}
+    r = sum(v["reference_ms"] for v in out.values() if isinstance(v, dict))
+    o = sum(v["ours_ms"] for v in out.values() if isinstance(v, dict))
+    out["reference_ops_per_step_ms"] = r
+    out["ours_same_ops_ms"] = o
+    out["ratio"] = r / o
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML (same data as the
     nvidia-smi clocks line of B200_PROFILING.md, but fast enough for a short
@@ -405,11 +488,19 @@ def run_gpu_arm(args):
         return
 
     peak, peak_src = measured_peaks()
-    # the HBM-bound kernels of the step and their algorithmic bytes
-    hbm_stages = {k: v for k, v in stage_ms.items() if k in ("do_pruning", "add_joiner", "pruned_loss")}
+    # Roofline of the dominant kernel: the stages that are ONE HBM-bound kernel each, timed live with
+    # CUDA events above (DESIGN.md lists every kernel with its bound; the lattice recursion kernels are
+    # dependency-chain bound and are reported in `stages_ms` / `lattice_cells_per_s` instead).
+    kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8>", "add_joiner": "add_kernel"}
+    hbm_stages = {k: v for k, v in stage_ms.items() if k in kernel_of_stage}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k][0])
     dom_ms, dom_bytes = hbm_stages[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram__bytes_{read,write}.sum per launch (ncu --set full)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(kernel_of_stage[dom], {}).get("dram_bytes_per_launch")
     cells = B * (S + 1) * (T + 1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -430,8 +521,8 @@ def run_gpu_arm(args):
                               "C-ABI launches, loss of every step read on the host"},
         "gpu_launches": kernels_per_step * args.steps,
         "kernels_per_step": kernels_per_step,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": kernel_of_stage[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
         "stages_ms": {k: round(v[0], 4) for k, v in stage_ms.items()},
         "stages_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in stage_ms.items()},
@@ -441,6 +532,14 @@ def run_gpu_arm(args):
         sample_B = 8 if args.workload == "c2" else None
         base, _ = cpu_bench(args.workload, 2, 1, sample_B)
         line["cpu_baseline"] = base
+    if world == 1 and not args.no_ref_gpu:
+        try:
+            pipe.step(*dev_sets[0])             # leaves ranges / logits of this input set in the pipeline buffers
+            ref_leg = reference_gpu_op_leg(pipe, *dev_sets[0])
+            if ref_leg is not None:
+                line["reference_gpu_op"] = ref_leg
+        except Exception as e:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+            line["reference_gpu_op"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -455,6 +554,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA op")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

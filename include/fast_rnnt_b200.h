@@ -77,6 +77,20 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary,
                    float *px_grad, float *py_grad, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* A4 on the pruning band (the recursion rnnt_loss_pruned runs, rnnt_loss.py:1116-1119,
+ * without materialising the dense lattice the reference builds at :968-1013):
+ *   pxc, pyc [B][T][R]   band log-probs: entry i of frame t is lattice row ranges[b,t,0]+i
+ *                        (what frn_pruned_logprobs scatters into the dense px/py)
+ *   ans [B]; pxc_grad, pyc_grad [B][T][R] occupation counts of the band arcs (NULL when
+ *   calc_gradients == 0).  R <= 8 and frn_band_mi_workspace_bytes() != 0, else
+ *   FRN_EUNSUPPORTED (use frn_pruned_logprobs + frn_mi_fwd_bwd). */
+size_t frn_band_mi_workspace_bytes(int B, int S, int T, int R);
+int frn_band_mi_fwd_bwd(const float *pxc, const float *pyc, const int32_t *ranges,
+                        const int32_t *boundary, int B, int S, int T, int R,
+                        int rnnt_type, float delay_penalty, int calc_gradients,
+                        float *ans, float *pxc_grad, float *pyc_grad, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* Replaces op "Cummin" (tf_fast_rnnt_op.cc:36-38,135-165; CumminCuda):
  * inclusive running minimum along the last axis of an int32 [rows][n] matrix. */
 int frn_cummin(const int32_t *in, int32_t *out, int rows, int n, void *stream);

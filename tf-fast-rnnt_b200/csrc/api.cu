@@ -77,6 +77,24 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, in
   return FRN_OK;
 }
 
+size_t frn_band_mi_workspace_bytes(int B, int S, int T, int R) {
+  if (B <= 0 || S < 0 || T <= 0 || R <= 0 || !band_dp_supported(S, T, R)) return 0;
+  return band_dp_workspace_bytes(B, T);
+}
+
+int frn_band_mi_fwd_bwd(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary, int B,
+                        int S, int T, int R, int rnnt_type, float delay_penalty, int calc_gradients, float *ans,
+                        float *pxc_grad, float *pyc_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && R <= S + 1);
+  FRN_REQUIRE(pxc && pyc && ranges && boundary && ans);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  FRN_REQUIRE(!calc_gradients || (pxc_grad && pyc_grad));
+  if (!band_dp_supported(S, T, R)) return FRN_EUNSUPPORTED;
+  if (!workspace || !aligned256(workspace) || workspace_bytes < band_dp_workspace_bytes(B, T)) return FRN_EWORKSPACE;
+  return launch_band_dp(pxc, pyc, ranges, boundary, B, S, T, R, rnnt_type, delay_penalty > 0.f ? delay_penalty : 0.f,
+                        calc_gradients != 0, workspace, pxc_grad, pyc_grad, ans, static_cast<cudaStream_t>(stream));
+}
+
 int frn_cummin(const int32_t *in, int32_t *out, int rows, int n, void *stream) {
   FRN_REQUIRE(rows >= 0 && n >= 0 && (rows == 0 || n == 0 || (in && out)));
   return launch_cummin(in, out, rows, n, static_cast<cudaStream_t>(stream));

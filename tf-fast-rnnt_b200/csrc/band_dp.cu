@@ -25,10 +25,10 @@
 // Evaluation in three short phases instead of S+T dependent steps:
 //   1. every chunk of L frames propagates the 8 unit vectors -> chunk matrix
 //      (8 threads per chunk, L dependent frame steps);
-//   2. one thread walks the chunk matrices (T/L matrix-vector products) and leaves
+//   2. eight lanes walk the chunk matrices (T/L matrix-vector products) and leave
 //      the state at every chunk boundary;
 //   3. every chunk replays its L frames from its boundary state and writes the
-//      per-frame states (log2 of the mantissas + frame) for the finalize kernel.
+//      per-frame states (mantissas + frame) for the finalize kernel.
 // Forward and backward directions run in different CTAs.
 //
 // Limits: band entries whose row index wraps around S+1 (only possible with
@@ -47,8 +47,8 @@ struct BandDpParams {
   const float *pxc, *pyc;      // [B][T][R] natural-log band log-probs
   const int32_t *ranges;       // [B][T][R]
   const int32_t *boundary;     // [B][4]
-  float *va, *ub;              // [B][T+1][8] forward / backward states by slot: log2 of the mantissa
-  float *oa, *ob;              // [B][T+1]    their frames
+  double *va, *ub;             // [B][T+1][8] forward / backward states by slot: mantissas
+  int *oa, *ob;                // [B][T+1]    their frames (kDeadFrame: all-zero state)
   int S, T, R, L, modified, rnnt_type;
   float delay_penalty;
 };
@@ -152,18 +152,10 @@ __device__ __forceinline__ void bwd_step(const BandTables &tb, int t, double (&u
   }
 }
 
-__device__ __forceinline__ void store_state(const double (&v)[8], int frame, float *out_v, float *out_o) {
-  float l[8];
+__device__ __forceinline__ void store_state(const double (&v)[8], int frame, double *out_v, int *out_o) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int hi = __double2hiint(v[k]);
-    if ((hi >> 20) == 0) { l[k] = kNeg; continue; }
-    const int e = (hi >> 20) - 1023;
-    l[k] = log2f((float)(v[k] * pow2d(-e))) + (float)e;
-  }
-  *reinterpret_cast<float4 *>(out_v) = make_float4(l[0], l[1], l[2], l[3]);
-  *reinterpret_cast<float4 *>(out_v + 4) = make_float4(l[4], l[5], l[6], l[7]);
-  *out_o = (float)(frame <= kDeadFrame / 2 ? 0 : frame);
+  for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2 *>(out_v + k) = make_double2(v[k], v[k + 1]);
+  *out_o = frame;
 }
 
 __host__ __device__ inline size_t band_smem_bytes(int T, int L) {
@@ -181,8 +173,8 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   const int T = p.T, R = p.R, L = p.L;
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int s_begin = bd.x, t_begin = bd.y, s_end = bd.z, t_end = bd.w;
-  float *out_v = (dir ? p.ub : p.va) + (size_t)b * (T + 1) * kBandR;
-  float *out_o = (dir ? p.ob : p.oa) + (size_t)b * (T + 1);
+  double *out_v = (dir ? p.ub : p.va) + (size_t)b * (T + 1) * kBandR;
+  int *out_o = (dir ? p.ob : p.oa) + (size_t)b * (T + 1);
   const int Tb = t_end - t_begin;
   if (s_end < s_begin || Tb < 0 || s_begin < 0 || t_begin < 0 || s_end > p.S || t_end > T) return;
 
@@ -279,57 +271,63 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   }
   __syncthreads();
 
-  // ---- phase 2: boundary states, one thread ----
-  if (tid == 0) {
+  // ---- phase 2: boundary states; lanes 0..7 of warp 0 each own one slot of the state ----
+  if (tid < 32) {
+    const int lane = tid, k = lane & 7;
     double x[8];
-    int frame = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = 0.0;
+    for (int q = 0; q < 8; ++q) x[q] = 0.0;
     if (!dir) {
       const unsigned i0 = (unsigned)(s_begin - R0[0]);
       if (i0 < (unsigned)R) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (k == (s_begin & 7)) ? 1.0 : 0.0;
+        for (int q = 0; q < 8; ++q) x[q] = (q == (s_begin & 7)) ? 1.0 : 0.0;
       }
       if (!p.modified && Tb > 0) {               // symbols emitted on the first frame: closure in column 0
         double px[8], a1[8];
         load8(PX, px);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a1[k] = px[(k - 1) & 7];
+        for (int q = 0; q < 8; ++q) a1[q] = px[(q - 1) & 7];
         closure8<1>(x, a1);
       }
     } else {
       const unsigned iE = (unsigned)(s_end - R0[Tb]);
       if (iE < (unsigned)R) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (k == (s_end & 7)) ? 1.0 : 0.0;
+        for (int q = 0; q < 8; ++q) x[q] = (q == (s_end & 7)) ? 1.0 : 0.0;
       }
     }
-    {
-      const int e = normalise8(x);
-      frame = (e == kDeadFrame) ? kDeadFrame : e;
-    }
+    int frame = normalise8(x);                   // every lane holds the whole (identical) state
+    auto mine = [&]() {                          // x[k] without a dynamically indexed register array
+      double r = x[0];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) VB[k] = x[k];
-    VBo[0] = frame;
+      for (int q = 1; q < 8; ++q) r = (k == q) ? x[q] : r;
+      return r;
+    };
+    if (lane < 8) VB[lane] = mine();
+    if (lane == 0) VBo[0] = frame;
     for (int c = 0; c < nC; ++c) {
-      double y[8];
+      // y[k] = sum_j x[j] * M[c][j][k] on lane k, two partial sums to halve the dependent chain
+      const double *M = Pm + (size_t)c * 64 + k;
+      double y0 = 0.0, y1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = 0.0;
-      const double *M = Pm + (size_t)c * 64;
+      for (int j = 0; j < 8; j += 2) {
+        y0 = fma(x[j], M[j * 8], y0);
+        y1 = fma(x[j + 1], M[(j + 1) * 8], y1);
+      }
+      const double yk = y0 + y1;
+      // all-gather the eight slots (lanes 8..31 mirror lanes 0..7)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double row[8];
-        load8(M + j * 8, row);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = fma(x[j], row[k], y[k]);
+      for (int q = 0; q < 8; ++q) {
+        const int hi = __shfl_sync(0xffffffffu, __double2hiint(yk), q);
+        const int lo = __shfl_sync(0xffffffffu, __double2loint(yk), q);
+        x[q] = __hiloint2double(hi, lo);
       }
       const int F = Poff[c];
-      const int e = normalise8(y);
+      const int e = normalise8(x);
       frame = (e == kDeadFrame || F <= kDeadFrame / 2 || frame <= kDeadFrame / 2) ? kDeadFrame : frame + F + e;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { x[k] = y[k]; VB[(size_t)(c + 1) * 8 + k] = y[k]; }
-      VBo[c + 1] = frame;
+      if (lane < 8) VB[(size_t)(c + 1) * 8 + lane] = mine();
+      if (lane == 0) VBo[c + 1] = frame;
     }
   }
   __syncthreads();
@@ -367,6 +365,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 
 // ---------------------------------------------------------------------------
 // scores + compact occupation counts from the band states.  Thread per (b,t,i).
+// occupation of an arc = alpha(tail) * P(arc) * beta(head) / total, all in the linear domain.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, float *gxc, float *gyc, float *scores,
                                                             int B) {
@@ -375,20 +374,25 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
   auto ok_bd = [&](const int4 &bd) {
     return bd.z >= bd.x && bd.w >= bd.y && bd.x >= 0 && bd.y >= 0 && bd.z <= p.S && bd.w <= T;
   };
-  auto total_of = [&](int b, const int4 &bd, float &tr, float &to) -> bool {
+  auto total_of = [&](int b, const int4 &bd, double &tm, int &to) -> bool {
     const int Tb = bd.w - bd.y;
     const int r0e = p.ranges[(size_t)(b * T + min(bd.y + max(Tb - 1, 0), T - 1)) * R];
     if ((unsigned)(bd.z - r0e) >= (unsigned)R) return false;
-    tr = p.va[((size_t)b * (T + 1) + Tb) * kBandR + (bd.z & 7)];
+    tm = p.va[((size_t)b * (T + 1) + Tb) * kBandR + (bd.z & 7)];
     to = p.oa[(size_t)b * (T + 1) + Tb];
-    return tr > kNegThresh;
+    return tm > 0.0 && to > kDeadFrame / 2;
   };
   if (idx < B && scores) {
     const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * idx);
     float v = 0.f;
     if (ok_bd(bd)) {
-      float tr, to;
-      v = total_of(idx, bd, tr, to) ? (float)(((double)tr + (double)to) * 0.6931471805599453) : -INFINITY;
+      double tm;
+      int to;
+      v = -INFINITY;
+      if (total_of(idx, bd, tm, to)) {
+        const int e = ((__double2hiint(tm) >> 20) & 0x7ff) - 1023;
+        v = (float)(((double)log2f((float)(tm * pow2d(-e))) + (double)(e + to)) * 0.6931471805599453);
+      }
     }
     scores[idx] = v;
   }
@@ -396,20 +400,24 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
   const int b = idx / TR, rem = idx - b * TR, ta = rem / R, i = rem - ta * R;
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   float vx = 0.f, vy = 0.f;
-  float tr, to;
-  if (ok_bd(bd) && ta >= bd.y && ta < bd.w && total_of(b, bd, tr, to)) {
+  double tm;
+  int to;
+  if (ok_bd(bd) && ta >= bd.y && ta < bd.w && total_of(b, bd, tm, to)) {
     const int t = ta - bd.y, Tb = bd.w - bd.y;
     const int r0 = p.ranges[(size_t)(b * T + ta) * R];
     const int d = (t + 1 < Tb) ? p.ranges[(size_t)(b * T + ta + 1) * R] - r0 : 0;
     const size_t base = (size_t)b * (T + 1);
-    const float *va = p.va + (base + t) * kBandR, *un = p.ub + (base + t + 1) * kBandR, *uc = p.ub + (base + t) * kBandR;
-    const float oa = p.oa[base + t], obn = p.ob[base + t + 1], obc = p.ob[base + t];
+    const double *va = p.va + (base + t) * kBandR, *un = p.ub + (base + t + 1) * kBandR, *uc = p.ub + (base + t) * kBandR;
+    const int oa = p.oa[base + t], obn = p.ob[base + t + 1], obc = p.ob[base + t];
+    const double inv_tot = 1.0 / tm;
     auto arc = [&](int ii, bool px_arc) -> float {
       const int s = r0 + ii;                       // rows that would wrap around S+1 are outside the band
       if (s < bd.x || s > bd.z) return 0.f;
-      const float a = va[s & 7];
-      if (!(a > kNegThresh)) return 0.f;
-      float score, head, ohead;
+      const double a = va[s & 7];
+      if (!(a > 0.0) || oa <= kDeadFrame / 2) return 0.f;
+      float score;
+      double head;
+      int ohead;
       if (!px_arc) {
         if ((unsigned)(ii - d) >= (unsigned)R) return 0.f;
         score = p.pyc[(size_t)(b * T + ta) * R + ii];
@@ -427,9 +435,11 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
           head = uc[(s + 1) & 7]; ohead = obc;
         }
       }
-      if (!(head > kNegThresh) || !(score > -INFINITY)) return 0.f;
-      const float e = ((a - tr) + head + score * kLog2e) + ((oa + ohead) - to);
-      return ex2_approx(e);
+      if (!(head > 0.0) || ohead <= kDeadFrame / 2) return 0.f;
+      // The mantissas are <= 2 but may be tiny relative to their column's frame (an entry far
+      // from the column's mass), so the frame difference can be large and positive; the true
+      // occupation is <= 1, so the product stays finite, and it flushes to 0 when negligible.
+      return (float)((((a * inv_tot) * head) * arc_prob(score)) * pow2d(min(oa + ohead - to, 1000)));
     };
     vx = arc(i, true);
     vy = arc(i, false);
@@ -441,8 +451,8 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
 
 // ---------------------------------------------------------------------------
 size_t band_dp_workspace_bytes(int B, int T) {
-  return 2 * round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(float), 256) +
-         2 * round_up_sz((size_t)B * (T + 1) * sizeof(float), 256);
+  return 2 * round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(double), 256) +
+         2 * round_up_sz((size_t)B * (T + 1) * sizeof(int), 256);
 }
 
 static int band_chunk_len(int T) {
@@ -457,12 +467,12 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
                    int T, int R, int rnnt_type, float delay_penalty, bool want_grad, void *workspace, float *gxc,
                    float *gyc, float *scores, cudaStream_t stream) {
   char *w = static_cast<char *>(workspace);
-  const size_t nv = round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(float), 256);
-  const size_t no = round_up_sz((size_t)B * (T + 1) * sizeof(float), 256);
+  const size_t nv = round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(double), 256);
+  const size_t no = round_up_sz((size_t)B * (T + 1) * sizeof(int), 256);
   BandDpParams p;
   p.pxc = pxc; p.pyc = pyc; p.ranges = ranges; p.boundary = boundary;
-  p.va = reinterpret_cast<float *>(w); p.ub = reinterpret_cast<float *>(w + nv);
-  p.oa = reinterpret_cast<float *>(w + 2 * nv); p.ob = reinterpret_cast<float *>(w + 2 * nv + no);
+  p.va = reinterpret_cast<double *>(w); p.ub = reinterpret_cast<double *>(w + nv);
+  p.oa = reinterpret_cast<int *>(w + 2 * nv); p.ob = reinterpret_cast<int *>(w + 2 * nv + no);
   p.S = S; p.T = T; p.R = R; p.modified = (rnnt_type != FRN_REGULAR); p.rnnt_type = rnnt_type;
   p.delay_penalty = delay_penalty;
   p.L = band_chunk_len(T);

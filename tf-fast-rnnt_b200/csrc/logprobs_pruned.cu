@@ -39,72 +39,108 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
                                                          const int32_t *ranges, int BTR, int TR, int S, int R,
                                                          int C, int term, float *pxc, float *pyc, float *lse_out) {
   constexpr int V = kVecElems<T>;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int kU = 4;   // 16-byte loads issued back to back per lane before any arithmetic
   const int lane = threadIdx.x & 31;
+  const int nv = C / V;
+  // fast path: rows are 16-byte aligned and fit one batch of kU vector loads per lane
+  const bool vec = (C % V == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15u) == 0);
+  const bool one_batch = vec && nv <= 32 * kU;
+
+  auto load_batch = [&](const uint4 *p, int cb, uint4 (&raw)[kU]) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int c = cb + u * 32 + lane;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (c < nv)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w) : "l"(p + c));
+    }
+  };
+  // symbol context of a band entry (rnnt_loss.py:954-958): -1 = no symbol arc
+  auto load_sym = [&](int row, bool &s_ok) {
+    int s, sym = -1;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(s) : "l"(ranges + row));
+    s_ok = (s >= 0 && s <= S);
+    if (s_ok) {
+      if (s < S) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(sym) : "l"(symbols + (size_t)(row / TR) * S + s));
+      else sym = term;
+    }
+    return (sym < 0 || sym >= C) ? -1 : sym;
+  };
+
+  // One row per warp (a persistent grid-stride variant with next-row prefetch measured 1.5x
+  // slower: fewer, longer-lived warps hide the memory latency worse than many short ones).  The
+  // row's vector loads are requested before the dependent index loads so that all are in flight
+  // together.
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= BTR) return;
-  const T *src = logits + (size_t)row * C;
-  float m = -INFINITY, ssum = 0.f;
-  const bool vec = (C % V == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
-  if (vec) {
-    const int nv = C / V;
-    const uint4 *p = reinterpret_cast<const uint4 *>(src);
-    constexpr int kU = 4;   // 16-byte loads issued back to back per lane before any arithmetic
-    for (int cb = 0; cb < nv; cb += 32 * kU) {
-      uint4 raw[kU];
+  {
+    const T *src = logits + (size_t)row * C;
+    uint4 raw[kU];
+    if (one_batch) load_batch(reinterpret_cast<const uint4 *>(src), 0, raw);
+    bool s_ok;
+    const int sym = load_sym(row, s_ok);
+    float m = -INFINITY, ssum = 0.f;     // running max and sum of 2^((x - m) log2e)
+    float g_sym = 0.f, g_term = 0.f;      // exactly one lane meets each index
+    if (vec) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(src);
+      for (int cb = 0; cb < nv; cb += 32 * kU) {
+        if (!one_batch) load_batch(p, cb, raw);
+        float x[kU][V];
+        float mx = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int c = cb + u * 32 + lane;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (c < nv)
-          asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w) : "l"(p + c));
-      }
-      float x[kU][V];
-      float mx = -INFINITY;
+        for (int u = 0; u < kU; ++u) {
+          const int c = cb + u * 32 + lane;
+          const bool ok = c < nv;
+          const T *e = reinterpret_cast<const T *>(&raw[u]);
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const bool ok = cb + u * 32 + lane < nv;
-        const T *e = reinterpret_cast<const T *>(&raw[u]);
+          for (int j = 0; j < V; ++j) {
+            x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+            mx = fmaxf(mx, x[u][j]);
+            const int col = c * V + j;
+            g_sym = (ok && col == sym) ? x[u][j] : g_sym;
+            g_term = (ok && col == term) ? x[u][j] : g_term;
+          }
+        }
+        const float mn = fmaxf(m, mx);
+        if (mn > -INFINITY) {
+          const float mn2 = mn * kLog2e;
+          float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          x[u][j] = ok ? to_f(e[j]) : -INFINITY;
-          mx = fmaxf(mx, x[u][j]);
+          for (int u = 0; u < kU; ++u)
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc += ex2_approx(fmaf(x[u][j], kLog2e, -mn2));
+          ssum = ssum * ex2_approx((m - mn) * kLog2e) + acc;
+          m = mn;
         }
       }
-      const float mn = fmaxf(m, mx);
-      if (mn > -INFINITY) {
-        float acc = 0.f;
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc += expf(x[u][j] - mn);
-        ssum = ssum * expf(m - mn) + acc;
-        m = mn;
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float x = to_f(src[c]);
+        g_sym = (c == sym) ? x : g_sym;
+        g_term = (c == term) ? x : g_term;
+        const float mn = fmaxf(m, x);
+        if (mn > -INFINITY) {
+          ssum = ssum * ex2_approx((m - mn) * kLog2e) + ex2_approx((x - mn) * kLog2e);
+          m = mn;
+        }
       }
     }
-  } else {
-    for (int c = lane; c < C; c += 32) {
-      const float x = to_f(src[c]);
-      const float mn = fmaxf(m, x);
-      ssum = ssum * expf(m - mn) + expf(x - mn);
-      m = mn;
+    // combine lanes
+    const float M = warp_max(m);
+    const float scaled = (m == -INFINITY) ? 0.f : ssum * ex2_approx((m - M) * kLog2e);
+    const float tot = warp_sum(scaled);
+    const float lse = (M == -INFINITY) ? -INFINITY : M + logf(tot);
+    g_sym = warp_sum(g_sym);
+    g_term = warp_sum(g_term);
+    if (lane == 0) {
+      float vx = -INFINITY, vy = -INFINITY;
+      if (s_ok) {
+        if (sym >= 0) vx = g_sym - lse;
+        vy = g_term - lse;
+      }
+      pxc[row] = vx; pyc[row] = vy; lse_out[row] = lse;
     }
-  }
-  // combine lanes
-  const float M = warp_max(m);
-  const float scaled = (m == -INFINITY) ? 0.f : ssum * expf(m - M);
-  const float tot = warp_sum(scaled);
-  const float lse = (M == -INFINITY) ? -INFINITY : M + logf(tot);
-  if (lane == 0) {
-    const int b = row / TR;
-    const int s = ranges[row];  // symbol context of this band entry (rnnt_loss.py:954-958)
-    float vx = -INFINITY, vy = -INFINITY;
-    if (s >= 0 && s <= S) {
-      const int sym = (s < S) ? symbols[(size_t)b * S + s] : term;
-      if (sym >= 0 && sym < C) vx = to_f(src[sym]) - lse;
-      vy = to_f(src[term]) - lse;
-    }
-    pxc[row] = vx; pyc[row] = vy; lse_out[row] = lse;
   }
 }
 

@@ -22,20 +22,50 @@ __device__ __forceinline__ float tiny_f32() { return __int_as_float(1); }
 // ---------------------------------------------------------------------------
 // row statistics: max (and sum of exp(x-max)) over C, one warp per row
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rowstats_kernel(const float *x, int rows, int C, float *rmax,
-                                                       float *rsum) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Rows of lm ([rows_lm][C]) and of am ([rows_am][C]) in one launch; 128-bit streaming loads when
+// the rows are 16-byte aligned (C % 4 == 0), all loads of a row issued before the reduction.
+__global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
+                                                       int C, float *lmmax, float *lmsum, float *ammax) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float *src = x + (size_t)row * C;
+  if (row >= rows_lm + rows_am) return;
+  const bool is_lm = row < rows_lm;
+  if (!is_lm) row -= rows_lm;
+  const float *src = (is_lm ? lm : am) + (size_t)row * C;
+  float *rmax = is_lm ? lmmax : ammax;
+  float *rsum = is_lm ? lmsum : nullptr;
   float m = -INFINITY;
-  for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
-  m = warp_max(m);
-  if (rsum) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += expf(src[c] - m);
-    s = warp_sum(s);
-    if (lane == 0) rsum[row] = s;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  if (vec && C <= 4 * 32 * 8) {
+    const int nv = C / 4;
+    const float4 *p = reinterpret_cast<const float4 *>(src);
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = u * 32 + lane;
+      v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (c < nv) v[u] = ld_stream_f4(p + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+    m = warp_max(m);
+    if (rsum) {
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u * 32 + lane < nv) s += (expf(v[u].x - m) + expf(v[u].y - m)) + (expf(v[u].z - m) + expf(v[u].w - m));
+      s = warp_sum(s);
+      if (lane == 0) rsum[row] = s;
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
+    m = warp_max(m);
+    if (rsum) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += expf(src[c] - m);
+      s = warp_sum(s);
+      if (lane == 0) rsum[row] = s;
+    }
   }
   if (lane == 0) rmax[row] = m;
 }
@@ -215,8 +245,8 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w);
-  count_launch(), rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, C, lmmax, smoothed ? lmsum : nullptr);
-  count_launch(), rowstats_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, B * T, C, ammax, nullptr);
+  count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax,
+                                                                                 smoothed ? lmsum : nullptr, ammax);
   if (smoothed) {
     count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
     count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);

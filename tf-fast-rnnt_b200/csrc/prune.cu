@@ -75,48 +75,49 @@ __device__ void block_rev_cummin(int32_t *x, int T, int32_t *warp_carry) {
   }
 }
 
-constexpr int kArgmaxThreads = 128, kArgmaxChunk = 16;
+constexpr int kArgmaxThreads = 128;   // maximum columns (t) per block; blockDim.x = columns actually used
 
+// The [S+1] x 128 tile of py_grad and the [S] x 128 tile of px_grad are brought into shared memory
+// with 4-byte cp.async (fire and forget: every load of the tile is in flight at once, one memory
+// round trip), then each thread walks its column sequentially out of shared memory.
 __global__ void __launch_bounds__(kArgmaxThreads) prune_argmax_kernel(const float *px_grad, const float *py_grad,
                                                                       const int32_t *boundary, int S, int T, int T1,
                                                                       int R, int32_t *s_begin) {
+  extern __shared__ float tile[];           // py: [S+1][cols], then px: [S][cols]
   const int b = blockIdx.y;
-  const int t = blockIdx.x * kArgmaxThreads + threadIdx.x;
-  if (t >= T) return;
+  const int tx = threadIdx.x, cols = blockDim.x;
+  const int t = blockIdx.x * cols + tx;
   const int s_end = boundary[4 * b + 2], t_end = boundary[4 * b + 3];
   const int S1 = S + 1;
   const int nk = S1 - R + 1;
+  float *spy = tile, *spx = tile + (size_t)S1 * cols;
+  const bool live = t < T && t < t_end - 1;   // this column needs the arg-max (others are padding frames)
+  if (live) {
+    const float *py = py_grad + (size_t)b * S1 * T + t;
+    const float *px = px_grad + (size_t)b * S * T1 + t;
+    const uint32_t dpy = smem_u32(spy + tx), dpx = smem_u32(spx + tx);
+    for (int s = 0; s < S1; ++s)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dpy + (uint32_t)(s * cols * 4)),
+                   "l"(py + (size_t)s * T) : "memory");
+    for (int s = 0; s < S; ++s)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dpx + (uint32_t)(s * cols * 4)),
+                   "l"(px + (size_t)s * T1) : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // each thread reads back only what it copied itself
+  if (t >= T) return;
   int best_k = 0;
-  if (t < t_end - 1) {
-    const float *__restrict__ py = py_grad + (size_t)b * S1 * T + t;
-    const float *__restrict__ px = px_grad + (size_t)b * S * T1 + t;
+  if (live) {
+    const float *cy = spy + tx, *cx = spx + tx;
     float cs_lo = 0.f, cs_hi = 0.f;
-    for (int s = 0; s < R; ++s) cs_hi = cs_hi + py[(size_t)s * T];  // cs[R], sequential
+    for (int s = 0; s < R; ++s) cs_hi = cs_hi + cy[s * cols];  // cs[R], sequential
     float best = 0.f;
-    for (int k0 = 0; k0 < nk; k0 += kArgmaxChunk) {
-      // All loads of the chunk are unconditional (indices clamped into the arrays) so that they are
-      // issued back to back; out-of-range terms are replaced by +0.f, which leaves the sums
-      // bit-identical to the sequential cumsum.
-      float lo[kArgmaxChunk], hi[kArgmaxChunk], pxv[kArgmaxChunk];
-#pragma unroll
-      for (int j = 0; j < kArgmaxChunk; ++j) {
-        const int k = k0 + j;
-        lo[j] = py[(size_t)min(k, S) * T];
-        hi[j] = py[(size_t)min(k + R, S) * T];
-        pxv[j] = px[(size_t)min(max(k - 1, 0), S - 1) * T1];
-      }
-#pragma unroll
-      for (int j = 0; j < kArgmaxChunk; ++j) {
-        const int k = k0 + j;
-        const bool valid = k < nk;
-        float fin = cs_hi - cs_lo;
-        fin = fin - (k > 0 ? pxv[j] : 0.f);
-        const bool take = valid && (k == 0 || fin > best);
-        best = take ? fin : best;
-        best_k = take ? k : best_k;
-        cs_lo = cs_lo + (valid ? lo[j] : 0.f);
-        cs_hi = cs_hi + ((valid && k + R < S1) ? hi[j] : 0.f);
-      }
+#pragma unroll 4
+    for (int k = 0; k < nk; ++k) {
+      float fin = cs_hi - cs_lo;
+      if (k > 0) fin = fin - cx[(k - 1) * cols];
+      if (k == 0 || fin > best) { best = fin; best_k = k; }
+      cs_lo = cs_lo + cy[k * cols];
+      if (k + R < S1) cs_hi = cs_hi + cy[(k + R) * cols];
     }
   } else {
     best_k = max(s_end - R + 1, 0);  // padding frames, rnnt_loss.py:744-748
@@ -297,8 +298,17 @@ int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_
     cudaError_t e = cudaFuncSetAttribute(prune_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return note_cuda_error(e);
   }
-  dim3 grid((T + kArgmaxThreads - 1) / kArgmaxThreads, B);
-  count_launch(), prune_argmax_kernel<<<grid, kArgmaxThreads, 0, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, s_begin_ws);
+  // columns per block: as many as keep the tile under ~100 KB (two blocks per SM)
+  int cols = kArgmaxThreads;
+  while (cols > 8 && (size_t)(2 * S + 1) * cols * sizeof(float) > 100 * 1024) cols >>= 1;
+  const size_t tile_bytes = (size_t)(2 * S + 1) * cols * sizeof(float);
+  if (tile_bytes > 200 * 1024) return FRN_EUNSUPPORTED;
+  dim3 grid((T + cols - 1) / cols, B);
+  if (tile_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(prune_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes);
+    if (e != cudaSuccess) return note_cuda_error(e);
+  }
+  count_launch(), prune_argmax_kernel<<<grid, cols, tile_bytes, stream>>>(px_grad, py_grad, boundary, S, T, T1, R, s_begin_ws);
   int rc = check_launch();
   if (rc) return rc;
   count_launch(), prune_fixup_kernel<<<B, kPruneThreads, smem, stream>>>(s_begin_ws, T, R, r_fix, ranges);

@@ -38,6 +38,9 @@ _SIGS = {
     "frn_kernel_launches": (ctypes.c_ulonglong, []),
     "frn_mi_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_mi_fwd_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_band_mi_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_band_mi_fwd_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P,
+                                    c_size_t, _P]),
     "frn_cummin": (c_int, [_P, _P, c_int, c_int, _P]),
     "frn_simple_logprobs_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_simple_logprobs": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
