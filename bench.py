@@ -49,6 +49,18 @@ METRIC = "utterances/sec (pruned loss fwd+bwd) at B32 T500 S100 C500; lattice ce
 UNIT = "utterances/s"
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to
+# file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the
+# JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -117,7 +129,7 @@ def run_reference_arm(args):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------
@@ -540,7 +552,7 @@ def run_gpu_arm(args):
                 line["reference_gpu_op"] = ref_leg
         except Exception as e:  # noqa: BLE001  (a baseline leg must never take the bench line down)
             line["reference_gpu_op"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
