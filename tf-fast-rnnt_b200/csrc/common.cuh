@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/fast_rnnt_b200.h"
 
@@ -174,6 +175,10 @@ inline DpGeom make_geom(int B, int S, int T, int T1) {
   g.B = B; g.S = S; g.T = T; g.T1 = T1;
   g.k = (T1 == T) ? 0 : 1;
   g.rpl = (S + 1 <= 256) ? 1 : ((S + 1 <= 512) ? 2 : 4);
+  if (const char *e = getenv("FRN_RPL")) {            // experiment knob: rows per lane of the chain kernel
+    const int r = atoi(e);
+    if ((r == 1 && S + 1 <= 256) || (r == 2 && S + 1 <= 512) || r == 4) g.rpl = r;
+  }
   g.P = round_up(S + 1, 32 * g.rpl);
   g.Dn = round_up(T + 1 + g.k * S, kChunk);
   return g;

@@ -189,22 +189,29 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   float2 carry = dead2;
   if (DIR && fed && (r0 + RPL) == Sb) carry = make_float2(1.f, 0.f);
 
+  // Per-chunk state is carried incrementally (no divisions, no 64-bit re-derivations per chunk).
+  int st = 0;                                   // ring stage of chunk i
+  uint32_t par = 0;                             // its mbarrier phase parity
+  int cbase = DIR ? (nchunk - 1) * CH : 0;      // first diagonal of chunk i
+  const float4 *xstage = ring + r0;             // this lane's column of stage `st`
+  const float2 *estage_in = fed ? edge + (size_t)w * NST * CH : dead_edge;     // feeding row's states, stage `st`
+  float2 *estage_out = edge + (size_t)(feeds ? wc : w) * NST * CH;            // our states for the fed warp
+  uint64_t *bar_xy = mbar_xy, *bar_in = mbar_edge + w * NST, *bar_out = mbar_edge + wc * NST;
+  // outputs walk the diagonals contiguously across chunks
+  float2 *pa = outA + (size_t)(DIR ? min(cbase + CH - 1, Db) : 1) * P;
+  float4 *pb = outB + (size_t)((DIR ? min(cbase + CH - 1, Db) : 1) - 1) * P;
+  const float4 *gnext = XYg + (size_t)(DIR ? (nchunk - 1 - NST) : NST) * stage_elems;   // next chunk to request
+
   for (int i = 0; i < nchunk; ++i) {
-    const int st = i % NST;
-    const uint32_t par = (uint32_t)((i / NST) & 1);
-    const int ci = DIR ? nchunk - 1 - i : i;
-    mbar_wait(&mbar_xy[st], par);
-    if (fed) mbar_wait(&mbar_edge[w * NST + st], par);   // the feeding warp has published this chunk
-    const int e_lo = max(ci * CH, 1), e_hi = min(ci * CH + CH - 1, Db);
+    mbar_wait(bar_xy, par);
+    if (fed) mbar_wait(bar_in, par);            // the feeding warp has published this chunk
+    const int e_lo = max(cbase, 1), e_hi = min(cbase + CH - 1, Db);
     const int n = e_hi - e_lo + 1;
-    const int e0 = DIR ? e_hi : e_lo;
-    const int el0 = e0 - ci * CH;
+    const int el0 = (DIR ? e_hi : e_lo) - cbase;
     // running pointers, all advanced by one diagonal per step
-    const float4 *xp = ring + (size_t)st * stage_elems + r0 + el0 * P;          // arcs of the current step
-    const float2 *pe = fed ? edge + (size_t)(w * NST + st) * CH + el0 : dead_edge;   // feeding row's state
-    float2 *po = edge + (size_t)((feeds ? wc : w) * NST + st) * CH + el0;        // our state for the fed warp
-    float2 *pa = outA + (size_t)e0 * P;
-    float4 *pb = outB + (size_t)(e0 - 1) * P;
+    const float4 *xp = xstage + el0 * P;                                 // arcs of the current step
+    const float2 *pe = fed ? estage_in + el0 : estage_in;                // feeding row's state
+    float2 *po = estage_out + el0;                                       // our state for the fed warp
     // operands of the first step of the chunk
     float4 a4[RPL];
     float2 xnext = dead2;
@@ -292,10 +299,24 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
 #pragma unroll
     for (int j = 0; j < RPL; ++j) normalise_pair(m[j], o[j]);
     carry = ev;   // the feeding row's state after the last step of this chunk
-    if (publish) mbar_arrive(&mbar_edge[wc * NST + st]);
+    if (publish) mbar_arrive(bar_out);
     if (is_tail) {
       __syncwarp();
-      if (lane == 0 && i + NST < nchunk) issue(i + NST, st);
+      if (lane == 0 && i + NST < nchunk) {      // recycle the stage: request chunk i + NST into it
+        mbar_arrive_expect_tx(bar_xy, chunk_bytes);
+        bulk_g2s(ring + (size_t)st * stage_elems, gnext, chunk_bytes, bar_xy);
+      }
+    }
+    gnext += step_sign * stage_elems;
+    cbase += step_sign * CH;
+    ++st; ++bar_xy; ++bar_in; ++bar_out;
+    xstage += stage_elems; estage_out += CH;
+    if (fed) estage_in += CH;
+    if (st == NST) {
+      st = 0; par ^= 1u;
+      bar_xy -= NST; bar_in -= NST; bar_out -= NST;
+      xstage -= (size_t)NST * stage_elems; estage_out -= NST * CH;
+      if (fed) estage_in -= NST * CH;
     }
   }
 }
