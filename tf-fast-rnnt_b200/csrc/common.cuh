@@ -72,7 +72,7 @@ __device__ __forceinline__ void normalise_pair(float &m, int &o) {
 __device__ __forceinline__ float2 encode_arc(float v_log2) {
   if (!(v_log2 > -1.0e8f)) return make_float2(0.f, __int_as_float(kNegI));   // total scores must stay above -2^27
   const float e = floorf(v_log2);
-  return make_float2(exp2f(v_log2 - e), __int_as_float((int)e));
+  return make_float2(ex2_approx(v_log2 - e), __int_as_float((int)e));   // argument in [0,1]: 2 ulp, like exp2f
 }
 
 // natural-log score of a lattice value {mantissa, frame}

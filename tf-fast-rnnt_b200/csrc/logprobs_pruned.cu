@@ -71,76 +71,88 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
   // One row per warp (a persistent grid-stride variant with next-row prefetch measured 1.5x
   // slower: fewer, longer-lived warps hide the memory latency worse than many short ones).  The
   // row's vector loads are requested before the dependent index loads so that all are in flight
-  // together.
+  // together; the two gathered logits are two more scalar loads issued as soon as their index is
+  // known (they hit L2 behind the row itself), which keeps per-element work to max / ex2 / add.
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= BTR) return;
-  {
-    const T *src = logits + (size_t)row * C;
-    uint4 raw[kU];
-    if (one_batch) load_batch(reinterpret_cast<const uint4 *>(src), 0, raw);
-    bool s_ok;
-    const int sym = load_sym(row, s_ok);
-    float m = -INFINITY, ssum = 0.f;     // running max and sum of 2^((x - m) log2e)
-    float g_sym = 0.f, g_term = 0.f;      // exactly one lane meets each index
-    if (vec) {
-      const uint4 *p = reinterpret_cast<const uint4 *>(src);
-      for (int cb = 0; cb < nv; cb += 32 * kU) {
-        if (!one_batch) load_batch(p, cb, raw);
-        float x[kU][V];
-        float mx = -INFINITY;
+  const T *src = logits + (size_t)row * C;
+  uint4 raw[kU];
+  if (one_batch) load_batch(reinterpret_cast<const uint4 *>(src), 0, raw);
+  float g_term = to_f(src[term]);
+  bool s_ok;
+  const int sym = load_sym(row, s_ok);
+  float g_sym = (sym >= 0) ? to_f(src[sym]) : 0.f;
+  float m = -INFINITY, ssum = 0.f;     // running max and sum of 2^((x - m) log2e)
+  if (one_batch) {
+    float x[kU][V];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int c = cb + u * 32 + lane;
-          const bool ok = c < nv;
-          const T *e = reinterpret_cast<const T *>(&raw[u]);
+    for (int u = 0; u < kU; ++u) {
+      const bool ok = u * 32 + lane < nv;
+      const T *e = reinterpret_cast<const T *>(&raw[u]);
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            x[u][j] = ok ? to_f(e[j]) : -INFINITY;
-            mx = fmaxf(mx, x[u][j]);
-            const int col = c * V + j;
-            g_sym = (ok && col == sym) ? x[u][j] : g_sym;
-            g_term = (ok && col == term) ? x[u][j] : g_term;
-          }
-        }
-        const float mn = fmaxf(m, mx);
-        if (mn > -INFINITY) {
-          const float mn2 = mn * kLog2e;
-          float acc = 0.f;
-#pragma unroll
-          for (int u = 0; u < kU; ++u)
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc += ex2_approx(fmaf(x[u][j], kLog2e, -mn2));
-          ssum = ssum * ex2_approx((m - mn) * kLog2e) + acc;
-          m = mn;
-        }
-      }
-    } else {
-      for (int c = lane; c < C; c += 32) {
-        const float x = to_f(src[c]);
-        g_sym = (c == sym) ? x : g_sym;
-        g_term = (c == term) ? x : g_term;
-        const float mn = fmaxf(m, x);
-        if (mn > -INFINITY) {
-          ssum = ssum * ex2_approx((m - mn) * kLog2e) + ex2_approx((x - mn) * kLog2e);
-          m = mn;
-        }
+      for (int j = 0; j < V; ++j) {
+        x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+        m = fmaxf(m, x[u][j]);
       }
     }
-    // combine lanes
-    const float M = warp_max(m);
-    const float scaled = (m == -INFINITY) ? 0.f : ssum * ex2_approx((m - M) * kLog2e);
-    const float tot = warp_sum(scaled);
-    const float lse = (M == -INFINITY) ? -INFINITY : M + logf(tot);
-    g_sym = warp_sum(g_sym);
-    g_term = warp_sum(g_term);
-    if (lane == 0) {
-      float vx = -INFINITY, vy = -INFINITY;
-      if (s_ok) {
-        if (sym >= 0) vx = g_sym - lse;
-        vy = g_term - lse;
-      }
-      pxc[row] = vx; pyc[row] = vy; lse_out[row] = lse;
+    m = warp_max(m);                   // one max for the whole row: no rescaling afterwards
+    if (m > -INFINITY) {
+      const float m2 = m * kLog2e;
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) ssum += ex2_approx(fmaf(x[u][j], kLog2e, -m2));
     }
+  } else if (vec) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    for (int cb = 0; cb < nv; cb += 32 * kU) {
+      load_batch(p, cb, raw);
+      float x[kU][V];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const bool ok = cb + u * 32 + lane < nv;
+        const T *e = reinterpret_cast<const T *>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+          mx = fmaxf(mx, x[u][j]);
+        }
+      }
+      const float mn = fmaxf(m, mx);
+      if (mn > -INFINITY) {
+        const float mn2 = mn * kLog2e;
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc += ex2_approx(fmaf(x[u][j], kLog2e, -mn2));
+        ssum = ssum * ex2_approx((m - mn) * kLog2e) + acc;
+        m = mn;
+      }
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      const float x = to_f(src[c]);
+      const float mn = fmaxf(m, x);
+      if (mn > -INFINITY) {
+        ssum = ssum * ex2_approx((m - mn) * kLog2e) + ex2_approx((x - mn) * kLog2e);
+        m = mn;
+      }
+    }
+  }
+  // combine lanes
+  const float M = warp_max(m);
+  const float scaled = (m == -INFINITY) ? 0.f : ssum * ex2_approx((m - M) * kLog2e);
+  const float tot = warp_sum(scaled);
+  const float lse = (M == -INFINITY) ? -INFINITY : M + logf(tot);
+  if (lane == 0) {
+    float vx = -INFINITY, vy = -INFINITY;
+    if (s_ok) {
+      if (sym >= 0) vx = g_sym - lse;
+      vy = g_term - lse;
+    }
+    pxc[row] = vx; pyc[row] = vy; lse_out[row] = lse;
   }
 }
 
@@ -289,22 +301,30 @@ __global__ void __launch_bounds__(256) pruned_logits_grad_kernel(const T *logits
     const int nv = C / V;
     const uint4 *p = reinterpret_cast<const uint4 *>(src);
     uint4 *q = reinterpret_cast<uint4 *>(dst);
+    // vectors holding the symbol / blank column get their fix-up in a (rarely taken) branch, so
+    // the common vector costs multiply-add, ex2, multiply per element and nothing else
+    const int vsym = (sym >= 0) ? sym / V : -1, vterm = term / V;
+    const bool zero_row = (gs == 0.f);                 // warp-uniform: no softmax term, nothing to read
     for (int c = lane; c < nv; c += 32) {
       uint4 raw = make_uint4(0, 0, 0, 0), outv;
-      if (gs != 0.f)
+      if (!zero_row)
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p + c));
       const T *e = reinterpret_cast<const T *>(&raw);
       T *o = reinterpret_cast<T *>(&outv);
+      float d[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const int cc = c * V + j;
-        float d = 0.f;
-        if (gs != 0.f) d = -gs * ex2_approx(to_f(e[j]) * kLog2e - l2);
-        if (cc == sym) d += gx;
-        if (cc == term) d += gy;
-        o[j] = from_f<T>(d);
+      for (int j = 0; j < V; ++j) d[j] = zero_row ? 0.f : -gs * ex2_approx(fmaf(to_f(e[j]), kLog2e, -l2));
+      if (c == vsym || c == vterm) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int cc = c * V + j;
+          if (cc == sym) d[j] += gx;
+          if (cc == term) d[j] += gy;
+        }
       }
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = from_f<T>(d[j]);
       asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(q + c), "r"(outv.x),
                    "r"(outv.y), "r"(outv.z), "r"(outv.w) : "memory");
     }

@@ -38,49 +38,59 @@ struct SkewDenseParams {
   float delay_penalty;      // added to px (rnnt_loss.py:316-321); 0 = none
 };
 
-// One block: 32 diagonals x 32 rows of one utterance.
+// One block: 128 diagonals x 32 rows of one utterance (the kernel is instruction-issue bound, so
+// the tile is wide: 1.24x over-read of px/py instead of 2x, no divisions in the index math).
+constexpr int kSkewDiags = 128;
 template <int K>
 __global__ void __launch_bounds__(256) skew_dense_kernel(SkewDenseParams p) {
-  constexpr int kPitch = 65 - K;
-  constexpr int kWidth = 32 + 31 * K;  // t' values touched by the tile
+  constexpr int kWidth = kSkewDiags + 31 * K;  // t' values touched by the tile
+  constexpr int kPitch = kWidth + (K ? 3 : 1);  // (kPitch - K) % 32 == 1: conflict-free transposed reads
   __shared__ float sx[32 * kPitch], sy[32 * kPitch];
   const int b = blockIdx.z;
-  const int d0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  const int d0 = blockIdx.x * kSkewDiags, s0 = blockIdx.y * 32;
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int s_begin = bd.x, t_begin = bd.y, Sb = bd.z - bd.x, Tb = bd.w - bd.y;
   const int off = K ? 0 : -1;
   const int tlo = d0 - K * (s0 + 31);  // smallest t' of the tile
   const float *pxb = p.px + (size_t)b * p.S * p.T1;
   const float *pyb = p.py + (size_t)b * (p.S + 1) * p.T;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
-  // load: row = s' - s0, col = t' - tlo, col fastest (coalesced along t)
-  for (int i = threadIdx.x; i < 32 * kWidth; i += blockDim.x) {
-    const int row = i / kWidth, col = i - row * kWidth;
-    const int sp = s0 + row, tp = tlo + col;  // destination cell (s', t')
-    float vx = kNeg, vy = kNeg;
-    if (sp <= Sb && tp <= Tb) {
-      // mutual_information_cuda.cu:295-303 (forward load rules)
-      if (sp >= 1 && tp + off >= 0) {
-        const int t_abs = t_begin + tp + off;
-        float v = pxb[(size_t)(s_begin + sp - 1) * p.T1 + t_abs];
-        if (p.delay_penalty != 0.f) v += delay_penalty_value(bd.w, t_abs, p.delay_penalty);
-        vx = fmaxf(v * kLog2e, kNeg);
+  // load: one warp per row s', lanes along t' (coalesced along t)
+  for (int row = wrp; row < 32; row += 8) {
+    const int sp = s0 + row;  // destination row s'
+    const bool row_ok = sp <= Sb;
+    const float *pxr = pxb + (size_t)(s_begin + sp - 1) * p.T1 + t_begin + off;
+    const float *pyr = pyb + (size_t)(s_begin + sp) * p.T + t_begin - 1;
+#pragma unroll
+    for (int c0 = 0; c0 < kWidth; c0 += 32) {
+      const int col = c0 + lane;
+      const int tp = tlo + col;  // destination cell (s', t')
+      float vx = kNeg, vy = kNeg;
+      if (col < kWidth && row_ok && tp <= Tb) {
+        // mutual_information_cuda.cu:295-303 (forward load rules)
+        if (sp >= 1 && tp + off >= 0) {
+          float v = pxr[tp];
+          if (p.delay_penalty != 0.f) v += delay_penalty_value(bd.w, t_begin + tp + off, p.delay_penalty);
+          vx = fmaxf(v * kLog2e, kNeg);
+        }
+        if (tp >= 1) vy = fmaxf(pyr[tp] * kLog2e, kNeg);
       }
-      if (tp >= 1) vy = fmaxf(pyb[(size_t)(s_begin + sp) * p.T + t_begin + tp - 1] * kLog2e, kNeg);
+      if (col < kWidth) {
+        sx[row * kPitch + col] = vx;
+        sy[row * kPitch + col] = vy;
+      }
     }
-    sx[row * kPitch + col] = vx;
-    sy[row * kPitch + col] = vy;
   }
   __syncthreads();
-  // store: s' fastest (one 16-byte arc pair per thread, 512 contiguous bytes per warp)
-  float4 *XYb = p.XY + (size_t)b * p.Dn * p.P;
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
-    const int dd = i >> 5, ss = i & 31;
+  // store: one warp per diagonal, lanes along s' (one 16-byte arc pair per thread, 512 contiguous bytes per warp)
+  float4 *XYb = p.XY + (size_t)b * p.Dn * p.P + s0 + lane;
+  const int colbase = K * (31 - lane) + lane * kPitch;
+  for (int dd = wrp; dd < kSkewDiags; dd += 8) {
     const int d = d0 + dd;
-    if (d >= p.Dn) continue;
-    const int col = dd + K * (31 - ss);
-    const float2 ax = encode_arc(sx[ss * kPitch + col]), ay = encode_arc(sy[ss * kPitch + col]);
-    XYb[(size_t)d * p.P + s0 + ss] = make_float4(ax.x, ax.y, ay.x, ay.y);
+    if (d >= p.Dn) break;
+    const float2 ax = encode_arc(sx[colbase + dd]), ay = encode_arc(sy[colbase + dd]);
+    XYb[(size_t)d * p.P] = make_float4(ax.x, ax.y, ay.x, ay.y);
   }
 }
 
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
 int launch_skew_dense(const float *px, const float *py, const int32_t *boundary, const DpGeom &g,
                       const DpWorkspace &w, float delay_penalty, cudaStream_t stream) {
   SkewDenseParams sp{px, py, boundary, w.XY, g.S, g.T, g.T1, g.P, g.Dn, delay_penalty};
-  dim3 grid((g.Dn + 31) / 32, g.P / 32, g.B);
+  dim3 grid((g.Dn + kSkewDiags - 1) / kSkewDiags, g.P / 32, g.B);
   if (g.k) count_launch(), skew_dense_kernel<1><<<grid, 256, 0, stream>>>(sp);
   else count_launch(), skew_dense_kernel<0><<<grid, 256, 0, stream>>>(sp);
   return check_launch();
