@@ -27,8 +27,9 @@
 //      (8 threads per chunk, L dependent frame steps);
 //   2. eight lanes walk the chunk matrices (T/L matrix-vector products) and leave
 //      the state at every chunk boundary;
-//   3. every chunk replays its L frames from its boundary state and writes the
-//      per-frame states (mantissas + frame) for the finalize kernel.
+//   3. every column in parallel: its state is the image (recorded in phase 1) of its
+//      chunk's boundary state, one 8x8 matrix-vector product; written (mantissas +
+//      frame) for the finalize kernel.
 // Forward and backward directions run in different CTAs.
 //
 // Limits: band entries whose row index wraps around S+1 (only possible with
@@ -36,11 +37,21 @@
 // of one column that are more than 2^1000 apart flush to zero.
 #include "common.cuh"
 #include "launchers.h"
+#ifdef FRN_BAND_TIMING   // diagnostic build: block (0,0) prints the cycle count of every phase
+#include <cstdio>
+#define BAND_T(i) do { if (tid == 0 && blockIdx.x == 0) tclk[i] = clock64(); } while (0)
+#else
+#define BAND_T(i) do { } while (0)
+#endif
 
 namespace frn {
 
 constexpr int kBandR = 8;          // maximum band width handled here = number of slots
 constexpr int kBandThreads = 512;
+#ifndef FRN_BAND_MIN_CHUNK
+#define FRN_BAND_MIN_CHUNK 16
+#endif
+constexpr int kBandMinChunk = FRN_BAND_MIN_CHUNK;   // frames per chunk (doubled until the tables fit shared memory)
 constexpr int kDeadFrame = -(1 << 29);
 
 struct BandDpParams {
@@ -49,6 +60,8 @@ struct BandDpParams {
   const int32_t *boundary;     // [B][4]
   double *va, *ub;             // [B][T+1][8] forward / backward states by slot: mantissas
   int *oa, *ob;                // [B][T+1]    their frames (kDeadFrame: all-zero state)
+  float *img;                  // [B][2][T+1][8 unit vectors][8] image of chunk-start unit vector j at this column
+  int *img_frame;              // [B][2][T+1][8]  its frame (kDeadFrame: zero image)
   int S, T, R, L, modified, rnnt_type;
   float delay_penalty;
 };
@@ -188,6 +201,10 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   int *Poff = Fv + (size_t)nC * 8;                                   // [nC]    common frame of a chunk matrix
   int *VBo = Poff + nC;                                              // [nC+1]
 
+#ifdef FRN_BAND_TIMING
+  long long tclk[6];
+#endif
+  BAND_T(0);
   // ---- phase 0: arc tables in slot order ----
   const float *__restrict__ pxc = p.pxc + (size_t)b * T * R;
   const float *__restrict__ pyc = p.pyc + (size_t)b * T * R;
@@ -197,36 +214,39 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
     R0[t] = rg[(size_t)ta * R];
   }
   __syncthreads();
+  // (loads are unconditional on clamped indices so that the unrolled iterations issue them together)
 #pragma unroll 4
   for (int idx = tid; idx < (Tb + 1) * 8; idx += kBandThreads) {
     const int t = idx >> 3, k = idx & 7;
+    const int tt = min(t, max(Tb - 1, 0));
+    const int r0 = R0[tt], r1 = R0[tt + 1];
+    const int i = (k - r0) & 7, s = r0 + i;
+    const int ic = min(i, R - 1);
+    const int ta = min(t_begin + tt, T - 1);
+    const float fy = pyc[(size_t)ta * R + ic];
+    const float fx0 = pxc[(size_t)ta * R + ic];
+    const float fy1 = pyc[(size_t)ta * R + min(ic + 1, R - 1)];
     double vx = 0.0, vy = 0.0;
-    if (t < Tb) {
-      const int r0 = R0[t], r1 = R0[t + 1];
-      const int i = (k - r0) & 7, s = r0 + i;
-      if (i < R && s >= s_begin && s <= s_end) {                      // (s <= s_end <= S: no wrap-around)
-        const int ta = t_begin + t;
-        const float fy = pyc[(size_t)ta * R + i];
-        const bool next_in_band = (i + 1 < R);
-        float fx = -INFINITY;
-        if (s < p.S && s < s_end) {
-          fx = pxc[(size_t)ta * R + i];
-          if (p.rnnt_type == FRN_CONSTRAINED) fx += next_in_band ? pyc[(size_t)ta * R + i + 1] : -INFINITY;
-          if (p.delay_penalty != 0.f) fx += delay_penalty_value(t_end, ta, p.delay_penalty);
-        }
-        const unsigned i1 = (unsigned)(s - r1);                       // band index of the same row in column t+1
-        if (i1 < (unsigned)R) vy = arc_prob(fy);
-        if (p.modified) {
-          if ((unsigned)(s + 1 - r1) < (unsigned)R) vx = arc_prob(fx);   // row s+1 inside the band of column t+1
-        } else if (next_in_band) {
-          vx = arc_prob(fx);
-        }
+    if (t < Tb && i < R && s >= s_begin && s <= s_end) {                // (s <= s_end <= S: no wrap-around)
+      const bool next_in_band = (i + 1 < R);
+      float fx = -INFINITY;
+      if (s < p.S && s < s_end) {
+        fx = fx0;
+        if (p.rnnt_type == FRN_CONSTRAINED) fx += next_in_band ? fy1 : -INFINITY;
+        if (p.delay_penalty != 0.f) fx += delay_penalty_value(t_end, ta, p.delay_penalty);
+      }
+      if ((unsigned)(s - r1) < (unsigned)R) vy = arc_prob(fy);          // same row still inside the band of column t+1
+      if (p.modified) {
+        if ((unsigned)(s + 1 - r1) < (unsigned)R) vx = arc_prob(fx);   // row s+1 inside the band of column t+1
+      } else if (next_in_band) {
+        vx = arc_prob(fx);
       }
     }
     PX[idx] = vx;
     PY[idx] = vy;
   }
   __syncthreads();
+  BAND_T(1);
   const BandTables tb{PX, PY, p.modified};
 
   // chunk c (in processing order of this direction) covers transitions
@@ -241,19 +261,31 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (k == j) ? 1.0 : 0.0;
       frame = 0;
+      // every intermediate image is kept (float mantissas + frame): the state of a column inside a
+      // chunk is then one 8x8 matrix-vector product with the chunk's boundary state (phase 3)
+      float *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
+      int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1)) * 8 + j;
+      auto record = [&](int col) {
+        float *q = img + (size_t)col * 64;
+        *reinterpret_cast<float4 *>(q) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        *reinterpret_cast<float4 *>(q + 4) = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+        imf[(size_t)col * 8] = frame;
+      };
       if (!dir) {
         const int t_lo = c * L, t_hi = min(t_lo + L, Tb);
-        for (int t = t_lo; t < t_hi && frame > kDeadFrame / 2; ++t) {
+        for (int t = t_lo; t < t_hi; ++t) {
           fwd_step(tb, t, v);
           const int e = normalise8(v);
-          frame = (e == kDeadFrame) ? kDeadFrame : frame + e;
+          frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
+          record(t + 1);
         }
       } else {
         const int t_hi = Tb - c * L, t_lo = max(t_hi - L, 0);
-        for (int t = t_hi - 1; t >= t_lo && frame > kDeadFrame / 2; --t) {
+        for (int t = t_hi - 1; t >= t_lo; --t) {
           bwd_step(tb, t, v);
           const int e = normalise8(v);
-          frame = (e == kDeadFrame) ? kDeadFrame : frame + e;
+          frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
+          record(t);
         }
       }
       Fv[w] = frame;
@@ -271,6 +303,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   }
   __syncthreads();
 
+  BAND_T(2);
   // ---- phase 2: boundary states; lanes 0..7 of warp 0 each own one slot of the state ----
   if (tid < 32) {
     const int lane = tid, k = lane & 7;
@@ -332,35 +365,59 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
   }
   __syncthreads();
 
-  // ---- phase 3: replay every chunk from its boundary state, write per-column states ----
-  for (int c = tid; c < nC + 1; c += kBandThreads) {
-    double v[8];
-    load8(VB + (size_t)c * 8, v);
-    int frame = VBo[c];
-    if (!dir) {
-      const int t_lo = min(c * L, Tb);    // column of this boundary state
-      const int t_hi = min(t_lo + L, Tb);
-      store_state(v, frame, out_v + (size_t)t_lo * kBandR, out_o + t_lo);
-      if (c == nC) continue;
-      for (int t = t_lo; t < t_hi - 1; ++t) {      // the last column of the chunk belongs to the next boundary
-        fwd_step(tb, t, v);
-        const int e = normalise8(v);
-        frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
-        store_state(v, frame, out_v + (size_t)(t + 1) * kBandR, out_o + t + 1);
-      }
+  BAND_T(3);
+  // ---- phase 3: every column in parallel: state = (recorded images of its chunk) x (boundary state) ----
+  __threadfence_block();
+  for (int t = tid; t <= Tb; t += kBandThreads) {
+    // chunk whose boundary state feeds column t, and whether t is that boundary itself
+    const int dist = dir ? Tb - t : t;                 // transitions between the direction's start column and t
+    const int c = (dist == 0) ? 0 : (dist - 1) / L;    // column t is produced by a transition of chunk c ...
+    const bool boundary_col = (dist % L == 0) || (dist == Tb);   // ... or is a stored boundary state
+    double y[8];
+    int frame;
+    if (boundary_col) {
+      const int cb = (dist == Tb) ? nC : dist / L;
+      load8(VB + (size_t)cb * 8, y);
+      frame = VBo[cb];
     } else {
-      const int t_hi = max(Tb - c * L, 0);   // column of this boundary state
-      const int t_lo = max(t_hi - L, 0);
-      store_state(v, frame, out_v + (size_t)t_hi * kBandR, out_o + t_hi);
-      if (c == nC) continue;
-      for (int t = t_hi - 1; t > t_lo; --t) {
-        bwd_step(tb, t, v);
-        const int e = normalise8(v);
-        frame = (e == kDeadFrame || frame <= kDeadFrame / 2) ? kDeadFrame : frame + e;
-        store_state(v, frame, out_v + (size_t)t * kBandR, out_o + t);
+      double x[8];
+      load8(VB + (size_t)c * 8, x);
+      const int fx = VBo[c];
+      const float *img = p.img + ((size_t)(b * 2 + dir) * (T + 1) + t) * 64;
+      const int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1) + t) * 8;
+      int fj[8], E = kDeadFrame;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        fj[j] = (x[j] > 0.0) ? imf[j] : kDeadFrame;
+        E = max(E, fj[j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = 0.0;
+      if (E > kDeadFrame / 2 && fx > kDeadFrame / 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double xs = (fj[j] > kDeadFrame / 2) ? x[j] * pow2d(fj[j] - E) : 0.0;
+          const float4 lo = *reinterpret_cast<const float4 *>(img + j * 8);
+          const float4 hi = *reinterpret_cast<const float4 *>(img + j * 8 + 4);
+          y[0] = fma(xs, (double)lo.x, y[0]); y[1] = fma(xs, (double)lo.y, y[1]);
+          y[2] = fma(xs, (double)lo.z, y[2]); y[3] = fma(xs, (double)lo.w, y[3]);
+          y[4] = fma(xs, (double)hi.x, y[4]); y[5] = fma(xs, (double)hi.y, y[5]);
+          y[6] = fma(xs, (double)hi.z, y[6]); y[7] = fma(xs, (double)hi.w, y[7]);
+        }
+        const int e = normalise8(y);
+        frame = (e == kDeadFrame) ? kDeadFrame : fx + E + e;
+      } else {
+        frame = kDeadFrame;
       }
     }
+    store_state(y, frame, out_v + (size_t)t * kBandR, out_o + t);
   }
+  BAND_T(4);
+#ifdef FRN_BAND_TIMING
+  if (tid == 0 && blockIdx.x == 0)
+    printf("band_dp dir %d Tb %d: tables %lld, unit vectors %lld, boundary walk %lld, columns %lld cycles\n", dir, Tb,
+           tclk[1] - tclk[0], tclk[2] - tclk[1], tclk[3] - tclk[2], tclk[4] - tclk[3]);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -452,11 +509,13 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
 // ---------------------------------------------------------------------------
 size_t band_dp_workspace_bytes(int B, int T) {
   return 2 * round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(double), 256) +
-         2 * round_up_sz((size_t)B * (T + 1) * sizeof(int), 256);
+         2 * round_up_sz((size_t)B * (T + 1) * sizeof(int), 256) +
+         round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(float), 256) +
+         round_up_sz((size_t)B * 2 * (T + 1) * 8 * sizeof(int), 256);
 }
 
 static int band_chunk_len(int T) {
-  for (int L = 16; L <= 256; L <<= 1)
+  for (int L = kBandMinChunk; L <= 256; L <<= 1)
     if ((T + L - 1) / L * 8 <= kBandThreads && band_smem_bytes(T, L) <= 220 * 1024) return L;
   return 0;
 }
@@ -473,6 +532,8 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
   p.pxc = pxc; p.pyc = pyc; p.ranges = ranges; p.boundary = boundary;
   p.va = reinterpret_cast<double *>(w); p.ub = reinterpret_cast<double *>(w + nv);
   p.oa = reinterpret_cast<int *>(w + 2 * nv); p.ob = reinterpret_cast<int *>(w + 2 * nv + no);
+  p.img = reinterpret_cast<float *>(w + 2 * nv + 2 * no);
+  p.img_frame = reinterpret_cast<int *>(w + 2 * nv + 2 * no + round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(float), 256));
   p.S = S; p.T = T; p.R = R; p.modified = (rnnt_type != FRN_REGULAR); p.rnnt_type = rnnt_type;
   p.delay_penalty = delay_penalty;
   p.L = band_chunk_len(T);
