@@ -158,6 +158,22 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_sym + TN);             // raw_full[2], mma_done
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
 
+  // The raw tiles do not depend on the row statistics: the first two slices are requested before
+  // anything else so that their (cold) latency hides behind the set-up loads below.
+  auto issue_tma = [&](int k, int stage) {
+    unsigned char *raw = smem + kOffRaw + stage * kRawStage;
+    mbar_arrive_expect_tx(&bars[stage], kRawStage);
+    tma_load_3d(raw, &map_am, &bars[stage], k * KC, t0, b);
+    tma_load_3d(raw + kRawAmBytes, &map_lm, &bars[stage], k * KC, s0, b);
+  };
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_am) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lm) : "memory");
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    issue_tma(0, 0);
+    if (nk > 1) issue_tma(1, 1);
+  }
   const float *lmb = p.lm + (size_t)b * S1 * C;
   const float *amb = p.am + (size_t)b * p.T * C;
   if (tid < TM) {
@@ -184,10 +200,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     s_lmmax[j] = lmmax; s_lmneg[j] = (s < S1) ? -lmmax * kLog2e : -INFINITY;
     s_pxlm[j] = pxlm; s_pylm[j] = pylm; s_lmonly[j] = lmonly; s_logusym[j] = logus; s_sym[j] = sym;
   }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
-    mbar_fence_init();
-  }
   if (w == 0) tmem_alloc(s_tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -195,16 +207,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   const uint32_t tmem_d = *s_tmem;
   TCT(1);
 
-  auto issue_tma = [&](int k, int stage) {
-    unsigned char *raw = smem + kOffRaw + stage * kRawStage;
-    mbar_arrive_expect_tx(&bars[stage], kRawStage);
-    tma_load_3d(raw, &map_am, &bars[stage], k * KC, t0, b);
-    tma_load_3d(raw + kRawAmBytes, &map_lm, &bars[stage], k * KC, s0, b);
-  };
-  if (tid == 0) {
-    issue_tma(0, 0);
-    if (nk > 1) issue_tma(1, 1);
-  }
   // epilogue mapping, also used inside the k loop: thread <-> frame (TMEM lane), the four
   // warps of a lane quarter take 28 symbol columns each
   const int q = w & 3, half = w >> 2;            // `half` = column part 0..3
