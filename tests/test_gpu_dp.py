@@ -109,3 +109,86 @@ def test_cummin_bit_exact():
         assert np.array_equal(out, np.minimum.accumulate(x, axis=1))
         assert np.array_equal(out, orc.cummin(x))
         assert np.array_equal(out, ref.cummin(x))
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+@pytest.mark.parametrize("R", [1, 3, 5, 8])
+@pytest.mark.parametrize("jumpy", [False, True])
+def test_band_recursion_equals_dense_lattice(rnnt_type, R, jumpy):
+    """frn_band_mi_fwd_bwd (the recursion on the [B,T,R] band, what rnnt_loss_pruned runs) against the
+    float64 oracle on the dense lattice the reference builds from the band (rnnt_loss.py:968-1018):
+    same scores, and band occupation counts = dense occupation counts gathered back onto the band.
+    `jumpy` bands move up by R-1 rows in single frames (every row but one leaves the band)."""
+    import torch
+    from tf_fast_rnnt import _lib
+    lib = _lib.lib
+    B, S, T = 3, 40, 90
+    rng = np.random.default_rng([R, int(jumpy), len(rnnt_type)])
+    bd = np.array([[0, 0, S, T], [0, 0, S - 7, T - 11], [0, 3, S - 1, T - 1]], np.int32)[:B]
+    # bands as get_rnnt_prune_ranges guarantees them: monotone, starting at s_begin, steps < R (one
+    # utterance deliberately violates that when R == 1), parked at s_end - R + 1 from frame t_end - 1 on
+    r0 = np.zeros((B, T), np.int64)
+    for b in range(B):
+        t_b, s_e, t_e = bd[b, 1], bd[b, 2], bd[b, 3]
+        target = max(s_e - R + 1, 0)
+        step = max(R - 1, 1) if jumpy else 1
+        njump = -(-target // step)
+        frames = np.arange(t_b + 1, t_e - 1)
+        inc = np.zeros(T, np.int64)
+        if njump <= len(frames):
+            inc[rng.choice(frames, njump, replace=False)] = step
+        else:
+            inc[frames] = step
+        r0[b] = np.minimum(np.cumsum(inc), target)
+        r0[b, t_e - 1:] = target
+    ranges = (r0[:, :, None] + np.arange(R)[None, None, :]).astype(np.int32)
+    pxc = (rng.standard_normal((B, T, R)) * 2 - 3).astype(np.float32)
+    pyc = (rng.standard_normal((B, T, R)) * 2 - 1).astype(np.float32)
+    rt = _lib.RNNT_TYPES[rnnt_type]
+    dev = torch.device("cuda")
+    d = lambda a: torch.from_numpy(a).to(dev)
+    pxc_d, pyc_d, rg_d, bd_d = d(pxc), d(pyc), d(ranges), d(bd)
+    n = lib.frn_band_mi_workspace_bytes(B, S, T, R)
+    assert n > 0
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    ans = torch.empty(B, device=dev)
+    gxc, gyc = torch.empty(B, T, R, device=dev), torch.empty(B, T, R, device=dev)
+    _lib.check(lib.frn_band_mi_fwd_bwd(pxc_d.data_ptr(), pyc_d.data_ptr(), rg_d.data_ptr(), bd_d.data_ptr(), B, S, T, R,
+                                       rt, 0.0, 1, ans.data_ptr(), gxc.data_ptr(), gyc.data_ptr(), ws.data_ptr(), n,
+                                       torch.cuda.current_stream().cuda_stream), "band_mi")
+    # dense lattice from the band, in numpy (the scatter of get_rnnt_logprobs_pruned)
+    T1 = T + 1 if rnnt_type == "regular" else T
+    px = np.full((B, S, T1), -np.inf, np.float32)
+    py = np.full((B, S + 1, T), -np.inf, np.float32)
+    for b in range(B):
+        for t in range(T):
+            for i in range(R):
+                s = ranges[b, t, i]
+                if s <= S:
+                    py[b, s, t] = pyc[b, t, i]
+                if s < S:
+                    v = pxc[b, t, i]
+                    if rnnt_type == "constrained":
+                        v = v + (pyc[b, t, i + 1] if i + 1 < R else -np.inf)
+                    px[b, s, t] = v
+        if rnnt_type == "regular":
+            px[b, :, bd[b, 3]] = -np.inf
+    o_ans, (o_gx, o_gy) = orc.mutual_information_recursion(px, py, bd, True, np.float64)
+    assert_close(ans.cpu().numpy(), o_ans, LOSS_RTOL, 1e-5, "band score")
+    ok = np.isfinite(o_ans)
+    gxc, gyc = gxc.cpu().numpy(), gyc.cpu().numpy()
+    for b in np.nonzero(ok)[0]:
+        for t in range(T):
+            for i in range(R):
+                s = ranges[b, t, i]
+                want_x = o_gx[b, s, t] if s < S else 0.0
+                want_y = o_gy[b, s, t] if s <= S else 0.0
+                if rnnt_type == "constrained" and i >= 1:
+                    want_y += o_gx[b, s - 1, t]        # that px arc borrowed this py entry
+                assert abs(gxc[b, t, i] - want_x) <= GRAD_ATOL + GRAD_RTOL * abs(want_x), (b, t, i, "px")
+                assert abs(gyc[b, t, i] - want_y) <= GRAD_ATOL + GRAD_RTOL * abs(want_y), (b, t, i, "py")
+    only = torch.empty(B, device=dev)
+    _lib.check(lib.frn_band_mi_fwd_bwd(pxc_d.data_ptr(), pyc_d.data_ptr(), rg_d.data_ptr(), bd_d.data_ptr(), B, S, T, R,
+                                       rt, 0.0, 0, only.data_ptr(), None, None, ws.data_ptr(), n,
+                                       torch.cuda.current_stream().cuda_stream), "band_mi")
+    assert torch.equal(only, ans)
