@@ -136,10 +136,14 @@ def run_reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------
 class Pipeline:
-    """Pre-allocated device buffers + the C-ABI call sequence of one step."""
+    """Pre-allocated device buffers + the C-ABI call sequence of one step.
 
+    `nsplit` > 1 runs the step as that many independent sub-batches, each on its own CUDA stream
+    (utterances are independent in every kernel): the dependency-chain-bound kernels of one
+    sub-batch (lattice recursions, normaliser) overlap the bandwidth-bound kernels of another.
+    Same calls, same results; the two loss sums are reduced over the whole batch at the end."""
 
-    def __init__(self, B, T, S, C, R, dev):
+    def __init__(self, B, T, S, C, R, dev, nsplit=1):
         import torch
         from tf_fast_rnnt import _lib
         self.torch, self.lib, self._lib = torch, _lib.lib, _lib
@@ -153,27 +157,42 @@ class Pipeline:
         self.logits, self.dlogits = e(B, T, R, C), e(B, T, R, C)
         self.losses = e(2)
         self.sgrad = torch.full((B,), -1.0, dtype=f32, device=dev)  # d(sum loss)/d scores
-        lib = self.lib
-        self.ws_simple = torch.empty(lib.frn_simple_loss_workspace_bytes(B, S, T, C), dtype=torch.uint8, device=dev)
-        self.ws_prune = torch.empty(lib.frn_prune_ranges_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
-        self.ws_pruned = torch.empty(lib.frn_pruned_loss_workspace_bytes(B, S, T, R), dtype=torch.uint8, device=dev)
+        self.full = self._part(0, B)
+        self.ws_pruned = self.full["ws_pruned"]
+        nsplit = max(1, min(nsplit, B))
+        self.parts, self.streams = [], []
+        if nsplit > 1:
+            edges = [round(i * B / nsplit) for i in range(nsplit + 1)]
+            self.parts = [self._part(edges[i], edges[i + 1] - edges[i]) for i in range(nsplit)]
+            self.streams = [torch.cuda.Stream(dev) for _ in range(nsplit)]
 
-    def stages(self, am, lm, sym, bd):
+    def _part(self, b0, Bh):
+        lib, T, S, C, R, dev = self.lib, self.T, self.S, self.C, self.R, self.dev
+        u8 = lambda n: self.torch.empty(max(int(n), 256), dtype=self.torch.uint8, device=dev)
+        return {"b0": b0, "B": Bh,
+                "ws_simple": u8(lib.frn_simple_loss_workspace_bytes(Bh, S, T, C)),
+                "ws_prune": u8(lib.frn_prune_ranges_workspace_bytes(Bh, T)),
+                "ws_pruned": u8(lib.frn_pruned_loss_workspace_bytes(Bh, S, T, R))}
+
+    def stages(self, am, lm, sym, bd, part=None, with_reduce=True):
         """List of (name, algorithmic bytes, callable) — SURVEY.md §8(d) byte counts."""
-        lib, B, T, S, C, R = self.lib, self.B, self.T, self.S, self.C, self.R
-        p = lambda t: t.data_ptr()
+        part = part or self.full
+        lib, T, S, C, R = self.lib, self.T, self.S, self.C, self.R
+        b0, B = part["b0"], part["B"]
+        p = lambda t: t.data_ptr() + b0 * t.stride(0) * t.element_size()     # sub-batch view of a [B,...] tensor
         term = C - 1
         st = lambda: self.torch.cuda.current_stream(self.dev).cuda_stream
         chk = self._lib.check
         n_logits = B * T * R * C
-        return [
+        ws_s, ws_p, ws_q = part["ws_simple"], part["ws_prune"], part["ws_pruned"]
+        out = [
             ("simple_loss", 4 * B * ((T + S + 1) * C + 2 * (S * (T + 1) + (S + 1) * T)),
              lambda: chk(lib.frn_simple_loss(p(lm), p(am), p(sym), p(bd), B, S, T, C, term, 0, 0, 0.0, 0.0, 0.0, 1,
-                                             p(self.scores), p(self.gx), p(self.gy), p(self.ws_simple),
-                                             self.ws_simple.numel(), st()), "simple_loss")),
+                                             p(self.scores), p(self.gx), p(self.gy), ws_s.data_ptr(), ws_s.numel(),
+                                             st()), "simple_loss")),
             ("prune_ranges", 4 * B * (S * (T + 1) + (S + 1) * T) + 4 * B * T * R,
              lambda: chk(lib.frn_prune_ranges(p(self.gx), p(self.gy), p(bd), B, S, T, T + 1, R, p(self.ranges),
-                                              p(self.ws_prune), self.ws_prune.numel(), st()), "prune_ranges")),
+                                              ws_p.data_ptr(), ws_p.numel(), st()), "prune_ranges")),
             ("do_pruning", 4 * B * (T * C + (S + 1) * C + T * R) + 8 * n_logits,
              lambda: chk(lib.frn_do_pruning(p(am), p(lm), p(self.ranges), B, S, T, R, C, p(self.am_p),
                                             p(self.lm_p), st()), "do_pruning")),
@@ -183,15 +202,33 @@ class Pipeline:
             ("pruned_loss", 4 * n_logits + 8 * B * T * R + 8 * n_logits + 16 * B * T * R,
              lambda: chk(lib.frn_pruned_loss(p(self.logits), 0, p(sym), p(self.ranges), p(bd), B, S, T, R, C, term,
                                              0, 0.0, p(self.sgrad), p(self.pscores), p(self.dlogits),
-                                             p(self.ws_pruned), self.ws_pruned.numel(), st()), "pruned_loss")),
-            ("reduce", 8 * B,
-             lambda: (chk(lib.frn_reduce(p(self.scores), B, 2, 0.0, p(self.losses), st()), "reduce"),
-                      chk(lib.frn_reduce(p(self.pscores), B, 2, 0.0, p(self.losses) + 4, st()), "reduce"))),
+                                             ws_q.data_ptr(), ws_q.numel(), st()), "pruned_loss")),
         ]
+        if with_reduce:
+            out.append(("reduce", 8 * self.B, self._reduce))
+        return out
+
+    def _reduce(self):
+        lib, chk, B = self.lib, self._lib.check, self.B
+        st = self.torch.cuda.current_stream(self.dev).cuda_stream
+        chk(lib.frn_reduce(self.scores.data_ptr(), B, 2, 0.0, self.losses.data_ptr(), st), "reduce")
+        chk(lib.frn_reduce(self.pscores.data_ptr(), B, 2, 0.0, self.losses.data_ptr() + 4, st), "reduce")
 
     def step(self, am, lm, sym, bd):
-        for _, _, fn in self.stages(am, lm, sym, bd):
-            fn()
+        torch = self.torch
+        if not self.parts:
+            for _, _, fn in self.stages(am, lm, sym, bd):
+                fn()
+            return
+        main = torch.cuda.current_stream(self.dev)
+        for part, s in zip(self.parts, self.streams):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                for _, _, fn in self.stages(am, lm, sym, bd, part, with_reduce=False):
+                    fn()
+        for s in self.streams:
+            main.wait_stream(s)
+        self._reduce()
 
 
 def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=5):
@@ -345,7 +382,7 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, T, S, C, R = WORKLOADS[args.workload]
-    pipe = Pipeline(B, T, S, C, R, dev)
+    pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams)
 
     # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
     # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
@@ -522,6 +559,7 @@ def run_gpu_arm(args):
             "workload": f"{args.workload}: full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning -> additive "
                         f"joiner -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
             "launch": "cuda_graph" if use_graph else "direct",
+            "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step",
             "l2": f"{NSETS} rotating input sets ({NSETS * h2d / 1e6:.0f} MB) + ~1.1 GB of streamed intermediates per step (> 126 MB L2)",
             "sharding": "utterances sharded across ranks, one 2-float NCCL all-reduce per step" if world > 1 else "single GPU",
             "loss_check": loss_check,
@@ -546,7 +584,8 @@ def run_gpu_arm(args):
         line["cpu_baseline"] = base
     if world == 1 and not args.no_ref_gpu:
         try:
-            pipe.step(*dev_sets[0])             # leaves ranges / logits of this input set in the pipeline buffers
+            for _, _, fn in pipe.stages(*dev_sets[0]):   # whole batch, one stream: leaves ranges / logits /
+                fn()                                     # band log-probs of this input set in the buffers
             ref_leg = reference_gpu_op_leg(pipe, *dev_sets[0])
             if ref_leg is not None:
                 line["reference_gpu_op"] = ref_leg
@@ -565,6 +604,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="run a step as this many independent sub-batches on separate CUDA streams")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA op")
     args = ap.parse_args()
