@@ -39,6 +39,38 @@ def test_partition_is_a_balanced_exact_cover():
     assert partition_batch(bd, 2)[0].tolist() == partition_batch(bd, 2)[0].tolist()   # deterministic
 
 
+def test_bucket_plan_covers_the_shard_and_cuts_padding():
+    from tf_fast_rnnt.sharding import plan_buckets
+    rng = np.random.default_rng(1)
+    B = 64
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 3] = rng.integers(200, 1501, B)                      # config c5: T 200-1500
+    bd[:, 2] = np.minimum(rng.integers(20, 401, B), bd[:, 3])
+    one = plan_buckets(bd, 5, 500, max_buckets=1)
+    assert len(one) == 1 and one[0]["T_max"] == bd[:, 3].max() and one[0]["padded_frames"] == B * bd[:, 3].max()
+    plan = plan_buckets(bd, 5, 500, max_buckets=4, min_bucket=4)
+    assert 1 <= len(plan) <= 4
+    allidx = np.concatenate([g["idx"] for g in plan])
+    assert sorted(allidx.tolist()) == list(range(B))          # exact cover
+    for g in plan:
+        assert len(g["idx"]) >= 4
+        assert g["T_max"] == bd[g["idx"], 3].max() and g["S_max"] == bd[g["idx"], 2].max()
+        assert g["bytes"] == 20 * g["padded_frames"] * 5 * 500
+    # buckets are contiguous in T: every utterance of a later bucket is no longer than any of an earlier one
+    for a, b in zip(plan, plan[1:]):
+        assert bd[a["idx"], 3].min() >= bd[b["idx"], 3].max()
+    padded = sum(g["padded_frames"] for g in plan)
+    assert padded < 0.75 * one[0]["padded_frames"]             # uniform T in [200,1500]: 4 buckets save > 25 %
+    assert padded >= int(bd[:, 3].sum())                       # never below the unpadded frame count
+    # optimality against brute force on a small case
+    small = bd[:10]
+    best = plan_buckets(small, 5, 500, max_buckets=2, min_bucket=1)
+    Ts = np.sort(small[:, 3])[::-1]
+    brute = min(i * Ts[0] + (10 - i) * Ts[i] for i in range(1, 10))
+    assert sum(g["padded_frames"] for g in best) == min(brute, 10 * Ts[0])
+    assert plan_buckets(np.zeros((0, 4), np.int32), 5, 500) == []
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

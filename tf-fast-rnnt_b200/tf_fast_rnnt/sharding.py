@@ -45,6 +45,60 @@ def shard_max_shapes(boundary: np.ndarray, idx: Sequence[int]):
     return int(b[:, 2].max()), int(b[:, 3].max())
 
 
+def plan_buckets(boundary: np.ndarray, s_range: int, vocab: int, max_buckets: int = 4,
+                 min_bucket: int = 4):
+    """Batch scheduler for ragged shards: split a shard into at most
+    ``max_buckets`` length buckets so that the bandwidth-bound kernels do not stream
+    padding.  The lattice recursions already stop at each utterance's own (S_b, T_b); what
+    padding costs is bytes: ``do_rnnt_pruning``, the joiner and the pruned log-softmax touch
+    ``T_max * s_range * vocab`` elements per utterance whatever T_b is.
+
+    Utterances are sorted by T_b and cut by dynamic programming into contiguous groups that
+    minimise  sum_g |g| * T_max(g)  (the padded frame count, proportional to the bytes of
+    those kernels), subject to ``len(g) >= min_bucket`` (each bucket is one more set of kernel
+    launches; tiny buckets cannot fill the GPU).  Returns a list of dicts
+    ``{"idx", "S_max", "T_max", "padded_frames", "bytes"}`` ordered by decreasing T_max;
+    ``bytes`` estimates the pruned-path traffic of the bucket (SURVEY.md §8d:
+    20 bytes per [t, i, c] element for pruning + joiner + log-softmax + logits gradient)."""
+    b = np.asarray(boundary, dtype=np.int64)
+    n = len(b)
+    if n == 0:
+        return []
+    order = np.argsort(-b[:, 3], kind="stable")             # decreasing T_b: a group's T_max is its first element
+    T_sorted = b[order, 3]
+    k_max = max(1, min(max_buckets, n // max(min_bucket, 1) or 1))
+    INF = float("inf")
+    # cost[k][j] = minimal padded frames covering the first j utterances with k groups
+    cost = np.full((k_max + 1, n + 1), INF)
+    back = np.zeros((k_max + 1, n + 1), dtype=np.int64)
+    cost[0, 0] = 0.0
+    for k in range(1, k_max + 1):
+        for j in range(1, n + 1):
+            for i in range(0, j):
+                if j - i < min_bucket and not (k == 1 and i == 0):
+                    continue
+                if cost[k - 1, i] == INF:
+                    continue
+                c = cost[k - 1, i] + (j - i) * T_sorted[i]
+                if c < cost[k, j]:
+                    cost[k, j] = c
+                    back[k, j] = i
+    k_best = int(np.argmin(cost[1:, n])) + 1
+    cuts, j = [], n
+    for k in range(k_best, 0, -1):
+        i = int(back[k, j])
+        cuts.append((i, j))
+        j = i
+    out = []
+    for i, j in reversed(cuts):
+        idx = order[i:j]
+        t_max, s_max = int(b[idx, 3].max()), int(b[idx, 2].max())
+        frames = int(len(idx) * t_max)
+        out.append({"idx": np.sort(idx), "S_max": s_max, "T_max": t_max, "padded_frames": frames,
+                    "bytes": int(20 * frames * s_range * vocab)})
+    return out
+
+
 def allreduce_loss(local_sum, local_count: int, reduction: str, group=None):
     """Complete 'sum' / 'mean' over the ranks of ``group`` from per-rank partial
     sums of the per-utterance losses.  ``local_sum`` is a 0-d/1-element torch
