@@ -396,9 +396,28 @@ def run_gpu_arm(args):
     host_out = torch.empty(2, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
+    # reduction='sum' across ranks: one 2-float NCCL all-reduce per step.  It runs on its own stream on
+    # a copy of the two sums, so the next step's kernels never wait for the collective (only for the
+    # 8-byte copy); the timed regions end with a barrier + synchronize over all streams.
+    red_stream = torch.cuda.Stream(dev) if world > 1 else None
+    red_bufs = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(2)]
+    red_copied = torch.cuda.Event()
+    red_n = [0]
+
     def allreduce_losses():
-        if world > 1:
-            dist.all_reduce(pipe.losses)
+        """-> (tensor holding the completed sums, stream it becomes valid on)"""
+        main = torch.cuda.current_stream(dev)
+        if world == 1:
+            return pipe.losses, main
+        buf = red_bufs[red_n[0] % 2]
+        red_n[0] += 1
+        red_stream.wait_stream(main)
+        with torch.cuda.stream(red_stream):
+            buf.copy_(pipe.losses)
+            red_copied.record(red_stream)
+            dist.all_reduce(buf)
+        main.wait_event(red_copied)
+        return buf, red_stream
 
     # kernels per step, counted by the library itself while one step is enqueued
     n0 = pipe.lib.frn_kernel_launches()
@@ -458,7 +477,7 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    loss_check = pipe.losses.cpu().tolist()
+    loss_check = (red_bufs[(red_n[0] - 1) % 2] if world > 1 else pipe.losses).cpu().tolist()
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses ----
     # Direct C-ABI launches (no graph).  Two landing buffers: the H2D copy of step i+1 (copy stream)
@@ -482,9 +501,10 @@ def run_gpu_arm(args):
             h2d_done[k].record(copy_stream)
         cur.wait_event(h2d_done[k])
         pipe.step(*stage_bufs[k])
-        allreduce_losses()
-        host_outs[k].copy_(pipe.losses, non_blocking=True)
-        step_done[k].record(cur)
+        res, res_stream = allreduce_losses()
+        with torch.cuda.stream(res_stream):
+            host_outs[k].copy_(res, non_blocking=True)
+            step_done[k].record(res_stream)
         if i > 0:                                           # the caller reads the previous step's loss
             step_done[(i - 1) % NBUF].synchronize()
             read_back.append(float(host_outs[(i - 1) % NBUF][0]))
