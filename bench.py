@@ -536,6 +536,48 @@ def run_gpu_arm(args):
     e2e_ms_per_step = float(t.item()) / args.steps
     h2d = sum(h.numel() * h.element_size() for h in host_sets[0])
 
+    # ---- extra (not the headline): the same step with the fused additive joiner of SURVEY.md §8(f)-2,
+    #      frn_pruned_add_joiner, in place of do_rnnt_pruning + add: am_pruned / lm_pruned never exist ----
+    fused_ms = None
+    if world == 1:
+        try:
+            lib, chk = pipe.lib, pipe._lib.check
+            ptr = lambda t: t.data_ptr()
+            sfn = lambda: torch.cuda.current_stream(dev).cuda_stream
+
+            def fused_step(am, lm, sym, bd):
+                st = pipe.stages(am, lm, sym, bd)
+                st[0][2](); st[1][2]()                                   # simple loss, prune ranges
+                chk(lib.frn_pruned_add_joiner(ptr(am), ptr(lm), ptr(pipe.ranges), B, S, T, R, C, 0, ptr(pipe.logits),
+                                              sfn()), "pruned_add_joiner")
+                st[4][2](); st[5][2]()                                   # pruned loss, reductions
+
+            fgraphs = []
+            with torch.cuda.stream(side):
+                fused_step(*dev_sets[0])
+                side.synchronize()
+                if use_graph:
+                    for i in range(NSETS):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            fused_step(*dev_sets[i])
+                        fgraphs.append(g)
+            torch.cuda.synchronize()
+            frun = (lambda i: fgraphs[i % NSETS].replay()) if fgraphs else (lambda i: fused_step(*dev_sets[i % NSETS]))
+            for i in range(3):
+                frun(i)
+            torch.cuda.synchronize()
+            fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = max(20, min(args.steps, 200))
+            fa.record()
+            for i in range(nrep):
+                frun(i)
+            fb.record()
+            torch.cuda.synchronize()
+            fused_ms = fa.elapsed_time(fb) / nrep
+        except Exception as e:  # noqa: BLE001
+            fused_ms = repr(e)
+
     # ---- per-stage device times (outside the timed region) -> roofline of the dominant kernel ----
     stage_ms = {}
     for name, nbytes, fn in pipe.stages(*dev_sets[0]):
@@ -598,6 +640,12 @@ def run_gpu_arm(args):
         "stages_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in stage_ms.items()},
         "lattice_cells_per_s": cells / (stage_ms["simple_loss"][0] * 1e-3),
     }
+    if fused_ms is not None:
+        line["fused_joiner_variant"] = {
+            "ms_per_step": fused_ms, "launch": "cuda_graph" if use_graph else "direct",
+            "utterances_per_s": (B / (fused_ms * 1e-3)) if isinstance(fused_ms, float) else None,
+            "what": "same step with frn_pruned_add_joiner instead of do_rnnt_pruning + add (SURVEY.md 8f-2); "
+                    "not the headline: the reference API materialises am_pruned / lm_pruned"}
     if world == 1 and not args.no_cpu:
         sample_B = 8 if args.workload == "c2" else None
         base, _ = cpu_bench(args.workload, 2, 1, sample_B)

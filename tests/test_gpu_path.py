@@ -235,3 +235,23 @@ def test_simple_loss_am_lm_gradients(rnnt_type):
     o_am1, o_lm1 = orc.simple_am_lm_grad(lm, am, sym, term, bd, rnnt_type, 0.2, None, np.float64)
     assert_close(am_t.grad.cpu().numpy(), o_am1, GRAD_RTOL, 2e-6, "autograd am grad")
     assert_close(lm_t.grad.cpu().numpy(), o_lm1, GRAD_RTOL, 2e-5, "autograd lm grad")
+
+
+@pytest.mark.parametrize("C", [500, 37])          # vector path (C % 4 == 0) and scalar path
+def test_fused_joiner_equals_pruning_plus_add(C):
+    """frn_pruned_add_joiner (SURVEY 8f-2) == do_rnnt_pruning followed by the addition, bit for bit;
+    out-of-range band entries contribute zeros like tf.gather on GPU."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, R = 3, 40, 12, 5
+    rng = np.random.default_rng(C)
+    am = rng.standard_normal((B, T, C), dtype=np.float32)
+    lm = rng.standard_normal((B, S + 1, C), dtype=np.float32)
+    r0 = np.sort(rng.integers(0, S + 2 - R, (B, T)), axis=1)
+    ranges = (r0[:, :, None] + np.arange(R)[None, None, :]).astype(np.int32)
+    ranges[0, 3, 4] = S + 5                        # out of range: zeros
+    am_d, lm_d, rg_d = (torch.from_numpy(x).cuda() for x in (am, lm, ranges))
+    am_p, lm_p = frn.do_rnnt_pruning(am_d, lm_d, rg_d)
+    fused = frn.pruned_add_joiner(am_d, lm_d, rg_d)
+    assert torch.equal(fused, am_p + lm_p)
+    assert torch.equal(fused[0, 3, 4], am_d[0, 3])

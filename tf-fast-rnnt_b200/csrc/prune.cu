@@ -280,6 +280,35 @@ __global__ void __launch_bounds__(256) pruned_add_joiner_kernel(const float *am,
   }
 }
 
+// float32 vector path of the fused joiner: one CTA of 128 threads per (b,t), thread <-> one
+// float4 column, the am row and all R lm rows loaded before the R streaming stores.
+template <int RMAX>
+__global__ void __launch_bounds__(128) pruned_add_joiner_vec_kernel(const float *am, const float *lm,
+                                                                    const int32_t *ranges, int T, int S1, int R,
+                                                                    int C4, float *logits) {
+  const int bt = blockIdx.x;
+  const int b = bt / T;
+  const int32_t *rg = ranges + (size_t)bt * R;
+  const float4 *am_row = reinterpret_cast<const float4 *>(am) + (size_t)bt * C4;
+  float4 *out = reinterpret_cast<float4 *>(logits) + (size_t)bt * R * C4;
+  const float4 *lm_b = reinterpret_cast<const float4 *>(lm) + (size_t)b * S1 * C4;
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+    const float4 a = __ldg(am_row + c);
+    float4 l[RMAX];
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      if (i < R) {
+        const int s = rg[i];
+        l[i] = (s >= 0 && s < S1) ? __ldg(lm_b + (size_t)s * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      if (i < R) st_stream_f4(out + (size_t)i * C4 + c, make_float4(a.x + l[i].x, a.y + l[i].y, a.z + l[i].z, a.w + l[i].w));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -344,6 +373,13 @@ int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const 
 int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
                              int C, int out_dtype, void *logits, cudaStream_t stream) {
   const int BT = B * T;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) |
+                                     reinterpret_cast<uintptr_t>(logits)) % 16 == 0);
+  if (out_dtype == FRN_F32 && vec && R <= 8) {
+    count_launch(), pruned_add_joiner_vec_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4,
+                                                                         static_cast<float *>(logits));
+    return check_launch();
+  }
   if (out_dtype == FRN_F32)
     count_launch(), pruned_add_joiner_kernel<float><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C,
                                                                       static_cast<float *>(logits));
