@@ -11,6 +11,16 @@ from tests.helpers import (GRAD_ATOL, GRAD_RTOL, LOSS_RTOL, RefKernels, assert_c
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["chain", "scan"], autouse=True)
+def dp_kernel(request, monkeypatch):
+    """Every test of this module runs with both dense-lattice recursions: the wavefront chain
+    (mi_dp.cu) and the row scan (mi_scan.cu); the library picks by shape otherwise."""
+    monkeypatch.delenv("FRN_DP_CHAIN", raising=False)
+    monkeypatch.delenv("FRN_DP_SCAN", raising=False)
+    monkeypatch.setenv("FRN_DP_CHAIN" if request.param == "chain" else "FRN_DP_SCAN", "1")
+    return request.param
+
+
 def _boundaries(rng, B, S, T, kind):
     bd = np.zeros((B, 4), np.int32)
     bd[:, 2], bd[:, 3] = S, T

@@ -69,6 +69,9 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, in
   DpGeom g = make_geom(B, S, T, T1);
   if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   if (!workspace || !aligned256(workspace) || workspace_bytes < carve_dp(nullptr, g).bytes) return FRN_EWORKSPACE;
+  if (scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= workspace_bytes)
+    return launch_scan_dp(px, py, boundary, B, S, T, T1, 0.f, calc_gradients != 0, workspace, ans, px_grad, py_grad,
+                          stream);
   DpWorkspace w = carve_dp(workspace, g);
   FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
   FRN_TRY(launch_chain(boundary, g, w, calc_gradients != 0, stream));
@@ -206,6 +209,9 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
   DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
                                  lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream));
+  if (scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= dw.bytes)
+    return launch_scan_dp(w.px, w.py, boundary, B, S, T, T1, delay_penalty > 0.f ? delay_penalty : 0.f,
+                          calc_gradients != 0, w.dp, scores, px_grad, py_grad, stream);
   FRN_TRY(launch_skew_dense(w.px, w.py, boundary, g, dw, delay_penalty > 0.f ? delay_penalty : 0.f, stream));
   FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
   FRN_TRY(launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,

@@ -10,6 +10,12 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
                  cudaStream_t stream);
 int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, float *ans,
                           float *px_grad, float *py_grad, cudaStream_t stream);
+// mi_scan.cu
+bool scan_dp_supported(int S, int T);
+size_t scan_dp_workspace_bytes(int B, int S, int T);
+int launch_scan_dp(const float *px, const float *py, const int32_t *boundary, int B, int S, int T, int T1,
+                   float delay_penalty, bool want_grad, void *workspace, float *ans, float *px_grad,
+                   float *py_grad, cudaStream_t stream);
 // prune.cu
 int launch_cummin(const int32_t *in, int32_t *out, int rows, int n, cudaStream_t stream);
 int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
