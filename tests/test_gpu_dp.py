@@ -57,6 +57,28 @@ def test_mi_against_float64_oracle(modified, shape, kind):
     assert np.array_equal(only, ans)
 
 
+@pytest.mark.parametrize("modified", [False, True])
+@pytest.mark.parametrize("cluster,cols", [(1, 2), (1, 4), (2, 1), (2, 2), (4, 1), (8, 1), (8, 4)])
+def test_row_scan_variants(monkeypatch, dp_kernel, modified, cluster, cols):
+    """Row-scan kernel with the chain of warps spread over a thread-block cluster and with
+    several lattice columns per thread (the variants long / many utterances select)."""
+    if dp_kernel != "scan":
+        pytest.skip("row-scan variants only")
+    import tf_fast_rnnt
+    monkeypatch.setenv("FRN_SCAN_CLUSTER", str(cluster))
+    monkeypatch.setenv("FRN_SCAN_K", str(cols))
+    B, S, T = 3, 45, 900
+    rng = np.random.default_rng([int(modified), cluster, cols])
+    px, py = random_pxpy(rng.integers(1 << 30), B, S, T, modified)
+    bd = _boundaries(rng, B, S, T, "begin")
+    bd[1] = [2, 3, 30, 333]          # ends inside the first CTA of a cluster
+    ans, (gx, gy) = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
+    ans64, (gx64, gy64) = orc.mutual_information_recursion(px, py, bd, True, np.float64)
+    assert_close(ans, ans64, LOSS_RTOL, 1e-5, "ans")
+    assert_close(gx, gx64, GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy, gy64, GRAD_RTOL, GRAD_ATOL, "py_grad")
+
+
 def test_mi_with_minus_inf_inputs():
     """px/py holding -inf (what get_rnnt_logprobs produces at t_end) and an
     unreachable end state."""
