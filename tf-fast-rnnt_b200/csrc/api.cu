@@ -125,7 +125,8 @@ int frn_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *
 int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
                    float *am_pruned, float *lm_pruned, void *stream) {
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
-  FRN_REQUIRE(am && lm && ranges && am_pruned && lm_pruned);
+  FRN_REQUIRE(am_pruned || lm_pruned);
+  FRN_REQUIRE((!am_pruned || am) && (!lm_pruned || (lm && ranges)));
   return launch_do_pruning(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, static_cast<cudaStream_t>(stream));
 }
 

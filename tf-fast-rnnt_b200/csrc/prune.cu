@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kPruneThreads) prune_fixup_kernel(const int32_
 // ---------------------------------------------------------------------------
 // Vector path: one CTA of 128 threads per (b,t); thread <-> one float4 column
 // (C <= 512 in one pass), all R source rows loaded before the 2R streaming stores.
-template <int RMAX>
+template <int RMAX, bool WITH_AM, bool WITH_LM>
 __global__ void __launch_bounds__(128) do_pruning_vec_kernel(const float *am, const float *lm, const int32_t *ranges,
                                                              int T, int S1, int R, int C4, float *am_p, float *lm_p) {
   const int bt = blockIdx.x;
@@ -163,20 +163,23 @@ __global__ void __launch_bounds__(128) do_pruning_vec_kernel(const float *am, co
   float4 *lm_out = reinterpret_cast<float4 *>(lm_p) + (size_t)bt * R * C4;
   const float4 *lm_b = reinterpret_cast<const float4 *>(lm) + (size_t)b * S1 * C4;
   for (int c = threadIdx.x; c < C4; c += blockDim.x) {
-    const float4 a = __ldg(am_row + c);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (WITH_AM) a = __ldg(am_row + c);
     float4 l[RMAX];
+    if (WITH_LM) {
 #pragma unroll
-    for (int i = 0; i < RMAX; ++i) {
-      if (i < R) {
-        const int s = rg[i];
-        l[i] = (s >= 0 && s < S1) ? __ldg(lm_b + (size_t)s * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < RMAX; ++i) {
+        if (i < R) {
+          const int s = rg[i];
+          l[i] = (s >= 0 && s < S1) ? __ldg(lm_b + (size_t)s * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < RMAX; ++i) {
       if (i < R) {
-        st_stream_f4(am_out + (size_t)i * C4 + c, a);
-        st_stream_f4(lm_out + (size_t)i * C4 + c, l[i]);
+        if (WITH_AM) st_stream_f4(am_out + (size_t)i * C4 + c, a);
+        if (WITH_LM) st_stream_f4(lm_out + (size_t)i * C4 + c, l[i]);
       }
     }
   }
@@ -349,7 +352,14 @@ int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, i
   const int BT = B * T;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) |
                                      reinterpret_cast<uintptr_t>(am_p) | reinterpret_cast<uintptr_t>(lm_p)) % 16 == 0);
-  if (vec && R <= 8) count_launch(), do_pruning_vec_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
+  // one half only (the am broadcast does not depend on the ranges, callers may run it early on another stream)
+  if (!am_p || !lm_p) {
+    if (!(vec && R <= 8)) return FRN_EUNSUPPORTED;
+    if (am_p) count_launch(), do_pruning_vec_kernel<8, true, false><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
+    else count_launch(), do_pruning_vec_kernel<8, false, true><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
+    return check_launch();
+  }
+  if (vec && R <= 8) count_launch(), do_pruning_vec_kernel<8, true, true><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
   else if (vec) count_launch(), do_pruning_kernel<true><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
   else count_launch(), do_pruning_kernel<false><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
   return check_launch();
