@@ -143,7 +143,7 @@ class Pipeline:
     sub-batch (lattice recursions, normaliser) overlap the bandwidth-bound kernels of another.
     Same calls, same results; the two loss sums are reduced over the whole batch at the end."""
 
-    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False):
+    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True):
         import torch
         from tf_fast_rnnt import _lib
         self.torch, self.lib, self._lib = torch, _lib.lib, _lib
@@ -160,7 +160,8 @@ class Pipeline:
         # am_pruned[b,t,i,:] = am[b,t,:] does not depend on the ranges (rnnt_loss.py:802-806 broadcasts am
         # before it gathers lm): with `overlap` that half of do_rnnt_pruning runs on a second stream
         # beside the dependency-chain-bound kernels of the simple loss, the lm half after the ranges.
-        self.overlap = overlap
+        self.overlap = overlap and not fuse_add
+        self.fuse_add = fuse_add
         self.side = torch.cuda.Stream(dev) if overlap else None
         self.full = self._part(0, B)
         self.ws_pruned = self.full["ws_pruned"]
@@ -211,6 +212,13 @@ class Pipeline:
         ]
         if with_reduce:
             out.append(("reduce", 8 * self.B, self._reduce))
+        if self.fuse_add:
+            # do_rnnt_pruning and the additive joiner in ONE pass (frn_do_pruning_add_joiner): am_pruned,
+            # lm_pruned and logits are all written, the two pruned tensors are not read back for the sum
+            out[2:4] = [("do_pruning+add_joiner", 4 * B * (T * C + (S + 1) * C + T * R) + 12 * n_logits,
+                         lambda: chk(lib.frn_do_pruning_add_joiner(p(am), p(lm), p(self.ranges), B, S, T, R, C,
+                                                                   p(self.am_p), p(self.lm_p), p(self.logits), st()),
+                                     "do_pruning_add_joiner"))]
         return out
 
     def _reduce(self):
@@ -233,7 +241,7 @@ class Pipeline:
             chk(lib.frn_do_pruning(0, lm.data_ptr(), self.ranges.data_ptr(), B, S, T, R, C, 0, self.lm_p.data_ptr(),
                                    main.cuda_stream), "do_pruning(lm)")
             main.wait_stream(self.side)
-            for _, _, fn in st[3:]:                                  # joiner, pruned loss, reductions
+            for _, _, fn in st[3:]:                                  # joiner, pruned loss, reductions (fuse_add is off here)
                 fn()
             return
         if not self.parts:
@@ -402,7 +410,7 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, T, S, C, R = WORKLOADS[args.workload]
-    pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1)
+    pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1, fuse_add=not args.no_fuse_add and not args.overlap)
 
     # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
     # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
@@ -566,11 +574,11 @@ def run_gpu_arm(args):
             sfn = lambda: torch.cuda.current_stream(dev).cuda_stream
 
             def fused_step(am, lm, sym, bd):
-                st = pipe.stages(am, lm, sym, bd)
-                st[0][2](); st[1][2]()                                   # simple loss, prune ranges
+                st = {name: fn for name, _, fn in pipe.stages(am, lm, sym, bd)}
+                st["simple_loss"](); st["prune_ranges"]()
                 chk(lib.frn_pruned_add_joiner(ptr(am), ptr(lm), ptr(pipe.ranges), B, S, T, R, C, 0, ptr(pipe.logits),
                                               sfn()), "pruned_add_joiner")
-                st[4][2](); st[5][2]()                                   # pruned loss, reductions
+                st["pruned_loss"](); st["reduce"]()
 
             fgraphs = []
             with torch.cuda.stream(side):
@@ -622,7 +630,8 @@ def run_gpu_arm(args):
     # Roofline of the dominant kernel: the stages that are ONE HBM-bound kernel each, timed live with
     # CUDA events above (DESIGN.md lists every kernel with its bound; the lattice recursion kernels are
     # dependency-chain bound and are reported in `stages_ms` / `lattice_cells_per_s` instead).
-    kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8>", "add_joiner": "add_kernel"}
+    kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8, 1, 1, 0>", "add_joiner": "add_kernel",
+                       "do_pruning+add_joiner": "do_pruning_vec_kernel<8, 1, 1, 1>"}
     hbm_stages = {k: v for k, v in stage_ms.items() if k in kernel_of_stage}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k][0])
     dom_ms, dom_bytes = hbm_stages[dom]
@@ -638,8 +647,10 @@ def run_gpu_arm(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning -> additive "
-                        f"joiner -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
+            "workload": f"{args.workload}: full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning"
+                        + (" + additive joiner in one pass, am_pruned / lm_pruned / logits all written"
+                           if pipe.fuse_add else " -> additive joiner")
+                        + f" -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
             "launch": "cuda_graph" if use_graph else "direct",
             "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step"
                        + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else ""),
@@ -698,6 +709,9 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="run the am half of do_rnnt_pruning on a second stream beside the simple loss (measured: "
                          "0.380 ms/step against 0.372 without - the copy slows the latency-bound kernels it overlaps)")
+    ap.add_argument("--no-fuse-add", action="store_true",
+                    help="do_rnnt_pruning and the additive joiner as two passes (frn_do_pruning, frn_add_joiner) "
+                         "instead of the one-pass frn_do_pruning_add_joiner")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA op")
     args = ap.parse_args()

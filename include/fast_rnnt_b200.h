@@ -165,6 +165,13 @@ int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad,
  * floats; stands in for the user's joiner network in the benchmark. */
 int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits, size_t n,
                    void *stream);
+/* do_rnnt_pruning and the additive joiner in one pass: am_pruned, lm_pruned AND
+ * logits = am_pruned + lm_pruned [B][T][R][C] are all written, the sum taken from the
+ * registers that hold the two rows (saves re-reading 2 x B T R C floats; bit-identical
+ * to frn_do_pruning followed by frn_add_joiner). */
+int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges,
+                              int B, int S, int T, int R, int C, float *am_pruned,
+                              float *lm_pruned, float *logits, void *stream);
 /* (f2) fused additive joiner: logits[b,t,i,:] = am[b,t,:] + lm[b,ranges[b,t,i],:]
  * without materialising am_pruned / lm_pruned. out_dtype: frn_dtype. */
 int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges,

@@ -255,3 +255,29 @@ def test_fused_joiner_equals_pruning_plus_add(C):
     fused = frn.pruned_add_joiner(am_d, lm_d, rg_d)
     assert torch.equal(fused, am_p + lm_p)
     assert torch.equal(fused[0, 3, 4], am_d[0, 3])
+
+
+@pytest.mark.parametrize("C,R", [(500, 5), (37, 5), (64, 11)])   # one-pass kernel; scalar and wide-band fall-backs
+def test_pruning_with_joiner_equals_separate_ops(C, R):
+    """frn_do_pruning_add_joiner == do_rnnt_pruning + addition, all three tensors bit for bit."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S = 3, 40, 12
+    rng = np.random.default_rng([C, R])
+    am = rng.standard_normal((B, T, C), dtype=np.float32)
+    lm = rng.standard_normal((B, S + 1, C), dtype=np.float32)
+    r0 = np.sort(rng.integers(0, S + 2 - R, (B, T)), axis=1)
+    ranges = (r0[:, :, None] + np.arange(R)[None, None, :]).astype(np.int32)
+    am_d, lm_d, rg_d = (torch.from_numpy(x).cuda() for x in (am, lm, ranges))
+    am_p, lm_p = frn.do_rnnt_pruning(am_d, lm_d, rg_d)
+    am_q, lm_q, logits = frn.do_rnnt_pruning_add_joiner(am_d, lm_d, rg_d)
+    assert torch.equal(am_q, am_p) and torch.equal(lm_q, lm_p)
+    assert torch.equal(logits, am_p + lm_p)
+    # halves of do_rnnt_pruning on their own (the am broadcast does not need the ranges)
+    lib, ptr = frn._lib.lib, lambda t: t.data_ptr()
+    if C % 4 == 0 and R <= 8:
+        a2, l2 = torch.zeros_like(am_p), torch.zeros_like(lm_p)
+        st = torch.cuda.current_stream().cuda_stream
+        frn._lib.check(lib.frn_do_pruning(ptr(am_d), 0, 0, B, S, T, R, C, ptr(a2), 0, st), "am half")
+        frn._lib.check(lib.frn_do_pruning(0, ptr(lm_d), ptr(rg_d), B, S, T, R, C, 0, ptr(l2), st), "lm half")
+        assert torch.equal(a2, am_p) and torch.equal(l2, lm_p)

@@ -130,6 +130,14 @@ int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int 
   return launch_do_pruning(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, static_cast<cudaStream_t>(stream));
 }
 
+int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
+                              int C, float *am_pruned, float *lm_pruned, float *logits, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
+  FRN_REQUIRE(am && lm && ranges && am_pruned && lm_pruned && logits);
+  return launch_do_pruning_add(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, logits,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad, const int32_t *ranges, int B,
                        int S, int T, int R, int C, float *am_grad, float *lm_grad, void *stream) {
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0 && ranges);

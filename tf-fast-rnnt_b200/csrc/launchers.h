@@ -22,6 +22,8 @@ int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_
                         int T1, int R, int32_t *ranges, int32_t *s_begin_ws, cudaStream_t stream);
 int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
                       float *am_p, float *lm_p, cudaStream_t stream);
+int launch_do_pruning_add(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
+                          float *am_p, float *lm_p, float *logits, cudaStream_t stream);
 int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const int32_t *ranges, int B, int S,
                           int T, int R, int C, float *am_grad, float *lm_grad, cudaStream_t stream);
 int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,

@@ -8,6 +8,7 @@
 // summation order of a sequential cumsum, with first-index
 // argmax; the int32 fix-ups along t are order independent.
 #include "common.cuh"
+#include "launchers.h"
 
 namespace frn {
 
@@ -152,15 +153,19 @@ __global__ void __launch_bounds__(kPruneThreads) prune_fixup_kernel(const int32_
 // ---------------------------------------------------------------------------
 // Vector path: one CTA of 128 threads per (b,t); thread <-> one float4 column
 // (C <= 512 in one pass), all R source rows loaded before the 2R streaming stores.
-template <int RMAX, bool WITH_AM, bool WITH_LM>
+// WITH_SUM: also logits[b,t,i,:] = am_pruned + lm_pruned (the additive joiner of the reference's tests) from
+// the registers that hold both rows, instead of a second pass that re-reads the two pruned tensors.
+template <int RMAX, bool WITH_AM, bool WITH_LM, bool WITH_SUM = false>
 __global__ void __launch_bounds__(128) do_pruning_vec_kernel(const float *am, const float *lm, const int32_t *ranges,
-                                                             int T, int S1, int R, int C4, float *am_p, float *lm_p) {
+                                                             int T, int S1, int R, int C4, float *am_p, float *lm_p,
+                                                             float *sum_p = nullptr) {
   const int bt = blockIdx.x;
   const int b = bt / T;
   const int32_t *rg = ranges + (size_t)bt * R;
   const float4 *am_row = reinterpret_cast<const float4 *>(am) + (size_t)bt * C4;
   float4 *am_out = reinterpret_cast<float4 *>(am_p) + (size_t)bt * R * C4;
   float4 *lm_out = reinterpret_cast<float4 *>(lm_p) + (size_t)bt * R * C4;
+  float4 *sum_out = reinterpret_cast<float4 *>(sum_p) + (size_t)bt * R * C4;
   const float4 *lm_b = reinterpret_cast<const float4 *>(lm) + (size_t)b * S1 * C4;
   for (int c = threadIdx.x; c < C4; c += blockDim.x) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -180,6 +185,8 @@ __global__ void __launch_bounds__(128) do_pruning_vec_kernel(const float *am, co
       if (i < R) {
         if (WITH_AM) st_stream_f4(am_out + (size_t)i * C4 + c, a);
         if (WITH_LM) st_stream_f4(lm_out + (size_t)i * C4 + c, l[i]);
+        if (WITH_SUM)
+          st_stream_f4(sum_out + (size_t)i * C4 + c, make_float4(a.x + l[i].x, a.y + l[i].y, a.z + l[i].z, a.w + l[i].w));
       }
     }
   }
@@ -362,6 +369,21 @@ int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, i
   if (vec && R <= 8) count_launch(), do_pruning_vec_kernel<8, true, true><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p);
   else if (vec) count_launch(), do_pruning_kernel<true><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
   else count_launch(), do_pruning_kernel<false><<<(BT + 7) / 8, 256, 0, stream>>>(am, lm, ranges, BT, T, S + 1, R, C, am_p, lm_p);
+  return check_launch();
+}
+
+int launch_do_pruning_add(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
+                          float *am_p, float *lm_p, float *logits, cudaStream_t stream) {
+  const int BT = B * T;
+  const bool vec = (C % 4 == 0) && R <= 8 &&
+                   ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) | reinterpret_cast<uintptr_t>(am_p) |
+                     reinterpret_cast<uintptr_t>(lm_p) | reinterpret_cast<uintptr_t>(logits)) % 16 == 0);
+  if (!vec) {   // general shapes: the two separate passes
+    int rc = launch_do_pruning(am, lm, ranges, B, S, T, R, C, am_p, lm_p, stream);
+    if (rc) return rc;
+    return launch_add(am_p, lm_p, logits, (size_t)BT * R * C, stream);
+  }
+  count_launch(), do_pruning_vec_kernel<8, true, true, true><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p, logits);
   return check_launch();
 }
 

@@ -12,7 +12,7 @@ from .rnnt_loss import get_rnnt_logprobs_pruned
 from .rnnt_loss import get_rnnt_logprobs_smoothed
 from .rnnt_loss import get_rnnt_prune_ranges
 from .rnnt_loss import mutual_information_recursion
-from .rnnt_loss import pruned_add_joiner
+from .rnnt_loss import do_rnnt_pruning_add_joiner, pruned_add_joiner
 from .rnnt_loss import pruned_loss_fwd_bwd
 from .rnnt_loss import rnnt_loss
 from .rnnt_loss import rnnt_loss_pruned

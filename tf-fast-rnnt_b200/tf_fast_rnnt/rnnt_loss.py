@@ -371,6 +371,25 @@ def do_rnnt_pruning_backward(am_pruned_grad: Tensor, lm_pruned_grad: Tensor, ran
     return io.out(am_g), io.out(lm_g)
 
 
+def do_rnnt_pruning_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor):
+    """(extension) do_rnnt_pruning (rnnt_loss.py:763-812) plus the additive joiner of the
+    reference's tests (simple_rnnt_loss_test.py:120-125) in one pass over the data:
+    -> (am_pruned, lm_pruned, am_pruned + lm_pruned)."""
+    io = _Io(am, lm)
+    am_d = io.dev_tensor(am, torch.float32)
+    lm_d = io.dev_tensor(lm, torch.float32)
+    rg = io.dev_tensor(ranges, torch.int32)
+    B, T, C = am_d.shape
+    S = lm_d.shape[1] - 1
+    R = rg.shape[2]
+    if tuple(rg.shape) != (B, T, R) or tuple(lm_d.shape) != (B, S + 1, C):
+        raise ValueError("am [B,T,C], lm [B,S+1,C], ranges [B,T,s_range] expected")
+    am_p, lm_p, lg = (torch.empty((B, T, R, C), dtype=torch.float32, device=io.dev) for _ in range(3))
+    check(lib.frn_do_pruning_add_joiner(_ptr(am_d), _ptr(lm_d), _ptr(rg), B, S, T, R, C, _ptr(am_p), _ptr(lm_p),
+                                        _ptr(lg), _stream(io.dev)), "frn_do_pruning_add_joiner")
+    return io.out(am_p), io.out(lm_p), io.out(lg)
+
+
 def pruned_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor, dtype=torch.float32):
     """(extension) logits = am_pruned + lm_pruned without
     materialising either."""
