@@ -128,8 +128,11 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols,
 /* A9. Gradient of sum_b scores_grad[b]*scores[b] w.r.t. am [B][T][C] and lm
  * [B][S+1][C] given the occupation counts returned by frn_simple_loss with the
  * same arguments (what TensorFlow autodiff + _RNNTLossGrad, __init__.py:154-162,
- * produce for rnnt_loss_simple; the smoothed variant is not covered).
- * scores_grad == NULL means all ones. */
+ * produce for rnnt_loss_simple).  scores_grad == NULL means all ones.
+ * frn_smoothed_loss_bwd: the same for rnnt_loss_smoothed (rnnt_loss.py:1266-1365),
+ * including the path through the batch-global unigram (rnnt_loss.py:1279-1280) into
+ * every lm row; occupation counts from frn_simple_loss(smoothed = 1) with the same
+ * scales.  Both use frn_simple_loss_bwd_workspace_bytes(). */
 size_t frn_simple_loss_bwd_workspace_bytes(int B, int S, int T, int C);
 int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols,
                         const int32_t *boundary, const float *px_grad,
@@ -137,6 +140,13 @@ int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols
                         int S, int T, int C, int termination_symbol,
                         int rnnt_type, float *am_grad, float *lm_grad,
                         void *workspace, size_t workspace_bytes, void *stream);
+int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbols,
+                          const int32_t *boundary, const float *px_grad,
+                          const float *py_grad, const float *scores_grad, int B,
+                          int S, int T, int C, int termination_symbol,
+                          int rnnt_type, float lm_only_scale, float am_only_scale,
+                          float *am_grad, float *lm_grad, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * A5. get_rnnt_prune_ranges (rnnt_loss.py:647-761): ranges [B][T][R_out],

@@ -512,3 +512,69 @@ def simple_am_lm_grad(lm, am, symbols, termination_symbol, boundary,
     lm_grad[:, :, termination_symbol] += gpy.sum(axis=2)
     g = np.ones((B,), dtype=dtype) if loss_grad is None else np.asarray(loss_grad, dtype=dtype)
     return -g[:, None, None] * am_grad, -g[:, None, None] * lm_grad
+
+
+def smoothed_am_lm_grad(lm, am, symbols, termination_symbol, boundary,
+                        lm_only_scale=0.1, am_only_scale=0.1,
+                        rnnt_type="regular", delay_penalty=0.0, loss_grad=None,
+                        dtype=np.float64):
+    """d(sum_b loss_grad[b]*loss[b]) / d(am, lm) for rnnt_loss_smoothed
+    (reduction 'none'): what TF autodiff derives through rnnt_loss.py:1266-1365
+    (A9 for A2), INCLUDING the path through the batch-global unigram
+    (rnnt_loss.py:1279-1280) into every lm row."""
+    dtype = np.dtype(dtype).type
+    lm = np.asarray(lm, dtype=dtype)
+    am = np.asarray(am, dtype=dtype)
+    sym = np.asarray(symbols)
+    B, T, C = am.shape
+    S = lm.shape[1] - 1
+    blank = termination_symbol
+    px, py = get_rnnt_logprobs_smoothed(lm, am, symbols, termination_symbol,
+                                        lm_only_scale, am_only_scale, boundary,
+                                        rnnt_type, dtype)
+    px = apply_delay_penalty(px, boundary, delay_penalty)
+    _, (gpx, gpy) = mutual_information_recursion(px, py, boundary, True, dtype)
+    if rnnt_type == "constrained":
+        gpy = gpy.copy()
+        gpy[:, 1:, :] += gpx
+    Gx = gpx[:, :, :T]                     # [B,S,T]   weight on px_i
+    Gy = gpy                               # [B,S+1,T] weight on py_i
+    G = Gy.copy()
+    G[:, :S, :] += Gx
+    comb = dtype(1.0 - lm_only_scale - am_only_scale)
+    lms = dtype(1.0e-20 if lm_only_scale == 0.0 else lm_only_scale)
+    ams = dtype(1.0e-20 if am_only_scale == 0.0 else am_only_scale)
+    norm, lm_probs, am_probs, lm_max, am_max = _normalizers(lm, am, dtype)
+    Z = np.matmul(lm_probs, np.swapaxes(am_probs, 1, 2)) + dtype(TINY)
+    W = G / Z
+    Zl = lm_probs.sum(axis=2, keepdims=True)
+    r = lm_probs / Zl                                              # softmax(lm rows)
+    N = B * (S + 1)
+    u = r.sum(axis=(0, 1)) / N + dtype(TINY)                       # [C]
+    D = am_probs @ u                                               # [B,T]
+    q = am_probs * u[None, None, :] / D[:, :, None]                # [B,T,C]
+    Gt = G.sum(axis=1)                                             # [B,T]
+    Gs = G.sum(axis=2)                                             # [B,S+1]
+    Sx = Gx.sum(axis=2)                                            # [B,S]
+    Sy = Gy.sum(axis=2)                                            # [B,S+1]
+    g = np.ones((B,), dtype=dtype) if loss_grad is None else np.asarray(loss_grad, dtype=dtype)
+    g = -g                                                         # loss = -score
+
+    am_grad = -comb * np.matmul(np.swapaxes(W, 1, 2), lm_probs) * am_probs - ams * q * Gt[:, :, None]
+    lm_grad = -comb * np.matmul(W, am_probs) * lm_probs - lms * r * Gs[:, :, None]
+    for b in range(B):
+        np.add.at(am_grad[b].T, sym[b], (comb + ams) * Gx[b])
+        np.add.at(lm_grad[b], (np.arange(S), sym[b]), (comb + lms) * Sx[b])
+    am_grad[:, :, blank] += (comb + ams) * Gy.sum(axis=1)
+    lm_grad[:, :, blank] += (comb + lms) * Sy
+    am_grad *= g[:, None, None]
+    lm_grad *= g[:, None, None]
+    # path through the unigram: d/du[c], then u = mean softmax(lm rows) + tiny
+    du = np.zeros((C,), dtype=dtype)
+    for b in range(B):
+        np.add.at(du, sym[b], g[b] * ams * Sx[b] / u[sym[b]])
+        du[blank] += g[b] * ams * Sy[b].sum() / u[blank]
+        du -= g[b] * ams * ((Gt[b] / D[b])[:, None] * am_probs[b]).sum(axis=0)
+    dot = (r * du[None, None, :]).sum(axis=2, keepdims=True)
+    lm_grad += r * (du[None, None, :] - dot) / N
+    return am_grad, lm_grad

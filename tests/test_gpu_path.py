@@ -281,3 +281,28 @@ def test_pruning_with_joiner_equals_separate_ops(C, R):
         frn._lib.check(lib.frn_do_pruning(ptr(am_d), 0, 0, B, S, T, R, C, ptr(a2), 0, st), "am half")
         frn._lib.check(lib.frn_do_pruning(0, ptr(lm_d), ptr(rg_d), B, S, T, R, C, 0, ptr(l2), st), "lm half")
         assert torch.equal(a2, am_p) and torch.equal(l2, lm_p)
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+@pytest.mark.parametrize("scales", [(0.25, 0.15), (0.25, 0.0)])
+def test_smoothed_loss_am_lm_gradients(rnnt_type, scales):
+    """A9 for rnnt_loss_smoothed: C-ABI frn_smoothed_loss_bwd and the autograd wrapper against the
+    float64 oracle (itself checked against finite differences on the CPU)."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 3, 70, 21, 28
+    lms, ams = scales
+    am, lm, sym, term, bd = make_inputs(23, B, T, S, C, ragged=True)
+    w = np.array([1.0, 0.5, -2.0], np.float32)
+    _, (gx, gy) = frn.rnnt_loss_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, 0.2, "none", True)
+    am_g, lm_g = frn.smoothed_loss_backward(lm, am, sym, term, bd, gx, gy, -w, lms, ams, rnnt_type)
+    o_am, o_lm = orc.smoothed_am_lm_grad(lm, am, sym, term, bd, lms, ams, rnnt_type, 0.2, w, np.float64)
+    assert_close(am_g, o_am, GRAD_RTOL, 2e-6, "am grad")
+    assert_close(lm_g, o_lm, GRAD_RTOL, 2e-5, "lm grad")
+    lm_t = torch.from_numpy(lm).cuda().requires_grad_(True)
+    am_t = torch.from_numpy(am).cuda().requires_grad_(True)
+    loss = frn.rnnt_loss_smoothed(lm_t, am_t, sym, term, lms, ams, bd, rnnt_type, 0.2, "sum")
+    loss.backward()
+    o_am1, o_lm1 = orc.smoothed_am_lm_grad(lm, am, sym, term, bd, lms, ams, rnnt_type, 0.2, None, np.float64)
+    assert_close(am_t.grad.cpu().numpy(), o_am1, GRAD_RTOL, 2e-6, "autograd am grad")
+    assert_close(lm_t.grad.cpu().numpy(), o_lm1, GRAD_RTOL, 2e-5, "autograd lm grad")

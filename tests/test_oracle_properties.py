@@ -89,3 +89,36 @@ def test_analytic_gradients_against_finite_differences():
         idx = tuple(rng.integers(0, n) for n in lm.shape)
         e = np.zeros(lm.shape); e[idx] = 1e-6
         np.testing.assert_allclose(gl[idx], (h(am, lm + e) - h(am, lm - e)) / 2e-6, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_smoothed_am_lm_grad_matches_finite_differences(rnnt_type):
+    """The analytic A9 gradient of the smoothed loss (incl. the batch-global unigram path)
+    against central differences of the oracle's own float64 loss."""
+    rng = np.random.default_rng(5)
+    B, T, S, C = 2, 5, 3, 4
+    am = rng.standard_normal((B, T, C))
+    lm = rng.standard_normal((B, S + 1, C))
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    bd = np.array([[0, 0, S, T], [0, 0, S - 1, T - 1]], np.int32)
+    w = np.array([1.0, -0.7])
+    args = dict(lm_only_scale=0.25, am_only_scale=0.15, rnnt_type=rnnt_type, delay_penalty=0.1)
+
+    def total(lm_, am_):
+        loss = orc.rnnt_loss_smoothed(lm_, am_, sym, C - 1, boundary=bd, reduction="none",
+                                      dtype=np.float64, **args)
+        return float((w * loss).sum())
+
+    am_g, lm_g = orc.smoothed_am_lm_grad(lm, am, sym, C - 1, bd, loss_grad=w, dtype=np.float64, **args)
+    eps = 1e-6
+    for arr, grad, which in ((am, am_g, "am"), (lm, lm_g, "lm")):
+        num = np.zeros_like(arr)
+        for idx in np.ndindex(arr.shape):
+            old = arr[idx]
+            arr[idx] = old + eps
+            hi = total(lm, am)
+            arr[idx] = old - eps
+            lo = total(lm, am)
+            arr[idx] = old
+            num[idx] = (hi - lo) / (2 * eps)
+        np.testing.assert_allclose(grad, num, rtol=2e-5, atol=2e-7, err_msg=which)

@@ -244,7 +244,22 @@ int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols
   if (!workspace || !aligned256(workspace) || workspace_bytes < simple_bwd_workspace_bytes(B, S, T, C))
     return FRN_EWORKSPACE;
   return launch_simple_bwd(lm, am, symbols, boundary, px_grad, py_grad, scores_grad, B, S, T, C, termination_symbol,
-                           rnnt_type, am_grad, lm_grad, workspace, static_cast<cudaStream_t>(stream));
+                           rnnt_type, 0, 0.f, 0.f, am_grad, lm_grad, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                          const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T,
+                          int C, int termination_symbol, int rnnt_type, float lm_only_scale, float am_only_scale,
+                          float *am_grad, float *lm_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
+  FRN_REQUIRE(lm && am && symbols && boundary && px_grad && py_grad && am_grad && lm_grad);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < simple_bwd_workspace_bytes(B, S, T, C))
+    return FRN_EWORKSPACE;
+  return launch_simple_bwd(lm, am, symbols, boundary, px_grad, py_grad, scores_grad, B, S, T, C, termination_symbol,
+                           rnnt_type, 1, lm_only_scale, am_only_scale, am_grad, lm_grad, workspace,
+                           static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ A7 / A8

@@ -37,11 +37,14 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
                            cudaStream_t stream);
+int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
+                           cudaStream_t stream);
 // simple_bwd.cu
 size_t simple_bwd_workspace_bytes(int B, int S, int T, int C);
 int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                       const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T, int C,
-                      int term, int rnnt_type, float *am_grad, float *lm_grad, void *workspace, cudaStream_t stream);
+                      int term, int rnnt_type, int smoothed, float lm_only_scale, float am_only_scale, float *am_grad,
+                      float *lm_grad, void *workspace, cudaStream_t stream);
 // logprobs_pruned.cu
 int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges, int B, int S,
                       int T, int R, int C, int term, float *pxc, float *pyc, float *lse, cudaStream_t stream);

@@ -233,6 +233,24 @@ size_t simple_stats_bytes(int B, int S, int T, int C) {
   return n;
 }
 
+// The statistics block of the smoothed log-probs on its own (used again by the backward pass):
+// lmmax, lmsum, ammax, amonly, unigram, log unigram.
+int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
+                           cudaStream_t stream) {
+  const int S1 = S + 1;
+  char *w = static_cast<char *>(stats_ws);
+  float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *lmsum = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *ammax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+  float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+  float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
+  float *logu = reinterpret_cast<float *>(w);
+  count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax);
+  count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
+  count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
+  return check_launch();
+}
+
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,

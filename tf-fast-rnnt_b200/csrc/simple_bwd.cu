@@ -9,6 +9,16 @@
 //   am_grad[t,c] = g ( [c=sym_s] sum_s gpx[s,t] + [c=blank] sum_s gpy[s,t] - amp[t,c] sum_s W[s,t] lmp[s,c] )
 //   lm_grad[s,c] = g ( [c=sym_s] sum_t gpx[s,t] + [c=blank] sum_t gpy[s,t] - lmp[s,c] sum_t W[s,t] amp[t,c] )
 //
+// Smoothed loss (rnnt_loss.py:1266-1365), out = comb x + lm_scale x_lmonly + am_scale x_amonly:
+//   the terms above get the factor comb (contractions) resp. comb + am_scale / comb + lm_scale (scatters), and
+//   am_grad[t,c] -= g am_scale q[t,c] Gt[t],          q = amp u / D,  D[t] = sum_c amp[t,c] u[c],  Gt = sum_s G
+//   lm_grad[s,c] -= g lm_scale r[s,c] Gs[s],          r = softmax(lm[s,:]),                        Gs = sum_t G
+//   and, through the batch-global unigram u = mean_{b,s} r + tiny (rnnt_loss.py:1279-1280):
+//   du[c] = sum_b g_b am_scale ( (sum_s Sx[s] [c=sym_s] + [c=blank] sum_s Sy[s]) / u[c] - sum_t Gt[t]/D[t] amp[t,c] )
+//   lm_grad[b,s,c] += r[b,s,c] (du[c] - sum_c' r[b,s,c'] du[c']) / (B (S+1))
+//   (Sx[s] = sum_t gpx[s,t], Sy[s] = sum_t gpy[s,t]; checked against finite differences of the float64 oracle,
+//   tests/test_oracle_properties.py).
+//
 // First version: exact-FP32 SIMT tiles for the two contractions ([T x S1].[S1 x C]
 // and [S1 x T].[T x C]); the tcgen05 version follows the forward kernel's scheme.
 #include "common.cuh"
@@ -26,7 +36,13 @@ struct BwdParams {
   float *W;                     // [B][S+1][T] workspace
   float *am_grad, *lm_grad;
   int B, S, T, T1, C, term, rnnt_type;
+  // smoothed loss only
+  int smoothed;
+  float comb, lm_scale, am_scale;           // 1 - lm - am; scales with the 1e-20 substitution
+  const float *lmsum, *amonly, *unigram;    // forward statistics: sum_c exp(lm - lmmax); log D + ammax; u[c]
+  float *Gt, *Sx, *Sy, *du, *partial;       // [B][T], [B][S+1], [B][S+1], [C], [chunks][C]
 };
+constexpr int kDuRows = 64;                 // am rows per block of the du partial sums
 
 // W[b,s,t] = G / Z with Z = exp(norm - lmmax - ammax), norm = am[t,blank] + lm[s,blank] - py[s,t]
 __global__ void __launch_bounds__(256) bwd_weights_kernel(BwdParams p) {
@@ -100,7 +116,7 @@ __global__ void __launch_bounds__(256) bwd_contract_kernel(BwdParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < C) out[(size_t)m * C + n] = -g * expf(x[(size_t)m * C + n] - xmax[m]) * acc[i][j];
+      if (n < C) out[(size_t)m * C + n] = -g * p.comb * expf(x[(size_t)m * C + n] - xmax[m]) * acc[i][j];
     }
   }
 }
@@ -111,7 +127,7 @@ __global__ void __launch_bounds__(128) bwd_scatter_am_kernel(BwdParams p) {
   const int bt = blockIdx.x * blockDim.x + threadIdx.x;
   if (bt >= p.B * p.T) return;
   const int b = bt / p.T, t = bt - b * p.T;
-  const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
+  const float g = (p.scores_grad ? p.scores_grad[b] : 1.f) * (p.smoothed ? p.comb + p.am_scale : 1.f);
   float *row = p.am_grad + (size_t)bt * p.C;
   const int32_t *sym = p.symbols + (size_t)b * p.S;
   float blank = 0.f;
@@ -141,46 +157,164 @@ __global__ void __launch_bounds__(256) bwd_scatter_lm_kernel(BwdParams p) {
     if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];
   }
   sx = warp_sum(sx); sy = warp_sum(sy);
+  const float g0 = p.scores_grad ? p.scores_grad[b] : 1.f;
+  float *row = p.lm_grad + (size_t)bs * p.C;
+  if (p.smoothed) {
+    // lm-only term and the unigram path: both need the softmax of this lm row
+    const float *x = p.lm + (size_t)bs * p.C;
+    const float mx = p.lmmax[bs], inv = 1.f / p.lmsum[bs];
+    float dot = 0.f;
+    for (int c = lane; c < p.C; c += 32) dot += expf(x[c] - mx) * inv * p.du[c];
+    dot = warp_sum(dot);
+    const float invN = 1.f / ((float)p.B * (float)S1);
+    const float k = g0 * p.lm_scale * (sx + sy);
+    for (int c = lane; c < p.C; c += 32) {
+      const float r = expf(x[c] - mx) * inv;
+      row[c] += r * ((p.du[c] - dot) * invN - k);
+    }
+    __syncwarp();
+  }
   if (lane == 0) {
-    const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
-    float *row = p.lm_grad + (size_t)bs * p.C;
+    const float g = g0 * (p.smoothed ? p.comb + p.lm_scale : 1.f);
     if (s < p.S) row[p.symbols[(size_t)b * p.S + s]] += g * sx;
     row[p.term] += g * sy;
   }
 }
 
+// ---- smoothed loss: column / row sums of the upstream weights ----
+__global__ void __launch_bounds__(128) bwd_gt_kernel(BwdParams p) {
+  const int S1 = p.S + 1;
+  const int bt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bt >= p.B * p.T) return;
+  const int b = bt / p.T, t = bt - b * p.T;
+  float acc = 0.f;
+  for (int s = 0; s < S1; ++s) {
+    acc += p.gpy[((size_t)b * S1 + s) * p.T + t];
+    if (s < p.S) acc += p.gpx[((size_t)b * p.S + s) * p.T1 + t] * (p.rnnt_type == FRN_CONSTRAINED ? 2.f : 1.f);
+  }
+  p.Gt[bt] = acc;     // constrained: gpx[s,t] weighs px[s,t] and, through the fold, py[s+1,t]
+}
+__global__ void __launch_bounds__(256) bwd_rowsums_kernel(BwdParams p) {
+  const int S1 = p.S + 1;
+  const int bs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (bs >= p.B * S1) return;
+  const int b = bs / S1, s = bs - b * S1;
+  float sx = 0.f, sy = 0.f;
+  for (int t = lane; t < p.T; t += 32) {
+    sy += p.gpy[(size_t)bs * p.T + t];
+    if (s < p.S) sx += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) { p.Sx[bs] = sx; p.Sy[bs] = sy; }
+}
+// am-only term of am_grad, and the partial sums over am rows of  coef[b,t] amp[b,t,c]  for du
+__global__ void __launch_bounds__(256) bwd_smooth_am_kernel(BwdParams p) {
+  __shared__ float coef[kDuRows], mx[kDuRows];
+  const int row0 = blockIdx.x * kDuRows, rows = min(kDuRows, p.B * p.T - row0);
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    const int bt = row0 + i, b = bt / p.T;
+    const float g = p.scores_grad ? p.scores_grad[b] : 1.f;
+    mx[i] = p.ammax[bt];
+    coef[i] = g * p.am_scale * p.Gt[bt] * expf(p.ammax[bt] - p.amonly[bt]);      // g am_scale Gt / D
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float u = p.unigram[c];
+    float acc = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      const size_t at = (size_t)(row0 + i) * p.C + c;
+      const float v = coef[i] * expf(p.am[at] - mx[i]);
+      acc += v;
+      p.am_grad[at] -= v * u;
+    }
+    p.partial[(size_t)blockIdx.x * p.C + c] = acc;
+  }
+}
+// du[c]: one thread per class, sequential (deterministic) sums
+__global__ void __launch_bounds__(128) bwd_du_kernel(BwdParams p, int chunks) {
+  const int S1 = p.S + 1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  float hist = 0.f;
+  for (int b = 0; b < p.B; ++b) {
+    const float g = (p.scores_grad ? p.scores_grad[b] : 1.f) * p.am_scale;
+    float h = 0.f;
+    for (int s = 0; s < p.S; ++s)
+      if (p.symbols[(size_t)b * p.S + s] == c) h += p.Sx[(size_t)b * S1 + s];
+    if (c == p.term)
+      for (int s = 0; s < S1; ++s) h += p.Sy[(size_t)b * S1 + s];
+    hist += g * h;
+  }
+  float v = 0.f;
+  for (int k = 0; k < chunks; ++k) v += p.partial[(size_t)k * p.C + c];
+  p.du[c] = hist / p.unigram[c] - v;
+}
+
 size_t simple_bwd_workspace_bytes(int B, int S, int T, int C) {
   const int T1 = T + 1;
+  const size_t chunks = ((size_t)B * T + kDuRows - 1) / kDuRows;
   return round_up_sz((size_t)B * S * T1 * sizeof(float), 256) + 2 * round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256) +
-         simple_stats_bytes(B, S, T, C);
+         simple_stats_bytes(B, S, T, C) + round_up_sz((size_t)B * T * sizeof(float), 256) +
+         2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256) + round_up_sz((size_t)C * sizeof(float), 256) +
+         round_up_sz(chunks * C * sizeof(float), 256);
 }
 
 int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                       const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T, int C,
-                      int term, int rnnt_type, float *am_grad, float *lm_grad, void *workspace, cudaStream_t stream) {
+                      int term, int rnnt_type, int smoothed, float lm_only_scale, float am_only_scale, float *am_grad,
+                      float *lm_grad, void *workspace, cudaStream_t stream) {
   const int S1 = S + 1, T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T;
+  const int chunks = (B * T + kDuRows - 1) / kDuRows;
   char *w = static_cast<char *>(workspace);
   float *px = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S * (T + 1) * sizeof(float), 256);
   float *py = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
   float *W = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
-  void *stats = w;
+  void *stats = w; w += simple_stats_bytes(B, S, T, C);
+  float *Gt = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+  float *Sx = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *Sy = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *du = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
+  float *partial = reinterpret_cast<float *>(w);
   // forward log-probs again (py gives Z); non-smoothed, and without the constrained px += py fold
   int rc = launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, term,
                                   rnnt_type == FRN_CONSTRAINED ? FRN_MODIFIED : rnnt_type, 0, 0.f, 0.f, px, py, stats,
                                   stream);
   if (rc) return rc;
+  if (smoothed) {   // row sums, unigram and am-only normalisers into the same statistics block
+    rc = launch_smoothing_stats(lm, am, B, S, T, C, stats, stream);
+    if (rc) return rc;
+  }
   char *sw = static_cast<char *>(stats);
   BwdParams p;
   p.lm = lm; p.am = am; p.symbols = symbols; p.boundary = boundary; p.gpx = px_grad; p.gpy = py_grad; p.py = py;
   p.lmmax = reinterpret_cast<float *>(sw);
+  p.lmsum = reinterpret_cast<float *>(sw + round_up_sz((size_t)B * S1 * sizeof(float), 256));
   p.ammax = reinterpret_cast<float *>(sw + 2 * round_up_sz((size_t)B * S1 * sizeof(float), 256));
+  p.amonly = reinterpret_cast<float *>(sw + 2 * round_up_sz((size_t)B * S1 * sizeof(float), 256) +
+                                       round_up_sz((size_t)B * T * sizeof(float), 256));
+  p.unigram = reinterpret_cast<float *>(sw + 2 * round_up_sz((size_t)B * S1 * sizeof(float), 256) +
+                                        2 * round_up_sz((size_t)B * T * sizeof(float), 256));
   p.scores_grad = scores_grad; p.W = W; p.am_grad = am_grad; p.lm_grad = lm_grad;
   p.B = B; p.S = S; p.T = T; p.T1 = T1; p.C = C; p.term = term; p.rnnt_type = rnnt_type;
+  p.smoothed = smoothed;
+  const double lms = (double)lm_only_scale, ams = (double)am_only_scale;      // rnnt_loss.py:1342-1349
+  p.comb = smoothed ? (float)(1.0 - lms - ams) : 1.f;
+  p.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
+  p.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
+  p.Gt = Gt; p.Sx = Sx; p.Sy = Sy; p.du = du; p.partial = partial;
   const size_t n = (size_t)B * S1 * T;
   count_launch(), bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
   dim3 g_am((C + 63) / 64, (T + 63) / 64, B), g_lm((C + 63) / 64, (S1 + 63) / 64, B);
   count_launch(), bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
   count_launch(), bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
+  if (smoothed) {
+    count_launch(), bwd_gt_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
+    count_launch(), bwd_rowsums_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
+    count_launch(), bwd_smooth_am_kernel<<<chunks, 256, 0, stream>>>(p);
+    count_launch(), bwd_du_kernel<<<(C + 127) / 128, 128, 0, stream>>>(p, chunks);
+  }
   count_launch(), bwd_scatter_am_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
   count_launch(), bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
   return check_launch();

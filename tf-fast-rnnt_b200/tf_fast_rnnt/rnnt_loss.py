@@ -231,10 +231,13 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
 
 
 def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad=None,
-                         rnnt_type: str = "regular"):
+                         rnnt_type: str = "regular", smoothed: bool = False, lm_only_scale: float = 0.0,
+                         am_only_scale: float = 0.0):
     """d(sum_b scores_grad[b] * scores[b]) / d(am, lm) for rnnt_loss_simple, from the
     occupation counts (px_grad, py_grad) that ``rnnt_loss_simple(..., calc_gradients=True)``
-    returned — the chain TensorFlow autodiff runs through rnnt_loss.py:175-221."""
+    returned — the chain TensorFlow autodiff runs through rnnt_loss.py:175-221.
+    ``smoothed``: the same for rnnt_loss_smoothed (rnnt_loss.py:1266-1365, with the
+    path through the batch-global unigram)."""
     io = _Io(lm, am)
     lm_d = io.dev_tensor(lm, torch.float32)
     am_d = io.dev_tensor(am, torch.float32)
@@ -249,10 +252,23 @@ def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad,
     am_g = torch.empty_like(am_d)
     lm_g = torch.empty_like(lm_d)
     ws = _workspace(lib.frn_simple_loss_bwd_workspace_bytes(B, S, T, C), io.dev)
-    check(lib.frn_simple_loss_bwd(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy), _ptr(sg),
-                                  B, S, T, C, int(termination_symbol), rt, _ptr(am_g), _ptr(lm_g), _ptr(ws),
-                                  ws.numel(), _stream(io.dev)), "frn_simple_loss_bwd")
+    if smoothed:
+        check(lib.frn_smoothed_loss_bwd(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy), _ptr(sg),
+                                        B, S, T, C, int(termination_symbol), rt, float(lm_only_scale),
+                                        float(am_only_scale), _ptr(am_g), _ptr(lm_g), _ptr(ws), ws.numel(),
+                                        _stream(io.dev)), "frn_smoothed_loss_bwd")
+    else:
+        check(lib.frn_simple_loss_bwd(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy), _ptr(sg),
+                                      B, S, T, C, int(termination_symbol), rt, _ptr(am_g), _ptr(lm_g), _ptr(ws),
+                                      ws.numel(), _stream(io.dev)), "frn_simple_loss_bwd")
     return io.out(am_g), io.out(lm_g)
+
+
+def smoothed_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad=None,
+                           lm_only_scale: float = 0.1, am_only_scale: float = 0.1, rnnt_type: str = "regular"):
+    """A9 for rnnt_loss_smoothed: see simple_loss_backward."""
+    return simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad,
+                                rnnt_type, True, lm_only_scale, am_only_scale)
 
 
 class _SimpleLossFn(torch.autograd.Function):
@@ -260,7 +276,8 @@ class _SimpleLossFn(torch.autograd.Function):
     _RNNTLossGrad (__init__.py:154-162) stand in the reference."""
 
     @staticmethod
-    def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty):
+    def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, smoothed=False,
+                lm_only_scale=0.0, am_only_scale=0.0):
         B, T, C = am.shape
         S = lm.shape[1] - 1
         rt = _rnnt_type(rnnt_type)
@@ -271,19 +288,21 @@ class _SimpleLossFn(torch.autograd.Function):
         ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), am.device)
         dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
         check(lib.frn_simple_loss(_ptr(lm), _ptr(am), _ptr(symbols), _ptr(boundary), B, S, T, C,
-                                  int(termination_symbol), rt, 0, 0.0, 0.0, dp, 1, _ptr(scores), _ptr(gx), _ptr(gy),
+                                  int(termination_symbol), rt, int(bool(smoothed)), float(lm_only_scale),
+                                  float(am_only_scale), dp, 1, _ptr(scores), _ptr(gx), _ptr(gy),
                                   _ptr(ws), ws.numel(), _stream(am.device)), "frn_simple_loss")
         ctx.save_for_backward(lm, am, symbols, boundary, gx, gy)
-        ctx.args = (termination_symbol, rnnt_type)
+        ctx.args = (termination_symbol, rnnt_type, bool(smoothed), float(lm_only_scale), float(am_only_scale))
         ctx.mark_non_differentiable(gx, gy)
         return scores, gx, gy
 
     @staticmethod
     def backward(ctx, g, _gx, _gy):
         lm, am, symbols, boundary, gx, gy = ctx.saved_tensors
-        term, rnnt_type = ctx.args
-        am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, gx, gy, g.contiguous(), rnnt_type)
-        return lm_g, am_g, None, None, None, None, None
+        term, rnnt_type, smoothed, lms, ams = ctx.args
+        am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, gx, gy, g.contiguous(), rnnt_type,
+                                          smoothed, lms, ams)
+        return lm_g, am_g, None, None, None, None, None, None, None, None
 
 
 def rnnt_loss_simple(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
@@ -315,7 +334,22 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
                        boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
                        delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
                        calc_gradients: bool = False, group=None):
-    """Reference: rnnt_loss.py:1369-1494."""
+    """Reference: rnnt_loss.py:1369-1494.  CUDA tensors that require grad get gradients
+    w.r.t. lm and am (through the batch-global unigram as well)."""
+    if (isinstance(lm, torch.Tensor) and isinstance(am, torch.Tensor) and lm.is_cuda and am.is_cuda
+            and (lm.requires_grad or am.requires_grad) and torch.is_grad_enabled()):
+        if reduction not in _lib.REDUCTIONS:
+            raise ValueError(
+                f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
+        io = _Io(lm, am)
+        B, T, _ = am.shape
+        S = lm.shape[1] - 1
+        scores, gx, gy = _SimpleLossFn.apply(lm.contiguous().float(), am.contiguous().float(),
+                                             io.dev_tensor(symbols, torch.int32), int(termination_symbol),
+                                             _boundary(io, boundary, B, S, T), rnnt_type, float(delay_penalty),
+                                             True, float(lm_only_scale), float(am_only_scale))
+        loss = -scores if reduction == "none" else (-scores.sum() if reduction == "sum" else -scores.mean())
+        return (loss, (gx, gy)) if calc_gradients else loss
     return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
                         reduction, calc_gradients, True, lm_only_scale, am_only_scale, group)
 

@@ -190,6 +190,69 @@ class FastRnntSimpleLossOp : public tf::OpKernel {
 };
 REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLoss").Device(tf::DEVICE_GPU), FastRnntSimpleLossOp);
 
+// gradient of FastRnntSimpleLoss w.r.t. lm and am (A9: what TF autodiff derives through
+// rnnt_loss.py:175-221 / 1266-1365 once _RNNTLossGrad, __init__.py:154-162, has supplied the
+// occupation counts); registered from Python with RegisterGradient("FastRnntSimpleLoss").
+REGISTER_OP("FastRnntSimpleLossGrad")
+    .Input("lm: float32")
+    .Input("am: float32")
+    .Input("symbols: int32")
+    .Input("boundary: int32")
+    .Input("px_grad: float32")
+    .Input("py_grad: float32")
+    .Input("scores_grad: float32")
+    .Attr("termination_symbol: int")
+    .Attr("rnnt_type: int = 0")
+    .Attr("smoothed: bool = false")
+    .Attr("lm_only_scale: float = 0.0")
+    .Attr("am_only_scale: float = 0.0")
+    .Output("lm_grad: float32")
+    .Output("am_grad: float32")
+    .SetShapeFn([](InferenceContext *c) {
+      c->set_output(0, c->input(0));
+      c->set_output(1, c->input(1));
+      return tf::OkStatus();
+    });
+
+class FastRnntSimpleLossGradOp : public tf::OpKernel {
+ public:
+  explicit FastRnntSimpleLossGradOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("termination_symbol", &term_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("rnnt_type", &type_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("smoothed", &smoothed_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("lm_only_scale", &lms_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("am_only_scale", &ams_));
+  }
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &lm = ctx->input(0), &am = ctx->input(1), &sym = ctx->input(2), &bd = ctx->input(3);
+    const tf::Tensor &gx = ctx->input(4), &gy = ctx->input(5), &sg = ctx->input(6);
+    const int B = am.dim_size(0), T = am.dim_size(1), C = am.dim_size(2), S = lm.dim_size(1) - 1;
+    tf::Tensor *lm_g = nullptr, *am_g = nullptr, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, lm.shape(), &lm_g));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, am.shape(), &am_g));
+    const size_t bytes = frn_simple_loss_bwd_workspace_bytes(B, S, T, C);
+    OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
+    const int rc =
+        smoothed_ ? frn_smoothed_loss_bwd(lm.flat<float>().data(), am.flat<float>().data(),
+                                          sym.flat<tf::int32>().data(), bd.flat<tf::int32>().data(),
+                                          gx.flat<float>().data(), gy.flat<float>().data(), sg.flat<float>().data(), B,
+                                          S, T, C, term_, type_, lms_, ams_, am_g->flat<float>().data(),
+                                          lm_g->flat<float>().data(), ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx))
+                  : frn_simple_loss_bwd(lm.flat<float>().data(), am.flat<float>().data(),
+                                        sym.flat<tf::int32>().data(), bd.flat<tf::int32>().data(),
+                                        gx.flat<float>().data(), gy.flat<float>().data(), sg.flat<float>().data(), B, S,
+                                        T, C, term_, type_, am_g->flat<float>().data(), lm_g->flat<float>().data(),
+                                        ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx));
+    OP_REQUIRES_OK(ctx, FromFrn(rc, "FastRnntSimpleLossGrad"));
+  }
+
+ private:
+  int term_, type_;
+  bool smoothed_;
+  float lms_, ams_;
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLossGrad").Device(tf::DEVICE_GPU), FastRnntSimpleLossGradOp);
+
 // ---------------------------------------------------------------------------
 // FastRnntPruneRanges (rnnt_loss.py:647-761) / FastRnntDoPruning (:763-812)
 // ---------------------------------------------------------------------------
@@ -257,6 +320,39 @@ class FastRnntDoPruningOp : public tf::OpKernel {
   }
 };
 REGISTER_KERNEL_BUILDER(Name("FastRnntDoPruning").Device(tf::DEVICE_GPU), FastRnntDoPruningOp);
+
+// do_rnnt_pruning plus the additive joiner of the reference's tests (logits = am_pruned + lm_pruned,
+// simple_rnnt_loss_test.py:120-125) in one pass; all three tensors are outputs.
+REGISTER_OP("FastRnntDoPruningAddJoiner")
+    .Input("am: float32")
+    .Input("lm: float32")
+    .Input("ranges: int32")
+    .Output("am_pruned: float32")
+    .Output("lm_pruned: float32")
+    .Output("logits: float32")
+    .SetShapeFn([](InferenceContext *c) {
+      for (int i = 0; i < 3; ++i) c->set_output(i, c->UnknownShapeOfRank(4));
+      return tf::OkStatus();
+    });
+
+class FastRnntDoPruningAddJoinerOp : public tf::OpKernel {
+ public:
+  explicit FastRnntDoPruningAddJoinerOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {}
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &am = ctx->input(0), &lm = ctx->input(1), &rg = ctx->input(2);
+    const int B = am.dim_size(0), T = am.dim_size(1), C = am.dim_size(2), S = lm.dim_size(1) - 1, R = rg.dim_size(2);
+    tf::Tensor *amp = nullptr, *lmp = nullptr, *lg = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, T, R, C}), &amp));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, T, R, C}), &lmp));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({B, T, R, C}), &lg));
+    OP_REQUIRES_OK(ctx, FromFrn(frn_do_pruning_add_joiner(am.flat<float>().data(), lm.flat<float>().data(),
+                                                          rg.flat<tf::int32>().data(), B, S, T, R, C,
+                                                          amp->flat<float>().data(), lmp->flat<float>().data(),
+                                                          lg->flat<float>().data(), StreamOf(ctx)),
+                                "FastRnntDoPruningAddJoiner"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntDoPruningAddJoiner").Device(tf::DEVICE_GPU), FastRnntDoPruningAddJoinerOp);
 
 // gradient of FastRnntDoPruning (registered from Python with RegisterGradient)
 REGISTER_OP("FastRnntDoPruningGrad")

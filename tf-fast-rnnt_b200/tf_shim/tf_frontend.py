@@ -43,6 +43,25 @@ def _do_pruning_grad(op, g_am, g_lm):
     return [am_g, lm_g, None]
 
 
+@ops.RegisterGradient("FastRnntDoPruningAddJoiner")
+def _do_pruning_add_joiner_grad(op, g_am, g_lm, g_logits):
+    S = op.inputs[1].shape[1] - 1
+    am_g, lm_g = _ops.fast_rnnt_do_pruning_grad(g_am + g_logits, g_lm + g_logits, op.inputs[2], S=S)
+    return [am_g, lm_g, None]
+
+
+@ops.RegisterGradient("FastRnntSimpleLoss")
+def _simple_loss_grad(op, g_scores, _g_px_grad, _g_py_grad):
+    """A9: d scores / d (lm, am) from the occupation counts the forward op produced (it must have
+    run with calc_gradients=True)."""
+    lm_g, am_g = _ops.fast_rnnt_simple_loss_grad(
+        op.inputs[0], op.inputs[1], op.inputs[2], op.inputs[3], op.outputs[1], op.outputs[2], g_scores,
+        termination_symbol=op.get_attr("termination_symbol"), rnnt_type=op.get_attr("rnnt_type"),
+        smoothed=op.get_attr("smoothed"), lm_only_scale=op.get_attr("lm_only_scale"),
+        am_only_scale=op.get_attr("am_only_scale"))
+    return [lm_g, am_g, None, None]
+
+
 def _reduce(scores, reduction):
     if reduction == "none":
         return -scores
@@ -66,7 +85,7 @@ def _simple(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_pena
     scores, gx, gy = _ops.fast_rnnt_simple_loss(
         lm, am, tf.cast(symbols, tf.int32), _boundary(boundary, B, S, T), termination_symbol=termination_symbol,
         rnnt_type=_TYPES[rnnt_type], smoothed=smoothed, lm_only_scale=lms, am_only_scale=ams,
-        delay_penalty=max(delay_penalty, 0.0), calc_gradients=calc_gradients)
+        delay_penalty=max(delay_penalty, 0.0), calc_gradients=True)      # the occupation counts feed the gradient op
     loss = _reduce(scores, reduction)
     return (loss, (gx, gy)) if calc_gradients else loss
 
@@ -90,6 +109,11 @@ def get_rnnt_prune_ranges(px_grad, py_grad, boundary, s_range):
 
 def do_rnnt_pruning(am, lm, ranges):
     return _ops.fast_rnnt_do_pruning(am, lm, ranges)
+
+
+def do_rnnt_pruning_add_joiner(am, lm, ranges):
+    """(extension) -> (am_pruned, lm_pruned, am_pruned + lm_pruned) in one pass."""
+    return _ops.fast_rnnt_do_pruning_add_joiner(am, lm, ranges)
 
 
 def rnnt_loss_pruned(logits, symbols, ranges, termination_symbol, boundary=None, rnnt_type="regular",
