@@ -44,6 +44,7 @@ WORKLOADS = {
     "c1": (2, 50, 10, 16, 5),
     "c2": (32, 500, 100, 500, 5),
     "c4": (16, 1500, 400, 5000, 5),
+    "c5": (256, 1500, 400, 500, 5),     # ragged: run_c5(); the CPU arm times 2 full-length utterances of it
 }
 METRIC = "utterances/sec (pruned loss fwd+bwd) at B32 T500 S100 C500; lattice cells/s; HBM %"
 UNIT = "utterances/s"
@@ -118,7 +119,7 @@ def run_reference_arm(args):
     workload = args.workload
     B = WORKLOADS[workload][0]
     steps = max(1, min(args.steps, 5))
-    base, dt = cpu_bench(workload, steps, min(args.warmup, 1))
+    base, dt = cpu_bench(workload, steps, min(args.warmup, 1), 2 if workload == "c5" else None)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -696,6 +697,140 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def c5_boundaries(B=256, T=1500, S=400, seed=5):
+    """BASELINE.json configs[4] / SURVEY.md 8(d): T_b ~ U[200,1500], S_b ~ U[20, min(400, T_b)]."""
+    rng = np.random.default_rng(seed)
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 3] = rng.integers(200, T + 1, B)
+    bd[:, 2] = np.minimum(rng.integers(20, S + 1, B), bd[:, 3])
+    return bd
+
+
+def run_c5(args):
+    """configs[4]: ONE ragged batch of 256 utterances (C=500, s_range=5, reduction=sum), sharded by utterance
+    over the ranks (greedy LPT on lattice cells, tf_fast_rnnt.sharding.partition_batch) - strong scaling.
+    Each rank cuts its shard into length buckets (sharding.plan_buckets) so that the bandwidth-bound kernels
+    do not stream padding, runs the full pipeline per bucket and completes the two sums with one all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from tf_fast_rnnt.sharding import partition_batch, plan_buckets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, R = 256, 500, 5
+    bd_all = c5_boundaries(B)
+    mine = partition_batch(bd_all, world)[rank]
+    buckets = plan_buckets(bd_all[mine], R, C, max_buckets=args.buckets)
+    pipes, inputs, host_inputs = [], [], []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    for bk in buckets:
+        idx = mine[bk["idx"]]
+        Bk, Sk, Tk = len(idx), bk["S_max"], bk["T_max"]
+        pipes.append(Pipeline(Bk, Tk, Sk, C, R, dev, fuse_add=not args.no_fuse_add))
+        am = torch.randn((Bk, Tk, C), generator=gen, device=dev)
+        lm = torch.randn((Bk, Sk + 1, C), generator=gen, device=dev)
+        sym = torch.randint(0, C - 1, (Bk, Sk), generator=gen, device=dev, dtype=torch.int32)
+        bd = torch.from_numpy(bd_all[idx].copy()).to(dev)
+        inputs.append((am, lm, sym, bd))
+    torch.cuda.synchronize()
+    total = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def step():
+        total.zero_()
+        for pipe, inp in zip(pipes, inputs):
+            pipe.step(*inp)
+            total.add_(pipe.losses)
+        if world > 1:
+            dist.all_reduce(total)
+
+    n0 = pipes[0].lib.frn_kernel_launches()
+    step()
+    kernels_per_step = int(pipes[0].lib.frn_kernel_launches() - n0)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.ready.wait(30.0)
+    sampler.samples.clear()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    loss_check = total.cpu().tolist()
+
+    # end to end: the shard's am / lm / symbols / boundary from pinned host memory every step, loss read back
+    host_inputs = [[x.cpu().pin_memory() for x in inp] for inp in inputs]
+    host_out = torch.empty(2, dtype=torch.float32).pin_memory()
+    n_e2e = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        for inp, hin in zip(inputs, host_inputs):
+            for d, h in zip(inp, hin):
+                d.copy_(h, non_blocking=True)
+        step()
+        host_out.copy_(total, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(host_out[0])
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n_e2e):
+        assert np.isfinite(e2e_step())
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / n_e2e
+    h2d = sum(x.numel() * x.element_size() for hin in host_inputs for x in hin)
+    frames = int(bd_all[mine, 3].sum())
+    padded = int(sum(bk["padded_frames"] for bk in buckets))
+    if rank == 0:
+        emit({
+            "metric": METRIC, "value": B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5: ragged batch B=256 (T_b 200-1500, S_b 20-400) C=500 s_range=5 fp32 regular sum, "
+                                   "full pruned pipeline per length bucket, batch sharded by utterance over the ranks",
+                       "launch": "direct", "sharding": f"greedy LPT on lattice cells, {len(mine)} utterances on rank 0",
+                       "buckets_rank0": [{"utterances": int(len(bk["idx"])), "T_max": bk["T_max"], "S_max": bk["S_max"]}
+                                         for bk in buckets],
+                       "frames_rank0": frames, "padded_frames_rank0": padded,
+                       "l2": "every step streams > 1 GB per rank (> 126 MB L2)", "loss_check": loss_check},
+            "clocks": sampler.summary(),
+            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms, "pipelining": "none (copy, compute, read back)"},
+            "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step,
+        })
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -703,6 +838,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--buckets", type=int, default=4, help="c5: length buckets per rank (1 = pad the shard to its maxima)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=1,
                     help="run a step as this many independent sub-batches on separate CUDA streams")
@@ -718,6 +854,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_gpu_arm(args)
 
