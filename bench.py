@@ -225,8 +225,8 @@ class Pipeline:
     def _reduce(self):
         lib, chk, B = self.lib, self._lib.check, self.B
         st = self.torch.cuda.current_stream(self.dev).cuda_stream
-        chk(lib.frn_reduce(self.scores.data_ptr(), B, 2, 0.0, self.losses.data_ptr(), st), "reduce")
-        chk(lib.frn_reduce(self.pscores.data_ptr(), B, 2, 0.0, self.losses.data_ptr() + 4, st), "reduce")
+        chk(lib.frn_reduce_pair(self.scores.data_ptr(), self.pscores.data_ptr(), B, 2, 0.0, self.losses.data_ptr(),
+                                self.losses.data_ptr() + 4, st), "reduce_pair")
 
     def step(self, am, lm, sym, bd):
         torch = self.torch

@@ -229,6 +229,9 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
  * when the sum is completed by an all-reduce across ranks). */
 int frn_reduce(const float *scores, int B, int reduction, float denominator,
                float *out, void *stream);
+/* The same for two score vectors of one step (simple and pruned loss) in one launch. */
+int frn_reduce_pair(const float *scores_a, const float *scores_b, int B, int reduction,
+                    float denominator, float *out_a, float *out_b, void *stream);
 
 #ifdef __cplusplus
 }

@@ -400,4 +400,11 @@ int frn_reduce(const float *scores, int B, int reduction, float denominator, flo
                        static_cast<cudaStream_t>(stream));
 }
 
+int frn_reduce_pair(const float *scores_a, const float *scores_b, int B, int reduction, float denominator,
+                    float *out_a, float *out_b, void *stream) {
+  FRN_REQUIRE(B > 0 && scores_a && scores_b && out_a && out_b && reduction >= FRN_NONE && reduction <= FRN_SUM);
+  return launch_reduce_pair(scores_a, scores_b, B, reduction, denominator > 0.f ? denominator : (float)B, out_a, out_b,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -67,6 +67,8 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
                    float *gyc, float *scores, cudaStream_t stream);
 // misc.cu
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream);
+int launch_reduce_pair(const float *a, const float *b, int B, int reduction, float denom, float *out_a, float *out_b,
+                       cudaStream_t stream);
 int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
 int launch_iota_ranges(int32_t *ranges, size_t n, int R, cudaStream_t stream);
 }  // namespace frn

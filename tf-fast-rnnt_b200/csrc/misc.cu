@@ -4,8 +4,10 @@
 namespace frn {
 
 // out = -scores (none) | -sum | -sum/denominator; one block, deterministic order.
+// Block 1 (frn_reduce_pair) does the same for a second vector.
 __global__ void __launch_bounds__(256) reduce_kernel(const float *scores, int B, int reduction, float denom,
-                                                     float *out) {
+                                                     float *out, const float *scores2, float *out2) {
+  if (blockIdx.x == 1) { scores = scores2; out = out2; }
   if (reduction == FRN_NONE) {
     for (int i = threadIdx.x; i < B; i += blockDim.x) out[i] = -scores[i];
     return;
@@ -50,7 +52,13 @@ int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_
 }
 
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream) {
-  count_launch(), reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out);
+  count_launch(), reduce_kernel<<<1, 256, 0, stream>>>(scores, B, reduction, denom, out, nullptr, nullptr);
+  return check_launch();
+}
+
+int launch_reduce_pair(const float *a, const float *b, int B, int reduction, float denom, float *out_a, float *out_b,
+                       cudaStream_t stream) {
+  count_launch(), reduce_kernel<<<2, 256, 0, stream>>>(a, B, reduction, denom, out_a, b, out_b);
   return check_launch();
 }
 
