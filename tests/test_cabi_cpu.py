@@ -108,3 +108,44 @@ def test_public_api_names_match_the_reference():
                                         "rnnt_type", "delay_penalty", "reduction", "calc_gradients"]
     sig = inspect.signature(tf_fast_rnnt.rnnt_loss_smoothed)
     assert sig.parameters["lm_only_scale"].default == 0.1 and sig.parameters["am_only_scale"].default == 0.1
+
+
+def test_tf_shim_type_checks_against_the_c_header():
+    """The TensorFlow op shim cannot be built here (no TensorFlow).  It is parsed and type-checked
+    with g++ -fsyntax-only against a minimal mock of the TF op API (tests/tf_mock) and the REAL
+    include/fast_rnnt_b200.h, so every frn_* call in it has the right arity and argument types."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the image"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-comment", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(root, "tests", "tf_mock"), "-I", cuda_inc,
+           os.path.join(root, "tf-fast-rnnt_b200", "tf_shim", "tf_fast_rnnt_b200_ops.cc")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+
+
+def test_tf_frontend_uses_only_registered_ops():
+    """Every _ops.<name> the TensorFlow front-end calls is an op the shim registers
+    (TensorFlow exposes REGISTER_OP("FastRnntFooBar") as fast_rnnt_foo_bar)."""
+    import ast
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "tf-fast-rnnt_b200", "tf_shim", "tf_fast_rnnt_b200_ops.cc")).read()
+    front = open(os.path.join(root, "tf-fast-rnnt_b200", "tf_shim", "tf_frontend.py")).read()
+    ast.parse(front)
+
+    def snake(name):
+        s = re.sub(r"([A-Z]+)([A-Z][a-z])", r"\1_\2", name)
+        return re.sub(r"([a-z0-9])([A-Z])", r"\1_\2", s).lower()
+
+    registered = {snake(n) for n in re.findall(r'REGISTER_OP\("(\w+)"\)', shim)}
+    used = set(re.findall(r"_ops\.(\w+)\(", front))
+    assert used and used <= registered, sorted(used - registered)
+    # the reference's public names (tf_fast_rnnt/__init__.py:24-33, 42, 151) all exist in the front-end
+    for name in ("do_rnnt_pruning", "get_rnnt_logprobs", "get_rnnt_logprobs_joint", "get_rnnt_logprobs_pruned",
+                 "get_rnnt_logprobs_smoothed", "get_rnnt_prune_ranges", "rnnt_loss", "rnnt_loss_pruned",
+                 "rnnt_loss_simple", "rnnt_loss_smoothed", "mutual_information_recursion", "cummin"):
+        assert re.search(rf"^def {name}\(", front, re.M), name

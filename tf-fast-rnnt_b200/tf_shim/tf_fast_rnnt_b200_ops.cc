@@ -19,6 +19,10 @@
 //       $(python -c "import tensorflow as tf; print(' '.join(tf.sysconfig.get_link_flags()))") \
 //       -I../../include -L../lib -lfast_rnnt_b200 -Wl,-rpath,'$ORIGIN/../lib' -DGOOGLE_CUDA=1
 #define EIGEN_USE_GPU
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
 #include "tensorflow/core/framework/op.h"
 #include "tensorflow/core/framework/op_kernel.h"
 #include "tensorflow/core/framework/shape_inference.h"
@@ -415,7 +419,7 @@ REGISTER_OP("FastRnntPrunedLoss")
       return tf::OkStatus();
     });
 
-template <typename T>
+template <typename DT>
 class FastRnntPrunedLossOp : public tf::OpKernel {
  public:
   explicit FastRnntPrunedLossOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
@@ -434,12 +438,12 @@ class FastRnntPrunedLossOp : public tf::OpKernel {
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, with_grad_ ? lg.shape() : tf::TensorShape({0}), &grad));
     const size_t bytes = frn_pruned_loss_workspace_bytes(B, S, T, R);
     OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
-    const int dtype = std::is_same<T, float>::value ? FRN_F32 : FRN_BF16;
-    OP_REQUIRES_OK(ctx, FromFrn(frn_pruned_loss(lg.flat<T>().data(), dtype, sym.flat<tf::int32>().data(),
+    const int dtype = std::is_same<DT, float>::value ? FRN_F32 : FRN_BF16;
+    OP_REQUIRES_OK(ctx, FromFrn(frn_pruned_loss(lg.flat<DT>().data(), dtype, sym.flat<tf::int32>().data(),
                                                 rg.flat<tf::int32>().data(), bd.flat<tf::int32>().data(), B, S, T, R,
                                                 C, term_, type_, dp_, sg.flat<float>().data(),
                                                 scores->flat<float>().data(),
-                                                with_grad_ ? static_cast<void *>(grad->flat<T>().data()) : nullptr,
+                                                with_grad_ ? static_cast<void *>(grad->flat<DT>().data()) : nullptr,
                                                 ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx)),
                                 "FastRnntPrunedLoss"));
   }
@@ -453,3 +457,171 @@ REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLoss").Device(tf::DEVICE_GPU).TypeCo
                         FastRnntPrunedLossOp<float>);
 REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLoss").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
                         FastRnntPrunedLossOp<tf::bfloat16>);
+
+// ---------------------------------------------------------------------------
+// FastRnntJointLoss: rnnt_loss on the full joiner output [B,T,S+1,C]
+// (rnnt_loss.py:340-551: get_rnnt_logprobs_joint + recursion), with its logits gradient.
+// ---------------------------------------------------------------------------
+REGISTER_OP("FastRnntJointLoss")
+    .Input("logits: T")
+    .Input("symbols: int32")
+    .Input("boundary: int32")
+    .Input("scores_grad: float32")
+    .Attr("T: {float32, bfloat16} = DT_FLOAT")
+    .Attr("termination_symbol: int")
+    .Attr("rnnt_type: int = 0")
+    .Attr("delay_penalty: float = 0.0")
+    .Attr("with_logits_grad: bool = true")
+    .Output("scores: float32")
+    .Output("logits_grad: T")
+    .SetShapeFn([](InferenceContext *c) {
+      c->set_output(0, c->Vector(c->Dim(c->input(0), 0)));
+      c->set_output(1, c->input(0));
+      return tf::OkStatus();
+    });
+
+template <typename DT>
+class FastRnntJointLossOp : public tf::OpKernel {
+ public:
+  explicit FastRnntJointLossOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("termination_symbol", &term_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("rnnt_type", &type_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("delay_penalty", &dp_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("with_logits_grad", &with_grad_));
+  }
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &lg = ctx->input(0), &sym = ctx->input(1), &bd = ctx->input(2), &sg = ctx->input(3);
+    OP_REQUIRES(ctx, lg.dims() == 4, tf::errors::InvalidArgument("logits must be [B,T,S+1,C]"));
+    const int B = lg.dim_size(0), T = lg.dim_size(1), C = lg.dim_size(3), S = sym.dim_size(1);
+    OP_REQUIRES(ctx, lg.dim_size(2) == S + 1, tf::errors::InvalidArgument("logits.shape[2] must be S+1"));
+    tf::Tensor *scores = nullptr, *grad = nullptr, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B}), &scores));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, with_grad_ ? lg.shape() : tf::TensorShape({0}), &grad));
+    const size_t bytes = frn_joint_loss_workspace_bytes(B, S, T);
+    OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
+    const int dtype = std::is_same<DT, float>::value ? FRN_F32 : FRN_BF16;
+    OP_REQUIRES_OK(ctx, FromFrn(frn_joint_loss(lg.flat<DT>().data(), dtype, sym.flat<tf::int32>().data(),
+                                               bd.flat<tf::int32>().data(), B, S, T, C, term_, type_, dp_,
+                                               sg.flat<float>().data(), scores->flat<float>().data(),
+                                               with_grad_ ? static_cast<void *>(grad->flat<DT>().data()) : nullptr,
+                                               ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx)),
+                                "FastRnntJointLoss"));
+  }
+
+ private:
+  int term_, type_;
+  float dp_;
+  bool with_grad_;
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntJointLoss").Device(tf::DEVICE_GPU).TypeConstraint<float>("T"),
+                        FastRnntJointLossOp<float>);
+REGISTER_KERNEL_BUILDER(Name("FastRnntJointLoss").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
+                        FastRnntJointLossOp<tf::bfloat16>);
+
+// ---------------------------------------------------------------------------
+// FastRnntSimpleLogprobs: get_rnnt_logprobs / get_rnnt_logprobs_smoothed (rnnt_loss.py:63-223,
+// 1132-1367) -> dense px [B,S,T1], py [B,S+1,T].  FastRnntPrunedLogprobs: get_rnnt_logprobs_pruned
+// (:853-1020) -> the same from pruned joiner logits.  Forward only (the public log-prob
+// functions; the losses above carry their own gradients).
+// ---------------------------------------------------------------------------
+REGISTER_OP("FastRnntSimpleLogprobs")
+    .Input("lm: float32")
+    .Input("am: float32")
+    .Input("symbols: int32")
+    .Input("boundary: int32")
+    .Attr("termination_symbol: int")
+    .Attr("rnnt_type: int = 0")
+    .Attr("smoothed: bool = false")
+    .Attr("lm_only_scale: float = 0.0")
+    .Attr("am_only_scale: float = 0.0")
+    .Output("px: float32")
+    .Output("py: float32")
+    .SetShapeFn([](InferenceContext *c) {
+      c->set_output(0, c->UnknownShapeOfRank(3));
+      c->set_output(1, c->UnknownShapeOfRank(3));
+      return tf::OkStatus();
+    });
+
+class FastRnntSimpleLogprobsOp : public tf::OpKernel {
+ public:
+  explicit FastRnntSimpleLogprobsOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("termination_symbol", &term_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("rnnt_type", &type_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("smoothed", &smoothed_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("lm_only_scale", &lms_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("am_only_scale", &ams_));
+  }
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &lm = ctx->input(0), &am = ctx->input(1), &sym = ctx->input(2), &bd = ctx->input(3);
+    OP_REQUIRES(ctx, lm.dims() == 3 && am.dims() == 3 && sym.dims() == 2, tf::errors::InvalidArgument("bad ranks"));
+    const int B = am.dim_size(0), T = am.dim_size(1), C = am.dim_size(2), S = lm.dim_size(1) - 1;
+    const int T1 = type_ == FRN_REGULAR ? T + 1 : T;
+    tf::Tensor *px = nullptr, *py = nullptr, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, S, T1}), &px));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, S + 1, T}), &py));
+    const size_t bytes = frn_simple_logprobs_workspace_bytes(B, S, T, C);
+    OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
+    OP_REQUIRES_OK(ctx, FromFrn(frn_simple_logprobs(lm.flat<float>().data(), am.flat<float>().data(),
+                                                    sym.flat<tf::int32>().data(), bd.flat<tf::int32>().data(), B, S,
+                                                    T, C, term_, type_, smoothed_ ? 1 : 0, lms_, ams_,
+                                                    px->flat<float>().data(), py->flat<float>().data(),
+                                                    ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx)),
+                                "FastRnntSimpleLogprobs"));
+  }
+
+ private:
+  int term_, type_;
+  bool smoothed_;
+  float lms_, ams_;
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLogprobs").Device(tf::DEVICE_GPU), FastRnntSimpleLogprobsOp);
+
+REGISTER_OP("FastRnntPrunedLogprobs")
+    .Input("logits: T")
+    .Input("symbols: int32")
+    .Input("ranges: int32")
+    .Input("boundary: int32")
+    .Attr("T: {float32, bfloat16} = DT_FLOAT")
+    .Attr("termination_symbol: int")
+    .Attr("rnnt_type: int = 0")
+    .Output("px: float32")
+    .Output("py: float32")
+    .SetShapeFn([](InferenceContext *c) {
+      c->set_output(0, c->UnknownShapeOfRank(3));
+      c->set_output(1, c->UnknownShapeOfRank(3));
+      return tf::OkStatus();
+    });
+
+template <typename DT>
+class FastRnntPrunedLogprobsOp : public tf::OpKernel {
+ public:
+  explicit FastRnntPrunedLogprobsOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("termination_symbol", &term_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("rnnt_type", &type_));
+  }
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &lg = ctx->input(0), &sym = ctx->input(1), &rg = ctx->input(2), &bd = ctx->input(3);
+    OP_REQUIRES(ctx, lg.dims() == 4, tf::errors::InvalidArgument("logits must be [B,T,s_range,C]"));
+    const int B = lg.dim_size(0), T = lg.dim_size(1), R = lg.dim_size(2), C = lg.dim_size(3), S = sym.dim_size(1);
+    const int T1 = type_ == FRN_REGULAR ? T + 1 : T;
+    tf::Tensor *px = nullptr, *py = nullptr, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, S, T1}), &px));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, S + 1, T}), &py));
+    const size_t bytes = frn_pruned_logprobs_workspace_bytes(B, S, T, R);
+    OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
+    const int dtype = std::is_same<DT, float>::value ? FRN_F32 : FRN_BF16;
+    OP_REQUIRES_OK(ctx, FromFrn(frn_pruned_logprobs(lg.flat<DT>().data(), dtype, sym.flat<tf::int32>().data(),
+                                                    rg.flat<tf::int32>().data(), bd.flat<tf::int32>().data(), B, S, T,
+                                                    R, C, term_, type_, px->flat<float>().data(),
+                                                    py->flat<float>().data(), ws.flat<tf::uint8>().data(), bytes,
+                                                    StreamOf(ctx)),
+                                "FastRnntPrunedLogprobs"));
+  }
+
+ private:
+  int term_, type_;
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobs").Device(tf::DEVICE_GPU).TypeConstraint<float>("T"),
+                        FastRnntPrunedLogprobsOp<float>);
+REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobs").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
+                        FastRnntPrunedLogprobsOp<tf::bfloat16>);

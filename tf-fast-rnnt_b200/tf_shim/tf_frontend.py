@@ -137,3 +137,56 @@ def rnnt_loss_pruned(logits, symbols, ranges, termination_symbol, boundary=None,
         return s, grad
 
     return _reduce(_scores(logits), reduction)
+
+
+def rnnt_loss(logits, symbols, termination_symbol, boundary=None, rnnt_type="regular", delay_penalty=0.0,
+              reduction="mean"):
+    """Reference: rnnt_loss.py:446-551 (full joiner output [B,T,S+1,C])."""
+    B, T = logits.shape[0], logits.shape[1]
+    S = symbols.shape[1]
+    bd = _boundary(boundary, B, S, T)
+    sym = tf.cast(symbols, tf.int32)
+    kw = dict(termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type], delay_penalty=max(delay_penalty, 0.0))
+
+    @tf.custom_gradient
+    def _scores(lg):
+        s, _ = _ops.fast_rnnt_joint_loss(lg, sym, bd, tf.ones([B], tf.float32), with_logits_grad=False, **kw)
+
+        def grad(upstream):
+            _, g = _ops.fast_rnnt_joint_loss(lg, sym, bd, upstream, with_logits_grad=True, **kw)
+            return g
+        return s, grad
+
+    return _reduce(_scores(logits), reduction)
+
+
+def get_rnnt_logprobs(lm, am, symbols, termination_symbol, rnnt_type="regular", boundary=None):
+    """Reference: rnnt_loss.py:63-223 (argument order as there)."""
+    B, T = am.shape[0], am.shape[1]
+    S = lm.shape[1] - 1
+    return _ops.fast_rnnt_simple_logprobs(lm, am, tf.cast(symbols, tf.int32), _boundary(boundary, B, S, T),
+                                          termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type])
+
+
+def get_rnnt_logprobs_smoothed(lm, am, symbols, termination_symbol, lm_only_scale=0.1, am_only_scale=0.1,
+                               boundary=None, rnnt_type="regular"):
+    """Reference: rnnt_loss.py:1132-1367."""
+    B, T = am.shape[0], am.shape[1]
+    S = lm.shape[1] - 1
+    return _ops.fast_rnnt_simple_logprobs(lm, am, tf.cast(symbols, tf.int32), _boundary(boundary, B, S, T),
+                                          termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type],
+                                          smoothed=True, lm_only_scale=lm_only_scale, am_only_scale=am_only_scale)
+
+
+def get_rnnt_logprobs_pruned(logits, symbols, ranges, termination_symbol, boundary, rnnt_type="regular"):
+    """Reference: rnnt_loss.py:853-1020."""
+    return _ops.fast_rnnt_pruned_logprobs(logits, tf.cast(symbols, tf.int32), ranges, tf.cast(boundary, tf.int32),
+                                          termination_symbol=termination_symbol, rnnt_type=_TYPES[rnnt_type])
+
+
+def get_rnnt_logprobs_joint(logits, symbols, termination_symbol, boundary=None, rnnt_type="regular"):
+    """Reference: rnnt_loss.py:340-444: the pruned log-probs with the identity band ranges[b,t,i] = i."""
+    B, T, S1 = logits.shape[0], logits.shape[1], logits.shape[2]
+    ranges = tf.tile(tf.reshape(tf.range(S1, dtype=tf.int32), [1, 1, S1]), [B, T, 1])
+    return get_rnnt_logprobs_pruned(logits, symbols, ranges, termination_symbol, _boundary(boundary, B, S1 - 1, T),
+                                    rnnt_type)
