@@ -144,6 +144,20 @@ def test_tf_frontend_uses_only_registered_ops():
     registered = {snake(n) for n in re.findall(r'REGISTER_OP\("(\w+)"\)', shim)}
     used = set(re.findall(r"_ops\.(\w+)\(", front))
     assert used and used <= registered, sorted(used - registered)
+    # keyword arguments of every call are attributes of that op, positional arguments do not exceed its inputs
+    ops_def = {}
+    for m in re.finditer(r'REGISTER_OP\("(\w+)"\)(.*?);', shim, re.S):
+        body = m.group(2)
+        ops_def[snake(m.group(1))] = (len(re.findall(r'\.Input\("', body)),
+                                      set(re.findall(r'\.Attr\("(\w+):', body)))
+    for node in ast.walk(ast.parse(front)):
+        if (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)
+                and isinstance(node.func.value, ast.Name) and node.func.value.id == "_ops"):
+            n_in, attrs = ops_def[node.func.attr]
+            assert len(node.args) <= n_in, (node.func.attr, len(node.args), n_in)
+            for kw in node.keywords:
+                if kw.arg is not None:
+                    assert kw.arg in attrs, (node.func.attr, kw.arg)
     # the reference's public names (tf_fast_rnnt/__init__.py:24-33, 42, 151) all exist in the front-end
     for name in ("do_rnnt_pruning", "get_rnnt_logprobs", "get_rnnt_logprobs_joint", "get_rnnt_logprobs_pruned",
                  "get_rnnt_logprobs_smoothed", "get_rnnt_prune_ranges", "rnnt_loss", "rnnt_loss_pruned",
