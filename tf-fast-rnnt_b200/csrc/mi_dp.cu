@@ -403,39 +403,27 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
   const float inv_tot = dead ? 0.f : 1.0f / tot.x;
   const int tot_o = __float_as_int(tot.y);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  // phase 1: lane <-> s (coalesced plane reads), 8 warps stride the diagonals; the plane reads of the
-  // thread's 4 diagonals are issued together (one L2 round trip instead of four)
-  float2 av[4];
-  float4 bv[4];
-  bool arc_x[4], arc_y[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int dd = wrp + 8 * k;
+  // phase 1: lane <-> s (coalesced plane reads), 8 warps stride the diagonals
+  for (int dd = wrp; dd < 32; dd += 8) {
     const int s = s0 + lane, t = d0 + dd - K * s;  // absolute cell
-    av[k] = make_float2(0.f, 0.f);
-    bv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    arc_x[k] = arc_y[k] = false;
+    float vx = 0.f, vy = 0.f;
     if (!dead && t >= 0) {
       const int sp = s - s_begin, tp = t - t_begin;
       if (sp >= 0 && tp >= 0 && sp <= Sb && tp <= Tb) {
         const int d = tp + K * sp;
         if (d < Db) {  // arcs leave diagonals 0..Db-1
           const size_t at = plane + (size_t)d * p.P + sp;
-          av[k] = p.A[at];
-          bv[k] = p.Bq[at];
+          const float2 a = p.A[at];
+          const float4 bq = p.Bq[at];
+          const float sc = occupation_scale(a, __float_as_int(bq.z), tot_o, inv_tot);
           // arc (s,t)->(s+1,t+noff): cu:727-746; arc (s,t)->(s,t+1): cu:747-753
-          arc_x[k] = sp < Sb && tp + noff <= Tb;
-          arc_y[k] = tp < Tb;
+          if (sp < Sb && tp + noff <= Tb) vx = bq.x * sc;
+          if (tp < Tb) vy = bq.y * sc;
         }
       }
     }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int dd = wrp + 8 * k;
-    const float sc = occupation_scale(av[k], __float_as_int(bv[k].z), tot_o, inv_tot);
-    sgx[lane][dd] = arc_x[k] ? bv[k].x * sc : 0.f;
-    sgy[lane][dd] = arc_y[k] ? bv[k].y * sc : 0.f;
+    sgx[lane][dd] = vx;
+    sgy[lane][dd] = vy;
   }
   __syncthreads();
   // phase 2: lane <-> t within a row segment
