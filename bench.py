@@ -398,6 +398,35 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and, by first touch, the pinned host buffers it allocates afterwards) to the
+    CPUs of the NUMA node its GPU hangs off: with one rank per GPU the H2D copies of the end-to-end leg
+    then read local memory instead of all ranks pulling from one socket.  Best effort; returns the node
+    or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -407,6 +436,7 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -656,7 +686,8 @@ def run_gpu_arm(args):
             "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step"
                        + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else ""),
             "l2": f"{NSETS} rotating input sets ({NSETS * h2d / 1e6:.0f} MB) + ~1.1 GB of streamed intermediates per step (> 126 MB L2)",
-            "sharding": "utterances sharded across ranks, one 2-float NCCL all-reduce per step" if world > 1 else "single GPU",
+            "sharding": ("utterances sharded across ranks, one 2-float NCCL all-reduce per step; rank 0 bound to NUMA "
+                         f"node {numa_node}") if world > 1 else "single GPU",
             "loss_check": loss_check,
         },
         "clocks": sampler.summary(),
