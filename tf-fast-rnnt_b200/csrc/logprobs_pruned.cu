@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
                                                          int C, int term, float *pxc, float *pyc, float *lse_out) {
   constexpr int V = kVecElems<T>;
   constexpr int kU = 4;   // 16-byte loads issued back to back per lane before any arithmetic
+  constexpr uint32_t kPad = sizeof(T) == 4 ? 0xff800000u : 0xff80ff80u;   // -inf as float32 / as two bfloat16
   const int lane = threadIdx.x & 31;
   const int nv = C / V;
   // fast path: rows are 16-byte aligned and fit one batch of kU vector loads per lane
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int c = cb + u * 32 + lane;
-      raw[u] = make_uint4(0, 0, 0, 0);
+      raw[u] = make_uint4(kPad, kPad, kPad, kPad);      // -inf in every element: absent vectors drop out of max / sum
       if (c < nv)
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w) : "l"(p + c));
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(s) : "l"(ranges + row));
     s_ok = (s >= 0 && s <= S);
     if (s_ok) {
-      if (s < S) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(sym) : "l"(symbols + (size_t)(row / TR) * S + s));
+      if (s < S) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(sym) : "l"(symbols + (size_t)blockIdx.y * S + s));
       else sym = term;
     }
     return (sym < 0 || sym >= C) ? -1 : sym;
@@ -73,8 +74,10 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
   // row's vector loads are requested before the dependent index loads so that all are in flight
   // together; the two gathered logits are two more scalar loads issued as soon as their index is
   // known (they hit L2 behind the row itself), which keeps per-element work to max / ex2 / add.
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= BTR) return;
+  // grid: x = groups of 8 rows inside an utterance, y = utterance (no integer division by T*R)
+  const int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (local >= TR) return;
+  const int row = blockIdx.y * TR + local;
   const T *src = logits + (size_t)row * C;
   uint4 raw[kU];
   if (one_batch) load_batch(reinterpret_cast<const uint4 *>(src), 0, raw);
@@ -87,11 +90,10 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
     float x[kU][V];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const bool ok = u * 32 + lane < nv;
       const T *e = reinterpret_cast<const T *>(&raw[u]);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+        x[u][j] = to_f(e[j]);
         m = fmaxf(m, x[u][j]);
       }
     }
@@ -111,11 +113,10 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
       float mx = -INFINITY;
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const bool ok = cb + u * 32 + lane < nv;
         const T *e = reinterpret_cast<const T *>(&raw[u]);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          x[u][j] = ok ? to_f(e[j]) : -INFINITY;
+          x[u][j] = to_f(e[j]);
           mx = fmaxf(mx, x[u][j]);
         }
       }
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(256) band_to_dense_kernel(const float *pxc, co
 int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges, int B, int S,
                       int T, int R, int C, int term, float *pxc, float *pyc, float *lse, cudaStream_t stream) {
   const int BTR = B * T * R;
-  const int grid = (BTR + 7) / 8;
+  const dim3 grid((T * R + 7) / 8, B);
   if (dtype == FRN_F32)
     count_launch(), pruned_lse_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols, ranges, BTR,
                                                       T * R, S, R, C, term, pxc, pyc, lse);
