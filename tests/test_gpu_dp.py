@@ -224,3 +224,35 @@ def test_band_recursion_equals_dense_lattice(rnnt_type, R, jumpy):
                                        rt, 0.0, 0, only.data_ptr(), None, None, ws.data_ptr(), n,
                                        torch.cuda.current_stream().cuda_stream), "band_mi")
     assert torch.equal(only, ans)
+
+
+def test_row_scan_equals_wavefront_on_random_lattices(monkeypatch, dp_kernel):
+    """Fuzz: the two dense-lattice recursions (independent kernels, different summation orders) agree on
+    random shapes, boundaries with offsets, both recursion types and inputs with -inf arcs."""
+    if dp_kernel != "scan":
+        pytest.skip("runs once")
+    import tf_fast_rnnt
+    rng = np.random.default_rng(2024)
+    for case in range(48):
+        modified = bool(case & 1)
+        B = int(rng.integers(1, 5))
+        S = int(rng.integers(1, 70))
+        T = int(rng.integers(max(S // 8, 1), 750))
+        px, py = random_pxpy(int(rng.integers(1 << 30)), B, S, T, modified)
+        if case % 3 == 0:                       # a few dead arcs
+            px[rng.random(px.shape) < 0.02] = -np.inf
+            py[rng.random(py.shape) < 0.01] = -np.inf
+        bd = _boundaries(rng, B, S, T, ["full", "ragged", "begin"][case % 3])
+        res = {}
+        for which in ("FRN_DP_CHAIN", "FRN_DP_SCAN"):
+            monkeypatch.delenv("FRN_DP_CHAIN", raising=False)
+            monkeypatch.delenv("FRN_DP_SCAN", raising=False)
+            monkeypatch.setenv(which, "1")
+            res[which] = tf_fast_rnnt.mutual_information_recursion(px, py, bd, calc_gradients=True)
+        (a0, (gx0, gy0)), (a1, (gx1, gy1)) = res["FRN_DP_CHAIN"], res["FRN_DP_SCAN"]
+        tag = f"case {case}: B={B} S={S} T={T} modified={modified}"
+        assert np.array_equal(np.isfinite(a0), np.isfinite(a1)), tag
+        ok = np.isfinite(a0)
+        assert_close(a1[ok], a0[ok], 2e-6, 1e-5, tag + " ans")
+        assert_close(gx1[ok], gx0[ok], 2e-5, 1e-6, tag + " px_grad")
+        assert_close(gy1[ok], gy0[ok], 2e-5, 1e-6, tag + " py_grad")
