@@ -306,3 +306,67 @@ def test_smoothed_loss_am_lm_gradients(rnnt_type, scales):
     o_am1, o_lm1 = orc.smoothed_am_lm_grad(lm, am, sym, term, bd, lms, ams, rnnt_type, 0.2, None, np.float64)
     assert_close(am_t.grad.cpu().numpy(), o_am1, GRAD_RTOL, 2e-6, "autograd am grad")
     assert_close(lm_t.grad.cpu().numpy(), o_lm1, GRAD_RTOL, 2e-5, "autograd lm grad")
+
+
+def test_fuzz_band_recursion_equals_dense_recursions(monkeypatch):
+    """Fuzz: rnnt_loss_pruned through the band recursion (band_dp.cu) against the same call forced onto the
+    dense-lattice kernels (FRN_BAND_DENSE=1, wavefront and row scan): three independent implementations of
+    the recursion on random shapes, ragged boundaries, all rnnt types, delay penalty and some -inf logits."""
+    import torch
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(77)
+    for case in range(36):
+        rnnt_type = ["regular", "modified", "constrained"][case % 3]
+        B = int(rng.integers(1, 4)); S = int(rng.integers(2, 40)); T = int(rng.integers(max(S, 4), 300))
+        C = int(rng.integers(3, 20)); R = int(rng.integers(1, min(8, S + 1) + 1))
+        am, lm, sym, term, bd = make_inputs(int(rng.integers(1 << 30)), B, T, S, C, ragged=True, begin=False)
+        dp = [0.0, 0.3][case % 2]
+        monkeypatch.delenv("FRN_BAND_DENSE", raising=False)
+        monkeypatch.delenv("FRN_DP_CHAIN", raising=False)
+        monkeypatch.delenv("FRN_DP_SCAN", raising=False)
+        _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True)
+        ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+        am_p, lm_p = frn.do_rnnt_pruning(am, lm, ranges)
+        logits = am_p + lm_p
+        if case % 4 == 0:
+            logits[rng.random(logits.shape) < 0.01] = -np.inf
+        w = rng.standard_normal(B).astype(np.float32)
+        res = []
+        for env in ({}, {"FRN_BAND_DENSE": "1", "FRN_DP_CHAIN": "1"}, {"FRN_BAND_DENSE": "1", "FRN_DP_SCAN": "1"}):
+            for k in ("FRN_BAND_DENSE", "FRN_DP_CHAIN", "FRN_DP_SCAN"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            sc, gr = frn.pruned_loss_fwd_bwd(torch.from_numpy(logits).cuda(), sym, ranges, term, bd, rnnt_type, dp,
+                                             torch.from_numpy(w).cuda())
+            res.append((sc.cpu().numpy(), gr.cpu().numpy()))
+        tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} R={R} dp={dp}"
+        (s0, g0) = res[0]
+        for which, (s1, g1) in zip(("wavefront", "row scan"), res[1:]):
+            assert np.array_equal(np.isfinite(s0), np.isfinite(s1)), tag + " " + which
+            ok = np.isfinite(s0)
+            assert_close(s1[ok], s0[ok], 2e-6, 1e-5, tag + f" scores vs {which}")
+            assert_close(np.nan_to_num(g1[ok]), np.nan_to_num(g0[ok]), 5e-5, 2e-6, tag + f" logits grad vs {which}")
+
+
+def test_fuzz_tensor_core_normaliser_equals_simt(monkeypatch):
+    """Fuzz: the tcgen05 normaliser (3 x bf16 split) against the exact-FP32 SIMT kernel of the same op on
+    random shapes (C % 4 == 0 so that both paths exist), simple and smoothed, all rnnt types."""
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(78)
+    for case in range(24):
+        rnnt_type = ["regular", "modified", "constrained"][case % 3]
+        B = int(rng.integers(1, 4)); S = int(rng.integers(1, 150)); T = int(rng.integers(1, 300))
+        C = 4 * int(rng.integers(1, 160))
+        am, lm, sym, term, bd = make_inputs(int(rng.integers(1 << 30)), B, T, S, C, ragged=True, begin=False)
+        am *= 3.0
+        out = []
+        for simt in ("0", "1"):
+            monkeypatch.setenv("FRN_SIMPLE_SIMT", simt)
+            if case % 2:
+                out.append(frn.get_rnnt_logprobs_smoothed(lm, am, sym, term, 0.25, 0.1, bd, rnnt_type))
+            else:
+                out.append(frn.get_rnnt_logprobs(lm, am, sym, term, rnnt_type, bd))
+        tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} smoothed={case % 2}"
+        assert_close(out[0][0], out[1][0], 2e-6, 2e-6, tag + " px")
+        assert_close(out[0][1], out[1][1], 2e-6, 2e-6, tag + " py")

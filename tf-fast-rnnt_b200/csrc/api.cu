@@ -19,6 +19,12 @@ int check_launch() { return note_cuda_error(cudaPeekAtLastError()); }
 
 static inline bool aligned256(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
 static inline int type_t1(int T, int rnnt_type) { return rnnt_type == FRN_REGULAR ? T + 1 : T; }
+// The band recursion keeps the R rows of a column as float64 mantissas in one frame.  A delay penalty p puts
+// e^(p (T/2 - t)) on every symbol arc, so rows k symbols apart differ by up to e^(k p T / 2) inside one column
+// or chunk image: beyond ~2^900 over R - 1 rows the dense-lattice kernels (one frame per row) take over.
+static inline bool band_delay_ok(int T, int R, float delay_penalty) {
+  return !(delay_penalty > 0.f) || (double)delay_penalty * T * (R > 1 ? R - 1 : 1) * 0.5 * 1.4427 < 900.0;
+}
 }  // namespace frn
 
 using namespace frn;
@@ -92,7 +98,7 @@ int frn_band_mi_fwd_bwd(const float *pxc, const float *pyc, const int32_t *range
   FRN_REQUIRE(pxc && pyc && ranges && boundary && ans);
   FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
   FRN_REQUIRE(!calc_gradients || (pxc_grad && pyc_grad));
-  if (!band_dp_supported(S, T, R)) return FRN_EUNSUPPORTED;
+  if (!band_dp_supported(S, T, R) || !band_delay_ok(T, R, delay_penalty)) return FRN_EUNSUPPORTED;
   if (!workspace || !aligned256(workspace) || workspace_bytes < band_dp_workspace_bytes(B, T)) return FRN_EWORKSPACE;
   return launch_band_dp(pxc, pyc, ranges, boundary, B, S, T, R, rnnt_type, delay_penalty > 0.f ? delay_penalty : 0.f,
                         calc_gradients != 0, workspace, pxc_grad, pyc_grad, ans, static_cast<cudaStream_t>(stream));
@@ -298,8 +304,9 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
   FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
   // narrow bands: transfer-matrix recursion on the band itself (band_dp.cu);
   // FRN_BAND_DENSE=1 forces the dense-lattice wavefront for A/B runs and cross-checks
-  static const bool force_dense = [] { const char *e = getenv("FRN_BAND_DENSE"); return e && e[0] == '1'; }();
-  if (!force_dense && band_dp_supported(S, T, R) && band_dp_workspace_bytes(B, T) <= dw.bytes) {
+  const bool force_dense = [] { const char *e = getenv("FRN_BAND_DENSE"); return e && e[0] == '1'; }();   // read per call
+  if (!force_dense && band_dp_supported(S, T, R) && band_delay_ok(T, R, delay_penalty) &&
+      band_dp_workspace_bytes(B, T) <= dw.bytes) {
     const bool want = logits_grad != nullptr;
     FRN_TRY(launch_band_dp(w.pxc, w.pyc, ranges, boundary, B, S, T, R, rnnt_type, delay_penalty > 0.f ? delay_penalty : 0.f,
                            want, w.dp, w.gxc, w.gyc, scores, stream));

@@ -60,7 +60,9 @@ struct BandDpParams {
   const int32_t *boundary;     // [B][4]
   double *va, *ub;             // [B][T+1][8] forward / backward states by slot: mantissas
   int *oa, *ob;                // [B][T+1]    their frames (kDeadFrame: all-zero state)
-  float *img;                  // [B][2][T+1][8 unit vectors][8] image of chunk-start unit vector j at this column
+  double *img;                 // [B][2][T+1][8 unit vectors][8] image of chunk-start unit vector j at this column
+                               // (float64 like the states: with a delay penalty the entries of one image are
+                               //  e^(penalty * symbols apart) from each other, far beyond float32's 2^126)
   int *img_frame;              // [B][2][T+1][8]  its frame (kDeadFrame: zero image)
   int S, T, R, L, modified, rnnt_type;
   float delay_penalty;
@@ -263,12 +265,12 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
       frame = 0;
       // every intermediate image is kept (float mantissas + frame): the state of a column inside a
       // chunk is then one 8x8 matrix-vector product with the chunk's boundary state (phase 3)
-      float *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
+      double *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
       int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1)) * 8 + j;
       auto record = [&](int col) {
-        float *q = img + (size_t)col * 64;
-        *reinterpret_cast<float4 *>(q) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-        *reinterpret_cast<float4 *>(q + 4) = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+        double *q = img + (size_t)col * 64;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2 *>(q + k) = make_double2(v[k], v[k + 1]);
         imf[(size_t)col * 8] = frame;
       };
       if (!dir) {
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
       double x[8];
       load8(VB + (size_t)c * 8, x);
       const int fx = VBo[c];
-      const float *img = p.img + ((size_t)(b * 2 + dir) * (T + 1) + t) * 64;
+      const double *img = p.img + ((size_t)(b * 2 + dir) * (T + 1) + t) * 64;
       const int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1) + t) * 8;
       int fj[8], E = kDeadFrame;
 #pragma unroll
@@ -397,12 +399,10 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const double xs = (fj[j] > kDeadFrame / 2) ? x[j] * pow2d(fj[j] - E) : 0.0;
-          const float4 lo = *reinterpret_cast<const float4 *>(img + j * 8);
-          const float4 hi = *reinterpret_cast<const float4 *>(img + j * 8 + 4);
-          y[0] = fma(xs, (double)lo.x, y[0]); y[1] = fma(xs, (double)lo.y, y[1]);
-          y[2] = fma(xs, (double)lo.z, y[2]); y[3] = fma(xs, (double)lo.w, y[3]);
-          y[4] = fma(xs, (double)hi.x, y[4]); y[5] = fma(xs, (double)hi.y, y[5]);
-          y[6] = fma(xs, (double)hi.z, y[6]); y[7] = fma(xs, (double)hi.w, y[7]);
+          double im[8];
+          load8(img + j * 8, im);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = fma(xs, im[k], y[k]);
         }
         const int e = normalise8(y);
         frame = (e == kDeadFrame) ? kDeadFrame : fx + E + e;
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
 size_t band_dp_workspace_bytes(int B, int T) {
   return 2 * round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(double), 256) +
          2 * round_up_sz((size_t)B * (T + 1) * sizeof(int), 256) +
-         round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(float), 256) +
+         round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(double), 256) +
          round_up_sz((size_t)B * 2 * (T + 1) * 8 * sizeof(int), 256);
 }
 
@@ -532,8 +532,8 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
   p.pxc = pxc; p.pyc = pyc; p.ranges = ranges; p.boundary = boundary;
   p.va = reinterpret_cast<double *>(w); p.ub = reinterpret_cast<double *>(w + nv);
   p.oa = reinterpret_cast<int *>(w + 2 * nv); p.ob = reinterpret_cast<int *>(w + 2 * nv + no);
-  p.img = reinterpret_cast<float *>(w + 2 * nv + 2 * no);
-  p.img_frame = reinterpret_cast<int *>(w + 2 * nv + 2 * no + round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(float), 256));
+  p.img = reinterpret_cast<double *>(w + 2 * nv + 2 * no);
+  p.img_frame = reinterpret_cast<int *>(w + 2 * nv + 2 * no + round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(double), 256));
   p.S = S; p.T = T; p.R = R; p.modified = (rnnt_type != FRN_REGULAR); p.rnnt_type = rnnt_type;
   p.delay_penalty = delay_penalty;
   p.L = band_chunk_len(T);

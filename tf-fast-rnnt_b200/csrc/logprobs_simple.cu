@@ -284,7 +284,7 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   sp.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
   // tensor-core path (tcgen05 + TMA); the exact-FP32 SIMT kernel serves shapes
   // TMA cannot address (C % 4 != 0) and FRN_SIMPLE_SIMT=1 forces it for A/B runs
-  static const bool force_simt = [] { const char *e = getenv("FRN_SIMPLE_SIMT"); return e && e[0] == '1'; }();
+  const bool force_simt = [] { const char *e = getenv("FRN_SIMPLE_SIMT"); return e && e[0] == '1'; }();   // read per call
   rc = force_simt ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
   if (rc == FRN_EUNSUPPORTED) {
     dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
