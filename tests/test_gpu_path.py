@@ -370,3 +370,42 @@ def test_fuzz_tensor_core_normaliser_equals_simt(monkeypatch):
         tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} smoothed={case % 2}"
         assert_close(out[0][0], out[1][0], 2e-6, 2e-6, tag + " px")
         assert_close(out[0][1], out[1][1], 2e-6, 2e-6, tag + " py")
+
+
+def test_fuzz_pipeline_against_float64_oracle(monkeypatch):
+    """Fuzz of the whole path against the float64 oracle: random shapes, ragged boundaries with offsets, all
+    rnnt types, delay penalties, s_range 1..9 (band recursion and dense fall-back), both dense-lattice kernels."""
+    import torch
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(4242)
+    for case in range(30):
+        rnnt_type = ["regular", "modified", "constrained"][case % 3]
+        B = int(rng.integers(1, 4)); S = int(rng.integers(1, 26)); T = int(rng.integers(max(S, 2), 130))
+        C = int(rng.integers(2, 12)) * 4 if case % 2 else int(rng.integers(3, 30))
+        R = int(rng.integers(2 if rnnt_type == "regular" else 1, 10))
+        am, lm, sym, term, bd = make_inputs(int(rng.integers(1 << 30)), B, T, S, C, ragged=True, begin=bool(case % 5 == 0))
+        dp = float([0.0, 0.25, 0.6][case % 3 if case % 2 else 0])
+        for k in ("FRN_DP_CHAIN", "FRN_DP_SCAN"):
+            monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("FRN_DP_SCAN" if case % 2 else "FRN_DP_CHAIN", "1")
+        tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} R={R} dp={dp} bd={bd.tolist()}"
+        loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, "none", True)
+        o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, "none", True, dtype=np.float64)
+        assert_close(loss, o_loss, LOSS_RTOL, 1e-5, tag + " simple loss")
+        assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, tag + " px_grad")
+        assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, tag + " py_grad")
+        ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+        assert np.array_equal(ranges, orc.get_rnnt_prune_ranges(gx, gy, bd, R)), tag + " ranges"
+        am_p, lm_p = frn.do_rnnt_pruning(am, lm, ranges)
+        o_am_p, o_lm_p = orc.do_rnnt_pruning(am, lm, ranges)
+        assert np.array_equal(am_p, o_am_p) and np.array_equal(lm_p, o_lm_p), tag + " pruning"
+        logits = (am_p + lm_p).astype(np.float32)
+        w = rng.standard_normal(B).astype(np.float32)
+        scores, grad = frn.pruned_loss_fwd_bwd(torch.from_numpy(logits).cuda(), sym, ranges, term, bd, rnnt_type, dp,
+                                               torch.from_numpy(-w).cuda())
+        o_grad, o_scores = orc.pruned_logits_grad(logits, sym, ranges, term, bd, rnnt_type, dp, w, np.float64,
+                                                  return_scores=True)
+        assert_close(scores.cpu().numpy(), o_scores, LOSS_RTOL, 1e-5, tag + " pruned scores")
+        ok = np.isfinite(o_scores)        # no path inside the band (score -inf): the gradient is undefined there
+        assert_close(grad.cpu().numpy()[ok], o_grad[ok], GRAD_RTOL, 2e-6, tag + " logits grad")
+        assert not np.isnan(grad.cpu().numpy()).any(), tag
