@@ -182,6 +182,15 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     mbar_fence_init();
     *dead_edge = make_float2(0.f, __int_as_float(kNegI));
   }
+  // Backward, last lane of the lattice: the symbol arc "into row r0 + RPL" is read at row P of a diagonal,
+  // i.e. at row 0 of the next diagonal in the ring.  Row 0 has no incoming symbol arc, so that entry is a dead
+  // arc in every diagonal the bulk copies deliver - but behind the last diagonal of the last stage lies the
+  // padding, and a stage whose first copy is still in flight holds whatever the shared memory held before: a
+  // garbage exponent there inflated the frames of the top rows and flushed their mantissas (found by the
+  // scan-vs-wavefront fuzz test).  Row 0 of every ring diagonal and of the padding starts out dead.
+  for (int i = tid; i <= NST * CH; i += blockDim.x)
+    ring[(size_t)i * P] = make_float4(0.f, __int_as_float(kNegI), 0.f, __int_as_float(kNegI));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ordered before the bulk copies into the ring
   __syncthreads();
   if (tid == 0)
     for (int i = 0; i < NST && i < nchunk; ++i) issue(i, i);
@@ -196,13 +205,6 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   constexpr int step_sign = DIR ? -1 : 1;
   const int pe_step = fed ? step_sign : 0;
   const float2 dead2 = make_float2(0.f, __int_as_float(kNegI));
-  // Backward: the symbol arc into row r0 + RPL multiplies the state of that row.  For the last lane of the
-  // lattice that row does not exist: reading "row P" of a diagonal lands on row 0 of the next diagonal in the
-  // ring (a dead arc, harmless) except behind the last diagonal of the last ring stage, where it is
-  // uninitialised shared memory - a garbage exponent there inflated the frames of the top rows and flushed
-  // their mantissas (found by the scan-vs-wavefront fuzz test).  Such a lane keeps the dead arc.
-  const bool x_in = (r0 + RPL) < P;
-
   float m[RPL];
   int o[RPL];
 #pragma unroll
@@ -253,7 +255,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     if (n > 0) {
 #pragma unroll
       for (int j = 0; j < RPL; ++j) a4[j] = xp[j];
-      if (DIR && x_in) xnext = *reinterpret_cast<const float2 *>(xp + RPL);
+      if (DIR) xnext = *reinterpret_cast<const float2 *>(xp + RPL);
     }
     int nb_o_sh = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
 #pragma unroll 2
@@ -264,7 +266,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
       float2 xnext2 = dead2;
 #pragma unroll
       for (int j = 0; j < RPL; ++j) b4[j] = xp[step_sign * P + j];
-      if (DIR && x_in) xnext2 = *reinterpret_cast<const float2 *>(xp + step_sign * P + RPL);
+      if (DIR) xnext2 = *reinterpret_cast<const float2 *>(xp + step_sign * P + RPL);
       const float2 ev2 = *pe;   // the feeding row's state after ITS step e = input of our next step (broadcast read)
 
       // ---- neighbour across the lane boundary (its frame was shuffled as soon as it was known) ----
