@@ -409,3 +409,60 @@ def test_fuzz_pipeline_against_float64_oracle(monkeypatch):
         ok = np.isfinite(o_scores)        # no path inside the band (score -inf): the gradient is undefined there
         assert_close(grad.cpu().numpy()[ok], o_grad[ok], GRAD_RTOL, 2e-6, tag + " logits grad")
         assert not np.isnan(grad.cpu().numpy()).any(), tag
+
+
+def test_fuzz_remaining_entry_points_against_oracle():
+    """Fuzz of the entry points the pipeline fuzz does not reach: smoothed loss, am/lm gradients of the simple and
+    smoothed losses (A9), the joint loss on the full joiner output, the pruning gradient and bf16 logits - random
+    shapes, ragged boundaries, all rnnt types, against the float64 oracle."""
+    import torch
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(909)
+    for case in range(18):
+        rnnt_type = ["regular", "modified", "constrained"][case % 3]
+        B = int(rng.integers(1, 4)); S = int(rng.integers(1, 20)); T = int(rng.integers(max(S, 2), 70))
+        C = 4 * int(rng.integers(1, 9)) if case % 2 else int(rng.integers(2, 25))
+        am, lm, sym, term, bd = make_inputs(int(rng.integers(1 << 30)), B, T, S, C, ragged=True, begin=bool(case % 4 == 0))
+        dp = float([0.0, 0.3][case % 2])
+        lms, ams = float(rng.uniform(0.0, 0.4)), float([0.0, 0.2][case % 2])
+        w = rng.standard_normal(B).astype(np.float32)
+        tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} dp={dp} scales=({lms:.2f},{ams:.2f}) bd={bd.tolist()}"
+        # smoothed loss forward + occupation counts
+        loss, (gx, gy) = frn.rnnt_loss_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, dp, "none", True)
+        o_loss, (o_gx, o_gy) = orc.rnnt_loss_smoothed(lm, am, sym, term, lms, ams, bd, rnnt_type, dp, "none", True,
+                                                      dtype=np.float64)
+        assert_close(loss, o_loss, LOSS_RTOL, 1e-5, tag + " smoothed loss")
+        assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, tag + " smoothed px_grad")
+        assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, tag + " smoothed py_grad")
+        # A9, smoothed and simple
+        am_g, lm_g = frn.smoothed_loss_backward(lm, am, sym, term, bd, gx, gy, -w, lms, ams, rnnt_type)
+        o_am, o_lm = orc.smoothed_am_lm_grad(lm, am, sym, term, bd, lms, ams, rnnt_type, dp, w, np.float64)
+        assert_close(am_g, o_am, GRAD_RTOL, 5e-6, tag + " smoothed am grad")
+        assert_close(lm_g, o_lm, GRAD_RTOL, 3e-5, tag + " smoothed lm grad")
+        _, (sgx, sgy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, dp, "none", True)
+        am_g, lm_g = frn.simple_loss_backward(lm, am, sym, term, bd, sgx, sgy, -w, rnnt_type)
+        o_am, o_lm = orc.simple_am_lm_grad(lm, am, sym, term, bd, rnnt_type, dp, w, np.float64)
+        assert_close(am_g, o_am, GRAD_RTOL, 5e-6, tag + " simple am grad")
+        assert_close(lm_g, o_lm, GRAD_RTOL, 3e-5, tag + " simple lm grad")
+        # joint loss on the full joiner output
+        full = (am[:, :, None, :] + lm[:, None, :, :]).astype(np.float32)
+        jl = frn.rnnt_loss(full, sym, term, bd, rnnt_type, dp, "none")
+        o_jl = orc.rnnt_loss(full, sym, term, bd, rnnt_type, dp, "none", dtype=np.float64)
+        assert_close(jl, o_jl, LOSS_RTOL, 1e-5, tag + " joint loss")
+        # pruning gradient
+        R = int(rng.integers(1, min(S, 6) + 1)) if rnnt_type != "regular" else int(rng.integers(2, 7))
+        ranges = frn.get_rnnt_prune_ranges(sgx, sgy, bd, R)
+        Rw = ranges.shape[2]
+        ga = rng.standard_normal((B, T, Rw, C), dtype=np.float32)
+        gl = rng.standard_normal((B, T, Rw, C), dtype=np.float32)
+        a_g, l_g = frn.do_rnnt_pruning_backward(ga, gl, ranges, S)
+        o_a, o_l = orc.do_rnnt_pruning_bwd(ga, gl, ranges, S + 1)
+        assert_close(a_g, o_a, 1e-5, 1e-5, tag + " pruning am grad")
+        assert_close(l_g, o_l, 1e-5, 1e-4, tag + " pruning lm grad")
+        # bf16 logits into the float32 pruned loss
+        lg = frn.pruned_add_joiner(torch.from_numpy(am).cuda(), torch.from_numpy(lm).cuda(),
+                                   torch.from_numpy(ranges).cuda(), dtype=torch.bfloat16)
+        scores, _ = frn.pruned_loss_fwd_bwd(lg, sym, ranges, term, bd, rnnt_type, dp, None)
+        o_pl = orc.rnnt_loss_pruned(lg.float().cpu().numpy(), sym, ranges, term, bd, rnnt_type, dp, "none",
+                                    dtype=np.float64)
+        assert_close(-scores.cpu().numpy(), o_pl, LOSS_RTOL, 1e-5, tag + " bf16 pruned loss")
