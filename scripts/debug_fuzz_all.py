@@ -10,7 +10,10 @@ rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 2024)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 48
 for case in range(n):
     modified = bool(case & 1)
-    B = int(rng.integers(1, 5)); S = int(rng.integers(1, 70)); T = int(rng.integers(max(S // 8, 1), 750))
+    if os.environ.get("FUZZ_BIG"):
+        B = int(rng.integers(1, 4)); S = int(rng.integers(120, 700)); T = int(rng.integers(max(S // 2, 1), 1500))
+    else:
+        B = int(rng.integers(1, 5)); S = int(rng.integers(1, 70)); T = int(rng.integers(max(S // 8, 1), 750))
     px, py = random_pxpy(int(rng.integers(1 << 30)), B, S, T, modified)
     dead = case % 3 == 0
     if dead:

@@ -10,9 +10,12 @@ def setenv(env):
         os.environ.pop(k, None)
     os.environ.update(env)
 ENVS = (("band", {}), ("chain", {"FRN_BAND_DENSE": "1", "FRN_DP_CHAIN": "1"}), ("scan", {"FRN_BAND_DENSE": "1", "FRN_DP_SCAN": "1"}))
-for case in range(36):
+for case in range(int(os.environ.get('FUZZ_N', '36'))):
     rnnt_type = ["regular", "modified", "constrained"][case % 3]
-    B = int(rng.integers(1, 4)); S = int(rng.integers(2, 40)); T = int(rng.integers(max(S, 4), 300))
+    if os.environ.get("FUZZ_BIG"):
+        B = int(rng.integers(1, 4)); S = int(rng.integers(40, 400)); T = int(rng.integers(max(S, 300), 1500))
+    else:
+        B = int(rng.integers(1, 4)); S = int(rng.integers(2, 40)); T = int(rng.integers(max(S, 4), 300))
     C = int(rng.integers(3, 20)); R = int(rng.integers(1, min(8, S + 1) + 1))
     am, lm, sym, term, bd = make_inputs(int(rng.integers(1 << 30)), B, T, S, C, ragged=True, begin=False)
     dp = [0.0, 0.3][case % 2]
@@ -35,9 +38,4 @@ for case in range(36):
     bad = max(d(('band',0),('chain',0)), d(('band',0),('scan',0)), d(('chain',0),('chain',1))) > 1e-4
     print(line + ("  <<<<" if bad else ""))
     if bad:
-        from oracle import rnnt_oracle as orc
-        o_grad, o_scores = orc.pruned_logits_grad(logits, sym, ranges, term, bd, rnnt_type, dp, w, np.float64, return_scores=True)
-        o_grad = -np.nan_to_num(o_grad)
-        for name in ("band", "chain"):
-            e = np.abs(out[(name, 0)][1] - o_grad)
-            print(f"      {name:5s} vs oracle: per-utt max err {e.max(axis=(1, 2, 3))}  scores {out[(name, 0)][0]} oracle {o_scores}")
+        print("      scores band", out[("band", 0)][0], "chain", out[("chain", 0)][0], "dp", dp)

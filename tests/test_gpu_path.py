@@ -466,3 +466,36 @@ def test_fuzz_remaining_entry_points_against_oracle():
         o_pl = orc.rnnt_loss_pruned(lg.float().cpu().numpy(), sym, ranges, term, bd, rnnt_type, dp, "none",
                                     dtype=np.float64)
         assert_close(-scores.cpu().numpy(), o_pl, LOSS_RTOL, 1e-5, tag + " bf16 pruned loss")
+
+
+@pytest.mark.parametrize("T,S,R,dp", [(500, 100, 5, 0.2), (700, 60, 3, 0.25), (400, 40, 8, 0.15), (650, 80, 4, 0.28)])
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified"])
+def test_band_recursion_with_large_delay_penalty(monkeypatch, T, S, R, dp, rnnt_type):
+    """The band recursion close to the delay-penalty spread at which frn_pruned_loss hands over to the dense
+    kernels (band_delay_ok: 250-393 of 400 bits here, incl. the c3 setting): it is the band kernel that runs
+    (4 launches against 6), and it agrees with the dense kernels."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, C = 2, 8
+    am, lm, sym, term, bd = make_inputs(T + R, B, T, S, C, ragged=True)
+    monkeypatch.delenv("FRN_BAND_DENSE", raising=False)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+    am_p, lm_p = frn.do_rnnt_pruning(am, lm, ranges)
+    logits = torch.from_numpy((am_p + lm_p).astype(np.float32)).cuda()
+    lib = frn._lib.lib
+    out, launches = [], []
+    for dense in ("0", "1"):
+        monkeypatch.setenv("FRN_BAND_DENSE", dense)
+        n0 = lib.frn_kernel_launches()
+        sc, gr = frn.pruned_loss_fwd_bwd(logits, sym, ranges, term, bd, rnnt_type, dp, None)
+        launches.append(lib.frn_kernel_launches() - n0)
+        out.append((sc.cpu().numpy(), gr.cpu().numpy()))
+    assert launches == [4, 6], launches
+    assert_close(out[0][0], out[1][0], 2e-6, 1e-4, "scores band vs dense")
+    assert_close(out[0][1], out[1][1], 5e-5, 2e-6, "logits grad band vs dense")
+    # beyond the limit the same call runs the dense kernels by itself
+    monkeypatch.delenv("FRN_BAND_DENSE", raising=False)
+    n0 = lib.frn_kernel_launches()
+    frn.pruned_loss_fwd_bwd(logits, sym, ranges, term, bd, rnnt_type, 4.0 * dp, None)
+    assert lib.frn_kernel_launches() - n0 == 6
