@@ -15,6 +15,9 @@ for case in range(n):
     else:
         B = int(rng.integers(1, 5)); S = int(rng.integers(1, 70)); T = int(rng.integers(max(S // 8, 1), 750))
     px, py = random_pxpy(int(rng.integers(1 << 30)), B, S, T, modified)
+    if os.environ.get("FUZZ_DP"):
+        tt = np.arange(px.shape[2], dtype=np.float64)
+        px = (px + ((T - 1) / 2.0 - tt)[None, None, :] * float(os.environ["FUZZ_DP"])).astype(np.float32)
     dead = case % 3 == 0
     if dead:
         px[rng.random(px.shape) < 0.02] = -np.inf
