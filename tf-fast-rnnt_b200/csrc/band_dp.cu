@@ -60,9 +60,12 @@ struct BandDpParams {
   const int32_t *boundary;     // [B][4]
   double *va, *ub;             // [B][T+1][8] forward / backward states by slot: mantissas
   int *oa, *ob;                // [B][T+1]    their frames (kDeadFrame: all-zero state)
-  double *img;                 // [B][2][T+1][8 unit vectors][8] image of chunk-start unit vector j at this column
-                               // (float64 like the states: with a delay penalty the entries of one image are
-                               //  e^(penalty * symbols apart) from each other, far beyond float32's 2^126)
+  uint32_t *img;               // [B][2][T+1][8 unit vectors][8] image of chunk-start unit vector j at this column:
+                               // the HIGH WORD of the float64 entry, rounded (sign, 11-bit exponent, 20-bit
+                               // mantissa).  The full exponent range matters - with a delay penalty the entries
+                               // of one image are e^(penalty * symbols apart) from each other, far beyond
+                               // float32's 2^126 (float32 images flushed them: wrong occupation counts) - the
+                               // mantissa does not: 2^-21 per entry, float32 storage cost, float64 range.
   int *img_frame;              // [B][2][T+1][8]  its frame (kDeadFrame: zero image)
   int S, T, R, L, modified, rnnt_type;
   float delay_penalty;
@@ -265,12 +268,16 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
       frame = 0;
       // every intermediate image is kept (float mantissas + frame): the state of a column inside a
       // chunk is then one 8x8 matrix-vector product with the chunk's boundary state (phase 3)
-      double *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
+      uint32_t *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
       int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1)) * 8 + j;
       auto record = [&](int col) {
-        double *q = img + (size_t)col * 64;
+        uint32_t *q = img + (size_t)col * 64;
+        uint32_t h[8];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2 *>(q + k) = make_double2(v[k], v[k + 1]);
+        for (int k = 0; k < 8; ++k)      // entries are >= 0: round the magnitude to the nearest 2^-20 of its binade
+          h[k] = (uint32_t)__double2hiint(v[k]) + ((uint32_t)__double2loint(v[k]) >> 31);
+        *reinterpret_cast<uint4 *>(q) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(q + 4) = make_uint4(h[4], h[5], h[6], h[7]);
         imf[(size_t)col * 8] = frame;
       };
       if (!dir) {
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
       double x[8];
       load8(VB + (size_t)c * 8, x);
       const int fx = VBo[c];
-      const double *img = p.img + ((size_t)(b * 2 + dir) * (T + 1) + t) * 64;
+      const uint32_t *img = p.img + ((size_t)(b * 2 + dir) * (T + 1) + t) * 64;
       const int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1) + t) * 8;
       int fj[8], E = kDeadFrame;
 #pragma unroll
@@ -399,10 +406,11 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const double xs = (fj[j] > kDeadFrame / 2) ? x[j] * pow2d(fj[j] - E) : 0.0;
-          double im[8];
-          load8(img + j * 8, im);
+          const uint4 lo = *reinterpret_cast<const uint4 *>(img + j * 8);
+          const uint4 hi = *reinterpret_cast<const uint4 *>(img + j * 8 + 4);
+          const uint32_t h[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[k] = fma(xs, im[k], y[k]);
+          for (int k = 0; k < 8; ++k) y[k] = fma(xs, __hiloint2double((int)h[k], 0), y[k]);
         }
         const int e = normalise8(y);
         frame = (e == kDeadFrame) ? kDeadFrame : fx + E + e;
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(256) band_finalize_kernel(BandDpParams p, floa
 size_t band_dp_workspace_bytes(int B, int T) {
   return 2 * round_up_sz((size_t)B * (T + 1) * kBandR * sizeof(double), 256) +
          2 * round_up_sz((size_t)B * (T + 1) * sizeof(int), 256) +
-         round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(double), 256) +
+         round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(uint32_t), 256) +
          round_up_sz((size_t)B * 2 * (T + 1) * 8 * sizeof(int), 256);
 }
 
@@ -532,8 +540,8 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
   p.pxc = pxc; p.pyc = pyc; p.ranges = ranges; p.boundary = boundary;
   p.va = reinterpret_cast<double *>(w); p.ub = reinterpret_cast<double *>(w + nv);
   p.oa = reinterpret_cast<int *>(w + 2 * nv); p.ob = reinterpret_cast<int *>(w + 2 * nv + no);
-  p.img = reinterpret_cast<double *>(w + 2 * nv + 2 * no);
-  p.img_frame = reinterpret_cast<int *>(w + 2 * nv + 2 * no + round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(double), 256));
+  p.img = reinterpret_cast<uint32_t *>(w + 2 * nv + 2 * no);
+  p.img_frame = reinterpret_cast<int *>(w + 2 * nv + 2 * no + round_up_sz((size_t)B * 2 * (T + 1) * 64 * sizeof(uint32_t), 256));
   p.S = S; p.T = T; p.R = R; p.modified = (rnnt_type != FRN_REGULAR); p.rnnt_type = rnnt_type;
   p.delay_penalty = delay_penalty;
   p.L = band_chunk_len(T);
