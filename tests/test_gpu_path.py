@@ -499,3 +499,28 @@ def test_band_recursion_with_large_delay_penalty(monkeypatch, T, S, R, dp, rnnt_
     n0 = lib.frn_kernel_launches()
     frn.pruned_loss_fwd_bwd(logits, sym, ranges, term, bd, rnnt_type, 4.0 * dp, None)
     assert lib.frn_kernel_launches() - n0 == 6
+
+
+@pytest.mark.parametrize("reduction", ["none", "mean", "sum"])
+def test_reduce_and_reduce_pair(reduction):
+    """frn_reduce / frn_reduce_pair (the reduction branches of rnnt_loss.py:327-338, 1121-1130): -scores, -sum,
+    -mean, for one vector and for the two vectors of a step in one launch."""
+    import torch
+    import tf_fast_rnnt as frn
+    lib, chk = frn._lib.lib, frn._lib.check
+    code = {"none": 0, "mean": 1, "sum": 2}[reduction]
+    rng = np.random.default_rng(3)
+    for B in (1, 31, 32, 257, 1000):
+        a = rng.standard_normal(B).astype(np.float32) * 100
+        b = rng.standard_normal(B).astype(np.float32) * 100
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        n = B if reduction == "none" else 1
+        oa, ob, oc = (torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(3))
+        st = torch.cuda.current_stream().cuda_stream
+        chk(lib.frn_reduce(da.data_ptr(), B, code, 0.0, oc.data_ptr(), st), "reduce")
+        chk(lib.frn_reduce_pair(da.data_ptr(), db.data_ptr(), B, code, 0.0, oa.data_ptr(), ob.data_ptr(), st), "pair")
+        want = {"none": lambda x: -x, "mean": lambda x: np.array([-x.astype(np.float64).mean()]),
+                "sum": lambda x: np.array([-x.astype(np.float64).sum()])}[reduction]
+        assert torch.equal(oa, oc)
+        np.testing.assert_allclose(oa.cpu().numpy(), want(a), rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(ob.cpu().numpy(), want(b), rtol=1e-5, atol=1e-3)
