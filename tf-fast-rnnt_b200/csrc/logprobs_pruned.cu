@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(256) band_to_dense_kernel(const float *pxc, co
 int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges, int B, int S,
                       int T, int R, int C, int term, float *pxc, float *pyc, float *lse, cudaStream_t stream) {
   const int BTR = B * T * R;
+  if (B > 65535) return FRN_EUNSUPPORTED;          // utterances ride on gridDim.y
   const dim3 grid((T * R + 7) / 8, B);
   if (dtype == FRN_F32)
     count_launch(), pruned_lse_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(logits), symbols, ranges, BTR,
