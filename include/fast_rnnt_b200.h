@@ -50,7 +50,7 @@ enum frn_status {
 enum frn_rnnt_type { FRN_REGULAR = 0, FRN_MODIFIED = 1, FRN_CONSTRAINED = 2 };
 
 /* element type of the joiner logits handed to the pruned loss */
-enum frn_dtype { FRN_F32 = 0, FRN_BF16 = 1 };
+enum frn_dtype { FRN_F32 = 0, FRN_BF16 = 1, FRN_F16 = 2 /* frn_cast_to_f32 only */ };
 
 /* reduction of the reference API (rnnt_loss.py:327-338) */
 enum frn_reduction { FRN_NONE = 0, FRN_MEAN = 1, FRN_SUM = 2 };
@@ -229,6 +229,9 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
  * when the sum is completed by an all-reduce across ranks). */
 int frn_reduce(const float *scores, int B, int reduction, float denominator,
                float *out, void *stream);
+/*  bf16 / fp16 am, lm (or logits) -> the float32 the kernels take:
+ * dst[i] = (float)src[i], n elements, one streaming pass. */
+int frn_cast_to_f32(const void *src, int src_dtype, size_t n, float *dst, void *stream);
 /* The same for two score vectors of one step (simple and pruned loss) in one launch. */
 int frn_reduce_pair(const float *scores_a, const float *scores_b, int B, int reduction,
                     float denominator, float *out_a, float *out_b, void *stream);

@@ -524,3 +524,29 @@ def test_reduce_and_reduce_pair(reduction):
         assert torch.equal(oa, oc)
         np.testing.assert_allclose(oa.cpu().numpy(), want(a), rtol=1e-5, atol=1e-3)
         np.testing.assert_allclose(ob.cpu().numpy(), want(b), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+def test_half_precision_am_lm_inputs(dtype):
+    """ bf16 / fp16 am and lm on the device: widened by frn_cast_to_f32 and then the float32
+    path - identical to feeding the up-cast values."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 2, 61, 17, 36
+    am, lm, sym, term, bd = make_inputs(12, B, T, S, C, ragged=True)
+    td = getattr(torch, dtype)
+    am_h, lm_h = torch.from_numpy(am).cuda().to(td), torch.from_numpy(lm).cuda().to(td)
+    n0 = frn._lib.lib.frn_kernel_launches()
+    loss_h, (gx_h, gy_h) = frn.rnnt_loss_simple(lm_h, am_h, sym, term, bd, "regular", 0.0, "none", True)
+    launched = frn._lib.lib.frn_kernel_launches() - n0
+    loss_f, (gx_f, gy_f) = frn.rnnt_loss_simple(lm_h.float(), am_h.float(), sym, term, bd, "regular", 0.0, "none", True)
+    assert torch.equal(loss_h, loss_f) and torch.equal(gx_h, gx_f) and torch.equal(gy_h, gy_f)
+    n1 = frn._lib.lib.frn_kernel_launches()
+    frn.rnnt_loss_simple(lm_h.float(), am_h.float(), sym, term, bd, "regular", 0.0, "none", True)
+    assert launched == (frn._lib.lib.frn_kernel_launches() - n1) + 2      # the two cast kernels are the library's
+    # odd element counts take the scalar tail
+    x = torch.randn(1003, device="cuda").to(td)
+    y = torch.empty(1003, dtype=torch.float32, device="cuda")
+    frn._lib.check(frn._lib.lib.frn_cast_to_f32(x.data_ptr(), 1 if dtype == "bfloat16" else 2, 1003, y.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "cast")
+    assert torch.equal(y, x.float())

@@ -409,6 +409,12 @@ int frn_reduce(const float *scores, int B, int reduction, float denominator, flo
                        static_cast<cudaStream_t>(stream));
 }
 
+int frn_cast_to_f32(const void *src, int src_dtype, size_t n, float *dst, void *stream) {
+  FRN_REQUIRE(n == 0 || (src && dst));
+  FRN_REQUIRE(src_dtype == FRN_BF16 || src_dtype == FRN_F16);
+  return launch_cast_to_f32(src, src_dtype, n, dst, static_cast<cudaStream_t>(stream));
+}
+
 int frn_reduce_pair(const float *scores_a, const float *scores_b, int B, int reduction, float denominator,
                     float *out_a, float *out_b, void *stream) {
   FRN_REQUIRE(B > 0 && scores_a && scores_b && out_a && out_b && reduction >= FRN_NONE && reduction <= FRN_SUM);

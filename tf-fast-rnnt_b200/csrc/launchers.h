@@ -66,6 +66,7 @@ int launch_band_dp(const float *pxc, const float *pyc, const int32_t *ranges, co
                    int T, int R, int rnnt_type, float delay_penalty, bool want_grad, void *workspace, float *gxc,
                    float *gyc, float *scores, cudaStream_t stream);
 // misc.cu
+int launch_cast_to_f32(const void *src, int dtype, size_t n, float *dst, cudaStream_t stream);
 int launch_reduce(const float *scores, int B, int reduction, float denom, float *out, cudaStream_t stream);
 int launch_reduce_pair(const float *a, const float *b, int B, int reduction, float denom, float *out_a, float *out_b,
                        cudaStream_t stream);

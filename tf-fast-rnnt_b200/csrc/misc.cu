@@ -1,5 +1,6 @@
 // Small utility kernels: loss reduction (A3) and identity band for the full joiner.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace frn {
 
@@ -41,6 +42,37 @@ __global__ void __launch_bounds__(256) add_kernel(const float *a, const float *b
   } else {
     for (size_t i = i4; i < n; ++i) out[i] = a[i] + b[i];
   }
+}
+
+// bf16 / fp16 -> float32, 8 elements (16 bytes in, 32 bytes out) per thread
+template <typename T>
+__global__ void __launch_bounds__(256) cast_to_f32_kernel(const T *src, float *dst, size_t n) {
+  const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 + 7 < n) {
+    uint4 raw;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(src + i8));
+    const T *e = reinterpret_cast<const T *>(&raw);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = static_cast<float>(e[j]);
+    st_stream_f4(reinterpret_cast<float4 *>(dst + i8), make_float4(v[0], v[1], v[2], v[3]));
+    st_stream_f4(reinterpret_cast<float4 *>(dst + i8 + 4), make_float4(v[4], v[5], v[6], v[7]));
+  } else {
+    for (size_t i = i8; i < n; ++i) dst[i] = static_cast<float>(src[i]);
+  }
+}
+
+int launch_cast_to_f32(const void *src, int dtype, size_t n, float *dst, cudaStream_t stream) {
+  if (n == 0) return FRN_OK;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) return FRN_EINVAL;
+  const unsigned grid = (unsigned)((n / 8 + 256) / 256);
+  if (dtype == FRN_BF16)
+    count_launch(), cast_to_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), dst, n);
+  else if (dtype == FRN_F16)
+    count_launch(), cast_to_f32_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half *>(src), dst, n);
+  else return FRN_EINVAL;
+  return check_launch();
 }
 
 int launch_add(const float *a, const float *b, float *out, size_t n, cudaStream_t stream) {

@@ -53,6 +53,7 @@ _SIGS = {
                                     _P, _P, _P, c_size_t, _P]),
     "frn_smoothed_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "frn_cast_to_f32": (c_int, [_P, c_int, c_size_t, _P, _P]),
     "frn_reduce_pair": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "frn_prune_ranges_width": (c_int, [c_int, c_int]),
     "frn_prune_ranges_workspace_bytes": (c_size_t, [c_int, c_int]),

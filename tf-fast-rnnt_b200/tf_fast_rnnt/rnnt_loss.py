@@ -54,6 +54,13 @@ class _Io:
             t = x
         else:
             t = torch.from_numpy(np.ascontiguousarray(x))
+        if (t.is_cuda and dtype == torch.float32 and t.dtype in (torch.bfloat16, torch.float16)
+                and not t.requires_grad):
+            # bf16 / fp16 am, lm on the device: widened by the library's own streaming kernel
+            src = t.contiguous()
+            t = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+            check(lib.frn_cast_to_f32(src.data_ptr(), 1 if src.dtype == torch.bfloat16 else 2, src.numel(),
+                                      t.data_ptr(), _stream(src.device)), "frn_cast_to_f32")
         if t.dtype != dtype:
             t = t.to(dtype)
         if not t.is_cuda:
