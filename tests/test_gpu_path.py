@@ -550,3 +550,27 @@ def test_half_precision_am_lm_inputs(dtype):
     frn._lib.check(frn._lib.lib.frn_cast_to_f32(x.data_ptr(), 1 if dtype == "bfloat16" else 2, 1003, y.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream), "cast")
     assert torch.equal(y, x.float())
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_joint_loss_autograd(rnnt_type):
+    """rnnt_loss on the full joiner output with CUDA logits that require grad: the logits gradient TF autodiff
+    derives through rnnt_loss.py:340-551 (frn_joint_loss), against the float64 oracle."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 2, 37, 11, 6
+    am, lm, sym, term, bd = make_inputs(51, B, T, S, C, ragged=True)
+    full = (am[:, :, None, :] + lm[:, None, :, :]).astype(np.float32)
+    lg = torch.from_numpy(full).cuda().requires_grad_(True)
+    w = np.array([1.5, -0.25], np.float32)
+    loss = frn.rnnt_loss(lg, sym, term, bd, rnnt_type, 0.15, "none")
+    (loss * torch.from_numpy(w).cuda()).sum().backward()
+    o_loss = orc.rnnt_loss(full, sym, term, bd, rnnt_type, 0.15, "none", dtype=np.float64)
+    ranges = np.broadcast_to(np.arange(S + 1, dtype=np.int32)[None, None, :], (B, T, S + 1)).copy()
+    o_grad = orc.pruned_logits_grad(full, sym, ranges, term, bd, rnnt_type, 0.15, w, np.float64)
+    assert_close(loss.detach().cpu().numpy(), o_loss, LOSS_RTOL, 0, "joint loss")
+    assert_close(lg.grad.cpu().numpy(), o_grad, GRAD_RTOL, 2e-6, "joint logits grad")
+    lg.grad = None
+    frn.rnnt_loss(lg, sym, term, bd, rnnt_type, 0.15, "mean").backward()
+    o_mean = orc.pruned_logits_grad(full, sym, ranges, term, bd, rnnt_type, 0.15, np.full(B, 1.0 / B), np.float64)
+    assert_close(lg.grad.cpu().numpy(), o_mean, GRAD_RTOL, 2e-6, "joint logits grad (mean)")

@@ -560,6 +560,39 @@ def get_rnnt_logprobs_joint(logits: Tensor, symbols: Tensor, termination_symbol:
     return io.out(px), io.out(py)
 
 
+def _joint_loss_call(lg, sym_d, bd, termination_symbol, rnnt_type, delay_penalty, scores_grad, want_grad):
+    """frn_joint_loss on device tensors -> (scores, logits_grad or None)."""
+    B, T, S1, C = lg.shape
+    S = S1 - 1
+    scores = torch.empty(B, dtype=torch.float32, device=lg.device)
+    grad = torch.empty_like(lg) if want_grad else None
+    ws = _workspace(lib.frn_joint_loss_workspace_bytes(B, S, T), lg.device)
+    dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    check(lib.frn_joint_loss(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                             int(termination_symbol), _rnnt_type(rnnt_type), dp, _ptr(scores_grad), _ptr(scores),
+                             _ptr(grad), _ptr(ws), ws.numel(), _stream(lg.device)), "frn_joint_loss")
+    return scores, grad
+
+
+class _JointLossFn(torch.autograd.Function):
+    """scores(logits) of the unpruned loss with its logits gradient (what TF autodiff derives through
+    rnnt_loss.py:340-551 + _RNNTLossGrad)."""
+
+    @staticmethod
+    def forward(ctx, logits, symbols, termination_symbol, boundary, rnnt_type, delay_penalty):
+        scores, _ = _joint_loss_call(logits, symbols, boundary, termination_symbol, rnnt_type, delay_penalty, None, False)
+        ctx.save_for_backward(logits, symbols, boundary)
+        ctx.args = (termination_symbol, rnnt_type, delay_penalty)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, symbols, boundary = ctx.saved_tensors
+        term, rnnt_type, dp = ctx.args
+        _, grad = _joint_loss_call(logits, symbols, boundary, term, rnnt_type, dp, g.contiguous().float(), True)
+        return grad, None, None, None, None, None
+
+
 def rnnt_loss(logits: Tensor, symbols: Tensor, termination_symbol: int, boundary: Optional[Tensor] = None,
               rnnt_type: str = "regular", delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
               calc_gradients: bool = False, group=None):
@@ -573,12 +606,12 @@ def rnnt_loss(logits: Tensor, symbols: Tensor, termination_symbol: int, boundary
     sym_d = io.dev_tensor(symbols, torch.int32)
     B, T, S1, C = lg.shape
     S = S1 - 1
-    rt = _rnnt_type(rnnt_type)
+    _rnnt_type(rnnt_type)
     bd = _boundary(io, boundary, B, S, T)
-    scores = torch.empty(B, dtype=torch.float32, device=io.dev)
-    ws = _workspace(lib.frn_joint_loss_workspace_bytes(B, S, T), io.dev)
-    dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
-    check(lib.frn_joint_loss(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(bd), B, S, T, C,
-                             int(termination_symbol), rt, dp, None, _ptr(scores), None, _ptr(ws), ws.numel(),
-                             _stream(io.dev)), "frn_joint_loss")
+    if lg.requires_grad and torch.is_grad_enabled():
+        scores = _JointLossFn.apply(lg, sym_d, int(termination_symbol), bd, rnnt_type, float(delay_penalty))
+        if reduction == "none":
+            return -scores
+        return -scores.sum() if reduction == "sum" else -scores.mean()
+    scores, _ = _joint_loss_call(lg, sym_d, bd, termination_symbol, rnnt_type, delay_penalty, None, False)
     return io.out(_reduce(scores, reduction, group))
