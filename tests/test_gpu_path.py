@@ -574,3 +574,33 @@ def test_joint_loss_autograd(rnnt_type):
     frn.rnnt_loss(lg, sym, term, bd, rnnt_type, 0.15, "mean").backward()
     o_mean = orc.pruned_logits_grad(full, sym, ranges, term, bd, rnnt_type, 0.15, np.full(B, 1.0 / B), np.float64)
     assert_close(lg.grad.cpu().numpy(), o_mean, GRAD_RTOL, 2e-6, "joint logits grad (mean)")
+
+
+@pytest.mark.parametrize("fused_joiner", [False, True])
+def test_training_step_gradients_end_to_end(fused_joiner):
+    """A whole training step through the public API with autograd (what a TF user gets from GradientTape):
+    loss = 0.5 * simple + pruned, gradients w.r.t. am and lm flow back through the pruned loss, the joiner,
+    do_rnnt_pruning and the simple loss; checked against the float64 oracle composed by hand."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 2, 45, 13, 12, 4
+    am, lm, sym, term, bd = make_inputs(61, B, T, S, C, ragged=True)
+    am_t = torch.from_numpy(am).cuda().requires_grad_(True)
+    lm_t = torch.from_numpy(lm).cuda().requires_grad_(True)
+    simple, (gx, gy) = frn.rnnt_loss_simple(lm_t, am_t, sym, term, bd, "regular", 0.0, "sum", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+    if fused_joiner:
+        _, _, logits = frn.do_rnnt_pruning_add_joiner(am_t, lm_t, ranges)
+    else:
+        am_p, lm_p = frn.do_rnnt_pruning(am_t, lm_t, ranges)
+        logits = am_p + lm_p
+    pruned = frn.rnnt_loss_pruned(logits, sym, ranges, term, bd, "regular", 0.0, "sum")
+    (0.5 * simple + pruned).backward()
+    # oracle: d simple / d(am, lm) + pruning-backward of d pruned / d logits
+    rg = ranges.cpu().numpy()
+    o_am, o_lm = orc.simple_am_lm_grad(lm, am, sym, term, bd, "regular", 0.0, None, np.float64)
+    o_am_p, o_lm_p = orc.do_rnnt_pruning(am, lm, rg)
+    o_lg = orc.pruned_logits_grad((o_am_p + o_lm_p).astype(np.float32), sym, rg, term, bd, "regular", 0.0, None, np.float64)
+    p_am, p_lm = orc.do_rnnt_pruning_bwd(o_lg, o_lg, rg, S + 1)
+    assert_close(am_t.grad.cpu().numpy(), 0.5 * o_am + p_am, GRAD_RTOL, 5e-6, "am grad")
+    assert_close(lm_t.grad.cpu().numpy(), 0.5 * o_lm + p_lm, GRAD_RTOL, 5e-5, "lm grad")

@@ -380,8 +380,47 @@ def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_
     return io.out(ranges)
 
 
+class _PruningFn(torch.autograd.Function):
+    """do_rnnt_pruning (optionally with the additive joiner) with the gradient TF autodiff derives for
+    rnnt_loss.py:802-811: am_grad = sum over the band, lm_grad = scatter-add over ranges."""
+
+    @staticmethod
+    def forward(ctx, am, lm, ranges, with_joiner):
+        B, T, C = am.shape
+        S = lm.shape[1] - 1
+        R = ranges.shape[2]
+        outs = [torch.empty((B, T, R, C), dtype=torch.float32, device=am.device) for _ in range(3 if with_joiner else 2)]
+        if with_joiner:
+            check(lib.frn_do_pruning_add_joiner(_ptr(am), _ptr(lm), _ptr(ranges), B, S, T, R, C, _ptr(outs[0]),
+                                                _ptr(outs[1]), _ptr(outs[2]), _stream(am.device)),
+                  "frn_do_pruning_add_joiner")
+        else:
+            check(lib.frn_do_pruning(_ptr(am), _ptr(lm), _ptr(ranges), B, S, T, R, C, _ptr(outs[0]), _ptr(outs[1]),
+                                     _stream(am.device)), "frn_do_pruning")
+        ctx.save_for_backward(ranges)
+        ctx.S = S
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (ranges,) = ctx.saved_tensors
+        ga, gl = grads[0], grads[1]
+        if len(grads) == 3:                     # logits = am_pruned + lm_pruned feeds both
+            ga, gl = ga + grads[2], gl + grads[2]
+        am_g, lm_g = do_rnnt_pruning_backward(ga.contiguous(), gl.contiguous(), ranges, ctx.S)
+        return am_g, lm_g, None, None
+
+
+def _wants_grad(*xs) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.is_cuda and x.requires_grad for x in xs)
+
+
 def do_rnnt_pruning(am: Tensor, lm: Tensor, ranges: Tensor):
-    """Reference: rnnt_loss.py:763-812."""
+    """Reference: rnnt_loss.py:763-812.  CUDA tensors that require grad get gradients w.r.t. am and lm."""
+    if _wants_grad(am, lm):
+        io = _Io(am, lm)
+        return _PruningFn.apply(io.dev_tensor(am, torch.float32), io.dev_tensor(lm, torch.float32),
+                                io.dev_tensor(ranges, torch.int32), False)
     io = _Io(am, lm)
     am_d = io.dev_tensor(am, torch.float32)
     lm_d = io.dev_tensor(lm, torch.float32)
@@ -416,6 +455,10 @@ def do_rnnt_pruning_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor):
     """(extension) do_rnnt_pruning (rnnt_loss.py:763-812) plus the additive joiner of the
     reference's tests (simple_rnnt_loss_test.py:120-125) in one pass over the data:
     -> (am_pruned, lm_pruned, am_pruned + lm_pruned)."""
+    if _wants_grad(am, lm):
+        io = _Io(am, lm)
+        return _PruningFn.apply(io.dev_tensor(am, torch.float32), io.dev_tensor(lm, torch.float32),
+                                io.dev_tensor(ranges, torch.int32), True)
     io = _Io(am, lm)
     am_d = io.dev_tensor(am, torch.float32)
     lm_d = io.dev_tensor(lm, torch.float32)
