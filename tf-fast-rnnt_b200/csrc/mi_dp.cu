@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(256) finalize_dense_kernel(FinalizeDenseParams
   __shared__ float sgx[32][33], sgy[32][33];
   const int b = blockIdx.z;
   const int d0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  // tiles of the skewed plane that hold no lattice cell at all (t = d - K s outside [0, T] for every row of
+  // the tile: the corners of the parallelogram) have nothing to read and nothing to write
+  if (K && (d0 + 31 < s0 || d0 - min(s0 + 31, p.S) > p.T) && !(blockIdx.x == 0 && blockIdx.y == 0)) return;
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int s_begin = bd.x, t_begin = bd.y;
   const int Sb = bd.z - bd.x, Tb = bd.w - bd.y;
