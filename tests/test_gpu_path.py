@@ -604,3 +604,36 @@ def test_training_step_gradients_end_to_end(fused_joiner):
     p_am, p_lm = orc.do_rnnt_pruning_bwd(o_lg, o_lg, rg, S + 1)
     assert_close(am_t.grad.cpu().numpy(), 0.5 * o_am + p_am, GRAD_RTOL, 5e-6, "am grad")
     assert_close(lm_t.grad.cpu().numpy(), 0.5 * o_lm + p_lm, GRAD_RTOL, 5e-5, "lm grad")
+
+
+def test_concurrent_streams_are_independent():
+    """The library keeps no hidden device state: two pipelines enqueued on two CUDA streams at once (own
+    workspaces) give the same bits as the same pipelines run one after the other."""
+    import torch
+    import tf_fast_rnnt as frn
+    shapes = [(3, 120, 30, 24, 4), (2, 333, 41, 16, 5)]
+    inputs = []
+    for k, (B, T, S, C, R) in enumerate(shapes):
+        am, lm, sym, term, bd = make_inputs(70 + k, B, T, S, C, ragged=True)
+        inputs.append((torch.from_numpy(am).cuda(), torch.from_numpy(lm).cuda(), sym, term, bd, R))
+
+    def pipeline(am, lm, sym, term, bd, R):
+        loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.1, "none", True)
+        ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+        am_p, lm_p, logits = frn.do_rnnt_pruning_add_joiner(am, lm, ranges)
+        scores, grad = frn.pruned_loss_fwd_bwd(logits, sym, ranges, term, bd, "regular", 0.1, None)
+        return loss, gx, gy, ranges, scores, grad
+
+    serial = [pipeline(*inp) for inp in inputs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in inputs]
+    for rep in range(3):
+        conc = []
+        for st, inp in zip(streams, inputs):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                conc.append(pipeline(*inp))
+        torch.cuda.synchronize()
+        for a, b in zip(serial, conc):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
