@@ -11,24 +11,36 @@
 // is a first-order LINEAR recurrence in t whose inhomogeneous part c_t only
 // needs the previous row: composing the affine maps  x -> y_t x + c_t  is
 // associative, so a row is one parallel prefix scan and the critical path is
-// (S+1) x log2(32) shuffle levels instead of S+T+1 steps (c2: 101 rows against
-// 601 diagonals).  Threads own lattice COLUMNS, so px/py are read in the
-// reference layout (t is the unit stride: coalesced) and no skewed copy of the
-// lattice is ever made; alpha/beta rows leave coalesced as well.
+// (S+1) x (log2(32) + 1) compositions instead of S+T+1 steps.  A composition
+// costs about as much as a wavefront step (shuffle, exponent alignment,
+// multiply-add), so the scan pays for long lattices - T >= 8 S, or more than 512
+// columns - and the wavefront kernel keeps the short ones (scan_dp_supported:
+// measured table).  Threads own lattice COLUMNS, so px/py are read in the
+// reference layout (t is the unit stride: coalesced), no skewed copy of the
+// lattice is made, alpha/beta rows leave coalesced, and a ragged batch costs
+// what its own rows and columns cost (warps beyond T_b exit at once).
 //
 // Numerics: the extended-range linear domain of mi_dp.cu (value = m * 2^e,
-// float32 mantissa, exact int32 exponent; common.cuh).  Composing two maps
-// aligns the two terms of the new offset on the larger exponent with exact
-// power-of-two factors; all terms are non-negative, so a term that falls out of
-// range is negligible against the partial sum it is added to and nothing can
-// under- or overflow.  No transcendental on the chain.
+// float32 mantissa, exact int32 exponent; common.cuh), here with one exponent
+// per CELL.  Composing two maps aligns the two terms of the new offset on the
+// larger exponent with exact power-of-two factors; all terms are non-negative,
+// so a term that falls out of range is negligible against the partial sum it is
+// added to and nothing can under- or overflow.  No transcendental on the chain
+// (arcs are decoded to (mantissa, exponent) one row ahead of their use).
 //
-// Execution: one CTA per (utterance, direction), one lattice column per
-// thread, up to 16 warps.  A warp scans its 32 columns with 5 shuffle levels.
-// Warps are chained: warp w needs alpha[s][32w-1] from warp w-1 to finish row
-// s, and gets it through a small shared-memory ring (release/acquire flags, no
-// block barrier).  Warp w therefore runs row s while warp w+1 runs row s-1: the
-// critical path is (S+1) warp scans plus one hand-off per warp.
+// Execution: one chain of warps per (utterance, direction); a thread owns K = 1,
+// 2 or 4 consecutive lattice columns, a warp 32 K.  Per row a warp folds its
+// threads' columns, scans the 32 thread totals with 5 branch-free Kogge-Stone
+// levels, takes the value of the column on its left from the previous warp of
+// the chain, finishes its columns and posts its last one to the next warp.
+// The hand-off goes through 8-deep mail boxes in shared memory (one 64-bit
+// store posts {mantissa, exponent}, the reader empties the box; no block
+// barrier), so warp w runs row s while warp w+1 runs row s-1 and the critical
+// path is (S+1) warp scans plus one hand-off per warp.  For rows of more than
+// 512 columns the chain is spread over a thread-block cluster of 2-8 CTAs (the
+// mail box of a CTA's first warp is written through distributed shared memory)
+// so that a thread still owns one column; with many chains (no room for
+// clusters) a thread takes 2 or 4 columns instead.
 // The backward recursion (cu:441-487) is the same scan on mirrored columns and
 // descending rows.  Occupation counts are formed by scan_finalize_kernel from
 // the alpha and beta planes (cu:472-481 in closed form: alpha * arc * beta' / Z).
