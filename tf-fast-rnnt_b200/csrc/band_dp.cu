@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kBandThreads, 1) band_dp_kernel(BandDpParams p
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (k == j) ? 1.0 : 0.0;
       frame = 0;
-      // every intermediate image is kept (float mantissas + frame): the state of a column inside a
+      // every intermediate image is kept (rounded float64 high words + frame): the state of a column inside a
       // chunk is then one 8x8 matrix-vector product with the chunk's boundary state (phase 3)
       uint32_t *img = p.img + ((size_t)(b * 2 + dir) * (T + 1)) * 64 + j * 8;
       int *imf = p.img_frame + ((size_t)(b * 2 + dir) * (T + 1)) * 8 + j;
