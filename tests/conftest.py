@@ -26,3 +26,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _debug_hooks_for_env_overrides(request):
+    """Tests that steer the library through FRN_* environment overrides (all of them do it with
+    `monkeypatch`) run on the -DFRN_DEBUG_HOOKS build; every other test runs on the product library,
+    which never reads the environment."""
+    if "monkeypatch" not in request.fixturenames or "gpu" not in request.keywords:
+        yield
+        return
+    from tf_fast_rnnt import _lib
+    _lib.use_debug_hooks(True)
+    try:
+        yield
+    finally:
+        _lib.use_debug_hooks(False)

@@ -163,3 +163,17 @@ def test_tf_frontend_uses_only_registered_ops():
                  "get_rnnt_logprobs_smoothed", "get_rnnt_prune_ranges", "rnnt_loss", "rnnt_loss_pruned",
                  "rnnt_loss_simple", "rnnt_loss_smoothed", "mutual_information_recursion", "cummin"):
         assert re.search(rf"^def {name}\(", front, re.M), name
+
+
+def test_product_library_never_reads_the_environment(lib):
+    """The FRN_* overrides (force one of two implementations of a stage) live only in the
+    -DFRN_DEBUG_HOOKS build; the product library does not import getenv and carries none of the names."""
+    dbg = LIB[:-3] + "_dbg.so"
+    assert os.path.exists(dbg), "make builds both libraries"
+    und = subprocess.run(["nm", "-D", "--undefined-only", LIB], capture_output=True, text=True, check=True).stdout
+    assert "getenv" not in und
+    blob = open(LIB, "rb").read()
+    for name in (b"FRN_DP_CHAIN", b"FRN_DP_SCAN", b"FRN_BAND_DENSE", b"FRN_SIMPLE_SIMT", b"FRN_SCAN_K", b"FRN_RPL"):
+        assert name not in blob, name
+    und = subprocess.run(["nm", "-D", "--undefined-only", dbg], capture_output=True, text=True, check=True).stdout
+    assert "getenv" in und

@@ -45,8 +45,8 @@ def test_c2_full_pipeline_against_oracle():
     # End to end the float32 log-probs themselves limit the occupation counts: every
     # arc score carries >= 3e-7 of representation error and a path has 600 arcs, so the
     # worst of the 1.6 M counts sits at ~1e-4 relative whatever the recursion does ...
-    assert_close(gx, o_gx, 2 * GRAD_RTOL, GRAD_ATOL, "px_grad (float32 log-probs)")
-    assert_close(gy, o_gy, 2 * GRAD_RTOL, GRAD_ATOL, "py_grad (float32 log-probs)")
+    assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, "px_grad")
+    assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, "py_grad")
     # ... while the recursion alone (same float32 px/py into the float64 oracle) meets
     # the 1e-4 of the north star with margin.
     px, py = frn.get_rnnt_logprobs(lm, am, sym, term, "regular", bd)

@@ -224,12 +224,23 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
     return FRN_EWORKSPACE;
   SimpleLossWs w = carve_simple_loss(workspace, B, S, T, T1, C);
   DpWorkspace dw = carve_dp(w.dp, g);
+  const float dp = delay_penalty > 0.f ? delay_penalty : 0.f;
+  const bool scan = scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= dw.bytes;
+  if (!scan && simple_arc_plane_supported(lm, am, C, rnnt_type)) {
+    // 4 launches: row statistics, normaliser (arcs straight into the recursion's plane), recursion, read-out
+    const ArcPlaneOut arcs{dw.XY, g.P, g.Dn, g.k, dp};
+    FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                   lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs));
+    FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
+    return launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
+                                 calc_gradients ? py_grad : nullptr, stream);
+  }
   FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
                                  lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream));
-  if (scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= dw.bytes)
-    return launch_scan_dp(w.px, w.py, boundary, B, S, T, T1, delay_penalty > 0.f ? delay_penalty : 0.f,
-                          calc_gradients != 0, w.dp, scores, px_grad, py_grad, stream);
-  FRN_TRY(launch_skew_dense(w.px, w.py, boundary, g, dw, delay_penalty > 0.f ? delay_penalty : 0.f, stream));
+  if (scan)
+    return launch_scan_dp(w.px, w.py, boundary, B, S, T, T1, dp, calc_gradients != 0, w.dp, scores, px_grad, py_grad,
+                          stream);
+  FRN_TRY(launch_skew_dense(w.px, w.py, boundary, g, dw, dp, stream));
   FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
   FRN_TRY(launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
                                 calc_gradients ? py_grad : nullptr, stream));
@@ -305,8 +316,8 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
   DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
   // narrow bands: transfer-matrix recursion on the band itself (band_dp.cu);
-  // FRN_BAND_DENSE=1 forces the dense-lattice wavefront for A/B runs and cross-checks
-  const bool force_dense = [] { const char *e = getenv("FRN_BAND_DENSE"); return e && e[0] == '1'; }();   // read per call
+  // FRN_BAND_DENSE=1 (debug-hooks build) forces the dense-lattice wavefront for A/B runs and cross-checks
+  const bool force_dense = debug_env_int("FRN_BAND_DENSE", 0) == 1;
   if (!force_dense && band_dp_supported(S, T, R) && band_delay_ok(T, R, delay_penalty) &&
       band_dp_workspace_bytes(B, T) <= dw.bytes) {
     const bool want = logits_grad != nullptr;

@@ -21,6 +21,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kMaxRowsDp = 1024;                // S + 1 <= 1024 (8 warps x 32 lanes x 4 rows)
 
+// Experiment / cross-check overrides (FRN_DP_CHAIN, FRN_DP_SCAN, FRN_BAND_DENSE, FRN_SIMPLE_SIMT, ...) exist
+// only in the -DFRN_DEBUG_HOOKS build (libfast_rnnt_b200_dbg.so, which the tests load to run two
+// implementations of one stage against each other); the product library never looks at the environment.
+#ifdef FRN_DEBUG_HOOKS
+inline int debug_env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+constexpr int debug_env_int(const char *, int dflt) { return dflt; }
+#endif
+
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -175,8 +187,7 @@ inline DpGeom make_geom(int B, int S, int T, int T1) {
   g.B = B; g.S = S; g.T = T; g.T1 = T1;
   g.k = (T1 == T) ? 0 : 1;
   g.rpl = (S + 1 <= 256) ? 1 : ((S + 1 <= 512) ? 2 : 4);
-  if (const char *e = getenv("FRN_RPL")) {            // experiment knob: rows per lane of the chain kernel
-    const int r = atoi(e);
+  if (const int r = debug_env_int("FRN_RPL", 0)) {    // experiment knob: rows per lane of the chain kernel
     if ((r == 1 && S + 1 <= 256) || (r == 2 && S + 1 <= 512) || r == 4) g.rpl = r;
   }
   g.P = round_up(S + 1, 32 * g.rpl);

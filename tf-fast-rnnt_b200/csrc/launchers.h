@@ -33,10 +33,13 @@ int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ra
 namespace frn {
 // logprobs_simple.cu
 size_t simple_stats_bytes(int B, int S, int T, int C);
+// arcs != nullptr: the arcs go straight into the recursion's diagonal-major plane instead of px/py
+struct ArcPlaneOut { float4 *XY; int P, Dn, k; float delay_penalty; };
+bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnnt_type);
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const ArcPlaneOut *arcs = nullptr);
 int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
                            cudaStream_t stream);
 // simple_bwd.cu

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launchers.h"
 #include "simple_params.cuh"
 
 namespace frn {
@@ -251,10 +252,18 @@ int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T
   return check_launch();
 }
 
+// One launcher for both outputs of the contraction: px/py in the reference layout (arcs == nullptr), or
+// the arcs of the dense-lattice recursion written straight into its diagonal-major plane (arcs != nullptr:
+// tensor-core kernel only, regular / modified; check simple_arc_plane_supported() first).
+bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnnt_type) {
+  if (debug_env_int("FRN_SIMPLE_SIMT", 0) == 1 || debug_env_int("FRN_SIMPLE_PXPY", 0) == 1) return false;
+  return rnnt_type != FRN_CONSTRAINED && simple_logprobs_tc_applicable(lm, am, C);
+}
+
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const ArcPlaneOut *arcs) {
   const int S1 = S + 1;
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
@@ -282,10 +291,12 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   sp.comb = (float)(1.0 - lms - ams);
   sp.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
   sp.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
-  // tensor-core path (tcgen05 + TMA); the exact-FP32 SIMT kernel serves shapes
-  // TMA cannot address (C % 4 != 0) and FRN_SIMPLE_SIMT=1 forces it for A/B runs
-  const bool force_simt = [] { const char *e = getenv("FRN_SIMPLE_SIMT"); return e && e[0] == '1'; }();   // read per call
-  rc = force_simt ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
+  if (arcs) {
+    sp.XY = arcs->XY; sp.P = arcs->P; sp.Dn = arcs->Dn; sp.k = arcs->k; sp.delay_penalty = arcs->delay_penalty;
+    return launch_simple_logprobs_tc(sp, stream);
+  }
+  // tensor-core path (tcgen05 + TMA); the exact-FP32 SIMT kernel serves shapes TMA cannot address (C % 4 != 0)
+  rc = debug_env_int("FRN_SIMPLE_SIMT", 0) == 1 ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
   if (rc == FRN_EUNSUPPORTED) {
     dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
     count_launch(), simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);

@@ -13,9 +13,21 @@
 //   3. one thread issues 6 tcgen05.mma (hh, hm, mh, mm, hl, lh — everything down
 //      to 2^-24 relative) per 16-wide k step into a 128 x N float32 accumulator
 //      in tensor memory and commits to an mbarrier.
-// Epilogue: tcgen05.ld the accumulator (one lattice frame per thread), log,
-// un-shift, symbol / blank gather, smoothing terms, boundary fix-ups, and store
-// px/py coalesced along t in the reference layout (rnnt_loss.py:186-221,1290-1365).
+// Epilogue: tcgen05.ld the accumulator (one lattice frame per thread), then either
+//   (a) log, un-shift, symbol / blank gather, smoothing terms, boundary fix-ups, and store
+//       px/py coalesced along t in the reference layout (rnnt_loss.py:186-221,1290-1365)
+//       - the public get_rnnt_logprobs{,_smoothed}; or
+//   (b) frn_simple_loss: every live arc goes straight into the diagonal-major plane the
+//       wavefront recursion streams (mi_dp.cu), as (mantissa in [1,2], integer exponent) of
+//       numerator / Z with boundary masks and the delay penalty applied.  The exponent is
+//       assembled from exact integers (floor parts of the shifted scores, the exponent field
+//       of Z) and the mantissa from one ex2 of a fraction in [0,1): no float32 log-prob of
+//       magnitude ~10 is ever formed, so an arc carries ~4e-7 instead of ~2e-6 relative
+//       error and the px/py round trip + the skew kernel are gone.  The tile is transposed
+//       through the (by then free) operand shared memory so that a warp writes 512
+//       contiguous bytes of one diagonal; the dead remainder of the plane is filled by the
+//       same launch (every CTA takes a share of the diagonals while its first TMA loads
+//       are in flight).
 //
 // float32-accurate by construction (the occupation counts downstream need ~2^-21
 // on the normaliser, which rules out plain bf16/tf32: DESIGN.md "numerics").
@@ -47,8 +59,31 @@ constexpr uint32_t kOffB = kOffA + 3 * kOpABytes;              // 3 x B operand
 constexpr uint32_t kOffRaw = kOffB + 3 * kOpBBytes;            // 2 x (am raw, lm raw)
 constexpr uint32_t kRawStage = kRawAmBytes + kRawLmBytes;
 constexpr uint32_t kOffSmall = kOffRaw + 2 * kRawStage;
-constexpr uint32_t kSmallBytes = 5120;
+constexpr uint32_t kSmallBytes = 8192;
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes + 1024;  // + alignment slack
+// Accumulator columns of a thread: the four warps of a TMEM lane quarter (`half` = 0..3) take 28
+// symbol columns each, 16 out of [0,64) and 12 out of [64,112): the arc-plane epilogue finishes the
+// tile in two passes over those column ranges (one pass of staging fits the free shared memory).
+constexpr int kColsPerHalf = TN / 4;          // 28 columns per thread, 7 batches of 4
+constexpr int kPassA = 64;
+__host__ __device__ constexpr int col_of(int half, int i) {
+  return i < 16 ? half * 16 + i : kPassA + half * 12 + (i - 16);
+}
+constexpr double kLog2eD = 1.4426950408889634074;
+constexpr float kLog2eLo = 1.92596299112661746e-8f;   // log2(e) - (float)log2(e)
+struct Small {                                        // per-CTA row / column constants
+  double sm_x[TN], sm_y[TN];                          // smoothed: lm_scale * log2e * (lm[s,sym|blank] - lmonly[s])
+  uint64_t bars[4];                                   // raw_full[2], mma_done
+  float amneg[TM], lmneg[TN];                         // -max * log2e (-inf: row masked)
+  float ammax[TM], lmmax[TN];
+  float pxlm[TN], pylm[TN], lmonly[TN], logusym[TN];
+  int sym[TN];
+  // arc-plane epilogue: (lm[s,sym] - lmmax) * log2e and (lm[s,blank] - lmmax) * log2e as integer + fraction in [0,1)
+  int bx_e[TN], by_e[TN];
+  float bx_f[TN], by_f[TN];
+  uint32_t tmem;
+};
+static_assert(sizeof(Small) <= kSmallBytes, "small shared-memory block");
 
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
                                             int c2) {
@@ -129,6 +164,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 
 }  // namespace tc
 
+template <bool kXY>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __grid_constant__ CUtensorMap map_lm,
                           SimpleParams p) {
@@ -148,15 +184,17 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   const int S1 = p.S + 1, C = p.C;
   const int nk = (C + KC - 1) / KC;
   const int n_rows = min(TN, round_up(S1 - s0, 16));   // MMA N for this tile (multiple of 16)
+  Small &sm = *reinterpret_cast<Small *>(smem + kOffSmall);
+  uint64_t *bars = sm.bars;
 
-  float *s_amneg = reinterpret_cast<float *>(smem + kOffSmall);          // [128] -ammax*log2e (-inf: row masked)
-  float *s_lmneg = s_amneg + TM;                                         // [112] -lmmax*log2e
-  float *s_ammax = s_lmneg + TN;                                         // [128]
-  float *s_lmmax = s_ammax + TM;                                         // [112]
-  float *s_pxlm = s_lmmax + TN, *s_pylm = s_pxlm + TN, *s_lmonly = s_pylm + TN, *s_logusym = s_lmonly + TN;
-  int *s_sym = reinterpret_cast<int *>(s_logusym + TN);                  // [112]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_sym + TN);             // raw_full[2], mma_done
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4);
+  // utterance geometry (arc-plane output only)
+  const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
+  const bool bd_ok = bd.z - bd.x >= 0 && bd.w - bd.y >= 0 && bd.x >= 0 && bd.y >= 0 && bd.z <= p.S && bd.w <= p.T;
+  const int s_begin = bd.x, t_begin = bd.y, Sb = bd_ok ? bd.z - bd.x : -1, Tb = bd_ok ? bd.w - bd.y : -1;
+  const float2 dead2 = make_float2(0.f, __int_as_float(kNegI));
+  float4 *XYb = kXY ? p.XY + (size_t)b * p.Dn * p.P : nullptr;
+  // a tile that holds no live arc has nothing to contract
+  const bool tile_dead = kXY && (!bd_ok || t0 >= bd.w || t0 + TM <= t_begin || s0 > bd.z || s0 + TN <= s_begin);
 
   // The raw tiles do not depend on the row statistics: the first two slices are requested before
   // anything else so that their (cold) latency hides behind the set-up loads below.
@@ -166,7 +204,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     tma_load_3d(raw, &map_am, &bars[stage], k * KC, t0, b);
     tma_load_3d(raw + kRawAmBytes, &map_lm, &bars[stage], k * KC, s0, b);
   };
-  if (tid == 0) {
+  if (tid == 0 && !tile_dead) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_am) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lm) : "memory");
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
@@ -174,13 +212,35 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     issue_tma(0, 0);
     if (nk > 1) issue_tma(1, 1);
   }
+  if constexpr (kXY) {
+    // Dead remainder of the arc plane.  Half X of cell (d, r) is the symbol arc from lattice row r-1 at
+    // relative frame tx, half Y the blank arc of row r at relative frame ty; an arc is live iff its source
+    // lies inside the boundary box (mutual_information_cuda.cu:295-303 load rules; rnnt_loss.py:51-60 makes
+    // frame t_end dead).  Live halves are written by the epilogue below, all others here: the tiles of an
+    // utterance share its diagonals evenly.  Only diagonals the recursion streams are touched.
+    const int ntile = gridDim.x * gridDim.y, lt = blockIdx.y * gridDim.x + blockIdx.x;
+    const int Dfill = bd_ok ? min(p.Dn, round_up(Tb + p.k * Sb + 1, kChunk)) : 0;
+    const int dlo = (int)((long long)Dfill * lt / ntile), dhi = (int)((long long)Dfill * (lt + 1) / ntile);
+    const float4 dead4 = make_float4(dead2.x, dead2.y, dead2.x, dead2.y);
+    for (int d = dlo + w; d < dhi; d += kThreads / 32)
+      for (int r = lane; r < p.P; r += 32) {
+        const int ty = d - 1 - p.k * r, tx = ty + p.k;
+        const bool xa = r >= 1 && r <= Sb && tx >= 0 && tx < Tb;
+        const bool ya = r <= Sb && ty >= 0 && ty < Tb;
+        float4 *dst = XYb + (size_t)d * p.P + r;
+        if (!xa && !ya) *dst = dead4;
+        else if (!xa) *reinterpret_cast<float2 *>(dst) = dead2;
+        else if (!ya) *(reinterpret_cast<float2 *>(dst) + 1) = dead2;
+      }
+    if (tile_dead) return;
+  }
   const float *lmb = p.lm + (size_t)b * S1 * C;
   const float *amb = p.am + (size_t)b * p.T * C;
   if (tid < TM) {
     const int t = t0 + tid;
     const float mx = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
-    s_ammax[tid] = mx;
-    s_amneg[tid] = (t < p.T) ? -mx * kLog2e : -INFINITY;   // exp2(x*log2e - inf) = 0 for masked rows
+    sm.ammax[tid] = mx;
+    sm.amneg[tid] = (t < p.T) ? -mx * kLog2e : -INFINITY;   // exp2(x*log2e - inf) = 0 for masked rows
   } else if (tid < TM + TN) {
     const int j = tid - TM, s = s0 + j;
     float lmmax = 0.f, pxlm = 0.f, pylm = 0.f, lmonly = 0.f, logus = 0.f;
@@ -197,35 +257,47 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
         logus = (sym >= 0) ? p.logu[sym] : 0.f;
       }
     }
-    s_lmmax[j] = lmmax; s_lmneg[j] = (s < S1) ? -lmmax * kLog2e : -INFINITY;
-    s_pxlm[j] = pxlm; s_pylm[j] = pylm; s_lmonly[j] = lmonly; s_logusym[j] = logus; s_sym[j] = sym;
+    sm.lmmax[j] = lmmax; sm.lmneg[j] = (s < S1) ? -lmmax * kLog2e : -INFINITY;
+    sm.pxlm[j] = pxlm; sm.pylm[j] = pylm; sm.lmonly[j] = lmonly; sm.logusym[j] = logus; sm.sym[j] = sym;
+    if constexpr (kXY) {
+      // shifted lm scores in log2 units, integer + fraction (formed once per column in float64)
+      auto split = [](float x, float mx, int &e, float &f) {
+        const double v = ((double)x - (double)mx) * kLog2eD;
+        if (!(v > -1.0e8)) { e = kNegI; f = 0.f; return; }
+        const double fl = floor(v);
+        e = (int)fl; f = (float)(v - fl);
+      };
+      split(pxlm, lmmax, sm.bx_e[j], sm.bx_f[j]);
+      split(pylm, lmmax, sm.by_e[j], sm.by_f[j]);
+      sm.sm_x[j] = (double)p.lm_scale * kLog2eD * ((double)pxlm - (double)lmonly);
+      sm.sm_y[j] = (double)p.lm_scale * kLog2eD * ((double)pylm - (double)lmonly);
+    }
   }
-  if (w == 0) tmem_alloc(s_tmem, kTmemCols);
+  if (w == 0) tmem_alloc(&sm.tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *s_tmem;
+  const uint32_t tmem_d = sm.tmem;
   TCT(1);
 
   // epilogue mapping, also used inside the k loop: thread <-> frame (TMEM lane), the four
-  // warps of a lane quarter take 28 symbol columns each
+  // warps of a lane quarter take 28 symbol columns each (col_of)
   const int q = w & 3, half = w >> 2;            // `half` = column part 0..3
   const int erow = q * 32 + lane, et = t0 + erow;
   const bool t_ok = et < p.T;
-  constexpr int kColsPerHalf = TN / 4;          // 28 columns per thread, 7 batches of 4
   const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
   const float py_am = __ldg(amb + (size_t)(t_ok ? et : 0) * C + p.term);
   const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
   const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
   // the symbols of this warp's columns, one per lane
-  const int my_sym0 = (lane < kColsPerHalf) ? s_sym[half * kColsPerHalf + lane] : -1;
+  const int my_sym0 = (lane < kColsPerHalf) ? sm.sym[col_of(half, lane)] : -1;
   float accr[kColsPerHalf];                     // float32 sum of the per-slice tensor-core partial sums
 #pragma unroll
   for (int i = 0; i < kColsPerHalf; ++i) accr[i] = 0.f;
   auto drain_accumulator = [&]() {              // TMEM partial sums of one slice -> registers
 #pragma unroll
     for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
-      const int c0 = half * kColsPerHalf + bi * 4;
+      const int c0 = col_of(half, bi * 4);
       if (c0 < n_rows) {                        // warp-uniform
         float part[4];
         tmem_ld4(lane_addr + (uint32_t)c0, part);
@@ -260,7 +332,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
         const int src_lane = __ffs(hit0) - 1;
         hit0 &= hit0 - 1;
         const int sym = __shfl_sync(0xffffffffu, my_sym0, src_lane);
-        const int j = half * kColsPerHalf + src_lane;
+        const int j = col_of(half, src_lane);
         const uint32_t v = __float_as_uint(raw_am[erow * KC + (sym - k0)]);
         asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_addr + (uint32_t)(kPxCol + j)), "r"(v)
                      : "memory");
@@ -300,8 +372,8 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
         *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
       }
     };
-    convert(raw_am, s_amneg, smem + kOffA, kOpABytes, TM * 8);
-    convert(raw_lm, s_lmneg, smem + kOffB, kOpBBytes, TN * 8);
+    convert(raw_am, sm.amneg, smem + kOffA, kOpABytes, TM * 8);
+    convert(raw_lm, sm.lmneg, smem + kOffB, kOpBBytes, TN * 8);
     fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -333,13 +405,13 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   drain_accumulator();
   TCT(40);
 
-  // ---- epilogue: one frame per thread (TMEM lane), 56 symbol columns per warp half.
-  //      Straight-line: everything is computed for all 8 columns of a batch, only the
-  //      stores are predicated. ----
-  {
+  if constexpr (!kXY) {
+    // ---- epilogue (a): one frame per thread (TMEM lane), 28 symbol columns per thread.
+    //      Straight-line: everything is computed for all 4 columns of a batch, only the
+    //      stores are predicated. ----
     const int t = et;
-    const int t_end = p.boundary[4 * b + 3];
-    const float ammax = s_ammax[erow];
+    const int t_end = bd.w;
+    const float ammax = sm.ammax[erow];
     float *pxb = p.px + (size_t)b * p.S * p.T1 + t;
     float *pyb = p.py + (size_t)b * S1 * p.T + t;
     const bool regular = (p.T1 == p.T + 1);
@@ -348,27 +420,135 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
     const bool smoothed = p.smoothed != 0;
 #pragma unroll
     for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
-      const int c0 = half * kColsPerHalf + bi * 4;
+      const int c0 = col_of(half, bi * 4);
       if (c0 < n_rows) {                 // warp-uniform
         float pxam[4];
         tmem_ld4(lane_addr + (uint32_t)(kPxCol + c0), pxam);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = c0 + e, s = s0 + j;
-          const float norm = log_plus_tiny(accr[bi * 4 + e]) + s_lmmax[j] + ammax;
-          const float py_lm = s_pylm[j], px_lm = s_pxlm[j], px_am = pxam[e];
+          const float norm = log_plus_tiny(accr[bi * 4 + e]) + sm.lmmax[j] + ammax;
+          const float py_lm = sm.pylm[j], px_lm = sm.pxlm[j], px_am = pxam[e];
           float py = py_am + py_lm - norm;
           float px = px_am + px_lm - norm;
           if (smoothed) {                // warp-uniform
-            const float lmonly = s_lmonly[j];
+            const float lmonly = sm.lmonly[j];
             py = py * p.comb + (py_lm - lmonly) * p.lm_scale + (py_am + logu_term - amonly) * p.am_scale;
-            px = px * p.comb + (px_lm - lmonly) * p.lm_scale + (px_am + s_logusym[j] - amonly) * p.am_scale;
+            px = px * p.comb + (px_lm - lmonly) * p.lm_scale + (px_am + sm.logusym[j] - amonly) * p.am_scale;
           }
           px = px_inf ? -INFINITY : px;
           if (t_ok && s < S1) pyb[(size_t)s * p.T] = py;
           if (px_col_ok && s < p.S) pxb[(size_t)s * p.T1] = px;
         }
       }
+    }
+  } else {
+    // ---- epilogue (b): arcs into the diagonal-major plane.  Thread (frame e = erow, column j) holds
+    //      symbol arc X = px[s0+j][t0+e] and blank arc Y = py[s0+j][t0+e]; both belong to plane diagonal
+    //      d = Delta + 1 + e + k*j (Delta = t0 - t_begin + k*(s0 - s_begin)), X to row s'+1, Y to row s'.
+    //      Two passes (columns [0,64), [64,112)): stage [column][frame] in the free operand memory,
+    //      then every warp writes whole diagonals, lanes along the rows. ----
+    const int kk = p.k;
+    const int pitch = 129 - kk;                 // (pitch - k) odd: the skewed read-out is bank-conflict free
+    float2 *stX = reinterpret_cast<float2 *>(smem);
+    float2 *stY = stX + kPassA * 129;
+    const float ammax = sm.ammax[erow];
+    const bool smoothed = p.smoothed != 0;
+    // per-frame constants: blank score and delay penalty in log2 units, integer + fraction
+    int ay_e = kNegI, pen_e = 0;
+    float ay_f = 0.f, pen_f = 0.f;
+    double pen_d = 0.0, amy_d = 0.0;
+    {
+      const double v = ((double)py_am - (double)ammax) * kLog2eD;
+      if (v > -1.0e8) { const double fl = floor(v); ay_e = (int)fl; ay_f = (float)(v - fl); }
+      if (p.delay_penalty != 0.f) {             // rnnt_loss.py:316-321: float64, rounded to float32, added to px
+        pen_d = (double)delay_penalty_value(bd.w, et, p.delay_penalty) * kLog2eD;
+        const double fl = floor(pen_d);
+        pen_e = (int)fl; pen_f = (float)(pen_d - fl);
+      }
+      if (smoothed) amy_d = (double)p.am_scale * kLog2eD * ((double)py_am + (double)logu_term - (double)amonly);
+    }
+    const double comb_d = (double)p.comb, amsc_d = (double)p.am_scale * kLog2eD;
+    auto finish = [&](int e_int, float f) {     // exponent + fraction in (-2, 4) -> (mantissa in [1,2], exponent)
+      const float kf = floorf(f);
+      const int ex = e_int + (int)kf;
+      return (ex > kNegIThresh) ? make_float2(ex2_approx(f - kf), __int_as_float(ex)) : dead2;
+    };
+    auto finish_d = [&](double v) {
+      if (!(v > -1.0e8)) return dead2;
+      const double fl = floor(v);
+      return make_float2(ex2_approx((float)(v - fl)), __int_as_float((int)fl));
+    };
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int jb = pass ? kPassA : 0, ncols = pass ? TN - kPassA : kPassA;
+      if (jb < n_rows) {                        // block-uniform
+#pragma unroll
+        for (int bi = (pass ? 4 : 0); bi < (pass ? 7 : 4); ++bi) {
+          const int c0 = col_of(half, bi * 4);
+          if (c0 < n_rows) {                    // warp-uniform
+            float pxam[4];
+            tmem_ld4(lane_addr + (uint32_t)(kPxCol + c0), pxam);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c0 + e;
+              // log2 Z = exponent field + lg2(mantissa); Z < FLT_MIN counts as the reference's log(0 + tiny)
+              const float z = accr[bi * 4 + e];
+              const uint32_t u = __float_as_uint(z);
+              const bool ztiny = z < 1.1754944e-38f;
+              const int ze = ztiny ? -149 : (int)(u >> 23) - 127;
+              const float lg = ztiny ? 0.f : lg2_approx(__uint_as_float((u & 0x007FFFFFu) | 0x3F800000u));
+              // (am[t,sym] - ammax) * log2e: product split exactly into head + tail
+              const float a = pxam[e] - ammax;
+              const float hi = a * kLog2e;
+              const float lo = fmaf(a, kLog2e, -hi) + a * kLog2eLo;
+              const float hfl = floorf(hi);
+              const bool x_ok = a > -1.0e8f;
+              const int ex_i = (x_ok ? (int)hfl : kNegI) + sm.bx_e[j] - ze;
+              const float fx = ((hi - hfl) + lo) + sm.bx_f[j] - lg;
+              const int ey_i = ay_e + sm.by_e[j] - ze;
+              const float fy = ay_f + sm.by_f[j] - lg;
+              float2 X, Y;
+              if (!smoothed) {                  // warp-uniform
+                X = finish(ex_i + pen_e, x_ok ? fx + pen_f : 0.f);
+                Y = finish(ey_i, fy);
+              } else {                          // rnnt_loss.py:1342-1360 in log2 units
+                const double vx = comb_d * ((double)ex_i + (double)fx) + sm.sm_x[j] +
+                                  amsc_d * ((double)pxam[e] + (double)sm.logusym[j] - (double)amonly) + pen_d;
+                const double vy = comb_d * ((double)ey_i + (double)fy) + sm.sm_y[j] + amy_d;
+                X = (x_ok && ex_i > kNegIThresh) ? finish_d(vx) : dead2;
+                Y = (ey_i > kNegIThresh) ? finish_d(vy) : dead2;
+              }
+              stX[(j - jb) * pitch + erow] = X;
+              stY[(j - jb) * pitch + erow] = Y;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (jb < n_rows) {
+        const int rho = s0 + jb - s_begin, Delta = (t0 - t_begin) + kk * rho;
+        const int ND = TM + kk * (ncols - 1), ngrp = (ncols + 1 + 31) / 32;
+        for (int delta = w; delta < ND; delta += kThreads / 32) {
+          const int d = Delta + 1 + delta;
+          for (int g = 0; g < ngrp; ++g) {
+            const int jp = g * 32 + lane, r = rho + jp;
+            // same liveness rule as the fill above, in plane coordinates
+            const int ty = d - 1 - kk * r, tx = ty + kk;
+            const int ex_ = delta - kk * (jp - 1), ey_ = delta - kk * jp;     // staged frame of either half
+            const bool xa = jp >= 1 && jp <= ncols && ex_ >= 0 && ex_ < TM && r >= 1 && r <= Sb && tx >= 0 && tx < Tb;
+            const bool ya = jp < ncols && ey_ >= 0 && ey_ < TM && r >= 0 && r <= Sb && ty >= 0 && ty < Tb;
+            float2 X = dead2, Y = dead2;
+            if (xa) X = stX[(jp - 1) * pitch + ex_];
+            if (ya) Y = stY[jp * pitch + ey_];
+            float4 *dst = XYb + (size_t)d * p.P + r;
+            if (xa && ya) *dst = make_float4(X.x, X.y, Y.x, Y.y);
+            else if (xa) *reinterpret_cast<float2 *>(dst) = X;
+            else if (ya) *(reinterpret_cast<float2 *>(dst) + 1) = Y;
+          }
+        }
+      }
+      if (pass == 0) __syncthreads();
     }
   }
   TCT(41);
@@ -421,20 +601,27 @@ static bool make_map_3d(CUtensorMap *map, const float *base, int rows, int C, in
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C) {
+  // TMA needs 16-byte global strides (C % 4 == 0) and aligned bases
+  return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0 &&
+         get_encode_fn() != nullptr;
+}
+
 // returns FRN_EUNSUPPORTED when the tensor-core path does not apply (caller falls
 // back to the SIMT kernel): C % 4 != 0 (TMA needs 16-byte global strides) or
-// misaligned bases.
+// misaligned bases.  sp.XY != nullptr selects the arc-plane output (regular / modified only).
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
-  if (sp.C % 4 != 0) return FRN_EUNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(sp.am) | reinterpret_cast<uintptr_t>(sp.lm)) & 15u) return FRN_EUNSUPPORTED;
+  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C)) return FRN_EUNSUPPORTED;
+  if (sp.XY != nullptr && sp.rnnt_type == FRN_CONSTRAINED) return FRN_EUNSUPPORTED;
   CUtensorMap map_am, map_lm;
   if (!make_map_3d(&map_am, sp.am, sp.T, sp.C, sp.B, tc::TM)) return FRN_EUNSUPPORTED;
   if (!make_map_3d(&map_lm, sp.lm, sp.S + 1, sp.C, sp.B, tc::TN)) return FRN_EUNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(simple_logprobs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::kSmemBytes);
+  auto kernel = sp.XY ? simple_logprobs_tc_kernel<true> : simple_logprobs_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return note_cuda_error(e);
-  dim3 grid((sp.T1 + tc::TM - 1) / tc::TM, (sp.S + 1 + tc::TN - 1) / tc::TN, sp.B);
-  count_launch(), simple_logprobs_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_am, map_lm, sp);
+  // arc-plane output: frames 0..T-1 carry arcs (the regular lattice's extra column T has none)
+  dim3 grid(((sp.XY ? sp.T : sp.T1) + tc::TM - 1) / tc::TM, (sp.S + 1 + tc::TN - 1) / tc::TN, sp.B);
+  count_launch(), kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_am, map_lm, sp);
   return check_launch();
 }
 

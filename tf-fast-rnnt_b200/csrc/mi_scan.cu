@@ -363,18 +363,13 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanParams p) {
 // cluster while that still fits the GPU in one wave (the row scan is instruction-issue bound: fewer warps
 // per SM sub-partition = faster rows).  FRN_SCAN_CLUSTER overrides (experiments).
 static int scan_cluster_size(int chains, int T) {
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
+  const int sms = 148;     // B200; only steers a heuristic (how many CTAs a chain may spread over)
   // one column per thread is the fastest variant: take the smallest cluster that allows it (measured on
   // B200: at T = 500 clusters of 2 / 4 change nothing, 0.083 ms; at T = 1500 a cluster of 4 with one column
   // per thread runs 0.49 ms, one CTA with four columns per thread 0.57 ms)
   int c = 1;
   while (c < 8 && 32 * kScanMaxWarps * c < T + 1 && chains * c * 2 <= 2 * sms) c *= 2;
-  if (const char *e = getenv("FRN_SCAN_CLUSTER")) {
-    const int v = atoi(e);
+  if (const int v = debug_env_int("FRN_SCAN_CLUSTER", 0)) {
     if (v == 1 || v == 2 || v == 4 || v == 8) c = v;
   }
   return c;
@@ -383,8 +378,7 @@ static int scan_cols_per_thread(int T, int cluster) {
   // fewest columns per thread that fit the lattice row into the cluster; FRN_SCAN_K overrides (experiments)
   int k = 1;
   while (32 * kScanMaxWarps * cluster * k < T + 1) k *= 2;
-  if (const char *e = getenv("FRN_SCAN_K")) {
-    const int v = atoi(e);
+  if (const int v = debug_env_int("FRN_SCAN_K", 0)) {
     if ((v == 1 || v == 2 || v == 4) && 32 * kScanMaxWarps * cluster * v >= T + 1) k = v;
   }
   return k;
@@ -394,11 +388,11 @@ static int scan_cols_per_thread(int T, int cluster) {
 //   T=500:  S=20 .053/.055  S=50 .054/.064  S=100 .083/.084  S=200 .20/.16  S=400 .42/.38   T=200 S=100 .075/.050
 //   T=1000: S=100 .13/.15   S=250 .32/.30   T=1500: S=100 .11/.17  S=400 .46/.68
 // so: long lattices (T >= 8 S), and beyond 512 columns when T >= 4 S or the wavefront needs > 1 row per lane.
-// FRN_DP_SCAN=1 / FRN_DP_CHAIN=1 force one of them (tests and A/B runs); read at every call.
+// FRN_DP_SCAN=1 / FRN_DP_CHAIN=1 force one of them in the debug-hooks build (tests and A/B runs).
 bool scan_dp_supported(int S, int T) {
   if (!(S >= 0 && T + 1 <= 32 * kScanMaxWarps * kScanMaxK && S + T <= 4095)) return false;   // one CTA must be able to hold a row
-  if (const char *e = getenv("FRN_DP_CHAIN")) if (e[0] == '1') return false;
-  if (const char *e = getenv("FRN_DP_SCAN")) if (e[0] == '1') return true;
+  if (debug_env_int("FRN_DP_CHAIN", 0) == 1) return false;
+  if (debug_env_int("FRN_DP_SCAN", 0) == 1) return true;
   if (T >= 8 * S) return true;
   return T + 1 > 512 && (T >= 4 * S || S + 1 > 256);
 }

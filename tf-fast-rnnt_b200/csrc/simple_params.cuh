@@ -12,6 +12,14 @@ struct SimpleParams {
   float *px, *py;                       // reference layout
   int B, S, T, T1, C, term, rnnt_type, smoothed;
   float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
+  // Arc-plane output (frn_simple_loss): instead of px/py the tensor-core kernel writes every live arc as
+  // (mantissa, exponent) straight into the diagonal-major plane the wavefront recursion streams
+  // (DpWorkspace::XY, mi_dp.cu) and fills the dead remainder of the plane; px/py are not touched.
+  float4 *XY = nullptr;
+  int P = 0, Dn = 0, k = 0;
+  float delay_penalty = 0.f;            // rnnt_loss.py:316-321, folded into the symbol arcs
 };
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream);
+// true when the tensor-core kernel can take this problem (TMA needs C % 4 == 0 and 16-byte aligned bases)
+bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C);
 }  // namespace frn

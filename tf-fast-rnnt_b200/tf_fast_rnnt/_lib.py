@@ -28,7 +28,42 @@ if not os.path.exists(LIB_PATH):
         f"fast_rnnt_b200: {LIB_PATH} not found. Build it with "
         "`make -C tf-fast-rnnt_b200/csrc` (or __graft_entry__.build()); "
         "there is no CPU fallback.")
-lib = ctypes.CDLL(LIB_PATH)
+
+
+class _Library:
+    """The loaded C-ABI library.  Normally the product build; `use_debug_hooks(True)` swaps in the
+    -DFRN_DEBUG_HOOKS build (libfast_rnnt_b200_dbg.so: same sources, plus the FRN_* environment overrides
+    that force one of two implementations of a stage) for the tests that cross-check kernels against
+    each other.  Attribute access goes to whichever build is current."""
+
+    def __init__(self, path):
+        self._product = ctypes.CDLL(path)
+        self._debug = None
+        self._cur = self._product
+
+    def __getattr__(self, name):
+        return getattr(self._cur, name)
+
+
+lib = _Library(LIB_PATH)
+DEBUG_LIB_PATH = LIB_PATH[:-3] + "_dbg.so"
+
+
+def _bind(cdll):
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(cdll, name)      # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+
+
+def use_debug_hooks(on: bool) -> None:
+    if on and lib._debug is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise ImportError(f"fast_rnnt_b200: {DEBUG_LIB_PATH} not found (make -C tf-fast-rnnt_b200/csrc)")
+        lib._debug = ctypes.CDLL(DEBUG_LIB_PATH)
+        _bind(lib._debug)
+    lib._cur = lib._debug if on else lib._product
+
 
 _P = c_void_p
 _SIGS = {
@@ -75,10 +110,7 @@ _SIGS = {
     "frn_reduce": (c_int, [_P, c_int, c_int, c_float, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
-for _name, (_res, _args) in _SIGS.items():
-    _fn = getattr(lib, _name)      # AttributeError here = header/library mismatch
-    _fn.restype = _res
-    _fn.argtypes = _args
+_bind(lib._product)
 
 
 class FastRnntError(RuntimeError):
