@@ -144,7 +144,7 @@ class Pipeline:
     sub-batch (lattice recursions, normaliser) overlap the bandwidth-bound kernels of another.
     Same calls, same results; the two loss sums are reduced over the whole batch at the end."""
 
-    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True):
+    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True, am_side=0):
         import torch
         from tf_fast_rnnt import _lib
         self.torch, self.lib, self._lib = torch, _lib.lib, _lib
@@ -163,7 +163,12 @@ class Pipeline:
         # beside the dependency-chain-bound kernels of the simple loss, the lm half after the ranges.
         self.overlap = overlap and not fuse_add
         self.fuse_add = fuse_add
-        self.side = torch.cuda.Stream(dev) if overlap else None
+        # `am_side` = G > 0: the same idea on the copy engine - frn_broadcast_am_pruned, a persistent grid of G
+        # single-warp CTAs doing nothing but bulk copies, with a shared-memory footprint that keeps the
+        # normaliser's / recursion's big CTAs on the other SMs; frn_do_pruning_add_joiner then writes
+        # lm_pruned and the logits only.
+        self.am_side = am_side if fuse_add else 0
+        self.side = torch.cuda.Stream(dev) if (overlap or self.am_side) else None
         self.full = self._part(0, B)
         self.ws_pruned = self.full["ws_pruned"]
         nsplit = max(1, min(nsplit, B))
@@ -230,6 +235,22 @@ class Pipeline:
 
     def step(self, am, lm, sym, bd):
         torch = self.torch
+        if not self.parts and self.am_side:
+            lib, chk, B, S, T, R, C = self.lib, self._lib.check, self.B, self.S, self.T, self.R, self.C
+            st = self.stages(am, lm, sym, bd)
+            main = torch.cuda.current_stream(self.dev)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                chk(lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, C, self.am_p.data_ptr(), self.am_side,
+                                                self.side.cuda_stream), "broadcast_am_pruned")
+            st[0][2](); st[1][2]()                                   # simple loss, prune ranges
+            main.wait_stream(self.side)
+            chk(lib.frn_do_pruning_add_joiner(am.data_ptr(), lm.data_ptr(), self.ranges.data_ptr(), B, S, T, R, C, 0,
+                                              self.lm_p.data_ptr(), self.logits.data_ptr(), main.cuda_stream),
+                "do_pruning_add_joiner(lm, logits)")
+            for _, _, fn in st[3:]:                                  # pruned loss, reductions
+                fn()
+            return
         if not self.parts and self.overlap:
             lib, chk, B, S, T, R, C = self.lib, self._lib.check, self.B, self.S, self.T, self.R, self.C
             st = self.stages(am, lm, sym, bd)
@@ -441,7 +462,8 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, T, S, C, R = WORKLOADS[args.workload]
-    pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1, fuse_add=not args.no_fuse_add and not args.overlap)
+    pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1, fuse_add=not args.no_fuse_add and not args.overlap,
+                    am_side=args.am_side)
 
     # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
     # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
@@ -479,10 +501,13 @@ def run_gpu_arm(args):
         return buf, red_stream
 
     # kernels per step, counted by the library itself while one step is enqueued
+    # (the counter lives in the -DFRN_DEBUG_HOOKS build only; everything timed below runs the product library)
+    pipe._lib.use_debug_hooks(True)
     n0 = pipe.lib.frn_kernel_launches()
     pipe.step(*dev_sets[0])
     kernels_per_step = int(pipe.lib.frn_kernel_launches() - n0)
     torch.cuda.synchronize()
+    pipe._lib.use_debug_hooks(False)
 
     # ---- CUDA graphs of one step per input set (launch-bound inner loop) ----
     use_graph = not args.no_graph
@@ -684,7 +709,9 @@ def run_gpu_arm(args):
                         + f" -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
             "launch": "cuda_graph" if use_graph else "direct",
             "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step"
-                       + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else ""),
+                       + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else "")
+                       + (f"; am_pruned broadcast by {pipe.am_side} copy-engine CTAs on a second stream beside the simple loss"
+                          if pipe.am_side and not pipe.parts else ""),
             "l2": f"{NSETS} rotating input sets ({NSETS * h2d / 1e6:.0f} MB) + ~1.1 GB of streamed intermediates per step (> 126 MB L2)",
             "sharding": ("utterances sharded across ranks, one 2-float NCCL all-reduce per step; rank 0 bound to NUMA "
                          f"node {numa_node}") if world > 1 else "single GPU",
@@ -781,10 +808,12 @@ def run_c5(args):
         if world > 1:
             dist.all_reduce(total)
 
+    pipes[0]._lib.use_debug_hooks(True)
     n0 = pipes[0].lib.frn_kernel_launches()
     step()
     kernels_per_step = int(pipes[0].lib.frn_kernel_launches() - n0)
     torch.cuda.synchronize()
+    pipes[0]._lib.use_debug_hooks(False)
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
@@ -876,6 +905,9 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="run the am half of do_rnnt_pruning on a second stream beside the simple loss (measured: "
                          "0.380 ms/step against 0.372 without - the copy slows the latency-bound kernels it overlaps)")
+    ap.add_argument("--am-side", type=int, default=0,
+                    help="G > 0: am half of do_rnnt_pruning by frn_broadcast_am_pruned (G persistent copy-engine CTAs) on a "
+                         "second stream beside the simple loss")
     ap.add_argument("--no-fuse-add", action="store_true",
                     help="do_rnnt_pruning and the additive joiner as two passes (frn_do_pruning, frn_add_joiner) "
                          "instead of the one-pass frn_do_pruning_add_joiner")

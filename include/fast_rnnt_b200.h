@@ -58,8 +58,10 @@ enum frn_reduction { FRN_NONE = 0, FRN_MEAN = 1, FRN_SUM = 2 };
 int frn_version(void);
 const char *frn_status_string(int status);
 int frn_last_cuda_error(void);
-/* Number of kernels this library has launched (or recorded into a CUDA graph
- * under stream capture) in this process so far; diagnostics / benchmarks. */
+/* Number of kernels the library has launched (or recorded into a CUDA graph under
+ * stream capture) in this process so far.  Counted only by the -DFRN_DEBUG_HOOKS build
+ * (libfast_rnnt_b200_dbg.so: tests, the benchmark's kernels-per-step figure); the
+ * product library keeps no such state and returns 0. */
 unsigned long long frn_kernel_launches(void);
 
 /* ------------------------------------------------------------------------
@@ -178,10 +180,20 @@ int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits
 /* do_rnnt_pruning and the additive joiner in one pass: am_pruned, lm_pruned AND
  * logits = am_pruned + lm_pruned [B][T][R][C] are all written, the sum taken from the
  * registers that hold the two rows (saves re-reading 2 x B T R C floats; bit-identical
- * to frn_do_pruning followed by frn_add_joiner). */
+ * to frn_do_pruning followed by frn_add_joiner).  am_pruned may be NULL (written by
+ * frn_broadcast_am_pruned). */
 int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges,
                               int B, int S, int T, int R, int C, float *am_pruned,
                               float *lm_pruned, float *logits, void *stream);
+/* The am half of do_rnnt_pruning alone, for overlap: am_pruned[b,t,i,:] = am[b,t,:] does not depend on
+ * the ranges (rnnt_loss.py:802-806 broadcasts am before it gathers lm), so it may run on a second stream
+ * beside frn_simple_loss / frn_prune_ranges, whose kernels are dependency-chain bound and leave SMs idle.
+ * A persistent grid of at most max_ctas (<= 0: 20) single-warp CTAs driven by the bulk-copy engine; sized
+ * not to take SMs or issue slots from the kernels it runs beside.  Then pass am_pruned = NULL to
+ * frn_do_pruning_add_joiner (lm_pruned and logits only).  C % 4 == 0, 16-byte aligned pointers, else
+ * FRN_EUNSUPPORTED. */
+int frn_broadcast_am_pruned(const float *am, int B, int T, int R, int C, float *am_pruned,
+                            int max_ctas, void *stream);
 /* (f2) fused additive joiner: logits[b,t,i,:] = am[b,t,:] + lm[b,ranges[b,t,i],:]
  * without materialising am_pruned / lm_pruned. out_dtype: frn_dtype. */
 int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges,
@@ -200,6 +212,17 @@ int frn_pruned_logprobs(const void *logits, int logits_dtype,
                         float *py, void *workspace, size_t workspace_bytes,
                         void *stream);
 
+/* Backward of frn_pruned_logprobs (what TensorFlow autodiff derives through
+ * rnnt_loss.py:942-1018): logits_grad [B][T][R][C] (dtype of logits) from the cotangents
+ * px_grad [B][S][T1], py_grad [B][S+1][T] of the dense log-probs.  Entries the forward
+ * overwrote with -inf pass nothing back.  Workspace: frn_pruned_logprobs_workspace_bytes(). */
+int frn_pruned_logprobs_bwd(const void *logits, int logits_dtype,
+                            const int32_t *symbols, const int32_t *ranges,
+                            const int32_t *boundary, const float *px_grad,
+                            const float *py_grad, int B, int S, int T, int R, int C,
+                            int termination_symbol, int rnnt_type, void *logits_grad,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * A7 + A3 + A8 fused: rnnt_loss_pruned (rnnt_loss.py:1022-1130), reduction
  * "none", on the band only.  scores [B].  If logits_grad != NULL it receives
@@ -208,6 +231,11 @@ int frn_pruned_logprobs(const void *logits, int logits_dtype,
  * through rnnt_loss.py:942-1018.
  * ---------------------------------------------------------------------- */
 size_t frn_pruned_loss_workspace_bytes(int B, int S, int T, int R);
+/* The workspace the path that will actually run needs: with a band of R <= 8 and no (or a moderate) delay
+ * penalty the recursion runs on the band itself and needs a few MB instead of the dense lattice's planes
+ * (40 bytes per cell); frn_pruned_loss accepts any workspace of at least this size.
+ * frn_pruned_loss_workspace_bytes() is the upper bound over all delay penalties. */
+size_t frn_pruned_loss_min_workspace_bytes(int B, int S, int T, int R, float delay_penalty);
 int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols,
                     const int32_t *ranges, const int32_t *boundary, int B, int S,
                     int T, int R, int C, int termination_symbol, int rnnt_type,

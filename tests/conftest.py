@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "debug_hooks: runs on the -DFRN_DEBUG_HOOKS build (launch counter, FRN_* overrides)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -31,9 +32,10 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(autouse=True)
 def _debug_hooks_for_env_overrides(request):
     """Tests that steer the library through FRN_* environment overrides (all of them do it with
-    `monkeypatch`) run on the -DFRN_DEBUG_HOOKS build; every other test runs on the product library,
-    which never reads the environment."""
-    if "monkeypatch" not in request.fixturenames or "gpu" not in request.keywords:
+    `monkeypatch`) or read its launch counter (marked `debug_hooks`) run on the -DFRN_DEBUG_HOOKS build;
+    every other test runs on the product library, which never reads the environment and keeps no counter."""
+    wants = "monkeypatch" in request.fixturenames or request.node.get_closest_marker("debug_hooks") is not None
+    if not wants or "gpu" not in request.keywords:
         yield
         return
     from tf_fast_rnnt import _lib

@@ -1,0 +1,281 @@
+"""Autograd through the building blocks (the reference composes them under TF autodiff: rnnt_loss_pruned is
+get_rnnt_logprobs_pruned followed by mutual_information_recursion, rnnt_loss.py:1088-1119, with the gradient of
+FastRNNTLoss registered at __init__.py:154-162), the length-bucket scheduler, and the small entry points added
+in round 2."""
+import numpy as np
+import pytest
+
+from oracle import rnnt_oracle as orc
+from tests.helpers import GRAD_ATOL, GRAD_RTOL, LOSS_RTOL, assert_close, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_logprobs64(lm, am, sym, term, bd, rnnt_type):
+    """float64 torch restatement of rnnt_loss.py:175-221 (test reference for arbitrary cotangents)."""
+    import torch
+    B, T, C = am.shape
+    S = lm.shape[1] - 1
+    norm = torch.logsumexp(lm[:, :, None, :] + am[:, None, :, :], dim=3)            # [B,S+1,T]
+    idx = sym.long()[:, :, None].expand(B, S, T)
+    px = am.transpose(1, 2).gather(1, idx) + lm[:, :S].gather(2, sym.long()[:, :, None]) - norm[:, :S]
+    py = am[:, :, term][:, None, :] + lm[:, :, term][:, :, None] - norm
+    if rnnt_type == "regular":
+        px = torch.cat([px, torch.full((B, S, 1), float("-inf"), dtype=px.dtype)], dim=2)
+        mask = torch.zeros(B, 1, T + 1, dtype=torch.bool)
+        mask[torch.arange(B), 0, bd[:, 3].long()] = True
+        px = torch.where(mask, torch.full_like(px, float("-inf")), px)
+    elif rnnt_type == "constrained":
+        px = px + py[:, 1:, :]
+    return px, py
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_simple_logprobs_backward_with_arbitrary_cotangents(rnnt_type):
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 2, 37, 11, 20
+    am, lm, sym, term, bd = make_inputs(41, B, T, S, C, ragged=True)
+    rng = np.random.default_rng(7)
+    T1 = T + 1 if rnnt_type == "regular" else T
+    cx = rng.standard_normal((B, S, T1)).astype(np.float32)
+    cy = rng.standard_normal((B, S + 1, T)).astype(np.float32)
+    lm_d = torch.from_numpy(lm).cuda().requires_grad_(True)
+    am_d = torch.from_numpy(am).cuda().requires_grad_(True)
+    px, py = frn.get_rnnt_logprobs(lm_d, am_d, torch.from_numpy(sym).cuda(), term, rnnt_type, torch.from_numpy(bd).cuda())
+    fin = torch.isfinite(px)
+    obj = (torch.where(fin, px, torch.zeros_like(px)) * torch.from_numpy(cx).cuda()).sum() + (py * torch.from_numpy(cy).cuda()).sum()
+    obj.backward()
+    lm64 = torch.from_numpy(lm).double().requires_grad_(True)
+    am64 = torch.from_numpy(am).double().requires_grad_(True)
+    rx, ry = _torch_logprobs64(lm64, am64, torch.from_numpy(sym), term, torch.from_numpy(bd), rnnt_type)
+    assert_close(px.detach().cpu().numpy(), rx.detach().numpy(), 1e-5, 1e-5, "px")
+    rfin = torch.isfinite(rx)
+    robj = (torch.where(rfin, rx, torch.zeros_like(rx)) * torch.from_numpy(cx).double()).sum() + (ry * torch.from_numpy(cy).double()).sum()
+    robj.backward()
+    assert_close(am_d.grad.cpu().numpy(), am64.grad.numpy(), 2e-4, 2e-5, "am grad")
+    assert_close(lm_d.grad.cpu().numpy(), lm64.grad.numpy(), 2e-4, 2e-5, "lm grad")
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified"])
+def test_logprobs_composed_with_recursion_equals_fused_loss(rnnt_type):
+    """get_rnnt_logprobs -> mutual_information_recursion under autograd == rnnt_loss_simple (fused) gradients."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 3, 61, 17, 24
+    am, lm, sym, term, bd = make_inputs(5, B, T, S, C, ragged=True)
+    sym_d, bd_d = torch.from_numpy(sym).cuda(), torch.from_numpy(bd).cuda()
+    w = torch.tensor([1.0, -0.5, 2.0], device="cuda")
+
+    def grads(fused):
+        lm_d = torch.from_numpy(lm).cuda().requires_grad_(True)
+        am_d = torch.from_numpy(am).cuda().requires_grad_(True)
+        if fused:
+            loss = frn.rnnt_loss_simple(lm_d, am_d, sym_d, term, bd_d, rnnt_type, 0.0, "none")
+        else:
+            px, py = frn.get_rnnt_logprobs(lm_d, am_d, sym_d, term, rnnt_type, bd_d)
+            loss = -frn.mutual_information_recursion(px, py, bd_d)
+        (loss * w).sum().backward()
+        return loss.detach().cpu().numpy(), am_d.grad.cpu().numpy(), lm_d.grad.cpu().numpy()
+
+    l0, a0, m0 = grads(True)
+    l1, a1, m1 = grads(False)
+    assert_close(l1, l0, LOSS_RTOL, 0, "loss")
+    assert_close(a1, a0, 2e-4, 2e-6, "am grad")
+    assert_close(m1, m0, 2e-4, 2e-6, "lm grad")
+    # and against the float64 oracle
+    o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True, dtype=np.float64)
+    assert_close(l1, o_loss, LOSS_RTOL, 0, "loss vs oracle")
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified", "constrained"])
+def test_pruned_logprobs_composed_with_recursion_equals_fused_loss(rnnt_type):
+    """get_rnnt_logprobs_pruned -> mutual_information_recursion under autograd == rnnt_loss_pruned gradients
+    (the reference's own composition, rnnt_loss.py:1088-1119)."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 3, 47, 13, 18, 4
+    am, lm, sym, term, bd = make_inputs(9, B, T, S, C, ragged=True)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd, R)
+    am_p, lm_p = frn.do_rnnt_pruning(am, lm, ranges)
+    logits = (am_p + lm_p).astype(np.float32)
+    sym_d, bd_d, rg_d = torch.from_numpy(sym).cuda(), torch.from_numpy(bd).cuda(), torch.from_numpy(ranges).cuda()
+    w = torch.tensor([1.0, 0.25, -3.0], device="cuda")
+
+    def grads(fused):
+        lg = torch.from_numpy(logits).cuda().requires_grad_(True)
+        if fused:
+            loss = frn.rnnt_loss_pruned(lg, sym_d, rg_d, term, bd_d, rnnt_type, 0.0, "none")
+        else:
+            px, py = frn.get_rnnt_logprobs_pruned(lg, sym_d, rg_d, term, bd_d, rnnt_type)
+            loss = -frn.mutual_information_recursion(px, py, bd_d)
+        (loss * w).sum().backward()
+        return loss.detach().cpu().numpy(), lg.grad.cpu().numpy()
+
+    l0, g0 = grads(True)
+    l1, g1 = grads(False)
+    assert_close(l1, l0, LOSS_RTOL, 0, "loss")
+    assert_close(g1, g0, 2e-4, 2e-6, "logits grad")
+
+
+def test_broadcast_am_pruned_and_joiner_without_am_output():
+    """frn_broadcast_am_pruned (copy-engine am half of do_rnnt_pruning) + frn_do_pruning_add_joiner(am_pruned = NULL)
+    == frn_do_pruning_add_joiner, bit for bit."""
+    import torch
+    import tf_fast_rnnt as frn
+    lib, chk = frn._lib.lib, frn._lib.check
+    B, T, S, C, R = 3, 70, 20, 64, 5
+    rng = np.random.default_rng(2)
+    am = torch.from_numpy(rng.standard_normal((B, T, C), dtype=np.float32)).cuda()
+    lm = torch.from_numpy(rng.standard_normal((B, S + 1, C), dtype=np.float32)).cuda()
+    r0 = rng.integers(0, S + 2 - R, (B, T, 1))
+    ranges = torch.from_numpy((r0 + np.arange(R)).astype(np.int32)).cuda()
+    ref = [torch.empty(B, T, R, C, device="cuda") for _ in range(3)]
+    st = torch.cuda.current_stream().cuda_stream
+    chk(lib.frn_do_pruning_add_joiner(am.data_ptr(), lm.data_ptr(), ranges.data_ptr(), B, S, T, R, C, ref[0].data_ptr(),
+                                      ref[1].data_ptr(), ref[2].data_ptr(), st), "ref")
+    for ctas in (1, 3, 20, 1000):
+        out = [torch.full((B, T, R, C), float("nan"), device="cuda") for _ in range(3)]
+        chk(lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, C, out[0].data_ptr(), ctas, st), "broadcast")
+        chk(lib.frn_do_pruning_add_joiner(am.data_ptr(), lm.data_ptr(), ranges.data_ptr(), B, S, T, R, C, 0,
+                                          out[1].data_ptr(), out[2].data_ptr(), st), "lm+logits")
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+    assert lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, 63, ref[0].data_ptr(), 4, st) == -4   # C % 4 != 0
+
+
+def test_pruning_backward_with_arbitrary_index_patterns():
+    """frn_do_pruning_bwd's lm side is a scatter-add over ranges: any index pattern, also non-consecutive and
+    repeated indices (hand-made ranges); wide bands take the per-element path."""
+    import torch
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(4)
+    for (B, T, S, C, R) in [(2, 33, 9, 12, 4), (2, 17, 40, 8, 37)]:
+        ranges = rng.integers(0, S + 1, (B, T, R)).astype(np.int32)
+        ga = rng.standard_normal((B, T, R, C)).astype(np.float32)
+        gl = rng.standard_normal((B, T, R, C)).astype(np.float32)
+        am_g, lm_g = frn.do_rnnt_pruning_backward(ga, gl, ranges, S)
+        want = np.zeros((B, S + 1, C), np.float64)
+        for b in range(B):
+            np.add.at(want[b], ranges[b].reshape(-1), gl[b].reshape(-1, C).astype(np.float64))
+        assert_close(lm_g, want, 1e-5, 1e-5, "lm grad")
+        assert_close(am_g, ga.astype(np.float64).sum(2), 1e-5, 1e-5, "am grad")
+
+
+def test_pruned_loss_beyond_1024_rows_and_with_the_small_workspace():
+    """The band recursion does not depend on S: S + 1 > 1024 works for the pruned loss (the dense wavefront does
+    not hold that many rows), and it needs only frn_pruned_loss_min_workspace_bytes."""
+    import torch
+    import tf_fast_rnnt as frn
+    lib = frn._lib.lib
+    B, T, S, C, R = 1, 1300, 1100, 8, 4
+    rng = np.random.default_rng(3)
+    logits = rng.standard_normal((B, T, R, C)).astype(np.float32)
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    bd = np.array([[0, 0, S, T]], np.int32)
+    # a monotone band that reaches S at the last frame
+    r0 = np.minimum(np.arange(T) * (S - R + 1) // (T - 1), S - R + 1).astype(np.int32)
+    ranges = (r0[None, :, None] + np.arange(R)[None, None, :]).astype(np.int32)
+    assert lib.frn_pruned_loss_min_workspace_bytes(B, S, T, R, 0.0) < (8 << 20)
+    loss = frn.rnnt_loss_pruned(logits, sym, ranges, C - 1, bd, "regular", 0.0, "none")
+    want = orc.rnnt_loss_pruned(logits, sym, ranges, C - 1, bd, "regular", 0.0, "none", dtype=np.float64)
+    assert_close(loss, want, LOSS_RTOL, 0, "pruned loss at S = 1100")
+    # c2 shape: the band path's workspace is a few MB, the dense planes ~100 MB
+    assert lib.frn_pruned_loss_min_workspace_bytes(32, 100, 500, 5, 0.0) < (16 << 20)
+    assert lib.frn_pruned_loss_workspace_bytes(32, 100, 500, 5) > (64 << 20)
+
+
+def test_simple_loss_beyond_1024_rows_runs_the_row_scan():
+    import tf_fast_rnnt as frn
+    B, T, S, C = 1, 1500, 1030, 8
+    am, lm, sym, term, bd = make_inputs(8, B, T, S, C, ragged=False)
+    loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True, dtype=np.float64)
+    assert_close(loss, o_loss, LOSS_RTOL, 0, "loss")
+    assert_close(gy, o_gy, 4 * GRAD_RTOL, GRAD_ATOL, "py_grad")
+
+
+@pytest.mark.parametrize("rnnt_type", ["regular", "modified"])
+@pytest.mark.parametrize("smoothed", [False, True])
+def test_bucketed_pipeline_equals_one_padded_batch(rnnt_type, smoothed):
+    """pruned_rnnt_pipeline (length buckets) against the same calls on the one padded batch and
+    against the float64 oracle run on every utterance alone (no padding at all).  Buckets pick their own kernel
+    variants by shape, so occupation counts differ in the last bits and a near-tie in the arg-max of
+    get_rnnt_prune_ranges may fall the other way: the pruned loss is therefore checked against the oracle on
+    the ranges each run actually used."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 12, 90, 30, 32, 4
+    rng = np.random.default_rng(11)
+    am, lm, sym, term, bd = make_inputs(13, B, T, S, C, ragged=True)
+    bd[:, 3] = rng.integers(25, T + 1, B)
+    bd[:, 2] = np.minimum(rng.integers(5, S + 1, B), bd[:, 3])
+    sym_d, bd_d = torch.from_numpy(sym).cuda(), torch.from_numpy(bd).cuda()
+    kw = dict(lm_only_scale=0.2, am_only_scale=0.0) if smoothed else {}
+    w = torch.from_numpy(rng.standard_normal(B).astype(np.float32)).cuda()
+
+    def run(max_buckets):
+        lm_d = torch.from_numpy(lm).cuda().requires_grad_(True)
+        am_d = torch.from_numpy(am).cuda().requires_grad_(True)
+        sl, pl, rg = frn.pruned_rnnt_pipeline(lm_d, am_d, sym_d, term, bd_d, R, None, rnnt_type, 0.0, "none",
+                                              max_buckets=max_buckets, min_bucket=2, return_ranges=True, **kw)
+        ((sl + pl) * w).sum().backward()
+        return (sl.detach().cpu().numpy(), pl.detach().cpu().numpy(), am_d.grad.cpu().numpy(), lm_d.grad.cpu().numpy(),
+                rg.cpu().numpy())
+
+    one = run(1)
+    many = run(4)
+    assert len(frn.make_buckets(bd, R, C, 4, 2)) > 1
+    same_ranges = [np.array_equal(one[4][b, :bd[b, 3]], many[4][b, :bd[b, 3]]) for b in range(B)]
+    assert sum(same_ranges) >= B - 2
+    for res in (one, many):
+        for b in range(B):
+            Sb, Tb = int(bd[b, 2]), int(bd[b, 3])
+            bd1 = np.array([[0, 0, Sb, Tb]], np.int32)
+            rg = res[4][b:b + 1, :Tb]
+            assert rg.max() <= Sb and rg.min() >= 0
+            logits = am[b:b + 1, :Tb, None, :] + lm[b, rg[0]][None]
+            o = orc.rnnt_loss_pruned(logits, sym[b:b + 1, :Sb], rg, term, bd1, rnnt_type, 0.0, "none", dtype=np.float64)
+            assert_close(res[1][b:b + 1], o, LOSS_RTOL, 0, f"pruned loss of utterance {b}")
+            if not smoothed:
+                o = orc.rnnt_loss_simple(lm[b:b + 1, :Sb + 1], am[b:b + 1, :Tb], sym[b:b + 1, :Sb], term, bd1, rnnt_type,
+                                         0.0, "none", False, dtype=np.float64)
+                assert_close(res[0][b:b + 1], o, LOSS_RTOL, 0, f"simple loss of utterance {b}")
+    if not smoothed:        # (the smoothed loss's unigram is batch-global: buckets change it by design)
+        assert_close(many[0], one[0], LOSS_RTOL, 0, "simple loss")
+        ok = np.array(same_ranges)
+        assert_close(many[1][ok], one[1][ok], LOSS_RTOL, 0, "pruned loss")
+        if ok.all():
+            assert_close(many[3], one[3], 5e-4, 5e-5, "lm grad")
+            assert_close(many[2], one[2], 5e-4, 5e-5, "am grad")
+
+
+def test_sum_and_mean_over_a_process_group_on_the_autograd_path():
+    """`group=` on the gradient path: value = global sum / mean, gradient at the global scale.
+    One rank here (NCCL, world size 1); the two-rank arithmetic is covered on gloo in test_sharding_cpu.py."""
+    import os
+    import torch
+    import torch.distributed as dist
+    import tf_fast_rnnt as frn
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29571")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        B, T, S, C = 3, 40, 9, 16
+        am, lm, sym, term, bd = make_inputs(2, B, T, S, C, ragged=True)
+        for red in ("sum", "mean"):
+            out = []
+            for group in (None, dist.group.WORLD):
+                lm_d = torch.from_numpy(lm).cuda().requires_grad_(True)
+                am_d = torch.from_numpy(am).cuda().requires_grad_(True)
+                loss = frn.rnnt_loss_simple(lm_d, am_d, sym, term, bd, "regular", 0.0, red, group=group)
+                loss.backward()
+                out.append((float(loss), am_d.grad.clone()))
+            assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+            assert torch.equal(out[0][1], out[1][1])
+    finally:
+        if created:
+            dist.destroy_process_group()

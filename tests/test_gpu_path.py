@@ -526,6 +526,7 @@ def test_reduce_and_reduce_pair(reduction):
         np.testing.assert_allclose(ob.cpu().numpy(), want(b), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.debug_hooks
 @pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
 def test_half_precision_am_lm_inputs(dtype):
     """ bf16 / fp16 am and lm on the device: widened by frn_cast_to_f32 and then the float32

@@ -110,3 +110,40 @@ def test_two_rank_reduction_equals_unsharded(reduction):
     am, lm, sym, term, bd = make_inputs(11, 6, 30, 8, 12, ragged=True)
     want = orc.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, reduction, dtype=np.float64)
     np.testing.assert_allclose(got, float(want), rtol=1e-12)
+
+
+def _grad_worker(rank, world, port, reduction, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tf_fast_rnnt.rnnt_loss import _reduce_autograd
+    sizes = [3, 5]                                     # unequal shards (partition_batch gives those)
+    scores = torch.arange(sizes[rank], dtype=torch.float64) + 10.0 * rank + 1.0
+    scores.requires_grad_(True)
+    loss = _reduce_autograd(scores, reduction, dist.group.WORLD)
+    loss.backward()
+    out.put((rank, float(loss), scores.grad.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+def test_group_reduction_on_the_autograd_path(reduction):
+    """`group=` with gradients enabled: every rank reports the GLOBAL sum / mean and its utterances
+    get the gradient of that global loss (-1 for 'sum', -1 / N_global for 'mean'), whatever the shard sizes."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, reduction, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(out.get() for _ in range(2))
+    all_scores = np.concatenate([np.arange(3) + 1.0, np.arange(5) + 11.0])
+    want = -all_scores.sum() if reduction == "sum" else -all_scores.mean()
+    scale = -1.0 if reduction == "sum" else -1.0 / 8
+    for rank, loss, grad in got:
+        np.testing.assert_allclose(loss, want, rtol=1e-12)
+        np.testing.assert_allclose(grad, [scale] * (3 if rank == 0 else 5), rtol=1e-12)

@@ -2,6 +2,7 @@
 // Argument validation, workspace carve-up and kernel sequencing only; all
 // kernels live in the other translation units.
 #include "common.cuh"
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -9,12 +10,14 @@
 
 namespace frn {
 static thread_local int g_last_cuda_error = 0;
+#ifdef FRN_DEBUG_HOOKS
 static std::atomic<unsigned long long> g_kernel_launches{0};
+void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+#endif
 int note_cuda_error(cudaError_t e) {
   g_last_cuda_error = (int)e;
   return e == cudaSuccess ? FRN_OK : FRN_ECUDA;
 }
-void count_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 int check_launch() { return note_cuda_error(cudaPeekAtLastError()); }
 
 static inline bool aligned256(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
@@ -24,6 +27,15 @@ static inline int type_t1(int T, int rnnt_type) { return rnnt_type == FRN_REGULA
 // or chunk image, and products of two such vectors (image x boundary state, alpha x beta) by twice that:
 // beyond 400 bits over R - 1 rows (measured: exact to 1e-6 at 230 bits, wrong at 570) the dense-lattice
 // kernels, which carry one frame per row, take over.
+// Which of the two dense-lattice recursions runs a shape, and the workspace that one needs (sized by the path
+// that will actually run: the wavefront's diagonal-major planes are 40 bytes per cell, the row scan's 16).
+static inline bool dense_dp_uses_scan(const DpGeom &g) {
+  return scan_dp_supported(g.S, g.T) || (g.P > kMaxRowsDp && scan_dp_feasible(g.S, g.T));
+}
+static inline size_t dense_dp_workspace_bytes(const DpGeom &g) {
+  if (dense_dp_uses_scan(g)) return scan_dp_workspace_bytes(g.B, g.S, g.T);
+  return g.P > kMaxRowsDp ? 0 : carve_dp(nullptr, g).bytes;     // 0: no dense recursion for this shape
+}
 static inline bool band_delay_ok(int T, int R, float delay_penalty) {
   return !(delay_penalty > 0.f) || (double)delay_penalty * T * (R > 1 ? R - 1 : 1) * 0.5 * 1.4427 < 400.0;
 }
@@ -58,13 +70,18 @@ const char *frn_status_string(int status) {
 
 int frn_last_cuda_error(void) { return g_last_cuda_error; }
 
-unsigned long long frn_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
+unsigned long long frn_kernel_launches(void) {
+#ifdef FRN_DEBUG_HOOKS
+  return g_kernel_launches.load(std::memory_order_relaxed);
+#else
+  return 0;     // not counted in the product build
+#endif
+}
 
 // ------------------------------------------------------------------ A4
 size_t frn_mi_workspace_bytes(int B, int S, int T, int T1) {
   if (B <= 0 || S < 0 || T < 0) return 0;
-  DpGeom g = make_geom(B, S, T, T1);
-  return carve_dp(nullptr, g).bytes;
+  return dense_dp_workspace_bytes(make_geom(B, S, T, T1));
 }
 
 int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, int B, int S, int T, int T1,
@@ -75,11 +92,12 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, in
   FRN_REQUIRE(px && py && boundary && ans);
   FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
-  if (!workspace || !aligned256(workspace) || workspace_bytes < carve_dp(nullptr, g).bytes) return FRN_EWORKSPACE;
-  if (scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= workspace_bytes)
+  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_mi_workspace_bytes(B, S, T, T1)) return FRN_EWORKSPACE;
+  // the row scan where it is the faster kernel, and for lattices with more rows than the wavefront holds
+  if (dense_dp_uses_scan(g))
     return launch_scan_dp(px, py, boundary, B, S, T, T1, 0.f, calc_gradients != 0, workspace, ans, px_grad, py_grad,
                           stream);
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   DpWorkspace w = carve_dp(workspace, g);
   FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
   FRN_TRY(launch_chain(boundary, g, w, calc_gradients != 0, stream));
@@ -141,9 +159,15 @@ int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int 
 int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
                               int C, float *am_pruned, float *lm_pruned, float *logits, void *stream) {
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
-  FRN_REQUIRE(am && lm && ranges && am_pruned && lm_pruned && logits);
+  FRN_REQUIRE(am && lm && ranges && lm_pruned && logits);      // am_pruned == NULL: see frn_broadcast_am_pruned
   return launch_do_pruning_add(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, logits,
                                static_cast<cudaStream_t>(stream));
+}
+
+int frn_broadcast_am_pruned(const float *am, int B, int T, int R, int C, float *am_pruned, int max_ctas,
+                            void *stream) {
+  FRN_REQUIRE(B > 0 && T > 0 && R > 0 && C > 0 && am && am_pruned);
+  return launch_broadcast_am(am, B, T, R, C, am_pruned, max_ctas, static_cast<cudaStream_t>(stream));
 }
 
 int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad, const int32_t *ranges, int B,
@@ -195,7 +219,7 @@ SimpleLossWs carve_simple_loss(void *base, int B, int S, int T, int T1, int C) {
   w.px = reinterpret_cast<float *>(p); p += round_up_sz((size_t)B * S * T1 * sizeof(float), 256);
   w.py = reinterpret_cast<float *>(p); p += round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256);
   w.stats = p; p += simple_stats_bytes(B, S, T, C);
-  w.dp = p; p += carve_dp(nullptr, make_geom(B, S, T, T1)).bytes;
+  w.dp = p; p += dense_dp_workspace_bytes(make_geom(B, S, T, T1));
   w.bytes = (size_t)(p - static_cast<char *>(base));
   return w;
 }
@@ -219,13 +243,13 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
   FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
   const int T1 = type_t1(T, rnnt_type);
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
+  const bool scan = dense_dp_uses_scan(g);
+  if (!scan && g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   if (!workspace || !aligned256(workspace) || workspace_bytes < carve_simple_loss(nullptr, B, S, T, T1, C).bytes)
     return FRN_EWORKSPACE;
   SimpleLossWs w = carve_simple_loss(workspace, B, S, T, T1, C);
-  DpWorkspace dw = carve_dp(w.dp, g);
+  DpWorkspace dw = scan ? DpWorkspace{} : carve_dp(w.dp, g);
   const float dp = delay_penalty > 0.f ? delay_penalty : 0.f;
-  const bool scan = scan_dp_supported(S, T) && scan_dp_workspace_bytes(B, S, T) <= dw.bytes;
   if (!scan && simple_arc_plane_supported(lm, am, C, rnnt_type)) {
     // 4 launches: row statistics, normaliser (arcs straight into the recursion's plane), recursion, read-out
     const ArcPlaneOut arcs{dw.XY, g.P, g.Dn, g.k, dp};
@@ -289,7 +313,17 @@ struct PrunedWs {
   void *dp;
   size_t bytes;
 };
-PrunedWs carve_pruned(void *base, int B, int S, int T, int T1, int R, bool with_dp, bool with_ranges) {
+// recursion workspace of the pruned loss: the band recursion's states where it can run (R <= 8), the dense
+// wavefront's planes where it may have to (wide bands, the full joiner, a delay penalty beyond band_delay_ok)
+enum PrunedDp { kNoDp, kDpAnyPath, kDpBandOnly };
+size_t pruned_dp_bytes(int B, int S, int T, int T1, int R, PrunedDp which) {
+  const size_t band = band_dp_supported(S, T, R) ? band_dp_workspace_bytes(B, T) : 0;
+  if (which == kDpBandOnly) return band;
+  const DpGeom g = make_geom(B, S, T, T1);
+  const size_t dense = g.P > kMaxRowsDp ? 0 : carve_dp(nullptr, g).bytes;
+  return std::max(band, dense);
+}
+PrunedWs carve_pruned(void *base, int B, int S, int T, int T1, int R, PrunedDp with_dp, bool with_ranges) {
   PrunedWs w;
   char *p = static_cast<char *>(base);
   const size_t n = round_up_sz((size_t)B * T * R * sizeof(float), 256);
@@ -301,25 +335,24 @@ PrunedWs carve_pruned(void *base, int B, int S, int T, int T1, int R, bool with_
   w.ranges = reinterpret_cast<int32_t *>(p);
   if (with_ranges) p += n;
   w.dp = p;
-  if (with_dp) p += carve_dp(nullptr, make_geom(B, S, T, T1)).bytes;
+  if (with_dp != kNoDp) p += pruned_dp_bytes(B, S, T, T1, R, with_dp);
   w.bytes = (size_t)(p - static_cast<char *>(base));
   return w;
 }
 
+// `dp_bytes`: what the caller's workspace holds behind w.dp
 int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges,
                      const int32_t *boundary, int B, int S, int T, int R, int C, int term, int rnnt_type,
                      float delay_penalty, const float *scores_grad, float *scores, void *logits_grad,
-                     const PrunedWs &w, cudaStream_t stream) {
+                     const PrunedWs &w, size_t dp_bytes, cudaStream_t stream) {
   const int T1 = type_t1(T, rnnt_type);
   DpGeom g = make_geom(B, S, T, T1);
-  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
-  DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_pruned_lse(logits, dtype, symbols, ranges, B, S, T, R, C, term, w.pxc, w.pyc, w.lse, stream));
   // narrow bands: transfer-matrix recursion on the band itself (band_dp.cu);
   // FRN_BAND_DENSE=1 (debug-hooks build) forces the dense-lattice wavefront for A/B runs and cross-checks
   const bool force_dense = debug_env_int("FRN_BAND_DENSE", 0) == 1;
   if (!force_dense && band_dp_supported(S, T, R) && band_delay_ok(T, R, delay_penalty) &&
-      band_dp_workspace_bytes(B, T) <= dw.bytes) {
+      band_dp_workspace_bytes(B, T) <= dp_bytes) {
     const bool want = logits_grad != nullptr;
     FRN_TRY(launch_band_dp(w.pxc, w.pyc, ranges, boundary, B, S, T, R, rnnt_type, delay_penalty > 0.f ? delay_penalty : 0.f,
                            want, w.dp, w.gxc, w.gyc, scores, stream));
@@ -328,6 +361,10 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
                                         term, logits_grad, stream));
     return FRN_OK;
   }
+  // dense-lattice wavefront on the planes the band is scattered into
+  if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
+  if (carve_dp(nullptr, g).bytes > dp_bytes) return FRN_EWORKSPACE;
+  DpWorkspace dw = carve_dp(w.dp, g);
   FRN_TRY(launch_skew_band(w.pxc, w.pyc, ranges, boundary, g, dw, R, rnnt_type,
                            delay_penalty > 0.f ? delay_penalty : 0.f, stream));
   const bool want_grad = logits_grad != nullptr;
@@ -343,7 +380,7 @@ int pruned_loss_impl(const void *logits, int dtype, const int32_t *symbols, cons
 
 size_t frn_pruned_logprobs_workspace_bytes(int B, int S, int T, int R) {
   if (B <= 0 || S < 0 || T <= 0 || R <= 0) return 0;
-  return carve_pruned(nullptr, B, S, T, T + 1, R, false, false).bytes;
+  return carve_pruned(nullptr, B, S, T, T + 1, R, kNoDp, false).bytes;
 }
 
 int frn_pruned_logprobs(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *ranges,
@@ -358,15 +395,42 @@ int frn_pruned_logprobs(const void *logits, int logits_dtype, const int32_t *sym
   if (!workspace || !aligned256(workspace) || workspace_bytes < frn_pruned_logprobs_workspace_bytes(B, S, T, R))
     return FRN_EWORKSPACE;
   const int T1 = type_t1(T, rnnt_type);
-  PrunedWs w = carve_pruned(workspace, B, S, T, T1, R, false, false);
+  PrunedWs w = carve_pruned(workspace, B, S, T, T1, R, kNoDp, false);
   FRN_TRY(launch_pruned_lse(logits, logits_dtype, symbols, ranges, B, S, T, R, C, termination_symbol, w.pxc,
                             w.pyc, w.lse, stream));
   return launch_band_to_dense(w.pxc, w.pyc, ranges, boundary, B, S, T, T1, R, rnnt_type, px, py, stream);
 }
 
+int frn_pruned_logprobs_bwd(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *ranges,
+                            const int32_t *boundary, const float *px_grad, const float *py_grad, int B, int S, int T,
+                            int R, int C, int termination_symbol, int rnnt_type, void *logits_grad, void *workspace,
+                            size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
+  FRN_REQUIRE(logits && symbols && ranges && boundary && px_grad && py_grad && logits_grad);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_pruned_logprobs_workspace_bytes(B, S, T, R))
+    return FRN_EWORKSPACE;
+  const int T1 = type_t1(T, rnnt_type);
+  PrunedWs w = carve_pruned(workspace, B, S, T, T1, R, kNoDp, false);
+  FRN_TRY(launch_pruned_lse(logits, logits_dtype, symbols, ranges, B, S, T, R, C, termination_symbol, w.pxc,
+                            w.pyc, w.lse, stream));
+  FRN_TRY(launch_dense_to_band(px_grad, py_grad, ranges, boundary, B, S, T, T1, R, rnnt_type, w.gxc, w.gyc, stream));
+  return launch_pruned_logits_grad(logits, logits_dtype, symbols, ranges, w.lse, w.gxc, w.gyc, nullptr, B, S, T, R, C,
+                                   termination_symbol, logits_grad, stream);
+}
+
 size_t frn_pruned_loss_workspace_bytes(int B, int S, int T, int R) {
   if (B <= 0 || S < 0 || T <= 0 || R <= 0) return 0;
-  return carve_pruned(nullptr, B, S, T, T + 1, R, true, false).bytes;
+  return carve_pruned(nullptr, B, S, T, T + 1, R, kDpAnyPath, false).bytes;
+}
+
+size_t frn_pruned_loss_min_workspace_bytes(int B, int S, int T, int R, float delay_penalty) {
+  if (B <= 0 || S < 0 || T <= 0 || R <= 0) return 0;
+  const bool band = band_dp_supported(S, T, R) && band_delay_ok(T, R, delay_penalty) &&
+                    debug_env_int("FRN_BAND_DENSE", 0) != 1;
+  return carve_pruned(nullptr, B, S, T, T + 1, R, band ? kDpBandOnly : kDpAnyPath, false).bytes;
 }
 
 int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *ranges,
@@ -377,17 +441,18 @@ int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols
   FRN_REQUIRE(logits && symbols && ranges && boundary && scores);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
   FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
-  if (!workspace || !aligned256(workspace) || workspace_bytes < frn_pruned_loss_workspace_bytes(B, S, T, R))
+  if (!workspace || !aligned256(workspace) ||
+      workspace_bytes < frn_pruned_loss_min_workspace_bytes(B, S, T, R, delay_penalty))
     return FRN_EWORKSPACE;
-  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, true, false);
+  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, kNoDp, false);
   return pruned_loss_impl(logits, logits_dtype, symbols, ranges, boundary, B, S, T, R, C, termination_symbol,
-                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w,
+                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w, workspace_bytes - w.bytes,
                           static_cast<cudaStream_t>(stream));
 }
 
 size_t frn_joint_loss_workspace_bytes(int B, int S, int T) {
   if (B <= 0 || S < 0 || T <= 0) return 0;
-  return carve_pruned(nullptr, B, S, T, T + 1, S + 1, true, true).bytes;
+  return carve_pruned(nullptr, B, S, T, T + 1, S + 1, kDpAnyPath, true).bytes;
 }
 
 int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols, const int32_t *boundary, int B,
@@ -402,10 +467,11 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
   if (!workspace || !aligned256(workspace) || workspace_bytes < frn_joint_loss_workspace_bytes(B, S, T))
     return FRN_EWORKSPACE;
   const int R = S + 1;
-  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, true, true);
+  PrunedWs w = carve_pruned(workspace, B, S, T, type_t1(T, rnnt_type), R, kNoDp, true);
   FRN_TRY(launch_iota_ranges(w.ranges, (size_t)B * T * R, R, stream));
   return pruned_loss_impl(logits, logits_dtype, symbols, w.ranges, boundary, B, S, T, R, C, termination_symbol,
-                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w, stream);
+                          rnnt_type, delay_penalty, scores_grad, scores, logits_grad, w, workspace_bytes - w.bytes,
+                          stream);
 }
 
 int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits, size_t n, void *stream) {

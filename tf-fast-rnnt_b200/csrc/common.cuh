@@ -39,7 +39,14 @@ __host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + 
 // thread-local last CUDA error for frn_last_cuda_error()
 int note_cuda_error(cudaError_t e);
 int check_launch();
-void count_launch();   // every launch of the library is written  count_launch(), kernel<<<...>>>(...);
+// every launch of the library is written  count_launch(), kernel<<<...>>>(...);  the count exists in the
+// -DFRN_DEBUG_HOOKS build only (frn_kernel_launches(): tests, the benchmark's kernels-per-step figure) - the
+// product library keeps no process-global mutable state
+#ifdef FRN_DEBUG_HOOKS
+void count_launch();
+#else
+inline void count_launch() {}
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -11,6 +11,7 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
 int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w, float *ans,
                           float *px_grad, float *py_grad, cudaStream_t stream);
 // mi_scan.cu
+bool scan_dp_feasible(int S, int T);
 bool scan_dp_supported(int S, int T);
 size_t scan_dp_workspace_bytes(int B, int S, int T);
 int launch_scan_dp(const float *px, const float *py, const int32_t *boundary, int B, int S, int T, int T1,
@@ -24,6 +25,7 @@ int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, i
                       float *am_p, float *lm_p, cudaStream_t stream);
 int launch_do_pruning_add(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
                           float *am_p, float *lm_p, float *logits, cudaStream_t stream);
+int launch_broadcast_am(const float *am, int B, int T, int R, int C, float *am_p, int max_ctas, cudaStream_t stream);
 int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const int32_t *ranges, int B, int S,
                           int T, int R, int C, float *am_grad, float *lm_grad, cudaStream_t stream);
 int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
@@ -59,6 +61,8 @@ int launch_finalize_band(const int32_t *ranges, const int32_t *boundary, const D
 int launch_pruned_logits_grad(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges,
                               const float *lse, const float *gxc, const float *gyc, const float *scores_grad,
                               int B, int S, int T, int R, int C, int term, void *dlogits, cudaStream_t stream);
+int launch_dense_to_band(const float *dpx, const float *dpy, const int32_t *ranges, const int32_t *boundary, int B,
+                         int S, int T, int T1, int R, int rnnt_type, float *gxc, float *gyc, cudaStream_t stream);
 int launch_band_to_dense(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary,
                          int B, int S, int T, int T1, int R, int rnnt_type, float *px, float *py,
                          cudaStream_t stream);

@@ -377,6 +377,29 @@ __global__ void __launch_bounds__(256) band_to_dense_kernel(const float *pxc, co
   }
 }
 
+// Transpose of band_to_dense_kernel: cotangents of the dense px / py -> cotangents of the band log-probs
+// (backward of the public get_rnnt_logprobs_pruned; TF autodiff through rnnt_loss.py:968-1018).  Entries the
+// forward overwrote with -inf (frame t_end of the regular lattice, :51-60) pass nothing back.
+__global__ void __launch_bounds__(256) dense_to_band_kernel(const float *dpx, const float *dpy,
+                                                            const int32_t *ranges, const int32_t *boundary,
+                                                            int B, int S, int T, int T1, int R, int rnnt_type,
+                                                            float *gxc, float *gyc) {
+  const int S1 = S + 1;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B * T * R) return;
+  const int bt = row / R, i = row - bt * R;
+  const int b = bt / T, t = bt - b * T;
+  int s = (ranges[(size_t)bt * R] + i) % S1;
+  if (s < 0) s += S1;
+  const bool x_dead = rnnt_type == FRN_REGULAR && t == boundary[4 * b + 3];
+  float gx = 0.f, gy = dpy[((size_t)b * S1 + s) * T + t];
+  if (s < S && !x_dead) gx = dpx[((size_t)b * S + s) * T1 + t];
+  // constrained: px[s-1,t] = pxc[s-1,t] + pyc[s,t] (rnnt_loss.py:1015-1018); row s-1 is band entry i-1
+  if (rnnt_type == FRN_CONSTRAINED && i >= 1 && s >= 1) gy += dpx[((size_t)b * S + s - 1) * T1 + t];
+  gxc[row] = gx;
+  gyc[row] = gy;
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -430,6 +453,14 @@ int launch_pruned_logits_grad(const void *logits, int dtype, const int32_t *symb
         static_cast<const __nv_bfloat16 *>(logits), symbols, ranges, lse, gxc, gyc, scores_grad, BTR, T * R, S,
         C, term, static_cast<__nv_bfloat16 *>(dlogits));
   else return FRN_EINVAL;
+  return check_launch();
+}
+
+int launch_dense_to_band(const float *dpx, const float *dpy, const int32_t *ranges, const int32_t *boundary, int B,
+                         int S, int T, int T1, int R, int rnnt_type, float *gxc, float *gyc, cudaStream_t stream) {
+  const int n = B * T * R;
+  count_launch(), dense_to_band_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dpx, dpy, ranges, boundary, B, S, T, T1, R,
+                                                                         rnnt_type, gxc, gyc);
   return check_launch();
 }
 

@@ -389,8 +389,11 @@ static int scan_cols_per_thread(int T, int cluster) {
 //   T=1000: S=100 .13/.15   S=250 .32/.30   T=1500: S=100 .11/.17  S=400 .46/.68
 // so: long lattices (T >= 8 S), and beyond 512 columns when T >= 4 S or the wavefront needs > 1 row per lane.
 // FRN_DP_SCAN=1 / FRN_DP_CHAIN=1 force one of them in the debug-hooks build (tests and A/B runs).
-bool scan_dp_supported(int S, int T) {
-  if (!(S >= 0 && T + 1 <= 32 * kScanMaxWarps * kScanMaxK && S + T <= 4095)) return false;   // one CTA must be able to hold a row
+bool scan_dp_feasible(int S, int T) {      // hard limits: one CTA must be able to hold a row
+  return S >= 0 && T + 1 <= 32 * kScanMaxWarps * kScanMaxK && S + T <= 4095;
+}
+bool scan_dp_supported(int S, int T) {     // feasible AND the faster of the two recursion kernels at this shape
+  if (!scan_dp_feasible(S, T)) return false;
   if (debug_env_int("FRN_DP_CHAIN", 0) == 1) return false;
   if (debug_env_int("FRN_DP_SCAN", 0) == 1) return true;
   if (T >= 8 * S) return true;

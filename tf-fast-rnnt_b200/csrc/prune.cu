@@ -7,6 +7,8 @@
 // construction: the float part walks s sequentially per (b,t) column, i.e. the
 // summation order of a sequential cumsum, with first-index
 // argmax; the int32 fix-ups along t are order independent.
+#include <algorithm>
+
 #include "common.cuh"
 #include "launchers.h"
 
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(128) do_pruning_vec_kernel(const float *am, co
   const float4 *lm_b = reinterpret_cast<const float4 *>(lm) + (size_t)b * S1 * C4;
   for (int c = threadIdx.x; c < C4; c += blockDim.x) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (WITH_AM) a = __ldg(am_row + c);
+    if (WITH_AM || WITH_SUM) a = __ldg(am_row + c);
     float4 l[RMAX];
     if (WITH_LM) {
 #pragma unroll
@@ -249,20 +251,38 @@ __global__ void __launch_bounds__(256) do_pruning_bwd_am_kernel(const float *am_
   }
 }
 
-// A6 backward, lm side: lm_grad[b,s,:] = sum over (t,i) with ranges[b,t,i]==s.
-// Gather formulation (deterministic, no atomics): one warp per (b,s) scans the
-// frames; since ranges[b,t,i] = ranges[b,t,0] + i the hit test is a subtraction.
+// A6 backward, lm side: lm_grad[b,s,:] = sum over (t,i) with ranges[b,t,i]==s  (the scatter-add TF autodiff
+// derives for the gather of rnnt_loss.py:807-811, as a gather: deterministic, no atomics).  One CTA per (b,s):
+// the T x R indices of the utterance are tested ONCE, cooperatively, into a per-frame hit mask in shared memory
+// (MASKED; any index pattern, R <= 32), then every thread sums its columns over the hits in (t, i) order.
+// Wider bands / very long utterances walk the indices per element.
+template <bool MASKED>
 __global__ void __launch_bounds__(256) do_pruning_bwd_lm_kernel(const float *lm_p_grad, const int32_t *ranges,
                                                                 int B, int S1, int T, int R, int C,
                                                                 float *lm_grad) {
+  extern __shared__ uint32_t hit_mask[];      // [T]
   const int bs = blockIdx.x;
   const int b = bs / S1, s = bs - b * S1;
   const int32_t *rg = ranges + (size_t)b * T * R;
+  const float *src = lm_p_grad + (size_t)b * T * R * C;
+  if (MASKED) {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      uint32_t m = 0;
+      for (int i = 0; i < R; ++i) m |= (rg[(size_t)t * R + i] == s) ? (1u << i) : 0u;
+      hit_mask[t] = m;
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (int t = 0; t < T; ++t) {
-      for (int i = 0; i < R; ++i)
-        if (rg[(size_t)t * R + i] == s) acc += lm_p_grad[(((size_t)b * T + t) * R + i) * C + c];
+      if (MASKED) {
+        for (uint32_t m = hit_mask[t]; m; m &= m - 1)
+          acc += src[((size_t)t * R + (__ffs(m) - 1)) * C + c];
+      } else {
+        for (int i = 0; i < R; ++i)
+          if (rg[(size_t)t * R + i] == s) acc += src[((size_t)t * R + i) * C + c];
+      }
     }
     lm_grad[(size_t)bs * C + c] = acc;
   }
@@ -319,6 +339,59 @@ __global__ void __launch_bounds__(128) pruned_add_joiner_vec_kernel(const float 
   }
 }
 
+// A6, am half on the copy engine: am_pruned[b,t,i,:] = am[b,t,:] does not depend on the ranges
+// (rnnt_loss.py:802-806 broadcasts am before lm is gathered), so a caller may run it on a second stream
+// beside the dependency-chain-bound kernels of the simple loss (normaliser: 128 CTAs, lattice recursion: 64
+// CTAs on 148 SMs).  For that it must not take issue slots or SMs from them: a persistent grid of a few
+// single-warp CTAs whose only instructions are 1-D bulk async copies (TMA engine; global -> shared ring ->
+// R x global), and a shared-memory footprint (kBcStages x kBcStageBytes) that keeps the 204-224 KB CTAs of
+// those kernels off the SMs it sits on instead of squeezing in beside them.
+constexpr int kBcStages = 4, kBcLook = 2;
+constexpr uint32_t kBcStageBytes = 32 * 1024;
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__global__ void __launch_bounds__(32) broadcast_am_kernel(const float *am, float *am_p, int BT, int R, int C,
+                                                          int rows_per_chunk) {
+  extern __shared__ __align__(128) unsigned char bc_smem[];
+  __shared__ uint64_t bars[kBcStages];
+  if (threadIdx.x != 0) return;
+  const uint32_t row_bytes = (uint32_t)C * sizeof(float);
+  const int nchunk_all = (BT + rows_per_chunk - 1) / rows_per_chunk;
+  const int n = (nchunk_all - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // chunks of this CTA
+  for (int s = 0; s < kBcStages; ++s) mbar_init(&bars[s], 1);
+  mbar_fence_init();
+  auto load = [&](int j) {
+    const int chunk = blockIdx.x + j * gridDim.x, row0 = chunk * rows_per_chunk;
+    const uint32_t bytes = (uint32_t)min(rows_per_chunk, BT - row0) * row_bytes;
+    const int s = j % kBcStages;
+    mbar_arrive_expect_tx(&bars[s], bytes);
+    bulk_g2s(bc_smem + (size_t)s * kBcStageBytes, am + (size_t)row0 * C, bytes, &bars[s]);
+  };
+  for (int j = 0; j < kBcLook && j < n; ++j) load(j);
+  for (int k = 0; k < n; ++k) {
+    const int j = k + kBcLook;
+    if (j < n) {
+      // stage j % kBcStages was last read by the stores of chunk j - kBcStages: at most
+      // kBcStages - kBcLook - 1 younger store groups may still be reading
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBcStages - kBcLook - 1) : "memory");
+      load(j);
+    }
+    const int s = k % kBcStages;
+    mbar_wait(&bars[s], (uint32_t)((k / kBcStages) & 1));
+    const int chunk = blockIdx.x + k * gridDim.x, row0 = chunk * rows_per_chunk;
+    const int rows = min(rows_per_chunk, BT - row0);
+    const unsigned char *src = bc_smem + (size_t)s * kBcStageBytes;
+    for (int r = 0; r < rows; ++r)
+      for (int i = 0; i < R; ++i)
+        bulk_s2g(am_p + ((size_t)(row0 + r) * R + i) * C, src + (size_t)r * row_bytes, row_bytes);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -372,9 +445,33 @@ int launch_do_pruning(const float *am, const float *lm, const int32_t *ranges, i
   return check_launch();
 }
 
+int launch_broadcast_am(const float *am, int B, int T, int R, int C, float *am_p, int max_ctas, cudaStream_t stream) {
+  const int BT = B * T;
+  const size_t row_bytes = (size_t)C * sizeof(float);
+  if (C % 4 != 0 || row_bytes > kBcStageBytes ||
+      ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(am_p)) % 16) != 0)
+    return FRN_EUNSUPPORTED;     // bulk copies move multiples of 16 bytes between 16-byte aligned addresses
+  const int rows = (int)(kBcStageBytes / row_bytes);
+  const int nchunk = (BT + rows - 1) / rows;
+  const int grid = std::max(1, std::min(max_ctas > 0 ? max_ctas : 20, nchunk));
+  const size_t smem = (size_t)kBcStages * kBcStageBytes;
+  cudaError_t e = cudaFuncSetAttribute(broadcast_am_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return note_cuda_error(e);
+  count_launch(), broadcast_am_kernel<<<grid, 32, smem, stream>>>(am, am_p, BT, R, C, rows);
+  return check_launch();
+}
+
 int launch_do_pruning_add(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
                           float *am_p, float *lm_p, float *logits, cudaStream_t stream) {
   const int BT = B * T;
+  if (!am_p) {     // am_pruned is written elsewhere (frn_broadcast_am_pruned): lm_pruned and the sum only
+    const bool v = (C % 4 == 0) && R <= 8 &&
+                   ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) | reinterpret_cast<uintptr_t>(lm_p) |
+                     reinterpret_cast<uintptr_t>(logits)) % 16 == 0);
+    if (!v) return FRN_EUNSUPPORTED;
+    count_launch(), do_pruning_vec_kernel<8, false, true, true><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4, am_p, lm_p, logits);
+    return check_launch();
+  }
   const bool vec = (C % 4 == 0) && R <= 8 &&
                    ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) | reinterpret_cast<uintptr_t>(am_p) |
                      reinterpret_cast<uintptr_t>(lm_p) | reinterpret_cast<uintptr_t>(logits)) % 16 == 0);
@@ -396,7 +493,11 @@ int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const 
     if (rc) return rc;
   }
   if (lm_grad) {
-    count_launch(), do_pruning_bwd_lm_kernel<<<B * (S + 1), 256, 0, stream>>>(lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
+    if (R <= 32 && (size_t)T * sizeof(uint32_t) <= 48 * 1024)
+      count_launch(), do_pruning_bwd_lm_kernel<true><<<B * (S + 1), 256, (size_t)T * sizeof(uint32_t), stream>>>(
+          lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
+    else
+      count_launch(), do_pruning_bwd_lm_kernel<false><<<B * (S + 1), 256, 0, stream>>>(lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
     return check_launch();
   }
   return FRN_OK;

@@ -44,6 +44,14 @@ struct BwdParams {
 };
 constexpr int kDuRows = 64;                 // am rows per block of the du partial sums
 
+// Weight on px[b,s,t].  Regular lattice: the forward overwrote frame t_end of every px row with -inf
+// (fix_for_boundary, rnnt_loss.py:51-60), a constant - whatever the caller put there passes nothing back
+// (occupation counts are 0 there anyway; arbitrary cotangents of get_rnnt_logprobs are not).
+__device__ __forceinline__ float gpx_at(const BwdParams &p, int b, int s, int t) {
+  if (p.rnnt_type == FRN_REGULAR && t == p.boundary[4 * b + 3]) return 0.f;
+  return p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+}
+
 // W[b,s,t] = G / Z with Z = exp(norm - lmmax - ammax), norm = am[t,blank] + lm[s,blank] - py[s,t]
 __global__ void __launch_bounds__(256) bwd_weights_kernel(BwdParams p) {
   const int S1 = p.S + 1;
@@ -54,8 +62,8 @@ __global__ void __launch_bounds__(256) bwd_weights_kernel(BwdParams p) {
   const int rem = (int)(i - (size_t)b * S1 * p.T);
   const int s = rem / p.T, t = rem - s * p.T;
   float G = p.gpy[i];
-  if (s < p.S) G += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
-  if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) G += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];  // px[s-1,t] += py[s,t]
+  if (s < p.S) G += gpx_at(p, b, s, t);
+  if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) G += gpx_at(p, b, s - 1, t);  // px[s-1,t] += py[s,t]
   float w = 0.f;
   if (G != 0.f) {
     const float norm = p.am[((size_t)b * p.T + t) * p.C + p.term] + p.lm[((size_t)b * S1 + s) * p.C + p.term] - p.py[i];
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(128) bwd_scatter_am_kernel(BwdParams p) {
   for (int s = 0; s < S1; ++s) {
     float gy = p.gpy[((size_t)b * S1 + s) * p.T + t];
     if (s < p.S) {
-      const float gx = p.gpx[((size_t)b * p.S + s) * p.T1 + t];
+      const float gx = gpx_at(p, b, s, t);
       row[sym[s]] += g * gx;
       if (p.rnnt_type == FRN_CONSTRAINED) blank += gx;   // px[s,t] also contains py[s+1,t]
     }
@@ -153,8 +161,8 @@ __global__ void __launch_bounds__(256) bwd_scatter_lm_kernel(BwdParams p) {
   float sx = 0.f, sy = 0.f;
   for (int t = lane; t < p.T; t += 32) {
     sy += p.gpy[(size_t)bs * p.T + t];
-    if (s < p.S) sx += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
-    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];
+    if (s < p.S) sx += gpx_at(p, b, s, t);
+    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += gpx_at(p, b, s - 1, t);
   }
   sx = warp_sum(sx); sy = warp_sum(sy);
   const float g0 = p.scores_grad ? p.scores_grad[b] : 1.f;
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(128) bwd_gt_kernel(BwdParams p) {
   float acc = 0.f;
   for (int s = 0; s < S1; ++s) {
     acc += p.gpy[((size_t)b * S1 + s) * p.T + t];
-    if (s < p.S) acc += p.gpx[((size_t)b * p.S + s) * p.T1 + t] * (p.rnnt_type == FRN_CONSTRAINED ? 2.f : 1.f);
+    if (s < p.S) acc += gpx_at(p, b, s, t) * (p.rnnt_type == FRN_CONSTRAINED ? 2.f : 1.f);
   }
   p.Gt[bt] = acc;     // constrained: gpx[s,t] weighs px[s,t] and, through the fold, py[s+1,t]
 }
@@ -203,8 +211,8 @@ __global__ void __launch_bounds__(256) bwd_rowsums_kernel(BwdParams p) {
   float sx = 0.f, sy = 0.f;
   for (int t = lane; t < p.T; t += 32) {
     sy += p.gpy[(size_t)bs * p.T + t];
-    if (s < p.S) sx += p.gpx[((size_t)b * p.S + s) * p.T1 + t];
-    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += p.gpx[((size_t)b * p.S + s - 1) * p.T1 + t];
+    if (s < p.S) sx += gpx_at(p, b, s, t);
+    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) sy += gpx_at(p, b, s - 1, t);
   }
   sx = warp_sum(sx); sy = warp_sum(sy);
   if (lane == 0) { p.Sx[bs] = sx; p.Sy[bs] = sy; }

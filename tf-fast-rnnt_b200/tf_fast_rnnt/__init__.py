@@ -19,5 +19,6 @@ from .rnnt_loss import rnnt_loss_pruned
 from .rnnt_loss import rnnt_loss_simple
 from .rnnt_loss import rnnt_loss_smoothed
 from .rnnt_loss import simple_loss_backward, smoothed_loss_backward
+from .scheduler import make_buckets, pruned_rnnt_pipeline
 
 __version__ = "1.2"  # the reference's version string (__init__.py:36)

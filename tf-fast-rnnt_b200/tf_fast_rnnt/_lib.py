@@ -95,13 +95,17 @@ _SIGS = {
     "frn_prune_ranges": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "frn_do_pruning": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "frn_do_pruning_add_joiner": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "frn_broadcast_am_pruned": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "frn_do_pruning_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "frn_add_joiner": (c_int, [_P, _P, _P, c_size_t, _P]),
     "frn_pruned_add_joiner": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "frn_pruned_logprobs_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_pruned_logprobs": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _P, _P, _P, c_size_t, _P]),
+    "frn_pruned_logprobs_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        _P, _P, c_size_t, _P]),
     "frn_pruned_loss_workspace_bytes": (c_size_t, [c_int] * 4),
+    "frn_pruned_loss_min_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_float]),
     "frn_pruned_loss": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_float, _P, _P, _P, _P, c_size_t, _P]),
     "frn_joint_loss_workspace_bytes": (c_size_t, [c_int] * 3),

@@ -21,6 +21,7 @@ Differences from the reference, all decisions of SURVEY.md §9:
 """
 from __future__ import annotations
 
+import functools
 from typing import Optional, Tuple, Union
 
 import numpy as np
@@ -38,6 +39,21 @@ def _device() -> torch.device:
         raise _lib.FastRnntError(
             "fast_rnnt_b200 needs a CUDA device (sm_100a); there is no CPU path")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def _on_device(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current: the C ABI launches on the process's
+    current device, and function attributes / streams are per device.  All CUDA inputs must share one device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        devs = {x.device for x in list(args) + list(kwargs.values()) if isinstance(x, torch.Tensor) and x.is_cuda}
+        if len(devs) > 1:
+            raise ValueError(f"all CUDA inputs must live on one device, got {sorted(map(str, devs))}")
+        if not devs:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 class _Io:
@@ -132,7 +148,52 @@ def _reduce(scores: torch.Tensor, reduction: str, group=None) -> torch.Tensor:
     return out.reshape(())
 
 
+def _reduce_autograd(scores: torch.Tensor, reduction: str, group=None) -> torch.Tensor:
+    """The same reductions on the autograd path.  With a process group the batch is sharded by utterance:
+    the returned VALUE is the global sum / mean (one scalar all-reduce of the detached local part), the
+    GRADIENT is that of the local part at the global scale (1 for 'sum', 1 / N_global for 'mean'), so every
+    rank's am / lm / logits gradients are exactly those of the unsharded loss."""
+    if reduction == "none":
+        return -scores
+    if group is None:
+        return -scores.sum() if reduction == "sum" else -scores.mean()
+    import torch.distributed as dist
+    local = -scores.sum()
+    if reduction == "mean":
+        n = torch.tensor([scores.shape[0]], dtype=torch.int64, device=scores.device)
+        dist.all_reduce(n, group=group)
+        local = local / float(n.item())
+    total = local.detach().clone()
+    dist.all_reduce(total, group=group)
+    return local + (total - local.detach())
+
+
 # ---------------------------------------------------------------- A4 / cummin
+class _MutualInformationFn(torch.autograd.Function):
+    """FastRNNTLoss with the gradient the reference registers for it (__init__.py:154-162):
+    d ans[b] / d px = px_grad[b], d ans[b] / d py = py_grad[b] (the occupation counts)."""
+
+    @staticmethod
+    def forward(ctx, px, py, boundary):
+        B, S, T1 = px.shape
+        T = py.shape[2]
+        ans = torch.empty(B, dtype=torch.float32, device=px.device)
+        gx, gy = torch.empty_like(px), torch.empty_like(py)
+        ws = _workspace(lib.frn_mi_workspace_bytes(B, S, T, T1), px.device)
+        check(lib.frn_mi_fwd_bwd(_ptr(px), _ptr(py), _ptr(boundary), B, S, T, T1, 1, _ptr(ans), _ptr(gx), _ptr(gy),
+                                 _ptr(ws), ws.numel(), _stream(px.device)), "frn_mi_fwd_bwd")
+        ctx.save_for_backward(gx, gy)
+        ctx.mark_non_differentiable(gx, gy)
+        return ans, gx, gy
+
+    @staticmethod
+    def backward(ctx, g, _gx, _gy):
+        gx, gy = ctx.saved_tensors
+        g = g.reshape(-1, 1, 1)
+        return g * gx, g * gy, None
+
+
+@_on_device
 def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tensor] = None,
                                  calc_gradients: bool = False):
     """Reference: tf_fast_rnnt/__init__.py:42-149 (op FastRNNTLoss)."""
@@ -146,6 +207,9 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
     if T1 not in (T, T + 1) or tuple(py_d.shape) != (B, S + 1, T):
         raise ValueError(f"bad shapes px {tuple(px_d.shape)} py {tuple(py_d.shape)}")
     bd = _boundary(io, boundary, B, S, T)
+    if _wants_grad(px, py):
+        ans, gx, gy = _MutualInformationFn.apply(px_d, py_d, bd)
+        return (ans, (gx, gy)) if calc_gradients else ans
     ans = torch.empty(B, dtype=torch.float32, device=io.dev)
     gx = torch.empty_like(px_d) if calc_gradients else None
     gy = torch.empty_like(py_d) if calc_gradients else None
@@ -159,6 +223,7 @@ def mutual_information_recursion(px: Tensor, py: Tensor, boundary: Optional[Tens
     return io.out(ans)
 
 
+@_on_device
 def cummin(x: Tensor):
     """Reference: tf_fast_rnnt/__init__.py:151-152 (op Cummin)."""
     io = _Io(x)
@@ -194,18 +259,55 @@ def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, s
     return io.out(px), io.out(py)
 
 
+class _SimpleLogprobsFn(torch.autograd.Function):
+    """(px, py)(lm, am) with the backward TensorFlow autodiff runs through rnnt_loss.py:175-221 (1266-1365 for
+    the smoothed variant): the same two contractions as the loss gradient, fed with the cotangents of px / py
+    instead of occupation counts."""
+
+    @staticmethod
+    def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, smoothed, lm_only_scale,
+                am_only_scale):
+        px, py = _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed,
+                                  lm_only_scale, am_only_scale)
+        ctx.save_for_backward(lm, am, symbols, boundary)
+        ctx.args = (termination_symbol, rnnt_type, smoothed, lm_only_scale, am_only_scale)
+        return px, py
+
+    @staticmethod
+    def backward(ctx, dpx, dpy):
+        lm, am, symbols, boundary = ctx.saved_tensors
+        term, rnnt_type, smoothed, lms, ams = ctx.args
+        am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, dpx.contiguous(), dpy.contiguous(), None,
+                                          rnnt_type, smoothed, lms, ams)
+        return lm_g, am_g, None, None, None, None, None, None, None
+
+
+def _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams):
+    if _wants_grad(lm, am):
+        io = _Io(lm, am)
+        B, T, _ = am.shape
+        S = lm.shape[1] - 1
+        return _SimpleLogprobsFn.apply(lm.contiguous().float(), am.contiguous().float(),
+                                       io.dev_tensor(symbols, torch.int32), int(termination_symbol),
+                                       _boundary(io, boundary, B, S, T), rnnt_type, bool(smoothed), float(lms),
+                                       float(ams))
+    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams)
+
+
+@_on_device
 def get_rnnt_logprobs(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                       rnnt_type: str = "regular", boundary: Optional[Tensor] = None):
-    """Reference: rnnt_loss.py:63-223."""
-    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, False, 0.0, 0.0)
+    """Reference: rnnt_loss.py:63-223.  CUDA tensors that require grad get gradients w.r.t. lm and am."""
+    return _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, False, 0.0, 0.0)
 
 
+@_on_device
 def get_rnnt_logprobs_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                                lm_only_scale: float = 0.1, am_only_scale: float = 0.1,
                                boundary: Optional[Tensor] = None, rnnt_type: str = "regular"):
-    """Reference: rnnt_loss.py:1132-1367."""
-    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, True,
-                            lm_only_scale, am_only_scale)
+    """Reference: rnnt_loss.py:1132-1367.  CUDA tensors that require grad get gradients w.r.t. lm and am."""
+    return _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, True,
+                                   lm_only_scale, am_only_scale)
 
 
 def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
@@ -237,6 +339,7 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
     return (loss, (io.out(gx), io.out(gy))) if calc_gradients else loss
 
 
+@_on_device
 def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad=None,
                          rnnt_type: str = "regular", smoothed: bool = False, lm_only_scale: float = 0.0,
                          am_only_scale: float = 0.0):
@@ -312,6 +415,7 @@ class _SimpleLossFn(torch.autograd.Function):
         return lm_g, am_g, None, None, None, None, None, None, None, None
 
 
+@_on_device
 def rnnt_loss_simple(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                      boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
                      delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
@@ -330,12 +434,13 @@ def rnnt_loss_simple(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol
         scores, gx, gy = _SimpleLossFn.apply(lm.contiguous().float(), am.contiguous().float(),
                                              io.dev_tensor(symbols, torch.int32), int(termination_symbol),
                                              _boundary(io, boundary, B, S, T), rnnt_type, float(delay_penalty))
-        loss = -scores if reduction == "none" else (-scores.sum() if reduction == "sum" else -scores.mean())
+        loss = _reduce_autograd(scores, reduction, group)
         return (loss, (gx, gy)) if calc_gradients else loss
     return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
                         reduction, calc_gradients, False, 0.0, 0.0, group)
 
 
+@_on_device
 def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                        lm_only_scale: float = 0.1, am_only_scale: float = 0.1,
                        boundary: Optional[Tensor] = None, rnnt_type: str = "regular",
@@ -355,13 +460,14 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
                                              io.dev_tensor(symbols, torch.int32), int(termination_symbol),
                                              _boundary(io, boundary, B, S, T), rnnt_type, float(delay_penalty),
                                              True, float(lm_only_scale), float(am_only_scale))
-        loss = -scores if reduction == "none" else (-scores.sum() if reduction == "sum" else -scores.mean())
+        loss = _reduce_autograd(scores, reduction, group)
         return (loss, (gx, gy)) if calc_gradients else loss
     return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
                         reduction, calc_gradients, True, lm_only_scale, am_only_scale, group)
 
 
 # ---------------------------------------------------------------- A5 / A6
+@_on_device
 def get_rnnt_prune_ranges(px_grad: Tensor, py_grad: Tensor, boundary: Tensor, s_range: int):
     """Reference: rnnt_loss.py:647-761."""
     io = _Io(px_grad, py_grad)
@@ -415,6 +521,7 @@ def _wants_grad(*xs) -> bool:
     return torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.is_cuda and x.requires_grad for x in xs)
 
 
+@_on_device
 def do_rnnt_pruning(am: Tensor, lm: Tensor, ranges: Tensor):
     """Reference: rnnt_loss.py:763-812.  CUDA tensors that require grad get gradients w.r.t. am and lm."""
     if _wants_grad(am, lm):
@@ -437,6 +544,7 @@ def do_rnnt_pruning(am: Tensor, lm: Tensor, ranges: Tensor):
     return io.out(am_p), io.out(lm_p)
 
 
+@_on_device
 def do_rnnt_pruning_backward(am_pruned_grad: Tensor, lm_pruned_grad: Tensor, ranges: Tensor, S: int):
     """Gradient of do_rnnt_pruning (what TF autodiff derives for rnnt_loss.py:802-811)."""
     io = _Io(am_pruned_grad, lm_pruned_grad)
@@ -451,6 +559,7 @@ def do_rnnt_pruning_backward(am_pruned_grad: Tensor, lm_pruned_grad: Tensor, ran
     return io.out(am_g), io.out(lm_g)
 
 
+@_on_device
 def do_rnnt_pruning_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor):
     """(extension) do_rnnt_pruning (rnnt_loss.py:763-812) plus the additive joiner of the
     reference's tests (simple_rnnt_loss_test.py:120-125) in one pass over the data:
@@ -474,6 +583,7 @@ def do_rnnt_pruning_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor):
     return io.out(am_p), io.out(lm_p), io.out(lg)
 
 
+@_on_device
 def pruned_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor, dtype=torch.float32):
     """(extension) logits = am_pruned + lm_pruned without
     materialising either."""
@@ -491,9 +601,45 @@ def pruned_add_joiner(am: Tensor, lm: Tensor, ranges: Tensor, dtype=torch.float3
 
 
 # ---------------------------------------------------------------- A7 / A8
+class _PrunedLogprobsFn(torch.autograd.Function):
+    """(px, py)(logits) with the backward TF autodiff runs through rnnt_loss.py:942-1018 (frn_pruned_logprobs_bwd)."""
+
+    @staticmethod
+    def forward(ctx, logits, symbols, ranges, termination_symbol, boundary, rnnt_type):
+        px, py = _pruned_logprobs(logits, symbols, ranges, termination_symbol, boundary, rnnt_type)
+        ctx.save_for_backward(logits, symbols, ranges, boundary)
+        ctx.args = (termination_symbol, rnnt_type)
+        return px, py
+
+    @staticmethod
+    def backward(ctx, dpx, dpy):
+        logits, symbols, ranges, boundary = ctx.saved_tensors
+        term, rnnt_type = ctx.args
+        B, T, R, C = logits.shape
+        S = symbols.shape[1]
+        grad = torch.empty_like(logits)
+        ws = _workspace(lib.frn_pruned_logprobs_workspace_bytes(B, S, T, R), logits.device)
+        check(lib.frn_pruned_logprobs_bwd(_ptr(logits), _logits_dtype(logits), _ptr(symbols), _ptr(ranges),
+                                          _ptr(boundary), _ptr(dpx.contiguous().float()), _ptr(dpy.contiguous().float()),
+                                          B, S, T, R, C, int(term), _rnnt_type(rnnt_type), _ptr(grad), _ptr(ws),
+                                          ws.numel(), _stream(logits.device)), "frn_pruned_logprobs_bwd")
+        return grad, None, None, None, None, None
+
+
+@_on_device
 def get_rnnt_logprobs_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, termination_symbol: int,
                              boundary: Tensor, rnnt_type: str = "regular"):
-    """Reference: rnnt_loss.py:853-1020."""
+    """Reference: rnnt_loss.py:853-1020.  CUDA logits that require grad get their gradient."""
+    if _wants_grad(logits):
+        io = _Io(logits)
+        sym_d = io.dev_tensor(symbols, torch.int32)
+        B, T = logits.shape[0], logits.shape[1]
+        return _PrunedLogprobsFn.apply(logits.contiguous(), sym_d, io.dev_tensor(ranges, torch.int32),
+                                       int(termination_symbol), _boundary(io, boundary, B, sym_d.shape[1], T), rnnt_type)
+    return _pruned_logprobs(logits, symbols, ranges, termination_symbol, boundary, rnnt_type)
+
+
+def _pruned_logprobs(logits, symbols, ranges, termination_symbol, boundary, rnnt_type):
     io = _Io(logits)
     lg = logits if isinstance(logits, torch.Tensor) and logits.is_cuda else io.dev_tensor(logits, torch.float32)
     lg = lg.contiguous()
@@ -513,6 +659,7 @@ def get_rnnt_logprobs_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, te
     return io.out(px), io.out(py)
 
 
+@_on_device
 def pruned_loss_fwd_bwd(logits, symbols, ranges, termination_symbol, boundary, rnnt_type="regular",
                         delay_penalty=0.0, scores_grad=None, want_logits_grad=True):
     """One fused call: scores [B] and d(sum_b scores_grad[b]*scores[b])/d logits
@@ -529,8 +676,8 @@ def pruned_loss_fwd_bwd(logits, symbols, ranges, termination_symbol, boundary, r
     scores = torch.empty(B, dtype=torch.float32, device=dev)
     grad = torch.empty_like(lg) if want_logits_grad else None
     sg = None if scores_grad is None else io.dev_tensor(scores_grad, torch.float32)
-    ws = _workspace(lib.frn_pruned_loss_workspace_bytes(B, S, T, R), dev)
     dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    ws = _workspace(lib.frn_pruned_loss_min_workspace_bytes(B, S, T, R, dp), dev)
     check(lib.frn_pruned_loss(_ptr(lg), _logits_dtype(lg), _ptr(sym_d), _ptr(rg), _ptr(bd), B, S, T, R, C,
                               int(termination_symbol), rt, dp, _ptr(sg), _ptr(scores), _ptr(grad), _ptr(ws),
                               ws.numel(), _stream(dev)), "frn_pruned_loss")
@@ -558,6 +705,7 @@ class _PrunedLossFn(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
+@_on_device
 def rnnt_loss_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, termination_symbol: int,
                      boundary: Tensor = None, rnnt_type: str = "regular", delay_penalty: float = 0.0,
                      reduction: Optional[str] = "mean", calc_gradients: bool = False, group=None):
@@ -579,16 +727,14 @@ def rnnt_loss_pruned(logits: Tensor, symbols: Tensor, ranges: Tensor, terminatio
     if lg.requires_grad and torch.is_grad_enabled():
         scores = _PrunedLossFn.apply(lg, sym_d, rg, int(termination_symbol), bd, rnnt_type,
                                      float(delay_penalty))
-        if reduction == "none":
-            return -scores
-        loss = -scores.sum() if reduction == "sum" else -scores.mean()
-        return loss
+        return _reduce_autograd(scores, reduction, group)
     scores, _ = pruned_loss_fwd_bwd(lg, sym_d, rg, termination_symbol, bd, rnnt_type, delay_penalty, None,
                                     want_logits_grad=False)
     return io.out(_reduce(scores, reduction, group))
 
 
 # ---------------------------------------------------------------- (f1) full joiner
+@_on_device
 def get_rnnt_logprobs_joint(logits: Tensor, symbols: Tensor, termination_symbol: int,
                             boundary: Optional[Tensor] = None, rnnt_type: str = "regular"):
     """Reference: rnnt_loss.py:340-452.  The full joiner is the pruned case with
@@ -636,6 +782,7 @@ class _JointLossFn(torch.autograd.Function):
         return grad, None, None, None, None, None
 
 
+@_on_device
 def rnnt_loss(logits: Tensor, symbols: Tensor, termination_symbol: int, boundary: Optional[Tensor] = None,
               rnnt_type: str = "regular", delay_penalty: float = 0.0, reduction: Optional[str] = "mean",
               calc_gradients: bool = False, group=None):
@@ -653,8 +800,6 @@ def rnnt_loss(logits: Tensor, symbols: Tensor, termination_symbol: int, boundary
     bd = _boundary(io, boundary, B, S, T)
     if lg.requires_grad and torch.is_grad_enabled():
         scores = _JointLossFn.apply(lg, sym_d, int(termination_symbol), bd, rnnt_type, float(delay_penalty))
-        if reduction == "none":
-            return -scores
-        return -scores.sum() if reduction == "sum" else -scores.mean()
+        return _reduce_autograd(scores, reduction, group)
     scores, _ = _joint_loss_call(lg, sym_d, bd, termination_symbol, rnnt_type, delay_penalty, None, False)
     return io.out(_reduce(scores, reduction, group))
