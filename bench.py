@@ -144,7 +144,8 @@ class Pipeline:
     sub-batch (lattice recursions, normaliser) overlap the bandwidth-bound kernels of another.
     Same calls, same results; the two loss sums are reduced over the whole batch at the end."""
 
-    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True, am_side=0):
+    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True, am_side=0, logits_bf16=False,
+                 training=False):
         import torch
         from tf_fast_rnnt import _lib
         self.torch, self.lib, self._lib = torch, _lib.lib, _lib
@@ -155,14 +156,26 @@ class Pipeline:
         self.gx, self.gy = e(B, S, T + 1), e(B, S + 1, T)
         self.ranges = e(B, T, R, dtype=i32)
         self.am_p, self.lm_p = e(B, T, R, C), e(B, T, R, C)
-        self.logits, self.dlogits = e(B, T, R, C), e(B, T, R, C)
+        # bf16 joiner logits into the float32 loss (BASELINE.json configs[3]): the joiner writes bf16
+        # (frn_pruned_add_joiner), frn_pruned_loss reads them and returns a bf16 logits gradient
+        self.logits_bf16 = logits_bf16
+        ldt = torch.bfloat16 if logits_bf16 else f32
+        self.logits, self.dlogits = e(B, T, R, C, dtype=ldt), e(B, T, R, C, dtype=ldt)
+        # training step (A9 + the gradient of do_rnnt_pruning): am / lm gradients of both losses
+        self.training = training
+        if training:
+            self.am_g_simple, self.lm_g_simple = e(B, T, C), e(B, S + 1, C)
+            self.am_g_pruned, self.lm_g_pruned = e(B, T, C), e(B, S + 1, C)
+            self.ws_bwd = torch.empty(max(int(self.lib.frn_simple_loss_bwd_workspace_bytes(B, S, T, C)), 256),
+                                      dtype=torch.uint8, device=dev)
+            assert not logits_bf16, "the training-step variant runs float32 logits"
         self.losses = e(2)
         self.sgrad = torch.full((B,), -1.0, dtype=f32, device=dev)  # d(sum loss)/d scores
         # am_pruned[b,t,i,:] = am[b,t,:] does not depend on the ranges (rnnt_loss.py:802-806 broadcasts am
         # before it gathers lm): with `overlap` that half of do_rnnt_pruning runs on a second stream
         # beside the dependency-chain-bound kernels of the simple loss, the lm half after the ranges.
         self.overlap = overlap and not fuse_add
-        self.fuse_add = fuse_add
+        self.fuse_add = fuse_add and not logits_bf16
         # `am_side` = G > 0: the same idea on the copy engine - frn_broadcast_am_pruned, a persistent grid of G
         # single-warp CTAs doing nothing but bulk copies, with a shared-memory footprint that keeps the
         # normaliser's / recursion's big CTAs on the other SMs; frn_do_pruning_add_joiner then writes
@@ -216,6 +229,28 @@ class Pipeline:
                                              0, 0.0, p(self.sgrad), p(self.pscores), p(self.dlogits),
                                              ws_q.data_ptr(), ws_q.numel(), st()), "pruned_loss")),
         ]
+        if self.logits_bf16:
+            ldt = 1
+            out[3] = ("add_joiner(bf16)", 4 * B * (T * C + (S + 1) * C + T * R) + 2 * n_logits,
+                      lambda: chk(lib.frn_pruned_add_joiner(p(am), p(lm), p(self.ranges), B, S, T, R, C, ldt,
+                                                            p(self.logits), st()), "pruned_add_joiner"))
+            out[4] = ("pruned_loss", 2 * n_logits + 8 * B * T * R + 4 * n_logits + 16 * B * T * R,
+                      lambda: chk(lib.frn_pruned_loss(p(self.logits), ldt, p(sym), p(self.ranges), p(bd), B, S, T, R, C,
+                                                      term, 0, 0.0, p(self.sgrad), p(self.pscores), p(self.dlogits),
+                                                      ws_q.data_ptr(), ws_q.numel(), st()), "pruned_loss"))
+        if self.training:
+            # backward of the step: A9 (am / lm gradients of the simple loss from its occupation counts) and the
+            # gradient of do_rnnt_pruning + additive joiner (d am_pruned = d lm_pruned = d logits)
+            ws_b = self.ws_bwd
+            out.append(("simple_loss_bwd", 4 * B * (2 * (T + S + 1) * C + 2 * (S * (T + 1) + (S + 1) * T)),
+                        lambda: chk(lib.frn_simple_loss_bwd(p(lm), p(am), p(sym), p(bd), p(self.gx), p(self.gy),
+                                                            p(self.sgrad), B, S, T, C, term, 0, p(self.am_g_simple),
+                                                            p(self.lm_g_simple), ws_b.data_ptr(), ws_b.numel(), st()),
+                                    "simple_loss_bwd")))
+            out.append(("do_pruning_bwd", 4 * n_logits * 2 + 4 * B * (T + S + 1) * C,
+                        lambda: chk(lib.frn_do_pruning_bwd(p(self.dlogits), p(self.dlogits), p(self.ranges), B, S, T, R, C,
+                                                           p(self.am_g_pruned), p(self.lm_g_pruned), st()),
+                                    "do_pruning_bwd")))
         if with_reduce:
             out.append(("reduce", 8 * self.B, self._reduce))
         if self.fuse_add:

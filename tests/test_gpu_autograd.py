@@ -273,7 +273,7 @@ def test_sum_and_mean_over_a_process_group_on_the_autograd_path():
                 am_d = torch.from_numpy(am).cuda().requires_grad_(True)
                 loss = frn.rnnt_loss_simple(lm_d, am_d, sym, term, bd, "regular", 0.0, red, group=group)
                 loss.backward()
-                out.append((float(loss), am_d.grad.clone()))
+                out.append((float(loss.detach()), am_d.grad.clone()))
             assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
             assert torch.equal(out[0][1], out[1][1])
     finally:

@@ -169,3 +169,36 @@ def test_c5_ragged_batch_sharded_sum():
             partial += float(frn.rnnt_loss_simple(lm[i, :s_max + 1].contiguous(), am[i, :t_max].contiguous(),
                                                   sym[i, :s_max].contiguous(), term, bd_d[i], "regular", 0.0, "sum"))
         np.testing.assert_allclose(partial, total, rtol=2e-6)
+
+
+def test_c2_am_lm_gradients_on_tensor_cores():
+    """A9 at the c2 shape (B=4 of the 32: the float64 oracle holds [B,S+1,T] x C products): am / lm gradients of
+    rnnt_loss_simple from the tcgen05 contraction kernel (simple_bwd_tc.cu) against the float64 oracle."""
+    import tf_fast_rnnt as frn
+    B, T, S, C = 4, 500, 100, 500
+    am, lm, sym, term, bd = make_inputs(77, B, T, S, C, ragged=True)
+    w = np.array([1.0, 0.5, -2.0, 1.5], np.float32)
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    am_g, lm_g = frn.simple_loss_backward(lm, am, sym, term, bd, gx, gy, -w, "regular")
+    o_am, o_lm = orc.simple_am_lm_grad(lm, am, sym, term, bd, "regular", 0.0, w, np.float64)
+    assert_close(am_g, o_am, GRAD_RTOL, 2e-6, "am grad")
+    assert_close(lm_g, o_lm, GRAD_RTOL, 2e-5, "lm grad")
+
+
+def test_c4_am_lm_gradients_on_tensor_cores():
+    """A9 at the c4 shape, two utterances (T=1500 S=400 C=5000: 4 x 20 + 12 x 40 tiles per utterance)."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C = 2, 1500, 400, 5000
+    rng = np.random.default_rng(44)
+    am = rng.standard_normal((B, T, C), dtype=np.float32)
+    lm = rng.standard_normal((B, S + 1, C), dtype=np.float32)
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    bd = np.array([[0, 0, S, T], [0, 0, 250, 1100]], np.int32)
+    term = C - 1
+    _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    am_g, lm_g = frn.simple_loss_backward(lm, am, sym, term, bd, gx, gy, None, "regular")
+    o_am, o_lm = orc.simple_am_lm_grad(lm, am, sym, term, bd, "regular", 0.0, -np.ones(B), np.float64)
+    # the occupation counts themselves carry ~2e-4 at this lattice size (test_c4_large_vocab_bf16)
+    assert_close(am_g, o_am, 4 * GRAD_RTOL, 2e-6, "c4 am grad")
+    assert_close(lm_g, o_lm, 4 * GRAD_RTOL, 2e-5, "c4 lm grad")

@@ -638,3 +638,27 @@ def test_concurrent_streams_are_independent():
         for a, b in zip(serial, conc):
             for x, y in zip(a, b):
                 assert torch.equal(x, y)
+
+
+def test_fuzz_tensor_core_gradient_contraction_equals_simt(monkeypatch):
+    """simple_bwd_tc.cu (tcgen05, MN-major / K-major swizzled operands) against the exact-FP32 SIMT tiles of
+    simple_bwd.cu on shapes that exercise every tile edge: partial K slices, several M tiles on either side,
+    partial and multiple N tiles, all rnnt types, smoothed and not."""
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(21)
+    shapes = [(2, 70, 21, 28), (1, 129, 5, 260), (2, 64, 130, 36), (1, 300, 200, 516), (3, 37, 11, 8), (1, 257, 63, 132)]
+    for n, (B, T, S, C) in enumerate(shapes):
+        rnnt_type = ["regular", "modified", "constrained"][n % 3]
+        smoothed = n % 2 == 1
+        am, lm, sym, term, bd = make_inputs(100 + n, B, T, S, C, ragged=True, begin=(n % 2 == 0))
+        sg = rng.standard_normal(B).astype(np.float32)
+        if smoothed:
+            _, (gx, gy) = frn.rnnt_loss_smoothed(lm, am, sym, term, 0.2, 0.1, bd, rnnt_type, 0.0, "none", True)
+        else:
+            _, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, rnnt_type, 0.0, "none", True)
+        out = []
+        for simt in ("0", "1"):
+            monkeypatch.setenv("FRN_BWD_SIMT", simt)
+            out.append(frn.simple_loss_backward(lm, am, sym, term, bd, gx, gy, sg, rnnt_type, smoothed, 0.2, 0.1))
+        assert_close(out[0][0], out[1][0], 2e-5, 1e-6, f"am grad {B, T, S, C}")
+        assert_close(out[0][1], out[1][1], 2e-5, 1e-6, f"lm grad {B, T, S, C}")

@@ -23,25 +23,10 @@
 // and [S1 x T].[T x C]); the tcgen05 version follows the forward kernel's scheme.
 #include "common.cuh"
 #include "launchers.h"
+#include "simple_bwd_params.cuh"
 
 namespace frn {
 
-struct BwdParams {
-  const float *lm, *am;
-  const int32_t *symbols, *boundary;
-  const float *gpx, *gpy;       // occupation counts, reference layout ([B,S,T1], [B,S+1,T])
-  const float *py;              // forward py [B,S+1,T] (recomputed), gives Z
-  const float *lmmax, *ammax;   // row maxima
-  const float *scores_grad;     // [B] or null (ones)
-  float *W;                     // [B][S+1][T] workspace
-  float *am_grad, *lm_grad;
-  int B, S, T, T1, C, term, rnnt_type;
-  // smoothed loss only
-  int smoothed;
-  float comb, lm_scale, am_scale;           // 1 - lm - am; scales with the 1e-20 substitution
-  const float *lmsum, *amonly, *unigram;    // forward statistics: sum_c exp(lm - lmmax); log D + ammax; u[c]
-  float *Gt, *Sx, *Sy, *du, *partial;       // [B][T], [B][S+1], [B][S+1], [C], [chunks][C]
-};
 constexpr int kDuRows = 64;                 // am rows per block of the du partial sums
 
 // Weight on px[b,s,t].  Regular lattice: the forward overwrote frame t_end of every px row with -inf
@@ -52,23 +37,27 @@ __device__ __forceinline__ float gpx_at(const BwdParams &p, int b, int s, int t)
   return p.gpx[((size_t)b * p.S + s) * p.T1 + t];
 }
 
-// W[b,s,t] = G / Z with Z = exp(norm - lmmax - ammax), norm = am[t,blank] + lm[s,blank] - py[s,t]
+// W[b,s,t] = G / Z with Z = exp(norm - lmmax - ammax), norm = am[t,blank] + lm[s,blank] - py[s,t]; written over
+// the padded [S1p][Tp] domain (zeros outside the lattice) so that the contraction tiles need no bounds checks
 __global__ void __launch_bounds__(256) bwd_weights_kernel(BwdParams p) {
   const int S1 = p.S + 1;
-  const size_t n = (size_t)p.B * S1 * p.T;
+  const size_t n = (size_t)p.B * p.S1p * p.Tp;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int b = (int)(i / ((size_t)S1 * p.T));
-  const int rem = (int)(i - (size_t)b * S1 * p.T);
-  const int s = rem / p.T, t = rem - s * p.T;
-  float G = p.gpy[i];
-  if (s < p.S) G += gpx_at(p, b, s, t);
-  if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) G += gpx_at(p, b, s - 1, t);  // px[s-1,t] += py[s,t]
+  const int b = (int)(i / ((size_t)p.S1p * p.Tp));
+  const int rem = (int)(i - (size_t)b * p.S1p * p.Tp);
+  const int s = rem / p.Tp, t = rem - s * p.Tp;
   float w = 0.f;
-  if (G != 0.f) {
-    const float norm = p.am[((size_t)b * p.T + t) * p.C + p.term] + p.lm[((size_t)b * S1 + s) * p.C + p.term] - p.py[i];
-    const float logZ = norm - p.lmmax[(size_t)b * S1 + s] - p.ammax[(size_t)b * p.T + t];
-    w = G * expf(-logZ);
+  if (s < S1 && t < p.T) {
+    const size_t at = ((size_t)b * S1 + s) * p.T + t;
+    float G = p.gpy[at];
+    if (s < p.S) G += gpx_at(p, b, s, t);
+    if (p.rnnt_type == FRN_CONSTRAINED && s >= 1) G += gpx_at(p, b, s - 1, t);  // px[s-1,t] += py[s,t]
+    if (G != 0.f) {
+      const float norm = p.am[((size_t)b * p.T + t) * p.C + p.term] + p.lm[((size_t)b * S1 + s) * p.C + p.term] - p.py[at];
+      const float logZ = norm - p.lmmax[(size_t)b * S1 + s] - p.ammax[(size_t)b * p.T + t];
+      w = G * expf(-logZ);
+    }
   }
   p.W[i] = w;
 }
@@ -87,7 +76,8 @@ __global__ void __launch_bounds__(256) bwd_contract_kernel(BwdParams p) {
   const float *y = (AM_SIDE ? p.lm + (size_t)b * S1 * C : p.am + (size_t)b * T * C);
   const float *xmax = AM_SIDE ? p.ammax + (size_t)b * T : p.lmmax + (size_t)b * S1;
   const float *ymax = AM_SIDE ? p.lmmax + (size_t)b * S1 : p.ammax + (size_t)b * T;
-  const float *Wb = p.W + (size_t)b * S1 * T;
+  const float *Wb = p.W + (size_t)b * p.S1p * p.Tp;
+  const int Tp = p.Tp;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += BK) {
@@ -95,7 +85,7 @@ __global__ void __launch_bounds__(256) bwd_contract_kernel(BwdParams p) {
       const int kk = i / TILE, mm = i - kk * TILE;      // mm fastest
       const int k = k0 + kk, m = m0 + mm;
       float w = 0.f;
-      if (k < K && m < M) w = AM_SIDE ? Wb[(size_t)k * T + m] : Wb[(size_t)m * T + k];
+      if (k < K && m < M) w = AM_SIDE ? Wb[(size_t)k * Tp + m] : Wb[(size_t)m * Tp + k];
       Ws[kk][mm] = w;
       const int n = n0 + mm;
       float pr = 0.f;
@@ -263,7 +253,8 @@ __global__ void __launch_bounds__(128) bwd_du_kernel(BwdParams p, int chunks) {
 size_t simple_bwd_workspace_bytes(int B, int S, int T, int C) {
   const int T1 = T + 1;
   const size_t chunks = ((size_t)B * T + kDuRows - 1) / kDuRows;
-  return round_up_sz((size_t)B * S * T1 * sizeof(float), 256) + 2 * round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256) +
+  return round_up_sz((size_t)B * S * T1 * sizeof(float), 256) + round_up_sz((size_t)B * (S + 1) * T * sizeof(float), 256) +
+         round_up_sz((size_t)B * round_up(S + 1, 128) * round_up(T, 128) * sizeof(float), 256) +
          simple_stats_bytes(B, S, T, C) + round_up_sz((size_t)B * T * sizeof(float), 256) +
          2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256) + round_up_sz((size_t)C * sizeof(float), 256) +
          round_up_sz(chunks * C * sizeof(float), 256);
@@ -278,7 +269,8 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
   char *w = static_cast<char *>(workspace);
   float *px = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S * (T + 1) * sizeof(float), 256);
   float *py = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
-  float *W = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * T * sizeof(float), 256);
+  const int S1p = round_up(S1, 128), Tp = round_up(T, 128);
+  float *W = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1p * Tp * sizeof(float), 256);
   void *stats = w; w += simple_stats_bytes(B, S, T, C);
   float *Gt = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *Sx = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
@@ -304,7 +296,7 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
                                        round_up_sz((size_t)B * T * sizeof(float), 256));
   p.unigram = reinterpret_cast<float *>(sw + 2 * round_up_sz((size_t)B * S1 * sizeof(float), 256) +
                                         2 * round_up_sz((size_t)B * T * sizeof(float), 256));
-  p.scores_grad = scores_grad; p.W = W; p.am_grad = am_grad; p.lm_grad = lm_grad;
+  p.scores_grad = scores_grad; p.W = W; p.S1p = S1p; p.Tp = Tp; p.am_grad = am_grad; p.lm_grad = lm_grad;
   p.B = B; p.S = S; p.T = T; p.T1 = T1; p.C = C; p.term = term; p.rnnt_type = rnnt_type;
   p.smoothed = smoothed;
   const double lms = (double)lm_only_scale, ams = (double)am_only_scale;      // rnnt_loss.py:1342-1349
@@ -312,11 +304,18 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
   p.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
   p.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
   p.Gt = Gt; p.Sx = Sx; p.Sy = Sy; p.du = du; p.partial = partial;
-  const size_t n = (size_t)B * S1 * T;
+  const size_t n = (size_t)B * S1p * Tp;
   count_launch(), bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
-  dim3 g_am((C + 63) / 64, (T + 63) / 64, B), g_lm((C + 63) / 64, (S1 + 63) / 64, B);
-  count_launch(), bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
-  count_launch(), bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
+  // the two contractions: tcgen05 (simple_bwd_tc.cu); the exact-FP32 SIMT tiles serve shapes it cannot take
+  // (C % 4 != 0) and FRN_BWD_SIMT=1 forces them in the debug-hooks build (cross-check)
+  rc = debug_env_int("FRN_BWD_SIMT", 0) == 1 ? FRN_EUNSUPPORTED : launch_bwd_contract_tc(p, stream);
+  if (rc == FRN_EUNSUPPORTED) {
+    dim3 g_am((C + 63) / 64, (T + 63) / 64, B), g_lm((C + 63) / 64, (S1 + 63) / 64, B);
+    count_launch(), bwd_contract_kernel<true><<<g_am, 256, 0, stream>>>(p);
+    count_launch(), bwd_contract_kernel<false><<<g_lm, 256, 0, stream>>>(p);
+  } else if (rc) {
+    return rc;
+  }
   if (smoothed) {
     count_launch(), bwd_gt_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
     count_launch(), bwd_rowsums_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
