@@ -369,7 +369,7 @@ def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=5):
                                 ptr(py), ptr(ws), ws.numel(), st), "simple_logprobs")
     out["simple_lattice"] = {"reference_ms": timed(ref_op), "ours_ms": timed(our_op)}
     # dense lattice of the pruned loss, as the reference runs it (rnnt_loss.py:968-1018, 1116-1119)
-    chk(lib.frn_pruned_logprobs(ptr(pipe.logits), 0, ptr(sym), ptr(pipe.ranges), ptr(bd), B, S, T, R, C, C - 1, 0,
+    chk(lib.frn_pruned_logprobs(ptr(pipe.logits), 1 if pipe.logits_bf16 else 0, ptr(sym), ptr(pipe.ranges), ptr(bd), B, S, T, R, C, C - 1, 0,
                                 ptr(px), ptr(py), ptr(ws), ws.numel(), st), "pruned_logprobs")
     # ... against the product path for that lattice: the recursion on the band itself.  pxc/pyc are the
     # first two [B][T][R] float32 segments of frn_pruned_loss's workspace (left there by pipe.step)
@@ -497,18 +497,33 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, T, S, C, R = WORKLOADS[args.workload]
+    logits_bf16 = args.workload == "c4" and not args.fp32_logits     # BASELINE.json configs[3]: bf16 joiner logits
     pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1, fuse_add=not args.no_fuse_add and not args.overlap,
-                    am_side=args.am_side)
+                    am_side=args.am_side, logits_bf16=logits_bf16, training=args.profile_training)
 
     # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
     # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
+    # Every input set is ONE contiguous block (am | lm | symbols | boundary, 256-byte aligned parts): the
+    # end-to-end leg moves a step's inputs with one cudaMemcpyAsync from one pinned block.
     NSETS = 4
-    host_sets, dev_sets = [], []
+    shapes = [((B, T, C), np.float32), ((B, S + 1, C), np.float32), ((B, S), np.int32), ((B, 4), np.int32)]
+    offs, total = [], 0
+    for shp, dt in shapes:
+        offs.append(total)
+        total += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
+
+    def views(block):
+        tdt = {np.float32: torch.float32, np.int32: torch.int32}
+        return [block[o:o + int(np.prod(shp)) * 4].view(tdt[dt]).view(shp) for o, (shp, dt) in zip(offs, shapes)]
+
+    host_blocks, host_sets, dev_sets = [], [], []
     for i in range(NSETS):
-        arrs = synth(B, T, S, C, 1234 + 17 * rank + i)
-        host_sets.append([torch.from_numpy(a).pin_memory() for a in arrs])
-        dev_sets.append([h.to(dev) for h in host_sets[-1]])
-    stage_buf = [torch.empty_like(d) for d in dev_sets[0]]  # e2e landing buffers
+        hb = torch.empty(total, dtype=torch.uint8).pin_memory()
+        for v, a in zip(views(hb), synth(B, T, S, C, 1234 + 17 * rank + i)):
+            v.copy_(torch.from_numpy(a))
+        host_blocks.append(hb)
+        host_sets.append(views(hb))
+        dev_sets.append(views(hb.to(dev)))
     host_out = torch.empty(2, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
@@ -604,7 +619,8 @@ def run_gpu_arm(args):
     # so every step's inputs cross PCIe and every step's result reaches the host inside the timed region.
     NBUF = 2
     copy_stream = torch.cuda.Stream(dev)
-    stage_bufs = [stage_buf] + [[torch.empty_like(d) for d in dev_sets[0]] for _ in range(NBUF - 1)]
+    stage_blocks = [torch.empty(total, dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    stage_bufs = [views(blk) for blk in stage_blocks]
     host_outs = [host_out] + [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(NBUF - 1)]
     h2d_done = [torch.cuda.Event() for _ in range(NBUF)]
     step_done = [torch.cuda.Event() for _ in range(NBUF)]
@@ -615,8 +631,7 @@ def run_gpu_arm(args):
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(step_done[k])           # landing buffer k is free again
-            for dst, src in zip(stage_bufs[k], host_sets[i % NSETS]):
-                dst.copy_(src, non_blocking=True)
+            stage_blocks[k].copy_(host_blocks[i % NSETS], non_blocking=True)     # one cudaMemcpyAsync per step
             h2d_done[k].record(copy_stream)
         cur.wait_event(h2d_done[k])
         pipe.step(*stage_bufs[k])
@@ -653,12 +668,58 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = float(t.item()) / args.steps
-    h2d = sum(h.numel() * h.element_size() for h in host_sets[0])
+    h2d = total
+
+    # ---- H2D ceiling: the bare copies of the end-to-end leg (same pinned blocks, same bytes, all ranks at
+    #      once, nothing else running) - what `e2e` can reach at best on this host ----
+    barrier()
+    nrep_c = max(10, min(args.steps, 100))
+    with torch.cuda.stream(copy_stream):
+        for i in range(3):
+            stage_blocks[i % NBUF].copy_(host_blocks[i % NSETS], non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+        for i in range(nrep_c):
+            stage_blocks[i % NBUF].copy_(host_blocks[i % NSETS], non_blocking=True)
+        c1.record(copy_stream)
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1) / nrep_c], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_ceiling_ms = float(t.item())
+
+    def time_variant(step_fn):
+        """ms per step of another arrangement of the step (CUDA graph per input set when graphs are on)."""
+        vgraphs = []
+        with torch.cuda.stream(side):
+            step_fn(*dev_sets[0])
+            side.synchronize()
+            if use_graph:
+                for i in range(NSETS):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        step_fn(*dev_sets[i])
+                    vgraphs.append(g)
+        torch.cuda.synchronize()
+        vrun = (lambda i: vgraphs[i % NSETS].replay()) if vgraphs else (lambda i: step_fn(*dev_sets[i % NSETS]))
+        for i in range(3):
+            vrun(i)
+        torch.cuda.synchronize()
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = max(20, min(args.steps, 200))
+        fa.record()
+        for i in range(nrep):
+            vrun(i)
+        fb.record()
+        torch.cuda.synchronize()
+        return fa.elapsed_time(fb) / nrep
 
     # ---- extra (not the headline): the same step with the fused additive joiner of SURVEY.md §8(f)-2,
     #      frn_pruned_add_joiner, in place of do_rnnt_pruning + add: am_pruned / lm_pruned never exist ----
     fused_ms = None
-    if world == 1:
+    if world == 1 and not pipe.logits_bf16:
         try:
             lib, chk = pipe.lib, pipe._lib.check
             ptr = lambda t: t.data_ptr()
@@ -671,31 +732,78 @@ def run_gpu_arm(args):
                                               sfn()), "pruned_add_joiner")
                 st["pruned_loss"](); st["reduce"]()
 
-            fgraphs = []
-            with torch.cuda.stream(side):
-                fused_step(*dev_sets[0])
-                side.synchronize()
-                if use_graph:
-                    for i in range(NSETS):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=side):
-                            fused_step(*dev_sets[i])
-                        fgraphs.append(g)
-            torch.cuda.synchronize()
-            frun = (lambda i: fgraphs[i % NSETS].replay()) if fgraphs else (lambda i: fused_step(*dev_sets[i % NSETS]))
-            for i in range(3):
-                frun(i)
-            torch.cuda.synchronize()
-            fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            nrep = max(20, min(args.steps, 200))
-            fa.record()
-            for i in range(nrep):
-                frun(i)
-            fb.record()
-            torch.cuda.synchronize()
-            fused_ms = fa.elapsed_time(fb) / nrep
+            fused_ms = time_variant(fused_step)
         except Exception as e:  # noqa: BLE001
             fused_ms = repr(e)
+
+    # ---- extra: the TRAINING step = the step above + its backward to am / lm: A9 (frn_simple_loss_bwd, the two
+    #      gradient contractions on tcgen05) and the gradient of do_rnnt_pruning + additive joiner
+    #      (frn_do_pruning_bwd fed with the logits gradient) ----
+    training = None
+    if world == 1 and not pipe.logits_bf16 and not args.no_training and not pipe.training:
+        try:
+            tpipe = Pipeline(B, T, S, C, R, dev, fuse_add=pipe.fuse_add, training=True)
+            t_ms = time_variant(tpipe.step)
+            t_stage = {}
+            for name, nbytes, fn in tpipe.stages(*dev_sets[0]):
+                if name not in ("simple_loss_bwd", "do_pruning_bwd"):
+                    fn()
+                    continue
+                fn(); fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                t_stage[name] = (a.elapsed_time(b) / 10, nbytes)
+            flops = 2 * 2.0 * B * (S + 1) * T * C                   # the two contractions, useful flops
+            training = {
+                "ms_per_step": t_ms, "utterances_per_s": B / (t_ms * 1e-3), "launch": "cuda_graph" if use_graph else "direct",
+                "what": "step + frn_simple_loss_bwd (A9: am / lm gradients, contractions on tcgen05) + frn_do_pruning_bwd "
+                        "(gradient of do_rnnt_pruning and the additive joiner from the logits gradient)",
+                "stages_ms": {k: round(v[0], 4) for k, v in t_stage.items()},
+                "stages_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in t_stage.items()},
+                "a9_useful_tflops": flops / (t_stage["simple_loss_bwd"][0] * 1e-3) / 1e12,
+            }
+            del tpipe
+        except Exception as e:  # noqa: BLE001
+            training = {"error": repr(e)}
+
+    # ---- the dependency-chain kernel alone (t >= (S+T+1) t_step whatever the bytes): the wavefront
+    #      recursion of frn_mi_fwd_bwd on this lattice, isolated with the debug-hooks build's FRN_MI_PHASE ----
+    chain_ms = None
+    if world == 1:
+        try:
+            lib, chk = pipe.lib, pipe._lib.check
+            px = torch.randn((B, S, T + 1), device=dev) - 3.0
+            py = torch.randn((B, S + 1, T), device=dev) - 3.0
+            pipe._lib.use_debug_hooks(True)
+            os.environ["FRN_DP_CHAIN"] = "1"
+            wsz = int(lib.frn_mi_workspace_bytes(B, S, T, T + 1))
+            ws = torch.empty(max(wsz, 256), dtype=torch.uint8, device=dev)
+            ans = torch.empty(B, device=dev)
+            call = lambda: chk(lib.frn_mi_fwd_bwd(px.data_ptr(), py.data_ptr(), dev_sets[0][3].data_ptr(), B, S, T, T + 1, 1,
+                                                  ans.data_ptr(), pipe.gx.data_ptr(), pipe.gy.data_ptr(), ws.data_ptr(),
+                                                  ws.numel(), torch.cuda.current_stream(dev).cuda_stream), "mi")
+            call()
+            os.environ["FRN_MI_PHASE"] = "2"
+            call(); call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                call()
+            b.record()
+            torch.cuda.synchronize()
+            chain_ms = a.elapsed_time(b) / 20
+        except Exception as e:  # noqa: BLE001
+            chain_ms = repr(e)
+        finally:
+            os.environ.pop("FRN_MI_PHASE", None)
+            os.environ.pop("FRN_DP_CHAIN", None)
+            pipe._lib.use_debug_hooks(False)
 
     # ---- per-stage device times (outside the timed region) -> roofline of the dominant kernel ----
     stage_ms = {}
@@ -722,7 +830,8 @@ def run_gpu_arm(args):
     # CUDA events above (DESIGN.md lists every kernel with its bound; the lattice recursion kernels are
     # dependency-chain bound and are reported in `stages_ms` / `lattice_cells_per_s` instead).
     kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8, 1, 1, 0>", "add_joiner": "add_kernel",
-                       "do_pruning+add_joiner": "do_pruning_vec_kernel<8, 1, 1, 1>"}
+                       "do_pruning+add_joiner": "do_pruning_vec_kernel<8, 1, 1, 1>",
+                       "add_joiner(bf16)": "pruned_add_joiner_vec_bf16_kernel<8>"}
     hbm_stages = {k: v for k, v in stage_ms.items() if k in kernel_of_stage}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k][0])
     dom_ms, dom_bytes = hbm_stages[dom]
@@ -731,17 +840,21 @@ def run_gpu_arm(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram__bytes_{read,write}.sum per launch (ncu --set full)
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(kernel_of_stage[dom], {}).get("dram_bytes_per_launch")
+            traffic = json.load(f).get(args.workload, {}).get(kernel_of_stage[dom], {}).get("dram_bytes_per_launch")
     cells = B * (S + 1) * (T + 1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning"
+            "workload": f"{args.workload}: " + ("TRAINING STEP (--profile-training): " if pipe.training else "")
+                        + "full pruned pipeline (simple fwd+bwd -> prune ranges -> pruning"
                         + (" + additive joiner in one pass, am_pruned / lm_pruned / logits all written"
-                           if pipe.fuse_add else " -> additive joiner")
-                        + f" -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} fp32 regular sum",
+                           if pipe.fuse_add else (" -> additive joiner writing bf16 logits" if pipe.logits_bf16
+                                                  else " -> additive joiner"))
+                        + f" -> pruned loss fwd+bwd) B={B}/GPU T={T} S={S} C={C} s_range={R} "
+                        + ("fp32 am/lm, bf16 joiner logits and logits gradient, fp32 losses" if pipe.logits_bf16 else "fp32")
+                        + " regular sum",
             "launch": "cuda_graph" if use_graph else "direct",
             "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step"
                        + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else "")
@@ -755,8 +868,13 @@ def run_gpu_arm(args):
         "clocks": sampler.summary(),
         "e2e": {"value": world * B / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms_per_step, "wall_ms_per_step": wall / args.steps * 1e3,
-                "pipelining": "H2D of step i+1 overlaps the kernels of step i (2 landing buffers); direct "
-                              "C-ABI launches, loss of every step read on the host"},
+                "pipelining": "H2D of step i+1 (ONE cudaMemcpyAsync of one pinned block) overlaps the kernels of step i "
+                              "(2 landing blocks); direct C-ABI launches, loss of every step read on the host",
+                "h2d_ceiling": {"ms_per_step": h2d_ceiling_ms, "gbs_per_gpu": h2d / (h2d_ceiling_ms * 1e-3) / 1e9,
+                                "value": world * B / (h2d_ceiling_ms * 1e-3), "unit": UNIT,
+                                "what": "the same per-step copies alone, all ranks at once (max over ranks): "
+                                        "the most any end-to-end pipeline can reach on this host"},
+                "frac_of_h2d_ceiling": h2d_ceiling_ms / e2e_ms_per_step},
         "gpu_launches": kernels_per_step * args.steps,
         "kernels_per_step": kernels_per_step,
         "roofline": {"bound": "hbm", "kernel": kernel_of_stage[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -766,6 +884,20 @@ def run_gpu_arm(args):
         "stages_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in stage_ms.items()},
         "lattice_cells_per_s": cells / (stage_ms["simple_loss"][0] * 1e-3),
     }
+    if training is not None:
+        line["training_step"] = training
+    if isinstance(chain_ms, float):
+        steps_dp = S + T + 1                       # dependent steps of one direction (both run concurrently)
+        mhz = line["clocks"].get("sm_mhz") or 1965.0
+        cps = chain_ms * 1e-3 * mhz * 1e6 / steps_dp
+        line["latency_roofline"] = {
+            "kernel": "dp_chain_kernel<1> (wavefront lattice recursion, forward and backward chains concurrently)",
+            "steps": steps_dp, "kernel_ms": chain_ms, "cycles_per_step": cps, "floor_cycles": 41.0,
+            "frac": 41.0 / cps, "sm_mhz": mhz,
+            "floor_source": "scripts/ubench/chain_latency: one step's dependent (shuffle, multiply-add) chain on this part",
+            "what": "t >= (S+T+1) t_step per direction whatever the bytes (SURVEY.md 8d); frac = floor / measured"}
+    elif chain_ms is not None:
+        line["latency_roofline"] = {"error": chain_ms}
     if fused_ms is not None:
         line["fused_joiner_variant"] = {
             "ms_per_step": fused_ms, "launch": "cuda_graph" if use_graph else "direct",
@@ -803,7 +935,10 @@ def run_c5(args):
     """configs[4]: ONE ragged batch of 256 utterances (C=500, s_range=5, reduction=sum), sharded by utterance
     over the ranks (greedy LPT on lattice cells, tf_fast_rnnt.sharding.partition_batch) - strong scaling.
     Each rank cuts its shard into length buckets (sharding.plan_buckets) so that the bandwidth-bound kernels
-    do not stream padding, runs the full pipeline per bucket and completes the two sums with one all-reduce."""
+    do not stream padding and every bucket gets the kernel variants of its own shape; the buckets are
+    independent sub-batches, so they run on their own CUDA streams (the dependency-chain-bound kernels of one
+    bucket beside the bandwidth-bound kernels of another), the whole step is one CUDA graph, and the two sums
+    are completed with one all-reduce."""
     import torch
     import torch.distributed as dist
     from tf_fast_rnnt.sharding import partition_batch, plan_buckets
@@ -820,108 +955,224 @@ def run_c5(args):
     bd_all = c5_boundaries(B)
     mine = partition_batch(bd_all, world)[rank]
     buckets = plan_buckets(bd_all[mine], R, C, max_buckets=args.buckets)
-    pipes, inputs, host_inputs = [], [], []
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    for bk in buckets:
-        idx = mine[bk["idx"]]
-        Bk, Sk, Tk = len(idx), bk["S_max"], bk["T_max"]
-        pipes.append(Pipeline(Bk, Tk, Sk, C, R, dev, fuse_add=not args.no_fuse_add))
-        am = torch.randn((Bk, Tk, C), generator=gen, device=dev)
-        lm = torch.randn((Bk, Sk + 1, C), generator=gen, device=dev)
-        sym = torch.randint(0, C - 1, (Bk, Sk), generator=gen, device=dev, dtype=torch.int32)
-        bd = torch.from_numpy(bd_all[idx].copy()).to(dev)
-        inputs.append((am, lm, sym, bd))
-    torch.cuda.synchronize()
-    total = torch.zeros(2, dtype=torch.float32, device=dev)
+    nb = len(buckets)
 
-    def step():
-        total.zero_()
-        for pipe, inp in zip(pipes, inputs):
-            pipe.step(*inp)
-            total.add_(pipe.losses)
-        if world > 1:
-            dist.all_reduce(total)
+    # one contiguous block holds every bucket's (am, lm, symbols, boundary): the end-to-end leg moves a step's
+    # inputs with one cudaMemcpyAsync; two landing blocks on the device + the resident set the timed loop uses
+    f32, i32 = torch.float32, torch.int32
+    layout, total_bytes = [], 0
+    for bk in buckets:
+        Bk, Sk, Tk = len(bk["idx"]), bk["S_max"], bk["T_max"]
+        parts = []
+        for shp, dt in (((Bk, Tk, C), f32), ((Bk, Sk + 1, C), f32), ((Bk, Sk), i32), ((Bk, 4), i32)):
+            parts.append((total_bytes, shp, dt))
+            total_bytes += (int(np.prod(shp)) * 4 + 255) // 256 * 256
+        layout.append(parts)
+
+    def views(block):
+        return [[block[o:o + int(np.prod(shp)) * 4].view(dt).view(shp) for o, shp, dt in parts] for parts in layout]
+
+    host_block = torch.empty(total_bytes, dtype=torch.uint8).pin_memory()
+    gen = torch.Generator()
+    gen.manual_seed(1234 + rank)
+    for bk, (am, lm, sym, bd) in zip(buckets, views(host_block)):
+        idx = mine[bk["idx"]]
+        am.copy_(torch.randn(am.shape, generator=gen))
+        lm.copy_(torch.randn(lm.shape, generator=gen))
+        sym.copy_(torch.randint(0, C - 1, sym.shape, generator=gen, dtype=i32))
+        bd.copy_(torch.from_numpy(bd_all[idx].copy()))
+    dev_blocks = [host_block.to(dev) for _ in range(3)]         # [0] resident set, [1], [2] landing blocks
+    inputs = [views(blk) for blk in dev_blocks]
+    pipes = [Pipeline(len(bk["idx"]), bk["T_max"], bk["S_max"], C, R, dev, fuse_add=not args.no_fuse_add) for bk in buckets]
+    streams = [torch.cuda.Stream(dev) for _ in range(nb)] if args.c5_streams else []
+    totals = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(3)]
+    torch.cuda.synchronize()
+
+    def compute(k):
+        """the shard's pipelines on input set k -> totals[k] (two sums over the shard)"""
+        main = torch.cuda.current_stream(dev)
+        if streams:
+            for st_, pipe, inp in zip(streams, pipes, inputs[k]):
+                st_.wait_stream(main)
+                with torch.cuda.stream(st_):
+                    pipe.step(*inp)
+            for st_ in streams:
+                main.wait_stream(st_)
+        else:
+            for pipe, inp in zip(pipes, inputs[k]):
+                pipe.step(*inp)
+        totals[k].zero_()
+        for pipe in pipes:
+            totals[k].add_(pipe.losses)
 
     pipes[0]._lib.use_debug_hooks(True)
     n0 = pipes[0].lib.frn_kernel_launches()
-    step()
+    compute(0)
     kernels_per_step = int(pipes[0].lib.frn_kernel_launches() - n0)
     torch.cuda.synchronize()
     pipes[0]._lib.use_debug_hooks(False)
+
+    use_graph = not args.no_graph
+    graphs = [None] * 3
+    if use_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            with torch.cuda.stream(side):
+                compute(0)
+                side.synchronize()
+                for k in range(3):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        compute(k)
+                    graphs[k] = g
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({e}); direct launches", file=sys.stderr)
+            graphs, use_graph = [None] * 3, False
+
+    def step(k=0):
+        if use_graph:
+            graphs[k].replay()
+        else:
+            compute(k)
+        if world > 1:
+            dist.all_reduce(totals[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(30.0)
     sampler.samples.clear()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     sampler.stop_flag = True
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    loss_check = total.cpu().tolist()
 
-    # end to end: the shard's am / lm / symbols / boundary from pinned host memory every step, loss read back
-    host_inputs = [[x.cpu().pin_memory() for x in inp] for inp in inputs]
-    host_out = torch.empty(2, dtype=torch.float32).pin_memory()
-    n_e2e = max(3, min(args.steps, 10))
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def e2e_step():
-        for inp, hin in zip(inputs, host_inputs):
-            for d, h in zip(inp, hin):
-                d.copy_(h, non_blocking=True)
-        step()
-        host_out.copy_(total, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return float(host_out[0])
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    loss_check = totals[0].cpu().tolist()
 
-    e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # ---- end to end: the shard's inputs from one pinned block every step (one cudaMemcpyAsync into one of two
+    #      landing blocks on a copy stream, overlapping the previous step's kernels), the two sums read back ----
+    copy_stream = torch.cuda.Stream(dev)
+    host_outs = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    step_done = [torch.cuda.Event() for _ in range(2)]
+    read_back = []
+    n_e2e = max(3, min(args.steps, 20))
+
+    def e2e_step(i):
+        k = i % 2
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(step_done[k])
+            dev_blocks[1 + k].copy_(host_block, non_blocking=True)
+            h2d_done[k].record(copy_stream)
+        cur.wait_event(h2d_done[k])
+        step(1 + k)
+        host_outs[k].copy_(totals[1 + k], non_blocking=True)
+        step_done[k].record(cur)
+        if i > 0:
+            step_done[(i - 1) % 2].synchronize()
+            read_back.append(float(host_outs[(i - 1) % 2][0]))
+
+    for ev in step_done:
+        ev.record(torch.cuda.current_stream(dev))
+    for i in range(2):
+        e2e_step(i)
+    step_done[1].synchronize()
+    barrier()
+    read_back.clear()
     e0.record()
-    for _ in range(n_e2e):
-        assert np.isfinite(e2e_step())
+    for i in range(n_e2e):
+        e2e_step(i)
+    step_done[(n_e2e - 1) % 2].synchronize()
+    read_back.append(float(host_outs[(n_e2e - 1) % 2][0]))
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / n_e2e
-    h2d = sum(x.numel() * x.element_size() for hin in host_inputs for x in hin)
+    barrier()
+    assert len(read_back) == n_e2e and all(np.isfinite(read_back))
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+    # the bare copies alone (ceiling of any end-to-end pipeline on this host)
+    with torch.cuda.stream(copy_stream):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dev_blocks[1].copy_(host_block, non_blocking=True)
+        c0.record(copy_stream)
+        for i in range(10):
+            dev_blocks[1 + i % 2].copy_(host_block, non_blocking=True)
+        c1.record(copy_stream)
+    barrier()
+    h2d_ceiling_ms = max_over_ranks(c0.elapsed_time(c1) / 10)
+
+    # ---- per-stage device times of the largest bucket -> roofline of the dominant HBM-bound kernel ----
+    big = max(range(nb), key=lambda j: pipes[j].B * pipes[j].T)
+    stage_ms = {}
+    for name, nbytes, fn in pipes[big].stages(*inputs[0][big]):
+        fn(); fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        stage_ms[name] = (a.elapsed_time(b) / 10, nbytes)
     frames = int(bd_all[mine, 3].sum())
     padded = int(sum(bk["padded_frames"] for bk in buckets))
     if rank == 0:
-        emit({
+        peak, peak_src = measured_peaks()
+        kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8, 1, 1, 0>", "add_joiner": "add_kernel",
+                           "do_pruning+add_joiner": "do_pruning_vec_kernel<8, 1, 1, 1>"}
+        hbm = {k: v for k, v in stage_ms.items() if k in kernel_of_stage}
+        dom = max(hbm, key=lambda k: hbm[k][0])
+        dom_ms, dom_bytes = hbm[dom]
+        line = {
             "metric": METRIC, "value": B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "c5: ragged batch B=256 (T_b 200-1500, S_b 20-400) C=500 s_range=5 fp32 regular sum, "
                                    "full pruned pipeline per length bucket, batch sharded by utterance over the ranks",
-                       "launch": "direct", "sharding": f"greedy LPT on lattice cells, {len(mine)} utterances on rank 0",
+                       "launch": "cuda_graph" if use_graph else "direct",
+                       "streams": f"{nb} bucket stream(s) per rank" if streams else "1 stream per rank",
+                       "sharding": f"greedy LPT on lattice cells, {len(mine)} utterances on rank 0",
                        "buckets_rank0": [{"utterances": int(len(bk["idx"])), "T_max": bk["T_max"], "S_max": bk["S_max"]}
                                          for bk in buckets],
                        "frames_rank0": frames, "padded_frames_rank0": padded,
                        "l2": "every step streams > 1 GB per rank (> 126 MB L2)", "loss_check": loss_check},
             "clocks": sampler.summary(),
-            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms, "pipelining": "none (copy, compute, read back)"},
+            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total_bytes, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms,
+                    "pipelining": "H2D of step i+1 (one cudaMemcpyAsync of the rank's pinned block) overlaps the kernels of "
+                                  "step i (2 landing blocks); loss of every step read on the host",
+                    "h2d_ceiling": {"ms_per_step": h2d_ceiling_ms, "gbs_per_gpu": total_bytes / (h2d_ceiling_ms * 1e-3) / 1e9,
+                                    "what": "the same per-step copies alone, all ranks at once (max over ranks)"},
+                    "frac_of_h2d_ceiling": h2d_ceiling_ms / e2e_ms},
             "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step,
-        })
+            "roofline": {"bound": "hbm", "kernel": kernel_of_stage[dom] + f" (largest bucket of rank 0: B={pipes[big].B} "
+                                                                          f"T={pipes[big].T} S={pipes[big].S})",
+                         "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
+            "stages_ms_largest_bucket": {k: round(v[0], 4) for k, v in stage_ms.items()},
+        }
+        if world == 1 and not args.no_cpu:
+            base, _ = cpu_bench("c5", 2, 1, 2)
+            line["cpu_baseline"] = base
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -935,6 +1186,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--buckets", type=int, default=4, help="c5: length buckets per rank (1 = pad the shard to its maxima)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--c5-streams", type=int, default=1, help="c5: 1 = every length bucket on its own CUDA stream (default), 0 = one stream")
     ap.add_argument("--streams", type=int, default=1,
                     help="run a step as this many independent sub-batches on separate CUDA streams")
     ap.add_argument("--overlap", action="store_true",
@@ -947,6 +1199,10 @@ def main():
                     help="do_rnnt_pruning and the additive joiner as two passes (frn_do_pruning, frn_add_joiner) "
                          "instead of the one-pass frn_do_pruning_add_joiner")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-training", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--profile-training", action="store_true",
+                    help="the timed step IS the training step (step + A9 + pruning gradient): for ncu launch lists; not a headline run")
+    ap.add_argument("--fp32-logits", action="store_true", help="c4 with float32 joiner logits (default there: bf16)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA op")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

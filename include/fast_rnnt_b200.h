@@ -151,6 +151,49 @@ int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbo
                           size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Batch sharded by utterance over several GPUs.  Every kernel works per utterance, with one
+ * exception: rnnt_loss_smoothed's unigram is the mean of softmax(lm rows) over the WHOLE batch
+ * (rnnt_loss.py:1279-1280).  For results identical to the unsharded batch:
+ *   1. frn_smoothed_unigram_sums: sums[c] = sum over this rank's B (S+1) lm rows of softmax(row)[c], c < C,
+ *      and sums[C] = B (S+1)  (workspace: frn_simple_logprobs_workspace_bytes(B, S, 1, C));
+ *   2. the caller all-reduces (sum) the C+1 floats over the ranks (frn_allreduce_sum or its own collective);
+ *   3. the *_sharded entry points take the all-reduced sums (NULL = this rank's batch is the whole batch).
+ * Backward: d loss / d unigram has to be summed over the ranks before it reaches the lm rows -
+ * frn_smoothed_loss_bwd_sharded(phase 1) leaves this rank's share in du [C], the caller all-reduces du,
+ * phase 2 (same arguments and workspace) completes lm_grad.  phase 0 = both on one rank.
+ * (Ranks must pad lm to the same S for the padded rows to enter the mean as they do unsharded.)
+ * ---------------------------------------------------------------------- */
+int frn_smoothed_unigram_sums(const float *lm, int B, int S, int C, float *sums,
+                              void *workspace, size_t workspace_bytes, void *stream);
+int frn_simple_logprobs_sharded(const float *lm, const float *am, const int32_t *symbols,
+                                const int32_t *boundary, int B, int S, int T, int C,
+                                int termination_symbol, int rnnt_type, int smoothed,
+                                float lm_only_scale, float am_only_scale,
+                                const float *unigram_sums, float *px, float *py,
+                                void *workspace, size_t workspace_bytes, void *stream);
+int frn_simple_loss_sharded(const float *lm, const float *am, const int32_t *symbols,
+                            const int32_t *boundary, int B, int S, int T, int C,
+                            int termination_symbol, int rnnt_type, int smoothed,
+                            float lm_only_scale, float am_only_scale,
+                            const float *unigram_sums, float delay_penalty,
+                            int calc_gradients, float *scores, float *px_grad,
+                            float *py_grad, void *workspace, size_t workspace_bytes,
+                            void *stream);
+int frn_smoothed_loss_bwd_sharded(const float *lm, const float *am, const int32_t *symbols,
+                                  const int32_t *boundary, const float *px_grad,
+                                  const float *py_grad, const float *scores_grad, int B,
+                                  int S, int T, int C, int termination_symbol,
+                                  int rnnt_type, float lm_only_scale, float am_only_scale,
+                                  const float *unigram_sums, float *du, int phase,
+                                  float *am_grad, float *lm_grad, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+/* In-place sum all-reduce of n floats over an NCCL communicator the caller owns (ncclComm_t as void*), enqueued
+ * on `stream` - the scalar of reduction='sum'|'mean' and the C+1 / C floats above.  libnccl.so.2 is bound lazily
+ * with dlopen (no link-time dependency; the instance already loaded in the process is the one found);
+ * FRN_EUNSUPPORTED if it cannot be bound, FRN_ECUDA if NCCL reports an error. */
+int frn_allreduce_sum(float *buf, size_t n, void *nccl_comm, void *stream);
+
+/* ------------------------------------------------------------------------
  * A5. get_rnnt_prune_ranges (rnnt_loss.py:647-761): ranges [B][T][R_out],
  * R_out = (s_range > S ? S+1 : s_range), see frn_prune_ranges_width().
  * ---------------------------------------------------------------------- */

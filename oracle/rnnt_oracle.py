@@ -159,10 +159,22 @@ def get_rnnt_logprobs(lm, am, symbols, termination_symbol, rnnt_type="regular",
     return px.astype(dtype), py.astype(dtype)
 
 
+def smoothed_unigram_sums(lm, dtype=np.float64):
+    """One shard's share of the batch-global unigram of rnnt_loss.py:1279-1280: the column sums of
+    softmax(lm rows) [C] and the row count.  Summed over the shards of a batch (an all-reduce on the GPUs) and
+    handed to get_rnnt_logprobs_smoothed / rnnt_loss_smoothed as `unigram_sums`, every shard sees the unigram of
+    the whole batch."""
+    dtype = np.dtype(dtype).type
+    lm = np.asarray(lm, dtype=dtype)
+    probs = np.exp(lm - lm.max(axis=2, keepdims=True))
+    r = probs / probs.sum(axis=2, keepdims=True)
+    return r.sum(axis=(0, 1)), float(lm.shape[0] * lm.shape[1])
+
+
 def get_rnnt_logprobs_smoothed(lm, am, symbols, termination_symbol,
                                lm_only_scale=0.1, am_only_scale=0.1,
                                boundary=None, rnnt_type="regular",
-                               dtype=np.float32):
+                               dtype=np.float32, unigram_sums=None):
     """rnnt_loss.py:1132-1367 (same D1 decision as get_rnnt_logprobs)."""
     assert rnnt_type in ("regular", "modified", "constrained")
     dtype = np.dtype(dtype).type
@@ -175,6 +187,9 @@ def get_rnnt_logprobs_smoothed(lm, am, symbols, termination_symbol,
     lmonly = lm_probs.sum(axis=2, keepdims=True)                       # :1276
     unigram = (lm_probs / lmonly).mean(axis=(0, 1), keepdims=True,
                                        dtype=dtype) + dtype(TINY)      # :1279
+    if unigram_sums is not None:                                       # sharded batch: the global mean
+        sums, count = unigram_sums
+        unigram = (np.asarray(sums, dtype=dtype) / dtype(count)).reshape(1, 1, C) + dtype(TINY)
     amonly = np.log(am_probs.reshape(-1, C) @ unigram.reshape(C)
                     ).reshape(B, T, 1) + am_max                        # :1281
     amonly = np.swapaxes(amonly, 1, 2).astype(dtype)                   # [B,1,T]
@@ -257,11 +272,11 @@ def rnnt_loss_simple(lm, am, symbols, termination_symbol, boundary,
 def rnnt_loss_smoothed(lm, am, symbols, termination_symbol, lm_only_scale=0.1,
                        am_only_scale=0.1, boundary=None, rnnt_type="regular",
                        delay_penalty=0.0, reduction="mean",
-                       calc_gradients=False, dtype=np.float32):
+                       calc_gradients=False, dtype=np.float32, unigram_sums=None):
     """rnnt_loss.py:1369-1494."""
     px, py = get_rnnt_logprobs_smoothed(lm, am, symbols, termination_symbol,
                                         lm_only_scale, am_only_scale, boundary,
-                                        rnnt_type, dtype)
+                                        rnnt_type, dtype, unigram_sums)
     return _loss_from_logprobs(px, py, boundary, delay_penalty, reduction,
                                calc_gradients, dtype)
 

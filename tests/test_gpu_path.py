@@ -237,7 +237,7 @@ def test_simple_loss_am_lm_gradients(rnnt_type):
     assert_close(lm_t.grad.cpu().numpy(), o_lm1, GRAD_RTOL, 2e-5, "autograd lm grad")
 
 
-@pytest.mark.parametrize("C", [500, 37])          # vector path (C % 4 == 0) and scalar path
+@pytest.mark.parametrize("C", [500, 37, 504])     # vector path (C % 4 == 0), scalar path, bf16 vector path (C % 8 == 0)
 def test_fused_joiner_equals_pruning_plus_add(C):
     """frn_pruned_add_joiner (SURVEY 8f-2) == do_rnnt_pruning followed by the addition, bit for bit;
     out-of-range band entries contribute zeros like tf.gather on GPU."""
@@ -255,6 +255,9 @@ def test_fused_joiner_equals_pruning_plus_add(C):
     fused = frn.pruned_add_joiner(am_d, lm_d, rg_d)
     assert torch.equal(fused, am_p + lm_p)
     assert torch.equal(fused[0, 3, 4], am_d[0, 3])
+    # bf16 output (BASELINE configs[3]): the float32 sum rounded to nearest even, vector (C % 8 == 0) or scalar kernel
+    fused16 = frn.pruned_add_joiner(am_d, lm_d, rg_d, dtype=torch.bfloat16)
+    assert fused16.dtype == torch.bfloat16 and torch.equal(fused16, (am_p + lm_p).to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("C,R", [(500, 5), (37, 5), (64, 11)])   # one-pass kernel; scalar and wide-band fall-backs

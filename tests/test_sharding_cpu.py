@@ -147,3 +147,48 @@ def test_group_reduction_on_the_autograd_path(reduction):
     for rank, loss, grad in got:
         np.testing.assert_allclose(loss, want, rtol=1e-12)
         np.testing.assert_allclose(grad, [scale] * (3 if rank == 0 else 5), rtol=1e-12)
+
+
+def _smoothed_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import rnnt_oracle as orc
+    from tf_fast_rnnt.sharding import partition_batch
+    am, lm, sym, term, bd = make_inputs(23, 6, 30, 8, 12, ragged=True)
+    mine = partition_batch(bd, world)[rank]
+    # the protocol of include/fast_rnnt_b200.h "batch sharded by utterance": local sums -> all-reduce -> loss
+    sums, count = orc.smoothed_unigram_sums(lm[mine])
+    buf = torch.from_numpy(np.concatenate([sums, [count]]))
+    dist.all_reduce(buf)
+    losses = orc.rnnt_loss_smoothed(lm[mine], am[mine], sym[mine], term, 0.25, 0.2, bd[mine], "regular", 0.0, "none",
+                                    dtype=np.float64, unigram_sums=(buf[:-1].numpy(), float(buf[-1])))
+    out.put((mine.tolist(), losses.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_smoothed_loss_with_am_only_scale_equals_unsharded():
+    """rnnt_loss_smoothed's unigram is batch-global (rnnt_loss.py:1279-1280): with the C+1 unigram sums
+    all-reduced before the am-only terms, two ranks reproduce the unsharded per-utterance losses
+    (am_only_scale = 0.2) to 1e-6."""
+    from oracle import rnnt_oracle as orc
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_smoothed_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    am, lm, sym, term, bd = make_inputs(23, 6, 30, 8, 12, ragged=True)
+    want = orc.rnnt_loss_smoothed(lm, am, sym, term, 0.25, 0.2, bd, "regular", 0.0, "none", dtype=np.float64)
+    got = np.zeros(6)
+    for _ in range(2):
+        idx, losses = out.get()
+        got[idx] = losses
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    # and without the exchange the shards do NOT agree with the batch (the coupling is real)
+    half = orc.rnnt_loss_smoothed(lm[:3], am[:3], sym[:3], term, 0.25, 0.2, bd[:3], "regular", 0.0, "none", dtype=np.float64)
+    assert np.abs(half - want[:3]).max() > 1e-6 * np.abs(want[:3]).max()

@@ -99,10 +99,14 @@ int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, in
                           stream);
   if (g.P > kMaxRowsDp) return FRN_EUNSUPPORTED;
   DpWorkspace w = carve_dp(workspace, g);
-  FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
-  FRN_TRY(launch_chain(boundary, g, w, calc_gradients != 0, stream));
-  FRN_TRY(launch_finalize_dense(boundary, g, w, ans, calc_gradients ? px_grad : nullptr,
-                                calc_gradients ? py_grad : nullptr, stream));
+  // FRN_MI_PHASE = 1 / 2 / 3 (debug-hooks build): only the skew / recursion / read-out kernel, on the planes a
+  // previous full call left in the workspace - how the benchmark times the dependency-chain kernel alone
+  const int phase = debug_env_int("FRN_MI_PHASE", 0);
+  if (phase == 0 || phase == 1) FRN_TRY(launch_skew_dense(px, py, boundary, g, w, 0.f, stream));
+  if (phase == 0 || phase == 2) FRN_TRY(launch_chain(boundary, g, w, calc_gradients != 0, stream));
+  if (phase == 0 || phase == 3)
+    FRN_TRY(launch_finalize_dense(boundary, g, w, ans, calc_gradients ? px_grad : nullptr,
+                                  calc_gradients ? py_grad : nullptr, stream));
   return FRN_OK;
 }
 
@@ -192,17 +196,38 @@ size_t frn_simple_logprobs_workspace_bytes(int B, int S, int T, int C) {
   return simple_stats_bytes(B, S, T, C);
 }
 
+int frn_allreduce_sum(float *buf, size_t n, void *nccl_comm, void *stream) {
+  FRN_REQUIRE(buf && n > 0 && nccl_comm);
+  return launch_allreduce_sum(buf, n, nccl_comm, static_cast<cudaStream_t>(stream));
+}
+
+int frn_smoothed_unigram_sums(const float *lm, int B, int S, int C, float *sums, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+  FRN_REQUIRE(B > 0 && S >= 0 && C >= 1 && lm && sums);
+  if (!workspace || !aligned256(workspace) || workspace_bytes < simple_stats_bytes(B, S, 1, C)) return FRN_EWORKSPACE;
+  return launch_unigram_sums(lm, B, S, C, workspace, sums, static_cast<cudaStream_t>(stream));
+}
+
 int frn_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary, int B,
                         int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
                         float lm_only_scale, float am_only_scale, float *px, float *py, void *workspace,
                         size_t workspace_bytes, void *stream) {
+  return frn_simple_logprobs_sharded(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                     lm_only_scale, am_only_scale, nullptr, px, py, workspace, workspace_bytes, stream);
+}
+
+int frn_simple_logprobs_sharded(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                                int B, int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
+                                float lm_only_scale, float am_only_scale, const float *unigram_sums, float *px,
+                                float *py, void *workspace, size_t workspace_bytes, void *stream) {
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px && py);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
   FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
   if (!workspace || !aligned256(workspace) || workspace_bytes < simple_stats_bytes(B, S, T, C)) return FRN_EWORKSPACE;
   return launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                lm_only_scale, am_only_scale, px, py, workspace, static_cast<cudaStream_t>(stream));
+                                lm_only_scale, am_only_scale, px, py, workspace, static_cast<cudaStream_t>(stream),
+                                nullptr, smoothed ? unigram_sums : nullptr);
 }
 
 // ------------------------------------------------------------------ A1/A2 + A3 + A4
@@ -235,6 +260,17 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
                     float lm_only_scale, float am_only_scale, float delay_penalty, int calc_gradients,
                     float *scores, float *px_grad, float *py_grad, void *workspace, size_t workspace_bytes,
                     void *stream_) {
+  return frn_simple_loss_sharded(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                 lm_only_scale, am_only_scale, nullptr, delay_penalty, calc_gradients, scores, px_grad,
+                                 py_grad, workspace, workspace_bytes, stream_);
+}
+
+int frn_simple_loss_sharded(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary, int B,
+                            int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
+                            float lm_only_scale, float am_only_scale, const float *unigram_sums, float delay_penalty,
+                            int calc_gradients, float *scores, float *px_grad, float *py_grad, void *workspace,
+                            size_t workspace_bytes, void *stream_) {
+  if (!smoothed) unigram_sums = nullptr;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && scores);
@@ -254,13 +290,13 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
     // 4 launches: row statistics, normaliser (arcs straight into the recursion's plane), recursion, read-out
     const ArcPlaneOut arcs{dw.XY, g.P, g.Dn, g.k, dp};
     FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                   lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs));
+                                   lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs, unigram_sums));
     FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
     return launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
                                  calc_gradients ? py_grad : nullptr, stream);
   }
   FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                 lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream));
+                                 lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream, nullptr, unigram_sums));
   if (scan)
     return launch_scan_dp(w.px, w.py, boundary, B, S, T, T1, dp, calc_gradients != 0, w.dp, scores, px_grad, py_grad,
                           stream);
@@ -294,6 +330,18 @@ int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbo
                           const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T,
                           int C, int termination_symbol, int rnnt_type, float lm_only_scale, float am_only_scale,
                           float *am_grad, float *lm_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  return frn_smoothed_loss_bwd_sharded(lm, am, symbols, boundary, px_grad, py_grad, scores_grad, B, S, T, C,
+                                       termination_symbol, rnnt_type, lm_only_scale, am_only_scale, nullptr, nullptr, 0,
+                                       am_grad, lm_grad, workspace, workspace_bytes, stream);
+}
+
+int frn_smoothed_loss_bwd_sharded(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                                  const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S,
+                                  int T, int C, int termination_symbol, int rnnt_type, float lm_only_scale,
+                                  float am_only_scale, const float *unigram_sums, float *du, int phase,
+                                  float *am_grad, float *lm_grad, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
+  FRN_REQUIRE(phase >= 0 && phase <= 2 && (phase == 0 || (unigram_sums && du)));
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px_grad && py_grad && am_grad && lm_grad);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
@@ -302,7 +350,7 @@ int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbo
     return FRN_EWORKSPACE;
   return launch_simple_bwd(lm, am, symbols, boundary, px_grad, py_grad, scores_grad, B, S, T, C, termination_symbol,
                            rnnt_type, 1, lm_only_scale, am_only_scale, am_grad, lm_grad, workspace,
-                           static_cast<cudaStream_t>(stream));
+                           static_cast<cudaStream_t>(stream), unigram_sums, du, phase);
 }
 
 // ------------------------------------------------------------------ A7 / A8

@@ -33,6 +33,8 @@ int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ra
 }  // namespace frn
 
 namespace frn {
+// collective.cu
+int launch_allreduce_sum(float *buf, size_t n, void *comm, cudaStream_t stream);
 // logprobs_simple.cu
 size_t simple_stats_bytes(int B, int S, int T, int C);
 // arcs != nullptr: the arcs go straight into the recursion's diagonal-major plane instead of px/py
@@ -41,15 +43,18 @@ bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnn
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
-                           cudaStream_t stream, const ArcPlaneOut *arcs = nullptr);
+                           cudaStream_t stream, const ArcPlaneOut *arcs = nullptr,
+                           const float *unigram_sums = nullptr);
 int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const float *unigram_sums = nullptr);
+int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, float *sums, cudaStream_t stream);
 // simple_bwd.cu
 size_t simple_bwd_workspace_bytes(int B, int S, int T, int C);
 int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                       const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T, int C,
                       int term, int rnnt_type, int smoothed, float lm_only_scale, float am_only_scale, float *am_grad,
-                      float *lm_grad, void *workspace, cudaStream_t stream);
+                      float *lm_grad, void *workspace, cudaStream_t stream, const float *unigram_sums = nullptr,
+                      float *du_io = nullptr, int phase = 0);
 // logprobs_pruned.cu
 int launch_pruned_lse(const void *logits, int dtype, const int32_t *symbols, const int32_t *ranges, int B, int S,
                       int T, int R, int C, int term, float *pxc, float *pyc, float *lse, cudaStream_t stream);

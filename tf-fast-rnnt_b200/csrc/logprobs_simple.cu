@@ -73,13 +73,17 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
 
 // unigram[c] = mean_rows( exp(lm-lmmax)/lmsum ) + tiny  (rnnt_loss.py:1279-1280),
 // deterministic column reduction: block = 32 columns x 8 row-striding warps.
+// Batch sharded by utterance: the mean runs over the GLOBAL batch, so the column sums and the row
+// count are exposed (`sums_out` [C+1], frn_smoothed_unigram_sums), all-reduced by the caller and handed back
+// (`ext_sums`): then unigram = ext_sums[c] / ext_sums[C] + tiny and no row is read here.
 __global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const float *lmmax, const float *lmsum,
-                                                      int rows, int C, float *unigram, float *log_unigram) {
+                                                      int rows, int C, const float *ext_sums, float *sums_out,
+                                                      float *unigram, float *log_unigram) {
   __shared__ float part[8][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  if (c < C)
+  if (c < C && !ext_sums)
     for (int r = w; r < rows; r += 8) acc += expf(lm[(size_t)r * C + c] - lmmax[r]) / lmsum[r];
   part[w][lane] = acc;
   __syncthreads();
@@ -87,7 +91,12 @@ __global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const flo
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += part[j][lane];
-    const float u = s / (float)rows + tiny_f32();
+    if (sums_out) {
+      sums_out[c] = s;
+      if (c == 0) sums_out[C] = (float)rows;
+      return;
+    }
+    const float u = (ext_sums ? ext_sums[c] / ext_sums[C] : s / (float)rows) + tiny_f32();
     unigram[c] = u;
     log_unigram[c] = logf(u);
   }
@@ -237,7 +246,7 @@ size_t simple_stats_bytes(int B, int S, int T, int C) {
 // The statistics block of the smoothed log-probs on its own (used again by the backward pass):
 // lmmax, lmsum, ammax, amonly, unigram, log unigram.
 int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const float *unigram_sums) {
   const int S1 = S + 1;
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
@@ -247,8 +256,22 @@ int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w);
   count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax);
-  count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
+  count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
+                                                                 unigram, logu);
   count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
+  return check_launch();
+}
+
+// sums[c] = sum over the B (S+1) lm rows of softmax(lm row)[c], sums[C] = B (S+1): this rank's share of the
+// batch-global unigram of rnnt_loss.py:1279-1280
+int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, float *sums, cudaStream_t stream) {
+  const int S1 = S + 1;
+  char *w = static_cast<char *>(stats_ws);
+  float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+  float *lmsum = reinterpret_cast<float *>(w);
+  count_launch(), rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, lm, 0, C, lmmax, lmsum, lmmax);
+  count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, nullptr, sums, nullptr,
+                                                                 nullptr);
   return check_launch();
 }
 
@@ -263,7 +286,7 @@ bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnn
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
-                           cudaStream_t stream, const ArcPlaneOut *arcs) {
+                           cudaStream_t stream, const ArcPlaneOut *arcs, const float *unigram_sums) {
   const int S1 = S + 1;
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
@@ -275,7 +298,8 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax,
                                                                                  smoothed ? lmsum : nullptr, ammax);
   if (smoothed) {
-    count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram, logu);
+    count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
+                                                                   unigram, logu);
     count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
   }
   int rc = check_launch();

@@ -250,41 +250,101 @@ __global__ void __launch_bounds__(256) do_pruning_bwd_am_kernel(const float *am_
     am_grad[(size_t)bt * C + c] = acc;
   }
 }
+// vector path: one CTA of 128 threads per (b,t), thread <-> one float4 column, the R rows loaded before the sum
+template <int RMAX>
+__global__ void __launch_bounds__(128) do_pruning_bwd_am_vec_kernel(const float *am_p_grad, int R, int C4,
+                                                                    float *am_grad) {
+  const int bt = blockIdx.x;
+  const float4 *src = reinterpret_cast<const float4 *>(am_p_grad) + (size_t)bt * R * C4;
+  float4 *dst = reinterpret_cast<float4 *>(am_grad) + (size_t)bt * C4;
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+    float4 v[RMAX];
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) v[i] = ld_stream_f4(src + (size_t)i * C4 + c);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+    dst[c] = acc;
+  }
+}
 
 // A6 backward, lm side: lm_grad[b,s,:] = sum over (t,i) with ranges[b,t,i]==s  (the scatter-add TF autodiff
 // derives for the gather of rnnt_loss.py:807-811, as a gather: deterministic, no atomics).  One CTA per (b,s):
-// the T x R indices of the utterance are tested ONCE, cooperatively, into a per-frame hit mask in shared memory
-// (MASKED; any index pattern, R <= 32), then every thread sums its columns over the hits in (t, i) order.
-// Wider bands / very long utterances walk the indices per element.
-template <bool MASKED>
-__global__ void __launch_bounds__(256) do_pruning_bwd_lm_kernel(const float *lm_p_grad, const int32_t *ranges,
-                                                                int B, int S1, int T, int R, int C,
-                                                                float *lm_grad) {
-  extern __shared__ uint32_t hit_mask[];      // [T]
+//   1. the T x R indices of the utterance are tested once, cooperatively (any index pattern: hand-made,
+//      repeated or non-consecutive ranges included): every thread takes a contiguous run of frames, counts its
+//      hits, a block-wide exclusive scan gives its slot, and it writes its hits - the list is in (t,i) order;
+//   2. every thread sums its float4 column over the list, four loads in flight.
+// Shapes the list does not fit (or C % 4 != 0) walk the indices per element (LIST = false).
+constexpr int kBwdLmThreads = 256;       // two groups of 128 column threads; the groups split the hit list
+template <bool LIST>
+__global__ void __launch_bounds__(kBwdLmThreads) do_pruning_bwd_lm_kernel(const float *lm_p_grad, const int32_t *ranges,
+                                                                          int B, int S1, int T, int R, int C,
+                                                                          float *lm_grad) {
+  extern __shared__ int32_t hit_list[];       // [T * R] row offsets t * R + i, then (16-byte aligned) the partial sums
+  __shared__ int warp_tot[kBwdLmThreads / 32];
   const int bs = blockIdx.x;
   const int b = bs / S1, s = bs - b * S1;
   const int32_t *rg = ranges + (size_t)b * T * R;
   const float *src = lm_p_grad + (size_t)b * T * R * C;
-  if (MASKED) {
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-      uint32_t m = 0;
-      for (int i = 0; i < R; ++i) m |= (rg[(size_t)t * R + i] == s) ? (1u << i) : 0u;
-      hit_mask[t] = m;
+  if (LIST) {
+    constexpr int NT = kBwdLmThreads, NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int fpt = (T + NT - 1) / NT;                   // frames per thread
+    const int t_lo = min(tid * fpt, T), t_hi = min(t_lo + fpt, T);
+    int cnt = 0;
+    for (int e = t_lo * R; e < t_hi * R; ++e) cnt += (rg[e] == s);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
+    if (lane == 31) warp_tot[w] = incl;
     __syncthreads();
-  }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < T; ++t) {
-      if (MASKED) {
-        for (uint32_t m = hit_mask[t]; m; m &= m - 1)
-          acc += src[((size_t)t * R + (__ffs(m) - 1)) * C + c];
-      } else {
-        for (int i = 0; i < R; ++i)
-          if (rg[(size_t)t * R + i] == s) acc += src[((size_t)t * R + i) * C + c];
+    int base = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { base += (j < w) ? warp_tot[j] : 0; total += warp_tot[j]; }
+    int slot = base + incl - cnt;
+    for (int e = t_lo * R; e < t_hi * R; ++e)
+      if (rg[e] == s) hit_list[slot++] = e;
+    __syncthreads();
+    // A lattice row the band rests on for hundreds of frames (the last rows of an utterance, typically) has
+    // hundreds of hits: the two thread groups take alternate runs of 8 hits, 8 loads in flight per thread.
+    const int C4 = C >> 2;
+    const int grp = tid >> 7, col = tid & 127;
+    const float4 *src4 = reinterpret_cast<const float4 *>(src);
+    float4 *dst = reinterpret_cast<float4 *>(lm_grad) + (size_t)bs * C4;
+    float4 *partial = reinterpret_cast<float4 *>(hit_list + ((T * R + 3) & ~3));     // [128] group 1's sums
+    for (int c0 = 0; c0 < C4; c0 += 128) {
+      const int c = c0 + col;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C4) {
+        for (int k0 = grp * 8; k0 < total; k0 += 16) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = (k0 + j < total) ? ld_stream_f4(src4 + (size_t)hit_list[k0 + j] * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
       }
+      if (grp == 1) partial[col] = acc;
+      __syncthreads();
+      if (grp == 0 && c < C4) {
+        const float4 o = partial[col];
+        dst[c] = make_float4(acc.x + o.x, acc.y + o.y, acc.z + o.z, acc.w + o.w);
+      }
+      __syncthreads();
     }
-    lm_grad[(size_t)bs * C + c] = acc;
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float acc = 0.f;
+      for (int e = 0; e < T * R; ++e)
+        if (rg[e] == s) acc += src[(size_t)e * C + c];
+      lm_grad[(size_t)bs * C + c] = acc;
+    }
   }
 }
 
@@ -392,6 +452,48 @@ __global__ void __launch_bounds__(32) broadcast_am_kernel(const float *am, float
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// bfloat16 output of the fused joiner (BASELINE configs[3]: bf16 joiner logits): thread <-> 8 columns, two
+// float4 of the am row and of every lm row in, one 16-byte store of 8 bf16 out
+template <int RMAX>
+__global__ void __launch_bounds__(128) pruned_add_joiner_vec_bf16_kernel(const float *am, const float *lm,
+                                                                         const int32_t *ranges, int T, int S1, int R,
+                                                                         int C8, __nv_bfloat16 *logits) {
+  const int bt = blockIdx.x;
+  const int b = bt / T;
+  const int32_t *rg = ranges + (size_t)bt * R;
+  const float4 *am_row = reinterpret_cast<const float4 *>(am) + (size_t)bt * C8 * 2;
+  uint4 *out = reinterpret_cast<uint4 *>(logits) + (size_t)bt * R * C8;
+  const float4 *lm_b = reinterpret_cast<const float4 *>(lm) + (size_t)b * S1 * C8 * 2;
+  for (int c = threadIdx.x; c < C8; c += blockDim.x) {
+    const float4 a0 = __ldg(am_row + 2 * c), a1 = __ldg(am_row + 2 * c + 1);
+    float4 l0[RMAX], l1[RMAX];
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      if (i < R) {
+        const int s = rg[i];
+        const bool ok = s >= 0 && s < S1;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        l0[i] = ok ? __ldg(lm_b + ((size_t)s * C8 + c) * 2) : z;
+        l1[i] = ok ? __ldg(lm_b + ((size_t)s * C8 + c) * 2 + 1) : z;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+      if (i < R) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(a0.x + l0[i].x, a0.y + l0[i].y);
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(a0.z + l0[i].z, a0.w + l0[i].w);
+        const __nv_bfloat162 p2 = __floats2bfloat162_rn(a1.x + l1[i].x, a1.y + l1[i].y);
+        const __nv_bfloat162 p3 = __floats2bfloat162_rn(a1.z + l1[i].z, a1.w + l1[i].w);
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t *>(&p0); v.y = *reinterpret_cast<const uint32_t *>(&p1);
+        v.z = *reinterpret_cast<const uint32_t *>(&p2); v.w = *reinterpret_cast<const uint32_t *>(&p3);
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + (size_t)i * C8 + c), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -487,17 +589,31 @@ int launch_do_pruning_add(const float *am, const float *lm, const int32_t *range
 int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const int32_t *ranges, int B, int S,
                           int T, int R, int C, float *am_grad, float *lm_grad, cudaStream_t stream) {
   const int BT = B * T;
+  auto aligned16 = [](const void *a, const void *b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+  };
   if (am_grad) {
-    count_launch(), do_pruning_bwd_am_kernel<<<(BT + 7) / 8, 256, 0, stream>>>(am_p_grad, BT, R, C, am_grad);
+    if (C % 4 == 0 && R <= 8 && aligned16(am_p_grad, am_grad))
+      count_launch(), do_pruning_bwd_am_vec_kernel<8><<<BT, 128, 0, stream>>>(am_p_grad, R, C / 4, am_grad);
+    else
+      count_launch(), do_pruning_bwd_am_kernel<<<(BT + 7) / 8, 256, 0, stream>>>(am_p_grad, BT, R, C, am_grad);
     int rc = check_launch();
     if (rc) return rc;
   }
   if (lm_grad) {
-    if (R <= 32 && (size_t)T * sizeof(uint32_t) <= 48 * 1024)
-      count_launch(), do_pruning_bwd_lm_kernel<true><<<B * (S + 1), 256, (size_t)T * sizeof(uint32_t), stream>>>(
+    const size_t list_bytes = (((size_t)T * R + 3) & ~(size_t)3) * sizeof(int32_t) + 128 * sizeof(float4);
+    if (C % 4 == 0 && aligned16(lm_p_grad, lm_grad) && list_bytes <= 160 * 1024) {
+      if (list_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(do_pruning_bwd_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)list_bytes);
+        if (e != cudaSuccess) return note_cuda_error(e);
+      }
+      count_launch(), do_pruning_bwd_lm_kernel<true><<<B * (S + 1), kBwdLmThreads, list_bytes, stream>>>(
           lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
-    else
-      count_launch(), do_pruning_bwd_lm_kernel<false><<<B * (S + 1), 256, 0, stream>>>(lm_p_grad, ranges, B, S + 1, T, R, C, lm_grad);
+    } else {
+      count_launch(), do_pruning_bwd_lm_kernel<false><<<B * (S + 1), kBwdLmThreads, 0, stream>>>(lm_p_grad, ranges, B, S + 1,
+                                                                                              T, R, C, lm_grad);
+    }
     return check_launch();
   }
   return FRN_OK;
@@ -511,6 +627,12 @@ int launch_pruned_add_joiner(const float *am, const float *lm, const int32_t *ra
   if (out_dtype == FRN_F32 && vec && R <= 8) {
     count_launch(), pruned_add_joiner_vec_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 4,
                                                                          static_cast<float *>(logits));
+    return check_launch();
+  }
+  if (out_dtype == FRN_BF16 && C % 8 == 0 && R <= 8 &&
+      ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm) | reinterpret_cast<uintptr_t>(logits)) % 16 == 0)) {
+    count_launch(), pruned_add_joiner_vec_bf16_kernel<8><<<BT, 128, 0, stream>>>(am, lm, ranges, T, S + 1, R, C / 8,
+                                                                              static_cast<__nv_bfloat16 *>(logits));
     return check_launch();
   }
   if (out_dtype == FRN_F32)

@@ -119,26 +119,57 @@ __global__ void __launch_bounds__(256) bwd_contract_kernel(BwdParams p) {
   }
 }
 
-// scatter terms; one thread per output row, sequential over the other axis (deterministic, no atomics)
-__global__ void __launch_bounds__(128) bwd_scatter_am_kernel(BwdParams p) {
-  const int S1 = p.S + 1;
-  const int bt = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bt >= p.B * p.T) return;
-  const int b = bt / p.T, t = bt - b * p.T;
-  const float g = (p.scores_grad ? p.scores_grad[b] : 1.f) * (p.smoothed ? p.comb + p.am_scale : 1.f);
-  float *row = p.am_grad + (size_t)bt * p.C;
-  const int32_t *sym = p.symbols + (size_t)b * p.S;
-  float blank = 0.f;
-  for (int s = 0; s < S1; ++s) {
-    float gy = p.gpy[((size_t)b * S1 + s) * p.T + t];
-    if (s < p.S) {
-      const float gx = gpx_at(p, b, s, t);
-      row[sym[s]] += g * gx;
-      if (p.rnnt_type == FRN_CONSTRAINED) blank += gx;   // px[s,t] also contains py[s+1,t]
-    }
-    blank += gy;
+// Scatter terms of am_grad:  am_grad[t, sym_s] += g gpx[s,t],  am_grad[t, blank] += g sum_s gpy[s,t].
+// Block = 32 consecutive frames of one utterance x 8 warps: lanes along t (the occupation counts are read
+// coalesced), warp w takes the symbols s = w, w + 8, ...  A class can occur several times in an utterance: all its
+// occurrences are summed, in a fixed order, by the thread holding the LAST one, so every address of a row
+// receives exactly one addition from the symbol terms and one from the blank term - as fire-and-forget
+// red.global.add, no read-modify-write latency chain (the first version walked the 101 symbols of a row with
+// dependent load-add-store round trips: 89 us at the c2 shape).  Deterministic unless a symbol equals the blank id.
+__global__ void __launch_bounds__(256) bwd_scatter_am_kernel(BwdParams p) {
+  extern __shared__ int32_t sc_smem[];          // sym[S], prev[S] (previous occurrence or -1), tail[S]
+  __shared__ float blank_part[8][32];
+  const int S = p.S, S1 = p.S + 1;
+  int32_t *s_sym = sc_smem, *s_prev = sc_smem + S, *s_tail = sc_smem + 2 * S;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + lane;
+  const int32_t *sym = p.symbols + (size_t)b * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s_sym[i] = sym[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const int c = s_sym[i];
+    int prev = -1, tail = 1;
+    for (int j = i - 1; j >= 0; --j)
+      if (s_sym[j] == c) { prev = j; break; }
+    for (int j = i + 1; j < S; ++j)
+      if (s_sym[j] == c) { tail = 0; break; }
+    s_prev[i] = prev; s_tail[i] = tail;
   }
-  row[p.term] += g * blank;
+  __syncthreads();
+  const bool t_ok = t < p.T;
+  const float g = (p.scores_grad ? p.scores_grad[b] : 1.f) * (p.smoothed ? p.comb + p.am_scale : 1.f);
+  float *row = p.am_grad + ((size_t)b * p.T + (t_ok ? t : 0)) * p.C;
+  float blank = 0.f;
+  for (int s = w; s < S1; s += 8) {
+    if (t_ok) blank += p.gpy[((size_t)b * S1 + s) * p.T + t];
+    if (s < S && t_ok) {
+      const float gx = gpx_at(p, b, s, t);
+      if (p.rnnt_type == FRN_CONSTRAINED) blank += gx;   // px[s,t] also contains py[s+1,t]
+      if (s_tail[s]) {
+        float v = gx;
+        for (int j = s_prev[s]; j >= 0; j = s_prev[j]) v += gpx_at(p, b, j, t);
+        atomicAdd(row + s_sym[s], g * v);
+      }
+    }
+  }
+  blank_part[w][lane] = blank;
+  __syncthreads();
+  if (w == 0 && t_ok) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += blank_part[j][lane];
+    atomicAdd(row + p.term, g * tot);
+  }
 }
 
 __global__ void __launch_bounds__(256) bwd_scatter_lm_kernel(BwdParams p) {
@@ -164,7 +195,7 @@ __global__ void __launch_bounds__(256) bwd_scatter_lm_kernel(BwdParams p) {
     float dot = 0.f;
     for (int c = lane; c < p.C; c += 32) dot += expf(x[c] - mx) * inv * p.du[c];
     dot = warp_sum(dot);
-    const float invN = 1.f / ((float)p.B * (float)S1);
+    const float invN = p.usums ? 1.f / p.usums[p.C] : 1.f / ((float)p.B * (float)S1);   // rows of the GLOBAL batch
     const float k = g0 * p.lm_scale * (sx + sy);
     for (int c = lane; c < p.C; c += 32) {
       const float r = expf(x[c] - mx) * inv;
@@ -260,10 +291,16 @@ size_t simple_bwd_workspace_bytes(int B, int S, int T, int C) {
          round_up_sz(chunks * C * sizeof(float), 256);
 }
 
+// `unigram_sums` / `du_io` / `phase`: batch sharded by utterance.  The unigram is a function of
+// every rank's lm, so d loss / d unigram (du, [C]) has to be summed over the ranks before it flows back into the
+// lm rows: phase 1 runs everything up to this rank's share of du (written to du_io), the caller all-reduces
+// du_io, phase 2 (same workspace, same arguments) adds the unigram and lm-only terms to lm_grad.  phase 0: one
+// rank, everything.
 int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                       const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T, int C,
                       int term, int rnnt_type, int smoothed, float lm_only_scale, float am_only_scale, float *am_grad,
-                      float *lm_grad, void *workspace, cudaStream_t stream) {
+                      float *lm_grad, void *workspace, cudaStream_t stream, const float *unigram_sums, float *du_io,
+                      int phase) {
   const int S1 = S + 1, T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T;
   const int chunks = (B * T + kDuRows - 1) / kDuRows;
   char *w = static_cast<char *>(workspace);
@@ -277,14 +314,18 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
   float *Sy = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
   float *du = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *partial = reinterpret_cast<float *>(w);
+  if (du_io) du = du_io;
+  int rc = FRN_OK;
+  if (phase != 2) {
   // forward log-probs again (py gives Z); non-smoothed, and without the constrained px += py fold
-  int rc = launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, term,
-                                  rnnt_type == FRN_CONSTRAINED ? FRN_MODIFIED : rnnt_type, 0, 0.f, 0.f, px, py, stats,
-                                  stream);
+  rc = launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, term,
+                              rnnt_type == FRN_CONSTRAINED ? FRN_MODIFIED : rnnt_type, 0, 0.f, 0.f, px, py, stats,
+                              stream);
   if (rc) return rc;
   if (smoothed) {   // row sums, unigram and am-only normalisers into the same statistics block
-    rc = launch_smoothing_stats(lm, am, B, S, T, C, stats, stream);
+    rc = launch_smoothing_stats(lm, am, B, S, T, C, stats, stream, unigram_sums);
     if (rc) return rc;
+  }
   }
   char *sw = static_cast<char *>(stats);
   BwdParams p;
@@ -303,7 +344,11 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
   p.comb = smoothed ? (float)(1.0 - lms - ams) : 1.f;
   p.lm_scale = (float)(lms == 0.0 ? 1.0e-20 : lms);
   p.am_scale = (float)(ams == 0.0 ? 1.0e-20 : ams);
-  p.Gt = Gt; p.Sx = Sx; p.Sy = Sy; p.du = du; p.partial = partial;
+  p.Gt = Gt; p.Sx = Sx; p.Sy = Sy; p.du = du; p.partial = partial; p.usums = unigram_sums;
+  if (phase == 2) {
+    count_launch(), bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
+    return check_launch();
+  }
   const size_t n = (size_t)B * S1p * Tp;
   count_launch(), bwd_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
   // the two contractions: tcgen05 (simple_bwd_tc.cu); the exact-FP32 SIMT tiles serve shapes it cannot take
@@ -322,8 +367,13 @@ int launch_simple_bwd(const float *lm, const float *am, const int32_t *symbols, 
     count_launch(), bwd_smooth_am_kernel<<<chunks, 256, 0, stream>>>(p);
     count_launch(), bwd_du_kernel<<<(C + 127) / 128, 128, 0, stream>>>(p, chunks);
   }
-  count_launch(), bwd_scatter_am_kernel<<<(B * T + 127) / 128, 128, 0, stream>>>(p);
-  count_launch(), bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
+  const size_t sc_bytes = 3 * (size_t)S * sizeof(int32_t);
+  if (sc_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_scatter_am_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_bytes);
+    if (e != cudaSuccess) return note_cuda_error(e);
+  }
+  count_launch(), bwd_scatter_am_kernel<<<dim3((T + 31) / 32, B), 256, sc_bytes, stream>>>(p);
+  if (phase != 1) count_launch(), bwd_scatter_lm_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(p);
   return check_launch();
 }
 

@@ -19,6 +19,7 @@ struct BwdParams {
   int smoothed;
   float comb, lm_scale, am_scale;           // 1 - lm - am; scales with the 1e-20 substitution
   const float *lmsum, *amonly, *unigram;    // forward statistics: sum_c exp(lm - lmmax); log D + ammax; u[c]
+  const float *usums;                       // sharded batch: all-reduced unigram sums [C+1] (count last), or null
   float *Gt, *Sx, *Sy, *du, *partial;       // [B][T], [B][S+1], [B][S+1], [C], [chunks][C]
 };
 // tcgen05 contraction: am_grad / lm_grad = -g comb probs(x) * (W-weighted sums); FRN_EUNSUPPORTED when the

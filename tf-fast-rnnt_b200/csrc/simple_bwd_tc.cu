@@ -263,13 +263,20 @@ __device__ __forceinline__ void bwd_tc_tile(const BwdParams &p, int b, int m0, i
       for (int e = 0; e < 32; ++e) patch[lane * 33 + e] = v[e];
       __syncwarp();
       const int n = n0 + c0 + lane;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int m = m0 + q * 32 + r;
-        const float nmx = __shfl_sync(0xffffffffu, my_nmx, r);
-        if (m < M && n < C) {
-          const size_t at = (size_t)m * C + n;
-          out[at] = scale * ex2_approx(fmaf(__ldg(x + at), kLog2e, nmx)) * patch[r * 33 + lane];
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {       // 8 rows' loads in flight before the first is used
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + q * 32 + r0 + j;
+          xv[j] = (m < M && n < C) ? __ldg(x + (size_t)m * C + n) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + q * 32 + r0 + j;
+          const float nmx = __shfl_sync(0xffffffffu, my_nmx, r0 + j);
+          if (m < M && n < C)
+            out[(size_t)m * C + n] = scale * ex2_approx(fmaf(xv[j], kLog2e, nmx)) * patch[(r0 + j) * 33 + lane];
         }
       }
       __syncwarp();

@@ -102,6 +102,14 @@ _SIGS = {
     "frn_pruned_logprobs_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_pruned_logprobs": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _P, _P, _P, c_size_t, _P]),
+    "frn_smoothed_unigram_sums": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "frn_simple_logprobs_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                            c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_loss_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                        c_float, _P, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_smoothed_loss_bwd_sharded": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_float, c_float, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "frn_allreduce_sum": (c_int, [_P, c_size_t, _P, _P]),
     "frn_pruned_logprobs_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         _P, _P, c_size_t, _P]),
     "frn_pruned_loss_workspace_bytes": (c_size_t, [c_int] * 4),

@@ -148,6 +148,22 @@ def _reduce(scores: torch.Tensor, reduction: str, group=None) -> torch.Tensor:
     return out.reshape(())
 
 
+def _unigram_sums(lm_d: torch.Tensor, group) -> Optional[torch.Tensor]:
+    """rnnt_loss_smoothed on a batch sharded by utterance: the unigram of rnnt_loss.py:1279-1280 is a mean over
+    the GLOBAL batch.  This rank's column sums of softmax(lm rows) and its row count (C+1 floats), all-reduced
+    over `group`; the *_sharded entry points turn them into the same unigram on every rank."""
+    if group is None:
+        return None
+    import torch.distributed as dist
+    B, S1, C = lm_d.shape
+    sums = torch.empty(C + 1, dtype=torch.float32, device=lm_d.device)
+    ws = _workspace(lib.frn_simple_logprobs_workspace_bytes(B, S1 - 1, 1, C), lm_d.device)
+    check(lib.frn_smoothed_unigram_sums(_ptr(lm_d), B, S1 - 1, C, _ptr(sums), _ptr(ws), ws.numel(),
+                                        _stream(lm_d.device)), "frn_smoothed_unigram_sums")
+    dist.all_reduce(sums, group=group)
+    return sums
+
+
 def _reduce_autograd(scores: torch.Tensor, reduction: str, group=None) -> torch.Tensor:
     """The same reductions on the autograd path.  With a process group the batch is sharded by utterance:
     the returned VALUE is the global sum / mean (one scalar all-reduce of the detached local part), the
@@ -237,7 +253,7 @@ def cummin(x: Tensor):
 
 # ---------------------------------------------------------------- A1 / A2
 def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed,
-                     lm_only_scale, am_only_scale):
+                     lm_only_scale, am_only_scale, usums=None):
     io = _Io(lm, am)
     lm_d = io.dev_tensor(lm, torch.float32)
     am_d = io.dev_tensor(am, torch.float32)
@@ -252,10 +268,10 @@ def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, s
     px = torch.empty((B, S, T1), dtype=torch.float32, device=io.dev)
     py = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev)
     ws = _workspace(lib.frn_simple_logprobs_workspace_bytes(B, S, T, C), io.dev)
-    check(lib.frn_simple_logprobs(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
-                                  int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
-                                  float(am_only_scale), _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
-                                  _stream(io.dev)), "frn_simple_logprobs")
+    check(lib.frn_simple_logprobs_sharded(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                                          int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                                          float(am_only_scale), _ptr(usums), _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
+                                          _stream(io.dev)), "frn_simple_logprobs")
     return io.out(px), io.out(py)
 
 
@@ -266,11 +282,13 @@ class _SimpleLogprobsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, smoothed, lm_only_scale,
-                am_only_scale):
+                am_only_scale, group=None):
+        usums = _unigram_sums(lm, group) if smoothed else None
         px, py = _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed,
-                                  lm_only_scale, am_only_scale)
+                                  lm_only_scale, am_only_scale, usums)
         ctx.save_for_backward(lm, am, symbols, boundary)
         ctx.args = (termination_symbol, rnnt_type, smoothed, lm_only_scale, am_only_scale)
+        ctx.group, ctx.usums = group, usums
         return px, py
 
     @staticmethod
@@ -278,11 +296,11 @@ class _SimpleLogprobsFn(torch.autograd.Function):
         lm, am, symbols, boundary = ctx.saved_tensors
         term, rnnt_type, smoothed, lms, ams = ctx.args
         am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, dpx.contiguous(), dpy.contiguous(), None,
-                                          rnnt_type, smoothed, lms, ams)
-        return lm_g, am_g, None, None, None, None, None, None, None
+                                          rnnt_type, smoothed, lms, ams, ctx.group, ctx.usums)
+        return lm_g, am_g, None, None, None, None, None, None, None, None
 
 
-def _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams):
+def _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams, group=None):
     if _wants_grad(lm, am):
         io = _Io(lm, am)
         B, T, _ = am.shape
@@ -290,8 +308,11 @@ def _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boun
         return _SimpleLogprobsFn.apply(lm.contiguous().float(), am.contiguous().float(),
                                        io.dev_tensor(symbols, torch.int32), int(termination_symbol),
                                        _boundary(io, boundary, B, S, T), rnnt_type, bool(smoothed), float(lms),
-                                       float(ams))
-    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams)
+                                       float(ams), group)
+    usums = None
+    if smoothed and group is not None:
+        usums = _unigram_sums(_Io(lm, am).dev_tensor(lm, torch.float32), group)
+    return _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed, lms, ams, usums)
 
 
 @_on_device
@@ -304,10 +325,11 @@ def get_rnnt_logprobs(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbo
 @_on_device
 def get_rnnt_logprobs_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symbol: int,
                                lm_only_scale: float = 0.1, am_only_scale: float = 0.1,
-                               boundary: Optional[Tensor] = None, rnnt_type: str = "regular"):
-    """Reference: rnnt_loss.py:1132-1367.  CUDA tensors that require grad get gradients w.r.t. lm and am."""
+                               boundary: Optional[Tensor] = None, rnnt_type: str = "regular", group=None):
+    """Reference: rnnt_loss.py:1132-1367.  CUDA tensors that require grad get gradients w.r.t. lm and am.
+    ``group``: the batch is sharded by utterance over that torch.distributed group (exact batch-global unigram)."""
     return _simple_logprobs_public(lm, am, symbols, termination_symbol, rnnt_type, boundary, True,
-                                   lm_only_scale, am_only_scale)
+                                   lm_only_scale, am_only_scale, group)
 
 
 def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, reduction,
@@ -331,10 +353,11 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
     gy = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev) if calc_gradients else None
     ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), io.dev)
     dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
-    check(lib.frn_simple_loss(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
-                              int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
-                              float(am_only_scale), dp, int(calc_gradients), _ptr(scores), _ptr(gx), _ptr(gy),
-                              _ptr(ws), ws.numel(), _stream(io.dev)), "frn_simple_loss")
+    usums = _unigram_sums(lm_d, group) if smoothed else None
+    check(lib.frn_simple_loss_sharded(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
+                                      int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                                      float(am_only_scale), _ptr(usums), dp, int(calc_gradients), _ptr(scores),
+                                      _ptr(gx), _ptr(gy), _ptr(ws), ws.numel(), _stream(io.dev)), "frn_simple_loss")
     loss = io.out(_reduce(scores, reduction, group))
     return (loss, (io.out(gx), io.out(gy))) if calc_gradients else loss
 
@@ -342,12 +365,14 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
 @_on_device
 def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad, py_grad, scores_grad=None,
                          rnnt_type: str = "regular", smoothed: bool = False, lm_only_scale: float = 0.0,
-                         am_only_scale: float = 0.0):
+                         am_only_scale: float = 0.0, group=None, unigram_sums=None):
     """d(sum_b scores_grad[b] * scores[b]) / d(am, lm) for rnnt_loss_simple, from the
     occupation counts (px_grad, py_grad) that ``rnnt_loss_simple(..., calc_gradients=True)``
     returned — the chain TensorFlow autodiff runs through rnnt_loss.py:175-221.
     ``smoothed``: the same for rnnt_loss_smoothed (rnnt_loss.py:1266-1365, with the
-    path through the batch-global unigram)."""
+    path through the batch-global unigram).  ``group`` (smoothed only): the batch is sharded by utterance over
+    that torch.distributed group - the unigram sums and d loss / d unigram are all-reduced (C+1 and C floats),
+    and every rank gets the gradients of the unsharded loss for its own utterances."""
     io = _Io(lm, am)
     lm_d = io.dev_tensor(lm, torch.float32)
     am_d = io.dev_tensor(am, torch.float32)
@@ -362,7 +387,19 @@ def simple_loss_backward(lm, am, symbols, termination_symbol, boundary, px_grad,
     am_g = torch.empty_like(am_d)
     lm_g = torch.empty_like(lm_d)
     ws = _workspace(lib.frn_simple_loss_bwd_workspace_bytes(B, S, T, C), io.dev)
-    if smoothed:
+    if smoothed and (group is not None or unigram_sums is not None):
+        import torch.distributed as dist
+        usums = unigram_sums if unigram_sums is not None else _unigram_sums(lm_d, group)
+        du = torch.empty(C, dtype=torch.float32, device=io.dev)
+        for phase in (1, 2):
+            check(lib.frn_smoothed_loss_bwd_sharded(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy),
+                                                    _ptr(sg), B, S, T, C, int(termination_symbol), rt,
+                                                    float(lm_only_scale), float(am_only_scale), _ptr(usums), _ptr(du),
+                                                    phase, _ptr(am_g), _ptr(lm_g), _ptr(ws), ws.numel(),
+                                                    _stream(io.dev)), "frn_smoothed_loss_bwd_sharded")
+            if phase == 1 and group is not None:
+                dist.all_reduce(du, group=group)
+    elif smoothed:
         check(lib.frn_smoothed_loss_bwd(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), _ptr(gx), _ptr(gy), _ptr(sg),
                                         B, S, T, C, int(termination_symbol), rt, float(lm_only_scale),
                                         float(am_only_scale), _ptr(am_g), _ptr(lm_g), _ptr(ws), ws.numel(),
@@ -387,7 +424,7 @@ class _SimpleLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty, smoothed=False,
-                lm_only_scale=0.0, am_only_scale=0.0):
+                lm_only_scale=0.0, am_only_scale=0.0, group=None):
         B, T, C = am.shape
         S = lm.shape[1] - 1
         rt = _rnnt_type(rnnt_type)
@@ -397,12 +434,14 @@ class _SimpleLossFn(torch.autograd.Function):
         gy = torch.empty((B, S + 1, T), dtype=torch.float32, device=am.device)
         ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), am.device)
         dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
-        check(lib.frn_simple_loss(_ptr(lm), _ptr(am), _ptr(symbols), _ptr(boundary), B, S, T, C,
-                                  int(termination_symbol), rt, int(bool(smoothed)), float(lm_only_scale),
-                                  float(am_only_scale), dp, 1, _ptr(scores), _ptr(gx), _ptr(gy),
-                                  _ptr(ws), ws.numel(), _stream(am.device)), "frn_simple_loss")
+        usums = _unigram_sums(lm, group) if smoothed else None
+        check(lib.frn_simple_loss_sharded(_ptr(lm), _ptr(am), _ptr(symbols), _ptr(boundary), B, S, T, C,
+                                          int(termination_symbol), rt, int(bool(smoothed)), float(lm_only_scale),
+                                          float(am_only_scale), _ptr(usums), dp, 1, _ptr(scores), _ptr(gx), _ptr(gy),
+                                          _ptr(ws), ws.numel(), _stream(am.device)), "frn_simple_loss")
         ctx.save_for_backward(lm, am, symbols, boundary, gx, gy)
         ctx.args = (termination_symbol, rnnt_type, bool(smoothed), float(lm_only_scale), float(am_only_scale))
+        ctx.group, ctx.usums = group, usums
         ctx.mark_non_differentiable(gx, gy)
         return scores, gx, gy
 
@@ -411,8 +450,8 @@ class _SimpleLossFn(torch.autograd.Function):
         lm, am, symbols, boundary, gx, gy = ctx.saved_tensors
         term, rnnt_type, smoothed, lms, ams = ctx.args
         am_g, lm_g = simple_loss_backward(lm, am, symbols, term, boundary, gx, gy, g.contiguous(), rnnt_type,
-                                          smoothed, lms, ams)
-        return lm_g, am_g, None, None, None, None, None, None, None, None
+                                          smoothed, lms, ams, ctx.group, ctx.usums)
+        return lm_g, am_g, None, None, None, None, None, None, None, None, None
 
 
 @_on_device
@@ -459,7 +498,7 @@ def rnnt_loss_smoothed(lm: Tensor, am: Tensor, symbols: Tensor, termination_symb
         scores, gx, gy = _SimpleLossFn.apply(lm.contiguous().float(), am.contiguous().float(),
                                              io.dev_tensor(symbols, torch.int32), int(termination_symbol),
                                              _boundary(io, boundary, B, S, T), rnnt_type, float(delay_penalty),
-                                             True, float(lm_only_scale), float(am_only_scale))
+                                             True, float(lm_only_scale), float(am_only_scale), group)
         loss = _reduce_autograd(scores, reduction, group)
         return (loss, (gx, gy)) if calc_gradients else loss
     return _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay_penalty,
