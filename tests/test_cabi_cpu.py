@@ -177,3 +177,11 @@ def test_product_library_never_reads_the_environment(lib):
         assert name not in blob, name
     und = subprocess.run(["nm", "-D", "--undefined-only", dbg], capture_output=True, text=True, check=True).stdout
     assert "getenv" in und
+
+
+def test_nvtx_ranges_only_in_the_debug_hooks_build(lib):
+    """every entry point that enqueues work opens an NVTX range - in the -DFRN_NVTX build
+    (the debug-hooks library); the product library carries no tracing code."""
+    dbg = LIB[:-3] + "_dbg.so"
+    assert b"NVTX_INJECTION64_PATH" in open(dbg, "rb").read()          # nvtx3's lazy injection loader
+    assert b"NVTX_INJECTION64_PATH" not in open(LIB, "rb").read()

@@ -8,6 +8,21 @@
 
 #include "launchers.h"
 
+// NVTX range around every entry point that enqueues work (tracing).  Compile-time switch: the
+// debug-hooks library is built with -DFRN_NVTX (Makefile), the product library carries no tracing code.
+#ifdef FRN_NVTX
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define FRN_RANGE() NvtxRange frn_nvtx_range__(__func__)
+#else
+#define FRN_RANGE() do { } while (0)
+#endif
+
 namespace frn {
 static thread_local int g_last_cuda_error = 0;
 #ifdef FRN_DEBUG_HOOKS
@@ -87,6 +102,7 @@ size_t frn_mi_workspace_bytes(int B, int S, int T, int T1) {
 int frn_mi_fwd_bwd(const float *px, const float *py, const int32_t *boundary, int B, int S, int T, int T1,
                    int calc_gradients, float *ans, float *px_grad, float *py_grad, void *workspace,
                    size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 0 && T >= 0 && (T1 == T || T1 == T + 1));
   FRN_REQUIRE(px && py && boundary && ans);
@@ -118,6 +134,7 @@ size_t frn_band_mi_workspace_bytes(int B, int S, int T, int R) {
 int frn_band_mi_fwd_bwd(const float *pxc, const float *pyc, const int32_t *ranges, const int32_t *boundary, int B,
                         int S, int T, int R, int rnnt_type, float delay_penalty, int calc_gradients, float *ans,
                         float *pxc_grad, float *pyc_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && R <= S + 1);
   FRN_REQUIRE(pxc && pyc && ranges && boundary && ans);
   FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
@@ -129,6 +146,7 @@ int frn_band_mi_fwd_bwd(const float *pxc, const float *pyc, const int32_t *range
 }
 
 int frn_cummin(const int32_t *in, int32_t *out, int rows, int n, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(rows >= 0 && n >= 0 && (rows == 0 || n == 0 || (in && out)));
   return launch_cummin(in, out, rows, n, static_cast<cudaStream_t>(stream));
 }
@@ -143,6 +161,7 @@ size_t frn_prune_ranges_workspace_bytes(int B, int T) {
 int frn_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *boundary, int B, int S, int T,
                      int T1, int s_range, int32_t *ranges, void *workspace, size_t workspace_bytes,
                      void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && (T1 == T || T1 == T + 1) && s_range >= 1);
   FRN_REQUIRE(px_grad && py_grad && boundary && ranges);
   if (!workspace || workspace_bytes < frn_prune_ranges_workspace_bytes(B, T)) return FRN_EWORKSPACE;
@@ -154,6 +173,7 @@ int frn_prune_ranges(const float *px_grad, const float *py_grad, const int32_t *
 // ------------------------------------------------------------------ A6
 int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R, int C,
                    float *am_pruned, float *lm_pruned, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
   FRN_REQUIRE(am_pruned || lm_pruned);
   FRN_REQUIRE((!am_pruned || am) && (!lm_pruned || (lm && ranges)));
@@ -162,6 +182,7 @@ int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int 
 
 int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
                               int C, float *am_pruned, float *lm_pruned, float *logits, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
   FRN_REQUIRE(am && lm && ranges && lm_pruned && logits);      // am_pruned == NULL: see frn_broadcast_am_pruned
   return launch_do_pruning_add(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, logits,
@@ -170,12 +191,14 @@ int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *r
 
 int frn_broadcast_am_pruned(const float *am, int B, int T, int R, int C, float *am_pruned, int max_ctas,
                             void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && T > 0 && R > 0 && C > 0 && am && am_pruned);
   return launch_broadcast_am(am, B, T, R, C, am_pruned, max_ctas, static_cast<cudaStream_t>(stream));
 }
 
 int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad, const int32_t *ranges, int B,
                        int S, int T, int R, int C, float *am_grad, float *lm_grad, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0 && ranges);
   FRN_REQUIRE((!am_grad || am_pruned_grad) && (!lm_grad || lm_pruned_grad));
   return launch_do_pruning_bwd(am_pruned_grad, lm_pruned_grad, ranges, B, S, T, R, C, am_grad, lm_grad,
@@ -184,6 +207,7 @@ int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad,
 
 int frn_pruned_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
                           int C, int out_dtype, void *logits, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0 && am && lm && ranges && logits);
   return launch_pruned_add_joiner(am, lm, ranges, B, S, T, R, C, out_dtype, logits,
                                   static_cast<cudaStream_t>(stream));
@@ -197,12 +221,14 @@ size_t frn_simple_logprobs_workspace_bytes(int B, int S, int T, int C) {
 }
 
 int frn_allreduce_sum(float *buf, size_t n, void *nccl_comm, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(buf && n > 0 && nccl_comm);
   return launch_allreduce_sum(buf, n, nccl_comm, static_cast<cudaStream_t>(stream));
 }
 
 int frn_smoothed_unigram_sums(const float *lm, int B, int S, int C, float *sums, void *workspace,
                               size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 0 && C >= 1 && lm && sums);
   if (!workspace || !aligned256(workspace) || workspace_bytes < simple_stats_bytes(B, S, 1, C)) return FRN_EWORKSPACE;
   return launch_unigram_sums(lm, B, S, C, workspace, sums, static_cast<cudaStream_t>(stream));
@@ -212,6 +238,7 @@ int frn_simple_logprobs(const float *lm, const float *am, const int32_t *symbols
                         int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
                         float lm_only_scale, float am_only_scale, float *px, float *py, void *workspace,
                         size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   return frn_simple_logprobs_sharded(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
                                      lm_only_scale, am_only_scale, nullptr, px, py, workspace, workspace_bytes, stream);
 }
@@ -220,6 +247,7 @@ int frn_simple_logprobs_sharded(const float *lm, const float *am, const int32_t 
                                 int B, int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
                                 float lm_only_scale, float am_only_scale, const float *unigram_sums, float *px,
                                 float *py, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px && py);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
@@ -260,6 +288,7 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols, co
                     float lm_only_scale, float am_only_scale, float delay_penalty, int calc_gradients,
                     float *scores, float *px_grad, float *py_grad, void *workspace, size_t workspace_bytes,
                     void *stream_) {
+  FRN_RANGE();
   return frn_simple_loss_sharded(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
                                  lm_only_scale, am_only_scale, nullptr, delay_penalty, calc_gradients, scores, px_grad,
                                  py_grad, workspace, workspace_bytes, stream_);
@@ -270,6 +299,7 @@ int frn_simple_loss_sharded(const float *lm, const float *am, const int32_t *sym
                             float lm_only_scale, float am_only_scale, const float *unigram_sums, float delay_penalty,
                             int calc_gradients, float *scores, float *px_grad, float *py_grad, void *workspace,
                             size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
   if (!smoothed) unigram_sums = nullptr;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
@@ -316,6 +346,7 @@ int frn_simple_loss_bwd(const float *lm, const float *am, const int32_t *symbols
                         const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T,
                         int C, int termination_symbol, int rnnt_type, float *am_grad, float *lm_grad,
                         void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px_grad && py_grad && am_grad && lm_grad);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
@@ -330,6 +361,7 @@ int frn_smoothed_loss_bwd(const float *lm, const float *am, const int32_t *symbo
                           const float *px_grad, const float *py_grad, const float *scores_grad, int B, int S, int T,
                           int C, int termination_symbol, int rnnt_type, float lm_only_scale, float am_only_scale,
                           float *am_grad, float *lm_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   return frn_smoothed_loss_bwd_sharded(lm, am, symbols, boundary, px_grad, py_grad, scores_grad, B, S, T, C,
                                        termination_symbol, rnnt_type, lm_only_scale, am_only_scale, nullptr, nullptr, 0,
                                        am_grad, lm_grad, workspace, workspace_bytes, stream);
@@ -341,6 +373,7 @@ int frn_smoothed_loss_bwd_sharded(const float *lm, const float *am, const int32_
                                   float am_only_scale, const float *unigram_sums, float *du, int phase,
                                   float *am_grad, float *lm_grad, void *workspace, size_t workspace_bytes,
                                   void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(phase >= 0 && phase <= 2 && (phase == 0 || (unigram_sums && du)));
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px_grad && py_grad && am_grad && lm_grad);
@@ -435,6 +468,7 @@ int frn_pruned_logprobs(const void *logits, int logits_dtype, const int32_t *sym
                         const int32_t *boundary, int B, int S, int T, int R, int C, int termination_symbol,
                         int rnnt_type, float *px, float *py, void *workspace, size_t workspace_bytes,
                         void *stream_) {
+  FRN_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
   FRN_REQUIRE(logits && symbols && ranges && boundary && px && py);
@@ -453,6 +487,7 @@ int frn_pruned_logprobs_bwd(const void *logits, int logits_dtype, const int32_t 
                             const int32_t *boundary, const float *px_grad, const float *py_grad, int B, int S, int T,
                             int R, int C, int termination_symbol, int rnnt_type, void *logits_grad, void *workspace,
                             size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
   FRN_REQUIRE(logits && symbols && ranges && boundary && px_grad && py_grad && logits_grad);
@@ -485,6 +520,7 @@ int frn_pruned_loss(const void *logits, int logits_dtype, const int32_t *symbols
                     const int32_t *boundary, int B, int S, int T, int R, int C, int termination_symbol,
                     int rnnt_type, float delay_penalty, const float *scores_grad, float *scores,
                     void *logits_grad, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && R >= 1 && C >= 1 && R <= S + 1);
   FRN_REQUIRE(logits && symbols && ranges && boundary && scores);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
@@ -507,6 +543,7 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
                    int S, int T, int C, int termination_symbol, int rnnt_type, float delay_penalty,
                    const float *scores_grad, float *scores, void *logits_grad, void *workspace,
                    size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(logits && symbols && boundary && scores);
@@ -523,18 +560,21 @@ int frn_joint_loss(const void *logits, int logits_dtype, const int32_t *symbols,
 }
 
 int frn_add_joiner(const float *am_pruned, const float *lm_pruned, float *logits, size_t n, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(am_pruned && lm_pruned && logits);
   return launch_add(am_pruned, lm_pruned, logits, n, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ A3
 int frn_reduce(const float *scores, int B, int reduction, float denominator, float *out, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && scores && out && reduction >= FRN_NONE && reduction <= FRN_SUM);
   return launch_reduce(scores, B, reduction, denominator > 0.f ? denominator : (float)B, out,
                        static_cast<cudaStream_t>(stream));
 }
 
 int frn_cast_to_f32(const void *src, int src_dtype, size_t n, float *dst, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(n == 0 || (src && dst));
   FRN_REQUIRE(src_dtype == FRN_BF16 || src_dtype == FRN_F16);
   return launch_cast_to_f32(src, src_dtype, n, dst, static_cast<cudaStream_t>(stream));
@@ -542,6 +582,7 @@ int frn_cast_to_f32(const void *src, int src_dtype, size_t n, float *dst, void *
 
 int frn_reduce_pair(const float *scores_a, const float *scores_b, int B, int reduction, float denominator,
                     float *out_a, float *out_b, void *stream) {
+  FRN_RANGE();
   FRN_REQUIRE(B > 0 && scores_a && scores_b && out_a && out_b && reduction >= FRN_NONE && reduction <= FRN_SUM);
   return launch_reduce_pair(scores_a, scores_b, B, reduction, denominator > 0.f ? denominator : (float)B, out_a, out_b,
                             static_cast<cudaStream_t>(stream));

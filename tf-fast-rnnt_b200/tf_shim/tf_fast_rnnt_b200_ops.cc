@@ -50,6 +50,23 @@ inline tf::Status Workspace(tf::OpKernelContext *ctx, size_t bytes, tf::Tensor *
   return ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(bytes < 256 ? 256 : bytes)}), ws);
 }
 
+// Shapes of the pruned-loss family: logits [B,T,R,C], symbols [B,S], ranges [B,T,R], boundary [B,4]
+// (the reference validates nothing, its Python asserts are commented out: rnnt_loss.py:158-171).
+inline tf::Status CheckPrunedShapes(const tf::Tensor &lg, const tf::Tensor &sym, const tf::Tensor *rg,
+                                    const tf::Tensor &bd) {
+  if (lg.dims() != 4) return tf::errors::InvalidArgument("logits must be [B,T,s_range,C]");
+  if (sym.dims() != 2 || sym.dim_size(0) != lg.dim_size(0)) return tf::errors::InvalidArgument("symbols must be [B,S]");
+  if (bd.dims() != 2 || bd.dim_size(0) != lg.dim_size(0) || bd.dim_size(1) != 4)
+    return tf::errors::InvalidArgument("boundary must be [B,4]");
+  if (rg != nullptr) {
+    if (rg->dims() != 3 || rg->dim_size(0) != lg.dim_size(0) || rg->dim_size(1) != lg.dim_size(1) ||
+        rg->dim_size(2) != lg.dim_size(2))
+      return tf::errors::InvalidArgument("ranges must be [B,T,s_range], matching logits");
+    if (lg.dim_size(2) > sym.dim_size(1) + 1) return tf::errors::InvalidArgument("s_range must be <= S + 1");
+  }
+  return tf::OkStatus();
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -414,8 +431,10 @@ REGISTER_OP("FastRnntPrunedLoss")
     .Output("scores: float32")
     .Output("logits_grad: T")
     .SetShapeFn([](InferenceContext *c) {
+      bool with_grad = true;
+      TF_RETURN_IF_ERROR(c->GetAttr("with_logits_grad", &with_grad));
       c->set_output(0, c->Vector(c->Dim(c->input(0), 0)));
-      c->set_output(1, c->input(0));
+      c->set_output(1, with_grad ? c->input(0) : c->Vector(0));
       return tf::OkStatus();
     });
 
@@ -431,12 +450,13 @@ class FastRnntPrunedLossOp : public tf::OpKernel {
   void Compute(tf::OpKernelContext *ctx) override {
     const tf::Tensor &lg = ctx->input(0), &sym = ctx->input(1), &rg = ctx->input(2), &bd = ctx->input(3),
                      &sg = ctx->input(4);
-    OP_REQUIRES(ctx, lg.dims() == 4, tf::errors::InvalidArgument("logits must be [B,T,s_range,C]"));
+    OP_REQUIRES_OK(ctx, CheckPrunedShapes(lg, sym, &rg, bd));
     const int B = lg.dim_size(0), T = lg.dim_size(1), R = lg.dim_size(2), C = lg.dim_size(3), S = sym.dim_size(1);
+    OP_REQUIRES(ctx, sg.dims() == 1 && sg.dim_size(0) == B, tf::errors::InvalidArgument("scores_grad must be [B]"));
     tf::Tensor *scores = nullptr, *grad = nullptr, ws;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B}), &scores));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, with_grad_ ? lg.shape() : tf::TensorShape({0}), &grad));
-    const size_t bytes = frn_pruned_loss_workspace_bytes(B, S, T, R);
+    const size_t bytes = frn_pruned_loss_min_workspace_bytes(B, S, T, R, dp_);     // sized by the path that runs
     OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
     const int dtype = std::is_same<DT, float>::value ? FRN_F32 : FRN_BF16;
     OP_REQUIRES_OK(ctx, FromFrn(frn_pruned_loss(lg.flat<DT>().data(), dtype, sym.flat<tf::int32>().data(),
@@ -601,7 +621,7 @@ class FastRnntPrunedLogprobsOp : public tf::OpKernel {
   }
   void Compute(tf::OpKernelContext *ctx) override {
     const tf::Tensor &lg = ctx->input(0), &sym = ctx->input(1), &rg = ctx->input(2), &bd = ctx->input(3);
-    OP_REQUIRES(ctx, lg.dims() == 4, tf::errors::InvalidArgument("logits must be [B,T,s_range,C]"));
+    OP_REQUIRES_OK(ctx, CheckPrunedShapes(lg, sym, &rg, bd));
     const int B = lg.dim_size(0), T = lg.dim_size(1), R = lg.dim_size(2), C = lg.dim_size(3), S = sym.dim_size(1);
     const int T1 = type_ == FRN_REGULAR ? T + 1 : T;
     tf::Tensor *px = nullptr, *py = nullptr, ws;
@@ -625,3 +645,65 @@ REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobs").Device(tf::DEVICE_GPU).Ty
                         FastRnntPrunedLogprobsOp<float>);
 REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobs").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
                         FastRnntPrunedLogprobsOp<tf::bfloat16>);
+
+// ---------------------------------------------------------------------------
+// FastRnntPrunedLogprobsGrad: backward of FastRnntPrunedLogprobs (what TF autodiff derives through
+// rnnt_loss.py:942-1018) - the reference composes get_rnnt_logprobs_pruned with
+// mutual_information_recursion under autodiff (rnnt_loss.py:1088-1119), so the building block needs its
+// own gradient.  Registered from Python with RegisterGradient("FastRnntPrunedLogprobs").
+// (FastRnntSimpleLogprobs uses FastRnntSimpleLossGrad: the same contractions, fed with the cotangents
+// of px / py instead of occupation counts.)
+// ---------------------------------------------------------------------------
+REGISTER_OP("FastRnntPrunedLogprobsGrad")
+    .Input("logits: T")
+    .Input("symbols: int32")
+    .Input("ranges: int32")
+    .Input("boundary: int32")
+    .Input("px_grad: float32")
+    .Input("py_grad: float32")
+    .Attr("T: {float32, bfloat16} = DT_FLOAT")
+    .Attr("termination_symbol: int")
+    .Attr("rnnt_type: int = 0")
+    .Output("logits_grad: T")
+    .SetShapeFn([](InferenceContext *c) {
+      c->set_output(0, c->input(0));
+      return tf::OkStatus();
+    });
+
+template <typename DT>
+class FastRnntPrunedLogprobsGradOp : public tf::OpKernel {
+ public:
+  explicit FastRnntPrunedLogprobsGradOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("termination_symbol", &term_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("rnnt_type", &type_));
+  }
+  void Compute(tf::OpKernelContext *ctx) override {
+    const tf::Tensor &lg = ctx->input(0), &sym = ctx->input(1), &rg = ctx->input(2), &bd = ctx->input(3),
+                     &gx = ctx->input(4), &gy = ctx->input(5);
+    OP_REQUIRES_OK(ctx, CheckPrunedShapes(lg, sym, &rg, bd));
+    const int B = lg.dim_size(0), T = lg.dim_size(1), R = lg.dim_size(2), C = lg.dim_size(3), S = sym.dim_size(1);
+    const int T1 = type_ == FRN_REGULAR ? T + 1 : T;
+    OP_REQUIRES(ctx, gx.dims() == 3 && gx.dim_size(0) == B && gx.dim_size(1) == S && gx.dim_size(2) == T1,
+                tf::errors::InvalidArgument("px_grad must be [B,S,T1]"));
+    OP_REQUIRES(ctx, gy.dims() == 3 && gy.dim_size(0) == B && gy.dim_size(1) == S + 1 && gy.dim_size(2) == T,
+                tf::errors::InvalidArgument("py_grad must be [B,S+1,T]"));
+    tf::Tensor *grad = nullptr, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, lg.shape(), &grad));
+    const size_t bytes = frn_pruned_logprobs_workspace_bytes(B, S, T, R);
+    OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
+    const int dtype = std::is_same<DT, float>::value ? FRN_F32 : FRN_BF16;
+    OP_REQUIRES_OK(ctx, FromFrn(frn_pruned_logprobs_bwd(lg.flat<DT>().data(), dtype, sym.flat<tf::int32>().data(),
+                                                        rg.flat<tf::int32>().data(), bd.flat<tf::int32>().data(),
+                                                        gx.flat<float>().data(), gy.flat<float>().data(), B, S, T, R, C,
+                                                        term_, type_, grad->flat<DT>().data(),
+                                                        ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx)),
+                                "FastRnntPrunedLogprobsGrad"));
+  }
+
+ private:
+  int term_, type_;
+};
+REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobsGrad").Device(tf::DEVICE_GPU).TypeConstraint<float>("T"),
+                        FastRnntPrunedLogprobsGradOp<float>);
+REGISTER_KERNEL_BUILDER(Name("FastRnntPrunedLogprobsGrad").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
+                        FastRnntPrunedLogprobsGradOp<tf::bfloat16>);

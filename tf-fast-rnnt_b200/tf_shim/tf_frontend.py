@@ -62,6 +62,29 @@ def _simple_loss_grad(op, g_scores, _g_px_grad, _g_py_grad):
     return [lm_g, am_g, None, None]
 
 
+@ops.RegisterGradient("FastRnntSimpleLogprobs")
+def _simple_logprobs_grad(op, g_px, g_py):
+    """Backward of get_rnnt_logprobs{,_smoothed}: the contractions of the loss gradient, fed with the
+    cotangents of px / py (the reference gets this from TF autodiff over rnnt_loss.py:175-221)."""
+    ones = tf.ones([tf.shape(op.inputs[1])[0]], tf.float32)
+    lm_g, am_g = _ops.fast_rnnt_simple_loss_grad(
+        op.inputs[0], op.inputs[1], op.inputs[2], op.inputs[3], g_px, g_py, ones,
+        termination_symbol=op.get_attr("termination_symbol"), rnnt_type=op.get_attr("rnnt_type"),
+        smoothed=op.get_attr("smoothed"), lm_only_scale=op.get_attr("lm_only_scale"),
+        am_only_scale=op.get_attr("am_only_scale"))
+    return [lm_g, am_g, None, None]
+
+
+@ops.RegisterGradient("FastRnntPrunedLogprobs")
+def _pruned_logprobs_grad(op, g_px, g_py):
+    """Backward of get_rnnt_logprobs_pruned (the reference composes it with mutual_information_recursion under
+    autodiff, rnnt_loss.py:1088-1119)."""
+    g = _ops.fast_rnnt_pruned_logprobs_grad(op.inputs[0], op.inputs[1], op.inputs[2], op.inputs[3], g_px, g_py,
+                                            termination_symbol=op.get_attr("termination_symbol"),
+                                            rnnt_type=op.get_attr("rnnt_type"))
+    return [g, None, None, None]
+
+
 def _reduce(scores, reduction):
     if reduction == "none":
         return -scores
@@ -190,3 +213,47 @@ def get_rnnt_logprobs_joint(logits, symbols, termination_symbol, boundary=None, 
     ranges = tf.tile(tf.reshape(tf.range(S1, dtype=tf.int32), [1, 1, S1]), [B, T, 1])
     return get_rnnt_logprobs_pruned(logits, symbols, ranges, termination_symbol, _boundary(boundary, B, S1 - 1, T),
                                     rnnt_type)
+
+
+def pruned_rnnt_pipeline(lm, am, symbols, termination_symbol, boundary, s_range, joiner=None, rnnt_type="regular",
+                         delay_penalty=0.0, reduction="sum", max_buckets=4, min_bucket=4, lm_only_scale=0.0,
+                         am_only_scale=0.0):
+    """(extension) The full pruned RNN-T step on a ragged batch, per length bucket: the batch is
+    cut into at most ``max_buckets`` buckets by frame count (``sharding.plan_buckets``: the plan is made on the
+    host, so ``boundary`` must be a host-readable value - eager tensor or NumPy array), every bucket runs
+    rnnt_loss_simple/_smoothed -> get_rnnt_prune_ranges -> do_rnnt_pruning -> joiner -> rnnt_loss_pruned
+    trimmed to its own (S_max, T_max), and the per-utterance losses go back in batch order.  Mirrors
+    tf_fast_rnnt/scheduler.py of the TensorFlow-free twin.  Returns (simple_loss, pruned_loss)."""
+    try:
+        from .sharding import plan_buckets
+    except ImportError:                      # tf_frontend.py deployed as a plain module next to sharding.py
+        from sharding import plan_buckets
+    import numpy as np
+    bd_host = np.asarray(boundary)
+    B, C = am.shape[0], am.shape[2]
+    bd = tf.cast(boundary, tf.int32)
+    sym = tf.cast(symbols, tf.int32)
+    simple_parts, pruned_parts, order = [], [], []
+    for bk in plan_buckets(bd_host, s_range, int(C), max_buckets=max_buckets, min_bucket=min_bucket):
+        idx = tf.constant(bk["idx"], tf.int32)
+        lm_k = tf.gather(lm, idx)[:, :bk["S_max"] + 1]
+        am_k = tf.gather(am, idx)[:, :bk["T_max"]]
+        sym_k = tf.gather(sym, idx)[:, :bk["S_max"]]
+        bd_k = tf.gather(bd, idx)
+        if lm_only_scale > 0.0 or am_only_scale > 0.0:
+            sl, (gx, gy) = rnnt_loss_smoothed(lm_k, am_k, sym_k, termination_symbol, lm_only_scale, am_only_scale, bd_k,
+                                              rnnt_type, delay_penalty, "none", True)
+        else:
+            sl, (gx, gy) = rnnt_loss_simple(lm_k, am_k, sym_k, termination_symbol, bd_k, rnnt_type, delay_penalty,
+                                            "none", True)
+        ranges = get_rnnt_prune_ranges(gx, gy, bd_k, s_range)
+        if joiner is None:
+            _, _, logits = do_rnnt_pruning_add_joiner(am_k, lm_k, ranges)
+        else:
+            logits = joiner(*do_rnnt_pruning(am_k, lm_k, ranges))
+        pl = rnnt_loss_pruned(logits, sym_k, ranges, termination_symbol, bd_k, rnnt_type, delay_penalty, "none")
+        simple_parts.append(sl); pruned_parts.append(pl); order.append(bk["idx"])
+    inv = tf.constant(np.argsort(np.concatenate(order)), tf.int32)            # back to batch order
+    simple = -tf.gather(tf.concat(simple_parts, 0), inv)
+    pruned = -tf.gather(tf.concat(pruned_parts, 0), inv)
+    return _reduce(simple, reduction), _reduce(pruned, reduction)
