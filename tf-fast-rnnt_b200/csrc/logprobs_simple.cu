@@ -25,14 +25,27 @@ __device__ __forceinline__ float tiny_f32() { return __int_as_float(1); }
 // ---------------------------------------------------------------------------
 // Rows of lm ([rows_lm][C]) and of am ([rows_am][C]) in one launch; 128-bit streaming loads when
 // the rows are 16-byte aligned (C % 4 == 0), all loads of a row issued before the reduction.
+// `pxam_t` != null: the warp that streams am row (b,t) also leaves am[b,t,symbols[b,s]], s < S, in
+// pxam_t[b][t][s] (the row is hot in L2 / L1 at that moment; the tensor-core kernel's epilogue reads its
+// frame's S values as one contiguous run instead of gathering across rows).
 __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
-                                                       int C, float *lmmax, float *lmsum, float *ammax) {
+                                                       int C, float *lmmax, float *lmsum, float *ammax,
+                                                       const int32_t *symbols = nullptr, int S = 0, int T = 1,
+                                                       float *pxam_t = nullptr) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows_lm + rows_am) return;
   const bool is_lm = row < rows_lm;
   if (!is_lm) row -= rows_lm;
   const float *src = (is_lm ? lm : am) + (size_t)row * C;
+  if (!is_lm && pxam_t) {
+    const int32_t *sym = symbols + (size_t)(row / T) * S;
+    float *dst = pxam_t + (size_t)row * S;
+    for (int s = lane; s < S; s += 32) {
+      const int c = sym[s];
+      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+    }
+  }
   float *rmax = is_lm ? lmmax : ammax;
   float *rsum = is_lm ? lmsum : nullptr;
   float m = -INFINITY;
@@ -239,7 +252,8 @@ __global__ void __launch_bounds__(256) constrained_fix_kernel(float *px, const f
 // ---------------------------------------------------------------------------
 size_t simple_stats_bytes(int B, int S, int T, int C) {
   size_t n = 2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256) +
-             2 * round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)C * sizeof(float), 256);
+             2 * round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)C * sizeof(float), 256) +
+             round_up_sz((size_t)B * T * S * sizeof(float), 256);        // pxam_t
   return n;
 }
 
@@ -294,9 +308,12 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   float *ammax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
-  float *logu = reinterpret_cast<float *>(w);
+  float *logu = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
+  float *pxam_t = reinterpret_cast<float *>(w);
+  const bool tc = simple_logprobs_tc_applicable(lm, am, C) && debug_env_int("FRN_SIMPLE_SIMT", 0) != 1;
   count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax,
-                                                                                 smoothed ? lmsum : nullptr, ammax);
+                                                                                 smoothed ? lmsum : nullptr, ammax, symbols,
+                                                                                 S, T, tc ? pxam_t : nullptr);
   if (smoothed) {
     count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
                                                                    unigram, logu);
@@ -307,7 +324,7 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   SimpleParams sp;
   sp.lm = lm; sp.am = am; sp.symbols = symbols; sp.boundary = boundary;
   sp.lmmax = lmmax; sp.ammax = ammax; sp.lmsum = lmsum; sp.amonly = amonly; sp.logu = logu;
-  sp.px = px; sp.py = py;
+  sp.px = px; sp.py = py; sp.pxam_t = tc ? pxam_t : nullptr;
   sp.B = B; sp.S = S; sp.T = T; sp.T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T; sp.C = C; sp.term = term;
   sp.rnnt_type = rnnt_type; sp.smoothed = smoothed;
   // Python-float arithmetic of rnnt_loss.py:1342-1349, then cast to float32

@@ -4,15 +4,21 @@
 //
 // One CTA = one (utterance, 128-frame tile, <=112-symbol tile).  Per 64-wide
 // slice of the vocabulary axis:
-//   1. TMA (cp.async.bulk.tensor.3d, tensor maps over am [B][T][C] and
-//      lm [B][S+1][C]) drops the raw float32 tiles into a 2-stage shared-memory
-//      ring behind mbarriers;
-//   2. all 512 threads turn them into probabilities exp(x - rowmax) and split
-//      each into three bfloat16 terms h+m+l (24 mantissa bits), written in the
-//      K-major SWIZZLE_128B layout tcgen05 reads;
-//   3. one thread issues 6 tcgen05.mma (hh, hm, mh, mm, hl, lh — everything down
-//      to 2^-24 relative) per 16-wide k step into a 128 x N float32 accumulator
-//      in tensor memory and commits to an mbarrier.
+//   1. all 512 threads load their 32-byte pieces of the am and lm tiles straight from global memory
+//      into registers - issued right after the previous slice's MMAs, so the loads fly while the
+//      tensor core works;
+//   2. they turn them into probabilities exp(x - rowmax) and split each into three bfloat16 terms
+//      h+m+l (24 mantissa bits), written in the K-major SWIZZLE_128B layout tcgen05 reads, into one
+//      of TWO operand stages: the conversion of slice k+1 overlaps the MMAs of slice k;
+//   3. one thread issues 6 tcgen05.mma (hh, hm, mh, mm, hl, lh - everything down to 2^-24
+//      relative) per 16-wide k step into one of two 128 x N float32 accumulators in tensor memory
+//      and commits to the stage's mbarrier; the partial sums of slice k-2 are drained into
+//      registers before its stage is overwritten (tensor-core accumulation truncates: every slice
+//      starts from zero and the slices are summed in float32 registers).
+// (The first version staged raw tiles through shared memory with TMA and single-buffered operands:
+// convert and MMA never overlapped and the raw tiles cost a third of the kernel's shared-memory
+// traffic; am[b,t,sym_s] was picked out of the raw tile - it now comes from the row-statistics
+// kernel, which has every am row in flight anyway: SimpleParams::pxam_t.)
 // Epilogue: tcgen05.ld the accumulator (one lattice frame per thread), then either
 //   (a) log, un-shift, symbol / blank gather, smoothing terms, boundary fix-ups, and store
 //       px/py coalesced along t in the reference layout (rnnt_loss.py:186-221,1290-1365)
@@ -32,12 +38,6 @@
 // float32-accurate by construction (the occupation counts downstream need ~2^-21
 // on the normaliser, which rules out plain bf16/tf32: DESIGN.md "numerics").
 #include <cuda.h>
-#ifdef FRN_TC_TIMING
-#include <cstdio>
-#define TCT(i) do { if (tid == 0 && blockIdx.x == 1 && blockIdx.z == 3) tct[i] = clock64(); } while (0)
-#else
-#define TCT(i) do { } while (0)
-#endif
 
 #include "common.cuh"
 #include "simple_params.cuh"
@@ -49,16 +49,13 @@ constexpr int TM = 128;   // frames per CTA  (MMA M)
 constexpr int TN = 112;   // symbols per CTA (MMA N, multiple of 16)
 constexpr int KC = 64;    // vocabulary slice per stage = one 128-byte swizzle row of bf16
 constexpr int kThreads = 512;   // 16 warps: 4 per TMEM lane quarter, 28 symbol columns each
-constexpr int kTmemCols = 256;  // [0,112) accumulator, [128,240) px_am staging
-constexpr int kPxCol = 128;
-constexpr uint32_t kRawAmBytes = TM * KC * 4, kRawLmBytes = TN * KC * 4;
+constexpr int kTmemCols = 256;  // two accumulators: [0,112) and [128,240)
+constexpr int kAccStride = 128;
 constexpr uint32_t kOpABytes = TM * KC * 2, kOpBBytes = TN * KC * 2;
-// shared memory map (byte offsets from a 1024-aligned base)
-constexpr uint32_t kOffA = 0;                                  // 3 x A operand (h, m, l)
-constexpr uint32_t kOffB = kOffA + 3 * kOpABytes;              // 3 x B operand
-constexpr uint32_t kOffRaw = kOffB + 3 * kOpBBytes;            // 2 x (am raw, lm raw)
-constexpr uint32_t kRawStage = kRawAmBytes + kRawLmBytes;
-constexpr uint32_t kOffSmall = kOffRaw + 2 * kRawStage;
+// shared memory map (byte offsets from a 1024-aligned base): two operand stages, then the small block
+constexpr uint32_t kOffB = 3 * kOpABytes;                      // inside a stage: 3 x A (h, m, l), then 3 x B
+constexpr uint32_t kStageBytes = 3 * kOpABytes + 3 * kOpBBytes;
+constexpr uint32_t kOffSmall = 2 * kStageBytes;
 constexpr uint32_t kSmallBytes = 8192;
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes + 1024;  // + alignment slack
 // Accumulator columns of a thread: the four warps of a TMEM lane quarter (`half` = 0..3) take 28
@@ -73,7 +70,7 @@ constexpr double kLog2eD = 1.4426950408889634074;
 constexpr float kLog2eLo = 1.92596299112661746e-8f;   // log2(e) - (float)log2(e)
 struct Small {                                        // per-CTA row / column constants
   double sm_x[TN], sm_y[TN];                          // smoothed: lm_scale * log2e * (lm[s,sym|blank] - lmonly[s])
-  uint64_t bars[4];                                   // raw_full[2], mma_done
+  uint64_t bars[4];                                   // full[2], done[2] (one each per operand stage)
   float amneg[TM], lmneg[TN];                         // -max * log2e (-inf: row masked)
   float ammax[TM], lmmax[TN];
   float pxlm[TN], pylm[TN], lmonly[TN], logusym[TN];
@@ -85,13 +82,6 @@ struct Small {                                        // per-CTA row / column co
 };
 static_assert(sizeof(Small) <= kSmallBytes, "small shared-memory block");
 
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(cols) : "memory");
@@ -166,8 +156,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 
 template <bool kXY>
 __global__ void __launch_bounds__(tc::kThreads, 1)
-simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __grid_constant__ CUtensorMap map_lm,
-                          SimpleParams p) {
+simple_logprobs_tc_kernel(SimpleParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B operands need a 1024-byte aligned base; keep the arithmetic on the
@@ -175,11 +164,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   // degrades them to generic LD/ST)
   unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-#ifdef FRN_TC_TIMING
-  long long tct[48];
-  for (int i = 0; i < 48; ++i) tct[i] = 0;
-#endif
-  TCT(0);
   const int b = blockIdx.z, t0 = blockIdx.x * TM, s0 = blockIdx.y * TN;
   const int S1 = p.S + 1, C = p.C;
   const int nk = (C + KC - 1) / KC;
@@ -196,21 +180,10 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   // a tile that holds no live arc has nothing to contract
   const bool tile_dead = kXY && (!bd_ok || t0 >= bd.w || t0 + TM <= t_begin || s0 > bd.z || s0 + TN <= s_begin);
 
-  // The raw tiles do not depend on the row statistics: the first two slices are requested before
-  // anything else so that their (cold) latency hides behind the set-up loads below.
-  auto issue_tma = [&](int k, int stage) {
-    unsigned char *raw = smem + kOffRaw + stage * kRawStage;
-    mbar_arrive_expect_tx(&bars[stage], kRawStage);
-    tma_load_3d(raw, &map_am, &bars[stage], k * KC, t0, b);
-    tma_load_3d(raw + kRawAmBytes, &map_lm, &bars[stage], k * KC, s0, b);
-  };
   if (tid == 0 && !tile_dead) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_am) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lm) : "memory");
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[0], kThreads / 32 - 1); mbar_init(&bars[1], kThreads / 32 - 1);    // full[2]: one arrival per converter warp
+    mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);                                    // done[2]: the tcgen05.commit
     mbar_fence_init();
-    issue_tma(0, 0);
-    if (nk > 1) issue_tma(1, 1);
   }
   if constexpr (kXY) {
     // Dead remainder of the arc plane.  Half X of cell (d, r) is the symbol arc from lattice row r-1 at
@@ -278,7 +251,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = sm.tmem;
-  TCT(1);
 
   // epilogue mapping, also used inside the k loop: thread <-> frame (TMEM lane), the four
   // warps of a lane quarter take 28 symbol columns each (col_of)
@@ -289,121 +261,148 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
   const float py_am = __ldg(amb + (size_t)(t_ok ? et : 0) * C + p.term);
   const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
   const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
-  // the symbols of this warp's columns, one per lane
-  const int my_sym0 = (lane < kColsPerHalf) ? sm.sym[col_of(half, lane)] : -1;
+  // am[b,t,sym_s] for this thread's frame: gathered by the row-statistics kernel while it had the row in flight
+  const float *pxam_row = p.pxam_t + ((size_t)b * p.T + (t_ok ? et : 0)) * p.S;
   float accr[kColsPerHalf];                     // float32 sum of the per-slice tensor-core partial sums
 #pragma unroll
   for (int i = 0; i < kColsPerHalf; ++i) accr[i] = 0.f;
-  auto drain_accumulator = [&]() {              // TMEM partial sums of one slice -> registers
+  auto drain_accumulator = [&](int acc) {       // TMEM partial sums of one slice -> registers
 #pragma unroll
     for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
       const int c0 = col_of(half, bi * 4);
       if (c0 < n_rows) {                        // warp-uniform
         float part[4];
-        tmem_ld4(lane_addr + (uint32_t)c0, part);
+        tmem_ld4(lane_addr + (uint32_t)(acc * kAccStride + c0), part);
 #pragma unroll
         for (int e = 0; e < 4; ++e) accr[bi * 4 + e] += part[e];
       }
     }
   };
-  TCT(2);
   const uint32_t idesc = umma_idesc(TM, n_rows);
-  const uint32_t a_base = smem_u32(smem + kOffA), b_base = smem_u32(smem + kOffB);
 
-  for (int k = 0; k < nk; ++k) {
-    const int stage = k & 1;
-    mbar_wait_bounded(&bars[stage], (uint32_t)((k >> 1) & 1));             // raw tiles landed
-    if (k < 8) TCT(4 + 4 * k);
-    if (k > 0) {
-      mbar_wait_bounded(&bars[2], (uint32_t)((k - 1) & 1));                // previous slice's MMAs done
-      tc_fence_after();
-      drain_accumulator();                                                 // (operands are free again, too)
-    }
-    if (k < 8) TCT(5 + 4 * k);
-    const float *raw_am = reinterpret_cast<const float *>(smem + kOffRaw + stage * kRawStage);
-    const float *raw_lm = raw_am + TM * KC;
+  // ---- roles.  Warps 0..14 (480 threads) convert: 1024 pieces of the am tile + 896 of the lm tile = 1920 = 4 per
+  //      thread (a piece = 8 consecutive values of one row: 32 bytes in, 3 x 16 bytes out).  Warp 15 issues the
+  //      MMAs: a thread that also converted made every slice wait for its 24 tcgen05.mma behind its share of the
+  //      conversion (23 % of all warp time sat in the per-slice block barrier).  There is no block barrier in
+  //      the loop: converters -> issuer through full[stage] (one arrival per converter warp), issuer -> everybody
+  //      through the tcgen05.commit on done[stage]. ----
+  constexpr int kConvWarps = kThreads / 32 - 1, kConvThreads = kConvWarps * 32, kPieces = (TM + TN) * 8 / kConvThreads;
+  static_assert(kPieces * kConvThreads == (TM + TN) * 8, "pieces divide evenly over the converter threads");
+  const bool issuer = (w == kConvWarps);
+  uint64_t *full = bars, *done = bars + 2;
+  float4 rr[kPieces][2];
+  // piece i of this thread -> (tile, row, 16-byte chunk); warp-uniform in `is_a`
+  auto piece = [&](int i, bool &is_a, int &row, int &j) {
+    int pi = tid + i * kConvThreads;
+    is_a = pi < TM * 8;
+    if (!is_a) pi -= TM * 8;
+    row = pi >> 3; j = pi & 7;
+  };
+  auto load_slice = [&](int k) {
     const int k0 = k * KC;
-    // ---- px_am[t][s] = am[b,t,sym_s]: picked out of the raw tile while it is in shared
-    //      memory and parked in spare tensor-memory columns (no global gather) ----
-    {
-      // lane l watches column l of its warp's part; a ballot gives the hits of this slice
-      uint32_t hit0 = __ballot_sync(0xffffffffu, my_sym0 >= k0 && my_sym0 < k0 + KC);
-      while (hit0) {                                                       // warp-uniform loop
-        const int src_lane = __ffs(hit0) - 1;
-        hit0 &= hit0 - 1;
-        const int sym = __shfl_sync(0xffffffffu, my_sym0, src_lane);
-        const int j = col_of(half, src_lane);
-        const uint32_t v = __float_as_uint(raw_am[erow * KC + (sym - k0)]);
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_addr + (uint32_t)(kPxCol + j)), "r"(v)
-                     : "memory");
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      bool is_a; int row, j;
+      piece(i, is_a, row, j);
+      const int c = k0 + j * 8;
+      rr[i][0] = rr[i][1] = z;                    // rows / columns outside the tensors stay zero
+      const bool row_ok = is_a ? (t0 + row < p.T) : (s0 + row < S1);
+      if (row_ok) {
+        const float *base = is_a ? amb + (size_t)(t0 + row) * C : lmb + (size_t)(s0 + row) * C;
+        const float4 *src = reinterpret_cast<const float4 *>(base + c);
+        if (c < C) rr[i][0] = __ldg(src);         // C % 4 == 0: a float4 is inside or outside the row
+        if (c + 4 < C) rr[i][1] = __ldg(src + 1);
       }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    // ---- convert: 16-byte operand chunks (8 probabilities); three-term bf16 split by
-    //      mantissa truncation: h = top 16 bits of p, m = top 16 bits of the (exact)
-    //      remainder, l likewise -> h+m+l = p to 2^-24, plain ALU ops ----
-    const int lim = C - k0;                     // columns of this slice that exist
-    auto convert = [&](const float *raw, const float *negmax, unsigned char *ops, uint32_t stride, int nchunks) {
-#pragma unroll 2
-      for (int li = tid; li < nchunks; li += kThreads) {
-        const int row = li >> 3, j = li & 7;
-        const float *src = raw + row * KC + j * 8;
-        const float nmx = negmax[row];
-        const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
-        const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t hb[8], mb[8], lb[8];
+  };
+  // ---- registers -> operand stage: exp, three-term bf16 split by mantissa truncation (h = top 16 bits of
+  //      p, m = top 16 bits of the exact remainder, l likewise: h+m+l = p to 2^-24, plain ALU ops),
+  //      16-byte chunks in the K-major SWIZZLE_128B layout ----
+  auto store_piece = [&](const float4 (&r)[2], float nmx, int lim, unsigned char *dst, uint32_t stride) {
+    const float x[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
+    uint32_t hb[8], mb[8], lb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float pr = ex2_approx(fmaf(x[e], kLog2e, nmx));
-          pr = (j * 8 + e < lim) ? pr : 0.f;
-          hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
-          const float r1 = pr - __uint_as_float(hb[e]);
-          mb[e] = __float_as_uint(r1);
-          const float r2 = r1 - __uint_as_float(mb[e] & 0xFFFF0000u);
-          lb[e] = __float_as_uint(r2);
-        }
-        unsigned char *dst = ops + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-        auto pack = [](const uint32_t (&v)[8]) {   // upper halves: element e low, e+1 high
-          return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
-                            __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
-        };
-        *reinterpret_cast<uint4 *>(dst) = pack(hb);
-        *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
-        *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
-      }
+    for (int e = 0; e < 8; ++e) {
+      float pr = ex2_approx(fmaf(x[e], kLog2e, nmx));
+      pr = (e < lim) ? pr : 0.f;
+      hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
+      const float r1 = pr - __uint_as_float(hb[e]);
+      mb[e] = __float_as_uint(r1);
+      const float r2 = r1 - __uint_as_float(mb[e] & 0xFFFF0000u);
+      lb[e] = __float_as_uint(r2);
+    }
+    auto pack = [](const uint32_t (&v)[8]) {   // upper halves: element e low, e+1 high
+      return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
+                        __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
     };
-    convert(raw_am, sm.amneg, smem + kOffA, kOpABytes, TM * 8);
-    convert(raw_lm, sm.lmneg, smem + kOffB, kOpBBytes, TN * 8);
-    fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    if (k < 8) TCT(6 + 4 * k);
-    if (tid == 0) {
-      if (k + 2 < nk) issue_tma(k + 2, stage);   // this raw stage has been consumed
-      tc_fence_after();
-      // Tensor-core FP32 accumulation truncates, so (i) every slice starts from a zeroed
-      // accumulator and is summed in registers, (ii) the five small products go first and
-      // h*h last: <= 4 truncations at full magnitude per slice.
-      const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
-      uint32_t first = 1;
+    *reinterpret_cast<uint4 *>(dst) = pack(hb);
+    *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
+    *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
+  };
+  auto store_slice = [&](int k, unsigned char *stage) {
+    const int k0 = k * KC;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-#pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {
-          const uint64_t ad = umma_desc(a_base + ia[c] * kOpABytes + ks * 32);
-          const uint64_t bd = umma_desc(b_base + ib[c] * kOpBBytes + ks * 32);
-          umma_bf16(tmem_d, ad, bd, idesc, first ? 0u : 1u);
-          first = 0;
-        }
-      }
-      umma_commit(&bars[2]);
+    for (int i = 0; i < kPieces; ++i) {
+      bool is_a; int row, j;
+      piece(i, is_a, row, j);
+      const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+      if (is_a) store_piece(rr[i], sm.amneg[row], C - k0 - j * 8, stage + off, kOpABytes);   // masked rows: -inf -> 0
+      else store_piece(rr[i], sm.lmneg[row], C - k0 - j * 8, stage + kOffB + off, kOpBBytes);
     }
-    if (k < 8) TCT(7 + 4 * k);
+  };
+
+  if (!issuer) load_slice(0);
+  for (int k = 0; k < nk; ++k) {
+    const int st = k & 1;
+    unsigned char *stage = smem + (uint32_t)st * kStageBytes;
+    if (k >= 2) {                                // slice k-2 used this stage and this accumulator
+      mbar_wait_bounded(&done[st], (uint32_t)(((k >> 1) - 1) & 1));
+      tc_fence_after();
+      drain_accumulator(st);
+      tc_fence_before();                         // the drain's tcgen05.ld before the arrival below / the next MMAs
+    }
+    if (!issuer) {
+      store_slice(k, stage);
+      if (k + 1 < nk) load_slice(k + 1);         // registers are free again: in flight until the next conversion
+      fence_async_smem();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    } else {
+      mbar_wait_bounded(&full[st], (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        // Tensor-core FP32 accumulation truncates, so (i) every slice starts from a zeroed
+        // accumulator and is summed in registers, (ii) the five small products go first and
+        // h*h last: <= 4 truncations at full magnitude per slice.
+        const uint32_t a_base = smem_u32(stage), b_base = smem_u32(stage + kOffB);
+        const uint32_t acc = tmem_d + (uint32_t)(st * kAccStride);
+        const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+        uint32_t first = 1;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t ad = umma_desc(a_base + ia[c] * kOpABytes + ks * 32);
+            const uint64_t bd = umma_desc(b_base + ib[c] * kOpBBytes + ks * 32);
+            umma_bf16(acc, ad, bd, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+        }
+        umma_commit(&done[st]);
+      }
+      __syncwarp();
+    }
   }
-  mbar_wait_bounded(&bars[2], (uint32_t)((nk - 1) & 1));
+  // the last two slices (in order: the sums are formed in slice order whatever the timing)
+  for (int k = max(nk - 2, 0); k < nk; ++k) {
+    mbar_wait_bounded(&done[k & 1], (uint32_t)((k >> 1) & 1));
+    tc_fence_after();
+    drain_accumulator(k & 1);
+  }
+  tc_fence_before();
+  __syncthreads();                               // every warp has left the operand stages: the epilogue reuses them
   tc_fence_after();
-  drain_accumulator();
-  TCT(40);
 
   if constexpr (!kXY) {
     // ---- epilogue (a): one frame per thread (TMEM lane), 28 symbol columns per thread.
@@ -423,7 +422,8 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
       const int c0 = col_of(half, bi * 4);
       if (c0 < n_rows) {                 // warp-uniform
         float pxam[4];
-        tmem_ld4(lane_addr + (uint32_t)(kPxCol + c0), pxam);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pxam[e] = (t_ok && s0 + c0 + e < p.S) ? pxam_row[s0 + c0 + e] : 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = c0 + e, s = s0 + j;
@@ -488,7 +488,8 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
           const int c0 = col_of(half, bi * 4);
           if (c0 < n_rows) {                    // warp-uniform
             float pxam[4];
-            tmem_ld4(lane_addr + (uint32_t)(kPxCol + c0), pxam);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pxam[e] = (t_ok && s0 + c0 + e < p.S) ? pxam_row[s0 + c0 + e] : 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = c0 + e;
@@ -551,77 +552,30 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_am, const __gr
       if (pass == 0) __syncthreads();
     }
   }
-  TCT(41);
   tc_fence_before();
   __syncthreads();
-  TCT(42);
-#ifdef FRN_TC_TIMING
-  if (tid == 0 && blockIdx.x == 1 && blockIdx.z == 3) {
-    printf("TC timing (cycles from start): setup %lld prologue %lld\n", tct[1] - tct[0], tct[2] - tct[0]);
-    for (int k = 0; k < 8 && k < nk; ++k)
-      printf("  k%d raw_wait->%lld mma_wait+drain->%lld stage+convert+sync->%lld issue->%lld\n", k, tct[4 + 4 * k] - tct[0],
-             tct[5 + 4 * k] - tct[0], tct[6 + 4 * k] - tct[0], tct[7 + 4 * k] - tct[0]);
-    printf("  last mma done %lld epilogue end %lld final sync %lld\n", tct[40] - tct[0], tct[41] - tct[0], tct[42] - tct[0]);
-  }
-#endif
   if (w == 0) tmem_dealloc(tmem_d, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------
-// host side: tensor maps + launch
+// host side
 // ---------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  return fn;
-}
-
-static bool make_map_3d(CUtensorMap *map, const float *base, int rows, int C, int B, int box_rows) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
-  cuuint32_t box[3] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C) {
-  // TMA needs 16-byte global strides (C % 4 == 0) and aligned bases
-  return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0 &&
-         get_encode_fn() != nullptr;
+  // 128-bit loads of 8-column pieces: C % 4 == 0 and 16-byte aligned bases
+  return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0;
 }
 
-// returns FRN_EUNSUPPORTED when the tensor-core path does not apply (caller falls
-// back to the SIMT kernel): C % 4 != 0 (TMA needs 16-byte global strides) or
-// misaligned bases.  sp.XY != nullptr selects the arc-plane output (regular / modified only).
+// returns FRN_EUNSUPPORTED when the tensor-core path does not apply (caller falls back to the SIMT kernel):
+// C % 4 != 0 or misaligned bases.  sp.XY != nullptr selects the arc-plane output (regular / modified only).
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
-  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C)) return FRN_EUNSUPPORTED;
+  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C) || sp.pxam_t == nullptr) return FRN_EUNSUPPORTED;
   if (sp.XY != nullptr && sp.rnnt_type == FRN_CONSTRAINED) return FRN_EUNSUPPORTED;
-  CUtensorMap map_am, map_lm;
-  if (!make_map_3d(&map_am, sp.am, sp.T, sp.C, sp.B, tc::TM)) return FRN_EUNSUPPORTED;
-  if (!make_map_3d(&map_lm, sp.lm, sp.S + 1, sp.C, sp.B, tc::TN)) return FRN_EUNSUPPORTED;
   auto kernel = sp.XY ? simple_logprobs_tc_kernel<true> : simple_logprobs_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return note_cuda_error(e);
   // arc-plane output: frames 0..T-1 carry arcs (the regular lattice's extra column T has none)
   dim3 grid(((sp.XY ? sp.T : sp.T1) + tc::TM - 1) / tc::TM, (sp.S + 1 + tc::TN - 1) / tc::TN, sp.B);
-  count_launch(), kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_am, map_lm, sp);
+  count_launch(), kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(sp);
   return check_launch();
 }
 

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) do_pruning_bwd_am_vec_kernel(const float 
 //      hits, a block-wide exclusive scan gives its slot, and it writes its hits - the list is in (t,i) order;
 //   2. every thread sums its float4 column over the list, four loads in flight.
 // Shapes the list does not fit (or C % 4 != 0) walk the indices per element (LIST = false).
-constexpr int kBwdLmThreads = 256;       // two groups of 128 column threads; the groups split the hit list
+constexpr int kBwdLmThreads = 512;       // four groups of 128 column threads; the groups split the hit list
 template <bool LIST>
 __global__ void __launch_bounds__(kBwdLmThreads) do_pruning_bwd_lm_kernel(const float *lm_p_grad, const int32_t *ranges,
                                                                           int B, int S1, int T, int R, int C,
@@ -310,18 +310,20 @@ __global__ void __launch_bounds__(kBwdLmThreads) do_pruning_bwd_lm_kernel(const 
     for (int e = t_lo * R; e < t_hi * R; ++e)
       if (rg[e] == s) hit_list[slot++] = e;
     __syncthreads();
-    // A lattice row the band rests on for hundreds of frames (the last rows of an utterance, typically) has
-    // hundreds of hits: the two thread groups take alternate runs of 8 hits, 8 loads in flight per thread.
+    // A lattice row the band rests on for hundreds of frames has hundreds of hits (with an untrained model
+    // nearly all frames of an utterance hit the same s_range rows): the thread groups take alternate runs of
+    // 8 hits, 8 loads in flight per thread, so one CTA keeps 64 KB in flight.
     const int C4 = C >> 2;
     const int grp = tid >> 7, col = tid & 127;
     const float4 *src4 = reinterpret_cast<const float4 *>(src);
     float4 *dst = reinterpret_cast<float4 *>(lm_grad) + (size_t)bs * C4;
-    float4 *partial = reinterpret_cast<float4 *>(hit_list + ((T * R + 3) & ~3));     // [128] group 1's sums
+    constexpr int NG = NT / 128;
+    float4 *partial = reinterpret_cast<float4 *>(hit_list + ((T * R + 3) & ~3));     // [NG - 1][128] sums of groups 1..
     for (int c0 = 0; c0 < C4; c0 += 128) {
       const int c = c0 + col;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C4) {
-        for (int k0 = grp * 8; k0 < total; k0 += 16) {
+        for (int k0 = grp * 8; k0 < total; k0 += 8 * NG) {
           float4 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -330,11 +332,15 @@ __global__ void __launch_bounds__(kBwdLmThreads) do_pruning_bwd_lm_kernel(const 
           for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         }
       }
-      if (grp == 1) partial[col] = acc;
+      if (grp > 0) partial[(grp - 1) * 128 + col] = acc;
       __syncthreads();
       if (grp == 0 && c < C4) {
-        const float4 o = partial[col];
-        dst[c] = make_float4(acc.x + o.x, acc.y + o.y, acc.z + o.z, acc.w + o.w);
+#pragma unroll
+        for (int g = 0; g < NG - 1; ++g) {
+          const float4 o = partial[g * 128 + col];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        dst[c] = acc;
       }
       __syncthreads();
     }
@@ -601,7 +607,8 @@ int launch_do_pruning_bwd(const float *am_p_grad, const float *lm_p_grad, const 
     if (rc) return rc;
   }
   if (lm_grad) {
-    const size_t list_bytes = (((size_t)T * R + 3) & ~(size_t)3) * sizeof(int32_t) + 128 * sizeof(float4);
+    const size_t list_bytes = (((size_t)T * R + 3) & ~(size_t)3) * sizeof(int32_t) +
+                              (kBwdLmThreads / 128 - 1) * 128 * sizeof(float4);
     if (C % 4 == 0 && aligned16(lm_p_grad, lm_grad) && list_bytes <= 160 * 1024) {
       if (list_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(do_pruning_bwd_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -126,122 +126,140 @@ __device__ __forceinline__ uint32_t swz(int r, int j) {
   return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((j ^ (r & 7)) << 4);
 }
 
-template <int TN> struct Smem {
+// NST operand stages: with two, the conversion of slice k+1 runs while the tensor core works on slice k
+template <int TN, int NST> struct Smem {
   static constexpr uint32_t kOpB = TN * KS * 2;
-  static constexpr uint32_t kOffA = 0, kOffB = 3 * kOpA, kOffSmall = kOffB + 3 * kOpB;
+  static constexpr uint32_t kStage = 3 * kOpA + 3 * kOpB;       // (h, m, l) x (W operand, exp operand)
+  static constexpr uint32_t kOffB = 3 * kOpA, kOffSmall = NST * kStage;
   static constexpr uint32_t kBytes = kOffSmall + 64 + 1024;     // + alignment slack
 };
 
 // One tile.  AM_SIDE: M = t, K = s, x = am, y = lm.  Otherwise: M = s, K = t, x = lm, y = am.
-template <bool AM_SIDE, int TN>
+template <bool AM_SIDE, int TN, int NST>
 __device__ __forceinline__ void bwd_tc_tile(const BwdParams &p, int b, int m0, int n0, unsigned char *smem) {
-  using L = Smem<TN>;
-  constexpr int kAChunks = TM * KS / 8 / kThreads;      // 2
-  constexpr int kBChunks = TN * KS / 8 / kThreads;      // 4 (TN = 256) / 2 (TN = 128)
+  using L = Smem<TN, NST>;
+  static_assert(NST == 2, "two operand stages: full[2] / done[2]");
+  // Roles: warps 0..14 convert (a piece = 8 consecutive values: 32 bytes in, 3 x 16 bytes out), warp 15 issues the
+  // MMAs.  No block barrier in the loop: converters -> issuer through full[stage] (one arrival per converter
+  // warp), issuer -> converters through the tcgen05.commit on done[stage].
+  constexpr int kConvWarps = kThreads / 32 - 1, kConvThreads = kConvWarps * 32;
+  constexpr int kTotal = (TM + TN) * KS / 8;                                   // pieces of one K slice
+  constexpr int kPieces = (kTotal + kConvThreads - 1) / kConvThreads;
   constexpr int kNB = TN / 8;                           // 16-byte chunks along n
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool issuer = (w == kConvWarps);
   const int S1 = p.S + 1, C = p.C, T = p.T;
   const int K = AM_SIDE ? S1 : T, M = AM_SIDE ? T : S1;
   const int nk = (K + KS - 1) / KS;
   const float *Wb = p.W + (size_t)b * p.S1p * p.Tp;
   const float *y = AM_SIDE ? p.lm + (size_t)b * S1 * C : p.am + (size_t)b * T * C;
   const float *ymax = AM_SIDE ? p.lmmax + (size_t)b * S1 : p.ammax + (size_t)b * T;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::kOffSmall);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffSmall + 16);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kOffSmall), *done = full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kOffSmall + 32);
 
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (tid == 0) {
+    mbar_init(&full[0], kConvWarps); mbar_init(&full[1], kConvWarps);
+    mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+    mbar_fence_init();
+  }
   if (w == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  float4 ra[kAChunks][2], rb[kBChunks][2];
-  float rmax[kBChunks];
+  float4 rr[kPieces][2];
+  float rmax[kPieces];
   auto load_slice = [&](int ks) {
     const int k0 = ks * KS;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < kAChunks; ++i) {
-      const int li = tid + i * kThreads;
-      const float *src;
-      if (AM_SIDE) { const int k = li >> 4, jm = li & 15; src = Wb + (size_t)(k0 + k) * p.Tp + m0 + jm * 8; }
-      else         { const int m = li >> 3, j = li & 7;   src = Wb + (size_t)(m0 + m) * p.Tp + k0 + j * 8; }
-      ra[i][0] = __ldg(reinterpret_cast<const float4 *>(src));
-      ra[i][1] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
-    }
-#pragma unroll
-    for (int i = 0; i < kBChunks; ++i) {
-      const int li = tid + i * kThreads;
-      const int k = li / kNB, jn = li - k * kNB;
-      const int kk = k0 + k, n = n0 + jn * 8;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[i][0] = rb[i][1] = z;
+    for (int i = 0; i < kPieces; ++i) {
+      const int pi = tid + i * kConvThreads;
+      rr[i][0] = rr[i][1] = z;
       rmax[i] = 0.f;
-      if (kk < K) {
-        const float4 *src = reinterpret_cast<const float4 *>(y + (size_t)kk * C + n);
-        if (n < C) rb[i][0] = __ldg(src);               // C % 4 == 0: a float4 is inside or outside the row
-        if (n + 4 < C) rb[i][1] = __ldg(src + 1);
-        rmax[i] = __ldg(ymax + kk);
+      if (pi < TM * KS / 8) {                           // W operand (zero-padded: no bounds)
+        const float *src;
+        if (AM_SIDE) { const int k = pi >> 4, jm = pi & 15; src = Wb + (size_t)(k0 + k) * p.Tp + m0 + jm * 8; }
+        else         { const int m = pi >> 3, j = pi & 7;   src = Wb + (size_t)(m0 + m) * p.Tp + k0 + j * 8; }
+        rr[i][0] = __ldg(reinterpret_cast<const float4 *>(src));
+        rr[i][1] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+      } else if (pi < kTotal) {                         // exp operand
+        const int q = pi - TM * KS / 8, k = q / kNB, jn = q - k * kNB;
+        const int kk = k0 + k, n = n0 + jn * 8;
+        if (kk < K) {
+          const float4 *src = reinterpret_cast<const float4 *>(y + (size_t)kk * C + n);
+          if (n < C) rr[i][0] = __ldg(src);             // C % 4 == 0: a float4 is inside or outside the row
+          if (n + 4 < C) rr[i][1] = __ldg(src + 1);
+          rmax[i] = __ldg(ymax + kk);
+        }
       }
     }
   };
-  auto store_slice = [&](int ks) {
+  auto store_slice = [&](int ks, unsigned char *stage) {
     const int k0 = ks * KS;
 #pragma unroll
-    for (int i = 0; i < kAChunks; ++i) {
-      const int li = tid + i * kThreads;
-      const float x[8] = {ra[i][0].x, ra[i][0].y, ra[i][0].z, ra[i][0].w, ra[i][1].x, ra[i][1].y, ra[i][1].z, ra[i][1].w};
-      uint32_t off;
-      if (AM_SIDE) { const int k = li >> 4, jm = li & 15; off = (uint32_t)(jm >> 3) * kPanel + swz(k, jm & 7); }
-      else         { const int m = li >> 3, j = li & 7;   off = swz(m, j); }
-      split_store(x, smem + L::kOffA + off, kOpA);
-    }
+    for (int i = 0; i < kPieces; ++i) {
+      const int pi = tid + i * kConvThreads;
+      const float v[8] = {rr[i][0].x, rr[i][0].y, rr[i][0].z, rr[i][0].w, rr[i][1].x, rr[i][1].y, rr[i][1].z, rr[i][1].w};
+      if (pi < TM * KS / 8) {
+        uint32_t off;
+        if (AM_SIDE) { const int k = pi >> 4, jm = pi & 15; off = (uint32_t)(jm >> 3) * kPanel + swz(k, jm & 7); }
+        else         { const int m = pi >> 3, j = pi & 7;   off = swz(m, j); }
+        split_store(v, stage + off, kOpA);
+      } else if (pi < kTotal) {
+        const int q = pi - TM * KS / 8, k = q / kNB, jn = q - k * kNB;
+        const int kk = k0 + k, n = n0 + jn * 8;
+        const float nmx = -rmax[i] * kLog2e;
+        float x[8];
 #pragma unroll
-    for (int i = 0; i < kBChunks; ++i) {
-      const int li = tid + i * kThreads;
-      const int k = li / kNB, jn = li - k * kNB;
-      const int kk = k0 + k, n = n0 + jn * 8;
-      const float nmx = -rmax[i] * kLog2e;
-      const float v[8] = {rb[i][0].x, rb[i][0].y, rb[i][0].z, rb[i][0].w, rb[i][1].x, rb[i][1].y, rb[i][1].z, rb[i][1].w};
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = (kk < K && n + e < C) ? ex2_approx(fmaf(v[e], kLog2e, nmx)) : 0.f;
-      split_store(x, smem + L::kOffB + (uint32_t)(jn >> 3) * kPanel + swz(k, jn & 7), L::kOpB);
+        for (int e = 0; e < 8; ++e) x[e] = (kk < K && n + e < C) ? ex2_approx(fmaf(v[e], kLog2e, nmx)) : 0.f;
+        split_store(x, stage + L::kOffB + (uint32_t)(jn >> 3) * kPanel + swz(k, jn & 7), L::kOpB);
+      }
     }
   };
 
-  const uint32_t a_base = smem_u32(smem + L::kOffA), b_base = smem_u32(smem + L::kOffB);
   constexpr uint32_t id = idesc(TM, TN, AM_SIDE, true);
-  load_slice(0);
+  if (!issuer) load_slice(0);
   for (int ks = 0; ks < nk; ++ks) {
-    if (ks > 0) {                                // the previous slice's MMAs have read the operands
-      mbar_wait_bounded(bar, (uint32_t)((ks - 1) & 1));
-      tc_fence_after();
-    }
-    store_slice(ks);
-    fence_async_smem();                          // generic-proxy stores -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      // small products first, h*h last (as the forward kernel)
-      const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-#pragma unroll
-        for (int k16 = 0; k16 < KS / 16; ++k16) {
-          const uint64_t ad = AM_SIDE ? desc_mnmajor(a_base + ia[c] * kOpA + k16 * 2048, kPanel)
-                                      : desc_kmajor(a_base + ia[c] * kOpA + k16 * 32);
-          const uint64_t bd = desc_mnmajor(b_base + ib[c] * L::kOpB + k16 * 2048, kPanel);
-          umma_bf16(tmem_d, ad, bd, id, (ks == 0 && c == 0 && k16 == 0) ? 0u : 1u);
-        }
+    const int st = ks & 1;
+    unsigned char *stage = smem + (uint32_t)st * L::kStage;
+    if (!issuer) {
+      if (ks >= 2) {                             // the MMAs of slice ks - 2 have read this stage
+        mbar_wait_bounded(&done[st], (uint32_t)(((ks >> 1) - 1) & 1));
+        tc_fence_after();
       }
-      umma_commit(bar);
+      store_slice(ks, stage);
+      if (ks + 1 < nk) load_slice(ks + 1);       // registers are free again: in flight until the next conversion
+      fence_async_smem();                        // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    } else {
+      mbar_wait_bounded(&full[st], (uint32_t)((ks >> 1) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(stage), b_base = smem_u32(stage + L::kOffB);
+        // small products first, h*h last (as the forward kernel)
+        const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+#pragma unroll
+          for (int k16 = 0; k16 < KS / 16; ++k16) {
+            const uint64_t ad = AM_SIDE ? desc_mnmajor(a_base + ia[c] * kOpA + k16 * 2048, kPanel)
+                                        : desc_kmajor(a_base + ia[c] * kOpA + k16 * 32);
+            const uint64_t bd = desc_mnmajor(b_base + ib[c] * L::kOpB + k16 * 2048, kPanel);
+            umma_bf16(tmem_d, ad, bd, id, (ks == 0 && c == 0 && k16 == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(&done[st]);
+      }
+      __syncwarp();
     }
-    if (ks + 1 < nk) load_slice(ks + 1);         // in flight while the tensor core works
   }
-  mbar_wait_bounded(bar, (uint32_t)((nk - 1) & 1));
+  // the last commit: all MMAs have finished (commits complete in issue order)
+  mbar_wait_bounded(&done[(nk - 1) & 1], (uint32_t)(((nk - 1) >> 1) & 1));
   tc_fence_after();
+  __syncthreads();                               // every warp has left the operand stages: the epilogue reuses them
 
   // ---- epilogue ----
   const int q = w & 3, part = w >> 2;            // TMEM lane quarter, column quarter
@@ -263,21 +281,18 @@ __device__ __forceinline__ void bwd_tc_tile(const BwdParams &p, int b, int m0, i
       for (int e = 0; e < 32; ++e) patch[lane * 33 + e] = v[e];
       __syncwarp();
       const int n = n0 + c0 + lane;
+      // all 32 rows' loads in flight before the first is used (the accumulator values sit in the patch, the
+      // registers are free): the AM-side tiles are two K slices and 64 KB of epilogue traffic - latency is the cost
+      float xv[32];
+      const float *xp = x + (size_t)(m0 + q * 32) * C + n;
+      float *op = out + (size_t)(m0 + q * 32) * C + n;
+      const int rows_ok = (n < C) ? min(32, M - (m0 + q * 32)) : 0;       // warp-uniform in r, per-lane in n
 #pragma unroll
-      for (int r0 = 0; r0 < 32; r0 += 8) {       // 8 rows' loads in flight before the first is used
-        float xv[8];
+      for (int r = 0; r < 32; ++r) xv[r] = (r < rows_ok) ? __ldg(xp + (size_t)r * C) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int m = m0 + q * 32 + r0 + j;
-          xv[j] = (m < M && n < C) ? __ldg(x + (size_t)m * C + n) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int m = m0 + q * 32 + r0 + j;
-          const float nmx = __shfl_sync(0xffffffffu, my_nmx, r0 + j);
-          if (m < M && n < C)
-            out[(size_t)m * C + n] = scale * ex2_approx(fmaf(xv[j], kLog2e, nmx)) * patch[(r0 + j) * 33 + lane];
-        }
+      for (int r = 0; r < 32; ++r) {
+        const float nmx = __shfl_sync(0xffffffffu, my_nmx, r);
+        if (r < rows_ok) op[(size_t)r * C] = scale * ex2_approx(fmaf(xv[r], kLog2e, nmx)) * patch[r * 33 + lane];
       }
       __syncwarp();
     }
@@ -297,12 +312,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_contract_tc_kernel(BwdParams 
   if (i < lm_tiles) {
     const int per_b = lm_ntiles * ((p.S + 1 + TM - 1) / TM);
     const int b = i / per_b, r = i - b * per_b;
-    bwd_tc_tile<false, TN_LM>(p, b, (r / lm_ntiles) * TM, (r % lm_ntiles) * TN_LM, smem);
+    bwd_tc_tile<false, TN_LM, 2>(p, b, (r / lm_ntiles) * TM, (r % lm_ntiles) * TN_LM, smem);
   } else {
     i -= lm_tiles;
     const int per_b = am_mtiles * am_ntiles;
     const int b = i / per_b, r = i - b * per_b;
-    bwd_tc_tile<true, TN_AM>(p, b, (r / am_ntiles) * TM, (r % am_ntiles) * TN_AM, smem);
+    bwd_tc_tile<true, TN_AM, 2>(p, b, (r / am_ntiles) * TM, (r % am_ntiles) * TN_AM, smem);
   }
 }
 }  // namespace bt
@@ -315,14 +330,14 @@ bool simple_bwd_tc_applicable(const BwdParams &p) {
 int launch_bwd_contract_tc(const BwdParams &p, cudaStream_t stream) {
   using namespace bt;
   if (!simple_bwd_tc_applicable(p)) return FRN_EUNSUPPORTED;
-  constexpr int TN_AM = 256, TN_LM = 128;
+  constexpr int TN_AM = 128, TN_LM = 128;
   const int S1 = p.S + 1;
   const int lm_ntiles = (p.C + TN_LM - 1) / TN_LM, lm_mtiles = (S1 + TM - 1) / TM;
   const int am_ntiles = (p.C + TN_AM - 1) / TN_AM, am_mtiles = (p.T + TM - 1) / TM;
   const long long lm_tiles = (long long)p.B * lm_ntiles * lm_mtiles, am_tiles = (long long)p.B * am_ntiles * am_mtiles;
   if (lm_tiles + am_tiles > 0x7fffffffLL) return FRN_EUNSUPPORTED;
   auto kernel = bwd_contract_tc_kernel<TN_AM, TN_LM>;
-  constexpr uint32_t smem = Smem<TN_AM>::kBytes > Smem<TN_LM>::kBytes ? Smem<TN_AM>::kBytes : Smem<TN_LM>::kBytes;
+  constexpr uint32_t smem = Smem<TN_AM, 2>::kBytes > Smem<TN_LM, 2>::kBytes ? Smem<TN_AM, 2>::kBytes : Smem<TN_LM, 2>::kBytes;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return note_cuda_error(e);
   count_launch(), kernel<<<(unsigned)(lm_tiles + am_tiles), kThreads, smem, stream>>>(p, (int)lm_tiles, lm_ntiles,

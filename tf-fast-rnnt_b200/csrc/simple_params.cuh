@@ -9,6 +9,7 @@ struct SimpleParams {
   const int32_t *symbols, *boundary;
   const float *lmmax, *ammax;           // row maxima
   const float *lmsum, *amonly, *logu;   // smoothed only (may be null)
+  const float *pxam_t = nullptr;        // [B][T][S] am[b,t,symbols[b,s]], written by the row-statistics kernel
   float *px, *py;                       // reference layout
   int B, S, T, T1, C, term, rnnt_type, smoothed;
   float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
