@@ -39,6 +39,8 @@
 // on the normaliser, which rules out plain bf16/tf32: DESIGN.md "numerics").
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "simple_params.cuh"
 
@@ -298,19 +300,30 @@ simple_logprobs_tc_kernel(SimpleParams p) {
     if (!is_a) pi -= TM * 8;
     row = pi >> 3; j = pi & 7;
   };
+  // per piece, once: where its row starts (element offset inside the utterance's am / lm, -1: row outside the
+  // tensor), where its operand chunk goes, and its row's -max * log2e
+  int src_off[kPieces];
+  uint32_t dst_off[kPieces];
+  float nmx_of[kPieces];
+#pragma unroll
+  for (int i = 0; i < kPieces; ++i) {
+    bool is_a; int row, j;
+    piece(i, is_a, row, j);
+    const bool row_ok = is_a ? (t0 + row < p.T) : (s0 + row < S1);
+    src_off[i] = row_ok ? (is_a ? t0 + row : s0 + row) * C + j * 8 : -1;
+    dst_off[i] = (is_a ? 0u : kOffB) + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+    nmx_of[i] = issuer ? 0.f : (is_a ? sm.amneg[row] : sm.lmneg[row]);      // masked rows: -inf -> exp2 = 0
+  }
   auto load_slice = [&](int k) {
     const int k0 = k * KC;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < kPieces; ++i) {
-      bool is_a; int row, j;
-      piece(i, is_a, row, j);
-      const int c = k0 + j * 8;
+      const bool is_a = tid + i * kConvThreads < TM * 8;
+      const int c = k0 + ((tid + i * kConvThreads) & 7) * 8;
       rr[i][0] = rr[i][1] = z;                    // rows / columns outside the tensors stay zero
-      const bool row_ok = is_a ? (t0 + row < p.T) : (s0 + row < S1);
-      if (row_ok) {
-        const float *base = is_a ? amb + (size_t)(t0 + row) * C : lmb + (size_t)(s0 + row) * C;
-        const float4 *src = reinterpret_cast<const float4 *>(base + c);
+      if (src_off[i] >= 0) {
+        const float4 *src = reinterpret_cast<const float4 *>((is_a ? amb : lmb) + src_off[i] + k0);
         if (c < C) rr[i][0] = __ldg(src);         // C % 4 == 0: a float4 is inside or outside the row
         if (c + 4 < C) rr[i][1] = __ldg(src + 1);
       }
@@ -319,13 +332,13 @@ simple_logprobs_tc_kernel(SimpleParams p) {
   // ---- registers -> operand stage: exp, three-term bf16 split by mantissa truncation (h = top 16 bits of
   //      p, m = top 16 bits of the exact remainder, l likewise: h+m+l = p to 2^-24, plain ALU ops),
   //      16-byte chunks in the K-major SWIZZLE_128B layout ----
-  auto store_piece = [&](const float4 (&r)[2], float nmx, int lim, unsigned char *dst, uint32_t stride) {
+  auto store_piece = [&](auto masked, const float4 (&r)[2], float nmx, int lim, unsigned char *dst, uint32_t stride) {
     const float x[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
     uint32_t hb[8], mb[8], lb[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float pr = ex2_approx(fmaf(x[e], kLog2e, nmx));
-      pr = (e < lim) ? pr : 0.f;
+      if (decltype(masked)::value) pr = (e < lim) ? pr : 0.f;    // only the last slice has columns beyond C
       hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
       const float r1 = pr - __uint_as_float(hb[e]);
       mb[e] = __float_as_uint(r1);
@@ -342,13 +355,17 @@ simple_logprobs_tc_kernel(SimpleParams p) {
   };
   auto store_slice = [&](int k, unsigned char *stage) {
     const int k0 = k * KC;
+    const bool full_slice = k0 + KC <= C;        // block-uniform: no column of this slice lies beyond C
+    if (full_slice) {
 #pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      bool is_a; int row, j;
-      piece(i, is_a, row, j);
-      const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-      if (is_a) store_piece(rr[i], sm.amneg[row], C - k0 - j * 8, stage + off, kOpABytes);   // masked rows: -inf -> 0
-      else store_piece(rr[i], sm.lmneg[row], C - k0 - j * 8, stage + kOffB + off, kOpBBytes);
+      for (int i = 0; i < kPieces; ++i)
+        store_piece(std::false_type{}, rr[i], nmx_of[i], 8, stage + dst_off[i],
+                    tid + i * kConvThreads < TM * 8 ? kOpABytes : kOpBBytes);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kPieces; ++i)
+        store_piece(std::true_type{}, rr[i], nmx_of[i], C - k0 - ((tid + i * kConvThreads) & 7) * 8, stage + dst_off[i],
+                    tid + i * kConvThreads < TM * 8 ? kOpABytes : kOpBBytes);
     }
   };
 
