@@ -147,12 +147,17 @@ struct ChainParams {
 // and every warp sits alone on its SM sub-partition.  XY chunks are shared by
 // all warps: NST > W stages of 1-D bulk copies; the tail warp of the pipeline
 // recycles a stage.
-template <int RPL, int DIR>
+//
+// PC != 0: the plane pitch P is the compile-time constant PC and a chunk is kChunk diagonals.  A full chunk
+// then runs as one straight-line block of kChunk steps in which every shared- and global-memory address is a
+// constant offset from the chunk's base pointers (no per-step pointer arithmetic): the step is bound by
+// instruction issue on one SM sub-partition, and this form issues about half the instructions per step.
+template <int RPL, int DIR, int PC>
 __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5;
-  const int P = p.P, CH = p.CH, NST = p.NST;
+  const int P = PC ? PC : p.P, CH = PC ? kChunk : p.CH, NST = p.NST;
   const int stage_elems = CH * P;
   // one diagonal of padding on either side of the ring: the operand prefetch of the last step of a
   // chunk reads one diagonal past it
@@ -160,7 +165,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   uint64_t *mbar_xy = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_elems + P);
   uint64_t *mbar_edge = mbar_xy + NST;                               // [W][NST], indexed by consumer warp
   float2 *edge = reinterpret_cast<float2 *>(mbar_edge + W * NST);    // [W][NST][CH], indexed by consumer warp
-  float2 *dead_edge = edge + (size_t)W * NST * CH;                   // one entry: what an unfed warp reads
+  float2 *dead_edge = edge + (size_t)W * NST * CH;                   // CH entries: what an unfed warp reads
 
   const int4 bd = *reinterpret_cast<const int4 *>(p.boundary + 4 * b);
   const int Sb = bd.z - bd.x, Tb = bd.w - bd.y;
@@ -180,8 +185,8 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   if (tid == 0) {
     for (int i = 0; i < NST + W * NST; ++i) mbar_init(&mbar_xy[i], 1);
     mbar_fence_init();
-    *dead_edge = make_float2(0.f, __int_as_float(kNegI));
   }
+  for (int i = tid; i < CH; i += blockDim.x) dead_edge[i] = make_float2(0.f, __int_as_float(kNegI));
   // Backward, last lane of the lattice: the symbol arc "into row r0 + RPL" is read at row P of a diagonal,
   // i.e. at row 0 of the next diagonal in the ring.  Row 0 has no incoming symbol arc, so that entry is a dead
   // arc in every diagonal the bulk copies deliver - but behind the last diagonal of the last stage lies the
@@ -203,7 +208,6 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   const bool lane_out = DIR ? (lane == 0) : (lane == 31);   // lane feeding the next warp
   const bool publish = lane_out && feeds;
   constexpr int step_sign = DIR ? -1 : 1;
-  const int pe_step = fed ? step_sign : 0;
   const float2 dead2 = make_float2(0.f, __int_as_float(kNegI));
   float m[RPL];
   int o[RPL];
@@ -244,12 +248,20 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
     const int el0 = (DIR ? e_hi : e_lo) - cbase;
     // running pointers, all advanced by one diagonal per step
     const float4 *xp = xstage + el0 * P;                                 // arcs of the current step
-    const float2 *pe = fed ? estage_in + el0 : estage_in;                // feeding row's state
+    const float2 *pe = estage_in + el0;                                  // feeding row's state
     float2 *po = estage_out + el0;                                       // our state for the fed warp
     // operands of the first step of the chunk
     float4 a4[RPL];
     float2 xnext = dead2;
+    // The feeding warp publishes its values as they are (un-normalised, like the ones the lanes of a warp hand
+    // each other): both warps were normalised at the same chunk boundary, so after q steps both are bounded by
+    // 2 * 4^q and the bound does not compound.  Only the value carried over a chunk boundary is normalised here.
     float2 ev = carry;
+    {
+      int ce = __float_as_int(ev.y);
+      normalise_pair(ev.x, ce);
+      ev.y = __int_as_float(ce);
+    }
 #pragma unroll
     for (int j = 0; j < RPL; ++j) a4[j] = make_float4(0.f, dead2.y, 0.f, dead2.y);
     if (n > 0) {
@@ -258,16 +270,17 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
       if (DIR) xnext = *reinterpret_cast<const float2 *>(xp + RPL);
     }
     int nb_o_sh = DIR ? __shfl_down_sync(0xffffffffu, o[0], 1) : __shfl_up_sync(0xffffffffu, o[RPL - 1], 1);
-#pragma unroll 2
-    for (int q = 0; q < n; ++q) {
+    // One step; `so` = its diagonal relative to the running pointers (0 in the generic loop, which advances
+    // the pointers every step; a compile-time constant in the straight-line form of a full chunk).
+    auto do_step = [&](const int so) {
       // ---- prefetch the operands of the next step (off the dependency chain).  After the last
       // step of a chunk this reads one diagonal past the chunk (the ring is padded); unused. ----
       float4 b4[RPL];
       float2 xnext2 = dead2;
 #pragma unroll
-      for (int j = 0; j < RPL; ++j) b4[j] = xp[step_sign * P + j];
-      if (DIR) xnext2 = *reinterpret_cast<const float2 *>(xp + step_sign * P + RPL);
-      const float2 ev2 = *pe;   // the feeding row's state after ITS step e = input of our next step (broadcast read)
+      for (int j = 0; j < RPL; ++j) b4[j] = xp[(so + step_sign) * P + j];
+      if (DIR) xnext2 = *reinterpret_cast<const float2 *>(xp + (so + step_sign) * P + RPL);
+      const float2 ev2 = pe[so];   // the feeding row's state after ITS step e = input of our next step (broadcast read)
 
       // ---- neighbour across the lane boundary (its frame was shuffled as soon as it was known) ----
       float nb_m = DIR ? __shfl_down_sync(0xffffffffu, m[0], 1) : __shfl_up_sync(0xffffffffu, m[RPL - 1], 1);
@@ -287,7 +300,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
           if (j == RPL - 1) nb_o_sh = __shfl_up_sync(0xffffffffu, on[j], 1);     // frame chain runs ahead
           const float gx = a4[j].x * pow2i(EA - on[j]);
           raw[j] = fmaf(fm, gx, m[j] * (a4[j].z * pow2i(EB - on[j])));
-          pa[j] = make_float2(raw[j], __int_as_float(on[j]));
+          pa[so * P + j] = make_float2(raw[j], __int_as_float(on[j]));
         }
       } else {
         // beta_{e-1}(s') = X[e][s'+1] * beta_e(s'+1) + Y[e][s'] * beta_e(s')
@@ -305,7 +318,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
           const float c = m[j] * (a4[j].z * pow2i(EB - on[j]));
           raw[j] = fmaf(fm, gx, c);
           // operands of diagonal e-1, expressed in the frame `on`
-          pb[j] = make_float4(fm * gx, c, __int_as_float(on[j]), 0.f);
+          pb[so * P + j] = make_float4(fm * gx, c, __int_as_float(on[j]), 0.f);
         }
       }
       // The frames evolve by integer ops only and the mantissas by one FMA: two short, independent
@@ -313,22 +326,31 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
       // at most x4 per step) and are re-normalised at the chunk boundary.
 #pragma unroll
       for (int j = 0; j < RPL; ++j) { m[j] = raw[j]; o[j] = on[j]; }
-      {                           // what the fed warp reads is always normalised (bounds do not compound)
-        float pm = DIR ? m[0] : m[RPL - 1];
-        int po_frame = DIR ? o[0] : o[RPL - 1];
-        normalise_pair(pm, po_frame);
-        if (publish) *po = make_float2(pm, __int_as_float(po_frame));
-      }
-      // rotate the prefetched operands in, advance the running pointers
+      if (publish) po[so] = make_float2(DIR ? m[0] : m[RPL - 1], __int_as_float(DIR ? o[0] : o[RPL - 1]));
+      // rotate the prefetched operands in
 #pragma unroll
       for (int j = 0; j < RPL; ++j) a4[j] = b4[j];
       xnext = xnext2;
       ev = ev2;
-      xp += step_sign * P;
-      pe += pe_step;
-      po += step_sign;
-      pa += step_sign * P;
-      pb += step_sign * P;
+    };
+    if (PC != 0 && n == kChunk) {
+#pragma unroll
+      for (int q = 0; q < kChunk; ++q) do_step(q * step_sign);
+      xp += step_sign * kChunk * P;
+      pe += step_sign * kChunk;
+      po += step_sign * kChunk;
+      pa += step_sign * kChunk * P;
+      pb += step_sign * kChunk * P;
+    } else {
+#pragma unroll 2
+      for (int q = 0; q < n; ++q) {
+        do_step(0);
+        xp += step_sign * P;
+        pe += step_sign;
+        po += step_sign;
+        pa += step_sign * P;
+        pb += step_sign * P;
+      }
     }
 #pragma unroll
     for (int j = 0; j < RPL; ++j) normalise_pair(m[j], o[j]);
@@ -357,10 +379,10 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
 
 // grid = (B, 2): blockIdx.y selects the direction so that the forward and the
 // backward chain of every utterance run concurrently on different SMs.
-template <int RPL>
+template <int RPL, int PC>
 __global__ void __launch_bounds__(256, 1) dp_chain_kernel(ChainParams p) {
-  if (blockIdx.y == 0) dp_chain_body<RPL, 0>(p);
-  else dp_chain_body<RPL, 1>(p);
+  if (blockIdx.y == 0) dp_chain_body<RPL, 0, PC>(p);
+  else dp_chain_body<RPL, 1, PC>(p);
 }
 
 // ---------------------------------------------------------------------------
@@ -469,7 +491,7 @@ static ChainConfig chain_config(const DpGeom &g) {
   c.W = g.P / (32 * g.rpl);
   auto bytes = [&](int nst, int ch) {
     return (size_t)(nst * ch + 2) * g.P * sizeof(float4) + (size_t)(nst + c.W * nst) * sizeof(uint64_t) +
-           (size_t)(c.W * nst * ch + 1) * sizeof(float2) + 128;
+           (size_t)(c.W * nst * ch + ch) * sizeof(float2) + 128;
   };
   const size_t budget = 200 * 1024;
   // ring = one stage per warp of the pipeline + look-ahead; prefer 32 diagonals of look-ahead (a bulk
@@ -494,13 +516,19 @@ int launch_chain(const int32_t *boundary, const DpGeom &g, const DpWorkspace &w,
   dim3 grid(g.B, both_directions ? 2 : 1);
   const int threads = 32 * c.W;
   cudaError_t e;
-#define FRN_LAUNCH_CHAIN(RPL_)                                                                              \
-  e = cudaFuncSetAttribute(dp_chain_kernel<RPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem); \
-  if (e != cudaSuccess) return note_cuda_error(e);                                                          \
-  count_launch(), dp_chain_kernel<RPL_><<<grid, threads, c.smem, stream>>>(cp);
-  if (g.rpl == 1) { FRN_LAUNCH_CHAIN(1) }
-  else if (g.rpl == 2) { FRN_LAUNCH_CHAIN(2) }
-  else { FRN_LAUNCH_CHAIN(4) }
+#define FRN_LAUNCH_CHAIN(RPL_, PC_)                                                                                \
+  e = cudaFuncSetAttribute(dp_chain_kernel<RPL_, PC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem); \
+  if (e != cudaSuccess) return note_cuda_error(e);                                                                \
+  count_launch(), dp_chain_kernel<RPL_, PC_><<<grid, threads, c.smem, stream>>>(cp);
+  // straight-line chunks for the pitches of short label sequences (S + 1 <= 128: c1, c2, c3)
+  const bool fixed = g.rpl == 1 && c.CH == kChunk && debug_env_int("FRN_CHAIN_GENERIC", 0) == 0;
+  if (fixed && g.P == 128) { FRN_LAUNCH_CHAIN(1, 128) }
+  else if (fixed && g.P == 96) { FRN_LAUNCH_CHAIN(1, 96) }
+  else if (fixed && g.P == 64) { FRN_LAUNCH_CHAIN(1, 64) }
+  else if (fixed && g.P == 32) { FRN_LAUNCH_CHAIN(1, 32) }
+  else if (g.rpl == 1) { FRN_LAUNCH_CHAIN(1, 0) }
+  else if (g.rpl == 2) { FRN_LAUNCH_CHAIN(2, 0) }
+  else { FRN_LAUNCH_CHAIN(4, 0) }
 #undef FRN_LAUNCH_CHAIN
   return check_launch();
 }
