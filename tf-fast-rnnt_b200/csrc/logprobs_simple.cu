@@ -38,14 +38,27 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
   const bool is_lm = row < rows_lm;
   if (!is_lm) row -= rows_lm;
   const float *src = (is_lm ? lm : am) + (size_t)row * C;
-  if (!is_lm && pxam_t) {
-    const int32_t *sym = symbols + (size_t)(row / T) * S;
-    float *dst = pxam_t + (size_t)row * S;
-    for (int s = lane; s < S; s += 32) {
-      const int c = sym[s];
-      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+  // am[b,t,sym[b,s]] for the normaliser's epilogue (SimpleParams::pxam_t): the symbol indices are fetched first,
+  // the gathers are issued right behind the row's own vector loads (same sectors, one memory round trip for
+  // both) and stored at the end - a gather in front of the row loads was a second, dependent round trip.
+  const bool gather = !is_lm && pxam_t != nullptr;
+  constexpr int kG = 4;                         // gathers in flight per lane beside the row (S <= 128: all of them)
+  int gidx[kG];
+  float gval[kG];
+  const int32_t *sym = gather ? symbols + (size_t)(row / T) * S : nullptr;
+  if (gather) {
+#pragma unroll
+    for (int u = 0; u < kG; ++u) {
+      const int s = lane + 32 * u;
+      gidx[u] = s < S ? sym[s] : -1;
     }
   }
+  auto issue_gathers = [&]() {
+    if (gather) {
+#pragma unroll
+      for (int u = 0; u < kG; ++u) gval[u] = (gidx[u] >= 0 && gidx[u] < C) ? __ldg(src + gidx[u]) : 0.f;
+    }
+  };
   float *rmax = is_lm ? lmmax : ammax;
   float *rsum = is_lm ? lmsum : nullptr;
   float m = -INFINITY;
@@ -60,6 +73,7 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
       v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       if (c < nv) v[u] = ld_stream_f4(p + c);
     }
+    issue_gathers();
 #pragma unroll
     for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
     m = warp_max(m);
@@ -72,6 +86,7 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
       if (lane == 0) rsum[row] = s;
     }
   } else {
+    issue_gathers();
     for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
     m = warp_max(m);
     if (rsum) {
@@ -82,6 +97,16 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
     }
   }
   if (lane == 0) rmax[row] = m;
+  if (gather) {
+    float *dst = pxam_t + (size_t)row * S;
+#pragma unroll
+    for (int u = 0; u < kG; ++u)
+      if (lane + 32 * u < S) dst[lane + 32 * u] = gval[u];
+    for (int s = lane + 32 * kG; s < S; s += 32) {      // long label sequences: the row is in L1 / L2 by now
+      const int c = sym[s];
+      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+    }
+  }
 }
 
 // unigram[c] = mean_rows( exp(lm-lmmax)/lmsum ) + tiny  (rnnt_loss.py:1279-1280),

@@ -138,6 +138,15 @@ struct ChainParams {
   int CH, NST;         // diagonals per bulk copy; ring stages (> warps)
 };
 
+#ifdef FRN_CHAIN_TIMING
+// diagnostic build only (scripts/chain_timing.py): cycles of block 0's warps spent waiting for arcs, waiting for
+// the feeding warp, in the steps, and in total: [direction][warp][4]
+__device__ unsigned long long g_chain_timing[2][8][4];
+#define FRN_CT(x) x
+#else
+#define FRN_CT(x)
+#endif
+
 // Execution.  One CTA per (utterance, direction); RPL consecutive lattice rows
 // per lane, 32*RPL rows per warp, W = P / (32*RPL) warps.  The warps form a
 // software pipeline: warp w runs one chunk (CH diagonals) behind the warp that
@@ -240,9 +249,13 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
   float4 *pb = outB + (size_t)((DIR ? min(cbase + CH - 1, Db) : 1) - 1) * P;
   const float4 *gnext = XYg + (size_t)(DIR ? (nchunk - 1 - NST) : NST) * stage_elems;   // next chunk to request
 
+  FRN_CT(long long ct_xy = 0; long long ct_in = 0; long long ct_steps = 0; const long long ct_begin = clock64();)
   for (int i = 0; i < nchunk; ++i) {
+    FRN_CT(const long long ct0 = clock64();)
     mbar_wait(bar_xy, par);
+    FRN_CT(const long long ct1 = clock64();)
     if (fed) mbar_wait(bar_in, par);            // the feeding warp has published this chunk
+    FRN_CT(const long long ct2 = clock64(); ct_xy += ct1 - ct0; ct_in += ct2 - ct1;)
     const int e_lo = max(cbase, 1), e_hi = min(cbase + CH - 1, Db);
     const int n = e_hi - e_lo + 1;
     const int el0 = (DIR ? e_hi : e_lo) - cbase;
@@ -352,6 +365,7 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
         pb += step_sign * P;
       }
     }
+    FRN_CT(ct_steps += clock64() - ct2;)
 #pragma unroll
     for (int j = 0; j < RPL; ++j) normalise_pair(m[j], o[j]);
     carry = ev;   // the feeding row's state after the last step of this chunk
@@ -375,6 +389,12 @@ __device__ __forceinline__ void dp_chain_body(const ChainParams &p) {
       if (fed) estage_in -= NST * CH;
     }
   }
+#ifdef FRN_CHAIN_TIMING
+  if (b == 0 && lane == 0 && w < 8) {
+    unsigned long long *t = g_chain_timing[DIR][w];
+    t[0] = ct_xy; t[1] = ct_in; t[2] = ct_steps; t[3] = clock64() - ct_begin;
+  }
+#endif
 }
 
 // grid = (B, 2): blockIdx.y selects the direction so that the forward and the
@@ -548,3 +568,9 @@ int launch_finalize_dense(const int32_t *boundary, const DpGeom &g, const DpWork
 }
 
 }  // namespace frn
+
+#ifdef FRN_CHAIN_TIMING
+extern "C" int frn_debug_chain_timing(unsigned long long *host_out) {
+  return cudaMemcpyFromSymbol(host_out, frn::g_chain_timing, sizeof(frn::g_chain_timing)) == cudaSuccess ? 0 : 1;
+}
+#endif
