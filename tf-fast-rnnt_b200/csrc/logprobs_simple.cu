@@ -9,6 +9,8 @@
 // products, the parity baseline).  The tcgen05/TMA split-precision version of
 // the contraction lives in logprobs_simple_tc.cu when enabled; both share the
 // row-statistics kernels and the epilogue below.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -28,10 +30,25 @@ __device__ __forceinline__ float tiny_f32() { return __int_as_float(1); }
 // `pxam_t` != null: the warp that streams am row (b,t) also leaves am[b,t,symbols[b,s]], s < S, in
 // pxam_t[b][t][s] (the row is hot in L2 / L1 at that moment; the tensor-core kernel's epilogue reads its
 // frame's S values as one contiguous run instead of gathering across rows).
+// `split` != null (tensor-core normaliser): the warp also leaves its row as the two-term float16 operand the
+// tensor cores contract, p = exp(x - rowmax) * 2^15 = h + l' * 2^-11 with h = fp16(p), l' = fp16((p - h) * 2^11)
+// (SplitPlanes; pitch Cp halves per row): every probability is exponentiated and split ONCE here instead of once
+// per 128 x 112 tile of the contraction (12 x for lm, 4 x for am at the c4 shape).
+__device__ __forceinline__ void split4(const float4 &x, float nmx, uint2 &h, uint2 &l) {
+  const float p0 = ex2_approx(fmaf(x.x, kLog2e, nmx)), p1 = ex2_approx(fmaf(x.y, kLog2e, nmx));
+  const float p2 = ex2_approx(fmaf(x.z, kLog2e, nmx)), p3 = ex2_approx(fmaf(x.w, kLog2e, nmx));
+  const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn((p0 - f01.x) * 2048.f, (p1 - f01.y) * 2048.f);
+  const __half2 l23 = __floats2half2_rn((p2 - f23.x) * 2048.f, (p3 - f23.y) * 2048.f);
+  h = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+  l = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+}
+
 __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
                                                        int C, float *lmmax, float *lmsum, float *ammax,
                                                        const int32_t *symbols = nullptr, int S = 0, int T = 1,
-                                                       float *pxam_t = nullptr) {
+                                                       float *pxam_t = nullptr, SplitPlanes split = SplitPlanes()) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows_lm + rows_am) return;
@@ -84,6 +101,49 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
         if (u * 32 + lane < nv) s += (expf(v[u].x - m) + expf(v[u].y - m)) + (expf(v[u].z - m) + expf(v[u].w - m));
       s = warp_sum(s);
       if (lane == 0) rsum[row] = s;
+    }
+    if (split.Cp) {
+      uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
+      uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
+      const float nmx = fmaf(-m, kLog2e, 15.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = u * 32 + lane;
+        if (c < nv) {
+          uint2 h, l;
+          split4(v[u], nmx, h, l);
+          hrow[c] = h; lrow[c] = l;
+        }
+      }
+    }
+  } else if (vec) {
+    // long rows (large vocabularies): three passes of 128-bit loads over a row that stays in L1 / L2
+    issue_gathers();
+    const int nv = C / 4;
+    const float4 *p = reinterpret_cast<const float4 *>(src);
+    for (int c = lane; c < nv; c += 32) {
+      const float4 x = __ldg(p + c);
+      m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+    }
+    m = warp_max(m);
+    if (rsum) {
+      float s = 0.f;
+      for (int c = lane; c < nv; c += 32) {
+        const float4 x = __ldg(p + c);
+        s += (expf(x.x - m) + expf(x.y - m)) + (expf(x.z - m) + expf(x.w - m));
+      }
+      s = warp_sum(s);
+      if (lane == 0) rsum[row] = s;
+    }
+    if (split.Cp) {
+      uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
+      uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
+      const float nmx = fmaf(-m, kLog2e, 15.f);
+      for (int c = lane; c < nv; c += 32) {
+        uint2 h, l;
+        split4(__ldg(p + c), nmx, h, l);
+        hrow[c] = h; lrow[c] = l;
+      }
     }
   } else {
     issue_gathers();
@@ -272,6 +332,98 @@ __global__ void __launch_bounds__(256) constrained_fix_kernel(float *px, const f
   px[i] += py[(size_t)b * (S + 1) * T + T + rem];
 }
 
+// Long rows (1024 < C <= 8192, large vocabularies): one BLOCK per row, the row held in registers (up to 8 float4
+// per thread), so the row is read from memory once for the maximum, the sum and the float16 split.  With a warp
+// per row the three passes re-read 20 KB rows that ~10 k resident warps had long pushed out of L2 (the kernel
+// read am and lm twice from DRAM at the c4 shape).
+__global__ void __launch_bounds__(256) rowstats_long_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
+                                                            int C, float *lmmax, float *lmsum, float *ammax,
+                                                            const int32_t *symbols, int S, int T, float *pxam_t,
+                                                            SplitPlanes split) {
+  __shared__ float red[8];
+  int row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool is_lm = row < rows_lm;
+  if (!is_lm) row -= rows_lm;
+  const float *src = (is_lm ? lm : am) + (size_t)row * C;
+  const int nv = C / 4;
+  const float4 *p = reinterpret_cast<const float4 *>(src);
+  float4 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = u * 256 + tid;
+    v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c < nv) v[u] = ld_stream_f4(p + c);
+  }
+  // am[b,t,sym[b,s]] (see rowstats_kernel): issued behind the row's loads
+  const bool gather = !is_lm && pxam_t != nullptr;
+  if (gather) {
+    const int32_t *sym = symbols + (size_t)(row / T) * S;
+    float *dst = pxam_t + (size_t)row * S;
+    for (int s = tid; s < S; s += 256) {
+      const int c = sym[s];
+      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  float *rsum = is_lm ? lmsum : nullptr;
+  if (rsum) {                                   // block-uniform
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (u * 256 + tid < nv) s += (expf(v[u].x - m) + expf(v[u].y - m)) + (expf(v[u].z - m) + expf(v[u].w - m));
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[w] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i];
+      rsum[row] = t;
+    }
+  }
+  if (tid == 0) (is_lm ? lmmax : ammax)[row] = m;
+  if (split.Cp) {
+    uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
+    uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
+    const float nmx = fmaf(-m, kLog2e, 15.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = u * 256 + tid;
+      if (c < nv) {
+        uint2 h, l;
+        split4(v[u], nmx, h, l);
+        hrow[c] = h; lrow[c] = l;
+      }
+    }
+  }
+}
+
+// row statistics of lm ([rows_lm][C]) and am ([rows_am][C]) in one launch: a warp per row, or a block per row for
+// long aligned rows
+static void launch_rowstats(const float *lm, int rows_lm, const float *am, int rows_am, int C, float *lmmax,
+                            float *lmsum, float *ammax, const int32_t *symbols, int S, int T, float *pxam_t,
+                            const SplitPlanes &split, cudaStream_t stream) {
+  const bool aligned = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0;
+  if (aligned && C > 4 * 32 * 8 && C <= 4 * 256 * 8 && rows_lm + rows_am > 0) {
+    count_launch(), rowstats_long_kernel<<<rows_lm + rows_am, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C, lmmax, lmsum,
+                                                                                 ammax, symbols, S, T, pxam_t, split);
+  } else {
+    count_launch(), rowstats_kernel<<<(rows_lm + rows_am + 7) / 8, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C, lmmax,
+                                                                                      lmsum, ammax, symbols, S, T, pxam_t,
+                                                                                      split);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------
@@ -279,6 +431,9 @@ size_t simple_stats_bytes(int B, int S, int T, int C) {
   size_t n = 2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256) +
              2 * round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)C * sizeof(float), 256) +
              round_up_sz((size_t)B * T * S * sizeof(float), 256);        // pxam_t
+  // two-term float16 operands of the tensor-core contraction (SplitPlanes): h and l planes of am and of lm
+  const size_t Cp = (size_t)round_up(C, 8);
+  n += 2 * round_up_sz((size_t)B * T * Cp * 2, 256) + 2 * round_up_sz((size_t)B * (S + 1) * Cp * 2, 256);
   return n;
 }
 
@@ -294,7 +449,7 @@ int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w);
-  count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax);
+  launch_rowstats(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax, nullptr, 0, 1, nullptr, SplitPlanes(), stream);
   count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
                                                                  unigram, logu);
   count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
@@ -308,7 +463,7 @@ int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, fl
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
   float *lmsum = reinterpret_cast<float *>(w);
-  count_launch(), rowstats_kernel<<<(B * S1 + 7) / 8, 256, 0, stream>>>(lm, B * S1, lm, 0, C, lmmax, lmsum, lmmax);
+  launch_rowstats(lm, B * S1, lm, 0, C, lmmax, lmsum, lmmax, nullptr, 0, 1, nullptr, SplitPlanes(), stream);
   count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, nullptr, sums, nullptr,
                                                                  nullptr);
   return check_launch();
@@ -334,11 +489,19 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
-  float *pxam_t = reinterpret_cast<float *>(w);
+  float *pxam_t = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * S * sizeof(float), 256);
   const bool tc = simple_logprobs_tc_applicable(lm, am, C) && debug_env_int("FRN_SIMPLE_SIMT", 0) != 1;
-  count_launch(), rowstats_kernel<<<(B * S1 + B * T + 7) / 8, 256, 0, stream>>>(lm, B * S1, am, B * T, C, lmmax,
-                                                                                 smoothed ? lmsum : nullptr, ammax, symbols,
-                                                                                 S, T, tc ? pxam_t : nullptr);
+  SplitPlanes split;
+  if (tc) {
+    split.Cp = round_up(C, 8);
+    const size_t am_plane = round_up_sz((size_t)B * T * split.Cp * 2, 256), lm_plane = round_up_sz((size_t)B * S1 * split.Cp * 2, 256);
+    split.amh = reinterpret_cast<unsigned short *>(w); w += am_plane;
+    split.aml = reinterpret_cast<unsigned short *>(w); w += am_plane;
+    split.lmh = reinterpret_cast<unsigned short *>(w); w += lm_plane;
+    split.lml = reinterpret_cast<unsigned short *>(w);
+  }
+  launch_rowstats(lm, B * S1, am, B * T, C, lmmax, smoothed ? lmsum : nullptr, ammax, symbols, S, T,
+                  tc ? pxam_t : nullptr, split, stream);
   if (smoothed) {
     count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
                                                                    unigram, logu);
@@ -349,7 +512,7 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   SimpleParams sp;
   sp.lm = lm; sp.am = am; sp.symbols = symbols; sp.boundary = boundary;
   sp.lmmax = lmmax; sp.ammax = ammax; sp.lmsum = lmsum; sp.amonly = amonly; sp.logu = logu;
-  sp.px = px; sp.py = py; sp.pxam_t = tc ? pxam_t : nullptr;
+  sp.px = px; sp.py = py; sp.pxam_t = tc ? pxam_t : nullptr; sp.split = split;
   sp.B = B; sp.S = S; sp.T = T; sp.T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T; sp.C = C; sp.term = term;
   sp.rnnt_type = rnnt_type; sp.smoothed = smoothed;
   // Python-float arithmetic of rnnt_loss.py:1342-1349, then cast to float32

@@ -2,23 +2,21 @@
 //
 //   norm[b,s,t] = log( sum_c exp(lm[b,s,c]-lmmax[b,s]) * exp(am[b,t,c]-ammax[b,t]) + tiny ) + maxes
 //
-// One CTA = one (utterance, 128-frame tile, <=112-symbol tile).  Per 64-wide
-// slice of the vocabulary axis:
-//   1. all 512 threads load their 32-byte pieces of the am and lm tiles straight from global memory
-//      into registers - issued right after the previous slice's MMAs, so the loads fly while the
-//      tensor core works;
-//   2. they turn them into probabilities exp(x - rowmax) and split each into three bfloat16 terms
-//      h+m+l (24 mantissa bits), written in the K-major SWIZZLE_128B layout tcgen05 reads, into one
-//      of TWO operand stages: the conversion of slice k+1 overlaps the MMAs of slice k;
-//   3. one thread issues 6 tcgen05.mma (hh, hm, mh, mm, hl, lh - everything down to 2^-24
-//      relative) per 16-wide k step into one of two 128 x N float32 accumulators in tensor memory
-//      and commits to the stage's mbarrier; the partial sums of slice k-2 are drained into
-//      registers before its stage is overwritten (tensor-core accumulation truncates: every slice
-//      starts from zero and the slices are summed in float32 registers).
-// (The first version staged raw tiles through shared memory with TMA and single-buffered operands:
-// convert and MMA never overlapped and the raw tiles cost a third of the kernel's shared-memory
-// traffic; am[b,t,sym_s] was picked out of the raw tile - it now comes from the row-statistics
-// kernel, which has every am row in flight anyway: SimpleParams::pxam_t.)
+// One CTA = one (utterance, 128-frame tile, <=112-symbol tile).  The operands are NOT built here: the
+// row-statistics kernel (logprobs_simple.cu), which streams every am / lm row anyway, leaves each probability
+// p = exp(x - rowmax) * 2^15 as a two-term float16 split  p = h + l * 2^-11  (h = fp16(p), l = fp16((p - h) 2^11):
+// 22 mantissa bits, and l has the range of h, so small probabilities keep their relative precision) - once per
+// element instead of once per tile (the in-kernel conversion was MUFU- and issue-bound: every CTA re-exponentiated
+// and re-split its 240 x 64 slice, 6 x redundant over the grid at the c4 shape).  What is left is a GEMM pipeline:
+//   warp 16   one thread: per 64-wide vocabulary slice four TMA boxes (A_h, A_l: 128 frames; B_h, B_l: 112 symbols;
+//             SWIZZLE_128B, i.e. exactly the K-major layout tcgen05 reads; rows / columns outside the tensors
+//             arrive as zeros) into one of THREE 60 KB stages, full[stage] counts the bytes;
+//   warp 17   one thread: per 16-wide k step three tcgen05.mma - l_a h_b and h_a l_b into the cross-term
+//             accumulator (kept over all slices, weight 2^-11), h_a h_b into one of two per-slice accumulators;
+//             tcgen05.commit frees the stage (empty[stage]) and publishes the slice (accfull[acc]);
+//   warps 0-15 drain the per-slice accumulator into float32 registers (tensor-core accumulation truncates: a
+//             slice starts from zero and the slices are summed in registers) and hand it back (accfree[acc]).
+// Dropped: l_a l_b (2^-22 relative).  Z = (sum h h + 2^-11 sum cross) * 2^-30.
 // Epilogue: tcgen05.ld the accumulator (one lattice frame per thread), then either
 //   (a) log, un-shift, symbol / blank gather, smoothing terms, boundary fix-ups, and store
 //       px/py coalesced along t in the reference layout (rnnt_loss.py:186-221,1290-1365)
@@ -50,14 +48,17 @@ namespace tc {
 constexpr int TM = 128;   // frames per CTA  (MMA M)
 constexpr int TN = 112;   // symbols per CTA (MMA N, multiple of 16)
 constexpr int KC = 64;    // vocabulary slice per stage = one 128-byte swizzle row of bf16
-constexpr int kThreads = 512;   // 16 warps: 4 per TMEM lane quarter, 28 symbol columns each
-constexpr int kTmemCols = 256;  // two accumulators: [0,112) and [128,240)
+constexpr int kEpiWarps = 16;   // drain / epilogue warps: 4 per TMEM lane quarter, 28 symbol columns each
+constexpr int kThreads = (kEpiWarps + 2) * 32;   // + the TMA producer warp + the MMA issuer warp
+constexpr int kStages = 3;
+constexpr int kTmemCols = 512;  // two per-slice accumulators [0,112), [128,240) and the cross-term accumulator [256,368)
 constexpr int kAccStride = 128;
+constexpr int kCrossCol = 256;
 constexpr uint32_t kOpABytes = TM * KC * 2, kOpBBytes = TN * KC * 2;
-// shared memory map (byte offsets from a 1024-aligned base): two operand stages, then the small block
-constexpr uint32_t kOffB = 3 * kOpABytes;                      // inside a stage: 3 x A (h, m, l), then 3 x B
-constexpr uint32_t kStageBytes = 3 * kOpABytes + 3 * kOpBBytes;
-constexpr uint32_t kOffSmall = 2 * kStageBytes;
+// shared memory map (byte offsets from a 1024-aligned base): three operand stages, then the small block
+constexpr uint32_t kOffB = 2 * kOpABytes;                      // inside a stage: A_h, A_l, then B_h, B_l
+constexpr uint32_t kStageBytes = 2 * kOpABytes + 2 * kOpBBytes;
+constexpr uint32_t kOffSmall = kStages * kStageBytes;
 constexpr uint32_t kSmallBytes = 8192;
 constexpr uint32_t kSmemBytes = kOffSmall + kSmallBytes + 1024;  // + alignment slack
 // Accumulator columns of a thread: the four warps of a TMEM lane quarter (`half` = 0..3) take 28
@@ -72,7 +73,7 @@ constexpr double kLog2eD = 1.4426950408889634074;
 constexpr float kLog2eLo = 1.92596299112661746e-8f;   // log2(e) - (float)log2(e)
 struct Small {                                        // per-CTA row / column constants
   double sm_x[TN], sm_y[TN];                          // smoothed: lm_scale * log2e * (lm[s,sym|blank] - lmonly[s])
-  uint64_t bars[4];                                   // full[2], done[2] (one each per operand stage)
+  uint64_t bars[2 * kStages + 4];                     // full[kStages], empty[kStages], accfull[2], accfree[2]
   float amneg[TM], lmneg[TN];                         // -max * log2e (-inf: row masked)
   float ammax[TM], lmmax[TN];
   float pxlm[TN], pylm[TN], lmonly[TN], logusym[TN];
@@ -103,11 +104,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (format 0), both K-major
 __device__ __forceinline__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -131,15 +139,13 @@ __device__ __forceinline__ float log_plus_tiny(float z) {
   const float r = (e + lg2_approx(m)) * kLn2;
   return (z < 1.1754944e-38f) ? -103.27893f : r;
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-  uint32_t r[4];
+// four accumulator columns of this thread's lane; the caller waits once (tmem_ld_wait) for a batch of loads
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // bounded mbarrier wait: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
@@ -158,7 +164,9 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 
 template <bool kXY>
 __global__ void __launch_bounds__(tc::kThreads, 1)
-simple_logprobs_tc_kernel(SimpleParams p) {
+simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __grid_constant__ CUtensorMap map_aml,
+                          const __grid_constant__ CUtensorMap map_lmh, const __grid_constant__ CUtensorMap map_lml,
+                          SimpleParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B operands need a 1024-byte aligned base; keep the arithmetic on the
@@ -182,11 +190,30 @@ simple_logprobs_tc_kernel(SimpleParams p) {
   // a tile that holds no live arc has nothing to contract
   const bool tile_dead = kXY && (!bd_ok || t0 >= bd.w || t0 + TM <= t_begin || s0 > bd.z || s0 + TN <= s_begin);
 
+  uint64_t *full = bars, *empty = bars + kStages, *accfull = bars + 2 * kStages, *accfree = accfull + 2;
   if (tid == 0 && !tile_dead) {
-    mbar_init(&bars[0], kThreads / 32 - 1); mbar_init(&bars[1], kThreads / 32 - 1);    // full[2]: one arrival per converter warp
-    mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);                                    // done[2]: the tcgen05.commit
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&accfull[0], 1); mbar_init(&accfull[1], 1);                      // the tcgen05.commit
+    mbar_init(&accfree[0], kEpiWarps); mbar_init(&accfree[1], kEpiWarps);      // one arrival per drain warp
     mbar_fence_init();
   }
+  __syncthreads();
+  // ---- TMA producer (warp 16, one thread): started before the dead-plane fill and the per-column constants, so
+  //      the first stages are in flight while the other warps set up.  Box coordinates: (vocabulary column,
+  //      frame / symbol row, utterance). ----
+  auto produce = [&](int k) {
+    const int st = k % kStages;
+    unsigned char *stage = smem + (uint32_t)st * kStageBytes;
+    if (k >= kStages) mbar_wait_bounded(&empty[st], (uint32_t)((k / kStages - 1) & 1));
+    mbar_arrive_expect_tx(&full[st], kStageBytes);
+    tma_load_3d(stage, &map_amh, &full[st], k * KC, t0, b);
+    tma_load_3d(stage + kOpABytes, &map_aml, &full[st], k * KC, t0, b);
+    tma_load_3d(stage + kOffB, &map_lmh, &full[st], k * KC, s0, b);
+    tma_load_3d(stage + kOffB + kOpBBytes, &map_lml, &full[st], k * KC, s0, b);
+  };
+  const bool producer = (w == kEpiWarps), issuer = (w == kEpiWarps + 1);
+  if (producer && lane == 0 && !tile_dead)
+    for (int k = 0; k < min(nk, kStages); ++k) produce(k);
   if constexpr (kXY) {
     // Dead remainder of the arc plane.  Half X of cell (d, r) is the symbol arc from lattice row r-1 at
     // relative frame tx, half Y the blank arc of row r at relative frame ty; an arc is live iff its source
@@ -255,8 +282,9 @@ simple_logprobs_tc_kernel(SimpleParams p) {
   const uint32_t tmem_d = sm.tmem;
 
   // epilogue mapping, also used inside the k loop: thread <-> frame (TMEM lane), the four
-  // warps of a lane quarter take 28 symbol columns each (col_of)
-  const int q = w & 3, half = w >> 2;            // `half` = column part 0..3
+  // warps of a lane quarter take 28 symbol columns each (col_of); warps 16 / 17 (TMA, MMA issue) hold no columns
+  const bool epi = w < kEpiWarps;
+  const int q = w & 3, half = epi ? (w >> 2) : 0;  // `half` = column part 0..3
   const int erow = q * 32 + lane, et = t0 + erow;
   const bool t_ok = et < p.T;
   const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -268,154 +296,69 @@ simple_logprobs_tc_kernel(SimpleParams p) {
   float accr[kColsPerHalf];                     // float32 sum of the per-slice tensor-core partial sums
 #pragma unroll
   for (int i = 0; i < kColsPerHalf; ++i) accr[i] = 0.f;
-  auto drain_accumulator = [&](int acc) {       // TMEM partial sums of one slice -> registers
+  // TMEM columns [col, col + 112) of this thread's lane -> registers: all loads issued, one wait
+  auto drain_accumulator = [&](uint32_t col, auto &&fold) {
+    uint32_t part[kColsPerHalf / 4][4];
 #pragma unroll
     for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
       const int c0 = col_of(half, bi * 4);
-      if (c0 < n_rows) {                        // warp-uniform
-        float part[4];
-        tmem_ld4(lane_addr + (uint32_t)(acc * kAccStride + c0), part);
+      if (c0 < n_rows) tmem_ld4_nowait(lane_addr + col + (uint32_t)c0, part[bi]);      // warp-uniform
+    }
+    tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) accr[bi * 4 + e] += part[e];
+    for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
+      const int c0 = col_of(half, bi * 4);
+      if (c0 < n_rows) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fold(accr[bi * 4 + e], __uint_as_float(part[bi][e]));
       }
     }
   };
   const uint32_t idesc = umma_idesc(TM, n_rows);
 
-  // ---- roles.  Warps 0..14 (480 threads) convert: 1024 pieces of the am tile + 896 of the lm tile = 1920 = 4 per
-  //      thread (a piece = 8 consecutive values of one row: 32 bytes in, 3 x 16 bytes out).  Warp 15 issues the
-  //      MMAs: a thread that also converted made every slice wait for its 24 tcgen05.mma behind its share of the
-  //      conversion (23 % of all warp time sat in the per-slice block barrier).  There is no block barrier in
-  //      the loop: converters -> issuer through full[stage] (one arrival per converter warp), issuer -> everybody
-  //      through the tcgen05.commit on done[stage]. ----
-  constexpr int kConvWarps = kThreads / 32 - 1, kConvThreads = kConvWarps * 32, kPieces = (TM + TN) * 8 / kConvThreads;
-  static_assert(kPieces * kConvThreads == (TM + TN) * 8, "pieces divide evenly over the converter threads");
-  const bool issuer = (w == kConvWarps);
-  uint64_t *full = bars, *done = bars + 2;
-  float4 rr[kPieces][2];
-  // piece i of this thread -> (tile, row, 16-byte chunk); warp-uniform in `is_a`
-  auto piece = [&](int i, bool &is_a, int &row, int &j) {
-    int pi = tid + i * kConvThreads;
-    is_a = pi < TM * 8;
-    if (!is_a) pi -= TM * 8;
-    row = pi >> 3; j = pi & 7;
-  };
-  // per piece, once: where its row starts (element offset inside the utterance's am / lm, -1: row outside the
-  // tensor), where its operand chunk goes, and its row's -max * log2e
-  int src_off[kPieces];
-  uint32_t dst_off[kPieces];
-  float nmx_of[kPieces];
+  if (producer) {
+    if (lane == 0)
+      for (int k = kStages; k < nk; ++k) produce(k);
+    __syncwarp();
+  } else if (issuer) {
+    if (lane == 0) {
+      for (int k = 0; k < nk; ++k) {
+        const int st = k % kStages, ab = k & 1;
+        mbar_wait_bounded(&full[st], (uint32_t)((k / kStages) & 1));
+        if (k >= 2) mbar_wait_bounded(&accfree[ab], (uint32_t)(((k >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t a_h = smem_u32(smem + (uint32_t)st * kStageBytes), a_l = a_h + kOpABytes;
+        const uint32_t b_h = a_h + kOffB, b_l = b_h + kOpBBytes;
+        const uint32_t acc = tmem_d + (uint32_t)(ab * kAccStride), cross = tmem_d + (uint32_t)kCrossCol;
+        // Tensor-core FP32 accumulation truncates: the full-magnitude products h_a h_b start from a zeroed
+        // accumulator every slice (4 truncations, then float32 adds in registers); the cross terms weigh
+        // 2^-11 and stay in tensor memory over all slices.
 #pragma unroll
-  for (int i = 0; i < kPieces; ++i) {
-    bool is_a; int row, j;
-    piece(i, is_a, row, j);
-    const bool row_ok = is_a ? (t0 + row < p.T) : (s0 + row < S1);
-    src_off[i] = row_ok ? (is_a ? t0 + row : s0 + row) * C + j * 8 : -1;
-    dst_off[i] = (is_a ? 0u : kOffB) + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-    nmx_of[i] = issuer ? 0.f : (is_a ? sm.amneg[row] : sm.lmneg[row]);      // masked rows: -inf -> exp2 = 0
-  }
-  auto load_slice = [&](int k) {
-    const int k0 = k * KC;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ks = 0; ks < KC / 16; ++ks)
+          umma_f16(cross, umma_desc(a_l + ks * 32), umma_desc(b_h + ks * 32), idesc, (k > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      const bool is_a = tid + i * kConvThreads < TM * 8;
-      const int c = k0 + ((tid + i * kConvThreads) & 7) * 8;
-      rr[i][0] = rr[i][1] = z;                    // rows / columns outside the tensors stay zero
-      if (src_off[i] >= 0) {
-        const float4 *src = reinterpret_cast<const float4 *>((is_a ? amb : lmb) + src_off[i] + k0);
-        if (c < C) rr[i][0] = __ldg(src);         // C % 4 == 0: a float4 is inside or outside the row
-        if (c + 4 < C) rr[i][1] = __ldg(src + 1);
+        for (int ks = 0; ks < KC / 16; ++ks)
+          umma_f16(cross, umma_desc(a_h + ks * 32), umma_desc(b_l + ks * 32), idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks)
+          umma_f16(acc, umma_desc(a_h + ks * 32), umma_desc(b_h + ks * 32), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&empty[st]);                 // the stage may be refilled
+        umma_commit(&accfull[ab]);               // the slice's partial sums are complete
       }
     }
-  };
-  // ---- registers -> operand stage: exp, three-term bf16 split by mantissa truncation (h = top 16 bits of
-  //      p, m = top 16 bits of the exact remainder, l likewise: h+m+l = p to 2^-24, plain ALU ops),
-  //      16-byte chunks in the K-major SWIZZLE_128B layout ----
-  auto store_piece = [&](auto masked, const float4 (&r)[2], float nmx, int lim, unsigned char *dst, uint32_t stride) {
-    const float x[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
-    uint32_t hb[8], mb[8], lb[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float pr = ex2_approx(fmaf(x[e], kLog2e, nmx));
-      if (decltype(masked)::value) pr = (e < lim) ? pr : 0.f;    // only the last slice has columns beyond C
-      hb[e] = __float_as_uint(pr) & 0xFFFF0000u;
-      const float r1 = pr - __uint_as_float(hb[e]);
-      mb[e] = __float_as_uint(r1);
-      const float r2 = r1 - __uint_as_float(mb[e] & 0xFFFF0000u);
-      lb[e] = __float_as_uint(r2);
-    }
-    auto pack = [](const uint32_t (&v)[8]) {   // upper halves: element e low, e+1 high
-      return make_uint4(__byte_perm(v[0], v[1], 0x7632), __byte_perm(v[2], v[3], 0x7632),
-                        __byte_perm(v[4], v[5], 0x7632), __byte_perm(v[6], v[7], 0x7632));
-    };
-    *reinterpret_cast<uint4 *>(dst) = pack(hb);
-    *reinterpret_cast<uint4 *>(dst + stride) = pack(mb);
-    *reinterpret_cast<uint4 *>(dst + 2 * stride) = pack(lb);
-  };
-  auto store_slice = [&](int k, unsigned char *stage) {
-    const int k0 = k * KC;
-    const bool full_slice = k0 + KC <= C;        // block-uniform: no column of this slice lies beyond C
-    if (full_slice) {
-#pragma unroll
-      for (int i = 0; i < kPieces; ++i)
-        store_piece(std::false_type{}, rr[i], nmx_of[i], 8, stage + dst_off[i],
-                    tid + i * kConvThreads < TM * 8 ? kOpABytes : kOpBBytes);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kPieces; ++i)
-        store_piece(std::true_type{}, rr[i], nmx_of[i], C - k0 - ((tid + i * kConvThreads) & 7) * 8, stage + dst_off[i],
-                    tid + i * kConvThreads < TM * 8 ? kOpABytes : kOpBBytes);
-    }
-  };
-
-  if (!issuer) load_slice(0);
-  for (int k = 0; k < nk; ++k) {
-    const int st = k & 1;
-    unsigned char *stage = smem + (uint32_t)st * kStageBytes;
-    if (k >= 2) {                                // slice k-2 used this stage and this accumulator
-      mbar_wait_bounded(&done[st], (uint32_t)(((k >> 1) - 1) & 1));
+    __syncwarp();
+  } else {
+    for (int k = 0; k < nk; ++k) {
+      const int ab = k & 1;
+      mbar_wait_bounded(&accfull[ab], (uint32_t)((k >> 1) & 1));
       tc_fence_after();
-      drain_accumulator(st);
-      tc_fence_before();                         // the drain's tcgen05.ld before the arrival below / the next MMAs
-    }
-    if (!issuer) {
-      store_slice(k, stage);
-      if (k + 1 < nk) load_slice(k + 1);         // registers are free again: in flight until the next conversion
-      fence_async_smem();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+      drain_accumulator((uint32_t)(ab * kAccStride), [](float &a, float v) { a += v; });
+      tc_fence_before();                         // the drain's tcgen05.ld before the arrival / the next MMAs
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[st]);
-    } else {
-      mbar_wait_bounded(&full[st], (uint32_t)((k >> 1) & 1));
-      tc_fence_after();
-      if (lane == 0) {
-        // Tensor-core FP32 accumulation truncates, so (i) every slice starts from a zeroed
-        // accumulator and is summed in registers, (ii) the five small products go first and
-        // h*h last: <= 4 truncations at full magnitude per slice.
-        const uint32_t a_base = smem_u32(stage), b_base = smem_u32(stage + kOffB);
-        const uint32_t acc = tmem_d + (uint32_t)(st * kAccStride);
-        const int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
-        uint32_t first = 1;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-#pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            const uint64_t ad = umma_desc(a_base + ia[c] * kOpABytes + ks * 32);
-            const uint64_t bd = umma_desc(b_base + ib[c] * kOpBBytes + ks * 32);
-            umma_bf16(acc, ad, bd, idesc, first ? 0u : 1u);
-            first = 0;
-          }
-        }
-        umma_commit(&done[st]);
-      }
-      __syncwarp();
+      if (lane == 0) mbar_arrive(&accfree[ab]);
     }
-  }
-  // the last two slices (in order: the sums are formed in slice order whatever the timing)
-  for (int k = max(nk - 2, 0); k < nk; ++k) {
-    mbar_wait_bounded(&done[k & 1], (uint32_t)((k >> 1) & 1));
-    tc_fence_after();
-    drain_accumulator(k & 1);
+    // every MMA has completed (the last commit covers all earlier ones): add the cross terms, undo the 2^15 x 2^15
+    drain_accumulator((uint32_t)kCrossCol, [](float &a, float v) { a = fmaf(v, 0x1p-11f, a) * 0x1p-30f; });
   }
   tc_fence_before();
   __syncthreads();                               // every warp has left the operand stages: the epilogue reuses them
@@ -437,7 +380,7 @@ simple_logprobs_tc_kernel(SimpleParams p) {
 #pragma unroll
     for (int bi = 0; bi < kColsPerHalf / 4; ++bi) {
       const int c0 = col_of(half, bi * 4);
-      if (c0 < n_rows) {                 // warp-uniform
+      if (epi && c0 < n_rows) {          // warp-uniform
         float pxam[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) pxam[e] = (t_ok && s0 + c0 + e < p.S) ? pxam_row[s0 + c0 + e] : 0.f;
@@ -503,7 +446,7 @@ simple_logprobs_tc_kernel(SimpleParams p) {
 #pragma unroll
         for (int bi = (pass ? 4 : 0); bi < (pass ? 7 : 4); ++bi) {
           const int c0 = col_of(half, bi * 4);
-          if (c0 < n_rows) {                    // warp-uniform
+          if (epi && c0 < n_rows) {             // warp-uniform
             float pxam[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) pxam[e] = (t_ok && s0 + c0 + e < p.S) ? pxam_row[s0 + c0 + e] : 0.f;
@@ -577,22 +520,65 @@ simple_logprobs_tc_kernel(SimpleParams p) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// One float16 operand plane [B][rows][Cp] as a 3-D tensor (column, row, utterance) that ENDS at column C: a box of
+// 64 columns x box_rows rows lands in shared memory in the K-major SWIZZLE_128B layout tcgen05 reads; whatever
+// lies beyond C, beyond the utterance's rows or beyond B arrives as zeros.
+static bool make_map_3d(CUtensorMap *map, const unsigned short *base, int rows, int C, int Cp, int B, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)Cp * 2, (cuuint64_t)rows * Cp * 2};
+  cuuint32_t box[3] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<unsigned short *>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C) {
-  // 128-bit loads of 8-column pieces: C % 4 == 0 and 16-byte aligned bases
-  return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0;
+  // the row-statistics kernel builds the operands with 128-bit loads (C % 4 == 0, 16-byte aligned bases); the
+  // contraction itself needs the driver's tensor-map encoder
+  return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0 &&
+         get_encode_fn() != nullptr;
 }
 
 // returns FRN_EUNSUPPORTED when the tensor-core path does not apply (caller falls back to the SIMT kernel):
 // C % 4 != 0 or misaligned bases.  sp.XY != nullptr selects the arc-plane output (regular / modified only).
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
-  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C) || sp.pxam_t == nullptr) return FRN_EUNSUPPORTED;
+  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C) || sp.pxam_t == nullptr || sp.split.Cp == 0)
+    return FRN_EUNSUPPORTED;
   if (sp.XY != nullptr && sp.rnnt_type == FRN_CONSTRAINED) return FRN_EUNSUPPORTED;
+  CUtensorMap map_amh, map_aml, map_lmh, map_lml;
+  if (!make_map_3d(&map_amh, sp.split.amh, sp.T, sp.C, sp.split.Cp, sp.B, tc::TM) ||
+      !make_map_3d(&map_aml, sp.split.aml, sp.T, sp.C, sp.split.Cp, sp.B, tc::TM) ||
+      !make_map_3d(&map_lmh, sp.split.lmh, sp.S + 1, sp.C, sp.split.Cp, sp.B, tc::TN) ||
+      !make_map_3d(&map_lml, sp.split.lml, sp.S + 1, sp.C, sp.split.Cp, sp.B, tc::TN))
+    return FRN_EUNSUPPORTED;
   auto kernel = sp.XY ? simple_logprobs_tc_kernel<true> : simple_logprobs_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return note_cuda_error(e);
   // arc-plane output: frames 0..T-1 carry arcs (the regular lattice's extra column T has none)
   dim3 grid(((sp.XY ? sp.T : sp.T1) + tc::TM - 1) / tc::TM, (sp.S + 1 + tc::TN - 1) / tc::TN, sp.B);
-  count_launch(), kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(sp);
+  count_launch(), kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_amh, map_aml, map_lmh, map_lml, sp);
   return check_launch();
 }
 

@@ -4,12 +4,20 @@
 #include "common.cuh"
 
 namespace frn {
+// Two-term float16 operands of the tensor-core normaliser, written by the row-statistics kernel:
+// exp(x - rowmax) * 2^15 = h + l * 2^-11, planes [rows][Cp] of halves (Cp = C rounded up to 8: 16-byte row pitch
+// for TMA; columns >= C are never read - the tensor maps end at C and TMA fills the rest of a box with zeros).
+struct SplitPlanes {
+  unsigned short *amh = nullptr, *aml = nullptr, *lmh = nullptr, *lml = nullptr;
+  int Cp = 0;                           // 0: not wanted
+};
 struct SimpleParams {
   const float *lm, *am;
   const int32_t *symbols, *boundary;
   const float *lmmax, *ammax;           // row maxima
   const float *lmsum, *amonly, *logu;   // smoothed only (may be null)
   const float *pxam_t = nullptr;        // [B][T][S] am[b,t,symbols[b,s]], written by the row-statistics kernel
+  SplitPlanes split;                    // tensor-core path: the contraction's operands
   float *px, *py;                       // reference layout
   int B, S, T, T1, C, term, rnnt_type, smoothed;
   float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
