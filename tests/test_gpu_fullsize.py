@@ -134,6 +134,57 @@ def test_c4_large_vocab_bf16():
     assert float(row_sums.abs().max()) < 2e-2
 
 
+def test_c5_pruned_half_and_bucketed_path_at_ragged_shapes():
+    """configs[4] shapes (T_b 200-1500, S_b 20-400, C=500, s_range=5), 40 utterances: prune ranges bit-exact,
+    pruned loss and logits gradient against the float64 oracle on picked utterances, range properties on all -
+    and the length-bucketed schedule bench.py runs for c5 (plan_buckets -> pipeline per bucket) against the one
+    padded batch."""
+    import torch
+    import tf_fast_rnnt as frn
+    B, T, S, C, R = 40, 1500, 400, 500, 5
+    rng = np.random.default_rng(55)
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 3] = rng.integers(200, T + 1, B)
+    bd[:, 2] = np.minimum(rng.integers(20, S + 1, B), bd[:, 3])
+    bd[0] = [0, 0, S, T]                      # the batch maxima are present
+    am_h = rng.standard_normal((B, T, C), dtype=np.float32)
+    lm_h = rng.standard_normal((B, S + 1, C), dtype=np.float32)
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    am, lm = torch.from_numpy(am_h).cuda(), torch.from_numpy(lm_h).cuda()
+    sym_d, bd_d = torch.from_numpy(sym).cuda(), torch.from_numpy(bd).cuda()
+    term = C - 1
+    loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym_d, term, bd_d, "regular", 0.0, "none", True)
+    ranges = frn.get_rnnt_prune_ranges(gx, gy, bd_d, R)
+    rg_h = ranges.cpu().numpy()
+    _range_properties(rg_h, bd, R)
+    logits = frn.pruned_add_joiner(am, lm, ranges)
+    scores, grad = frn.pruned_loss_fwd_bwd(logits, sym_d, ranges, term, bd_d, "regular", 0.0, None)
+    scores_h = scores.cpu().numpy()
+    assert np.isfinite(scores_h).all()
+    assert (-scores_h >= loss.cpu().numpy() * (1 - 1e-5)).all()      # pruning can only lose probability mass
+    pick = [0, 7, int(np.argmin(bd[:, 3])), int(np.argmin(bd[:, 2]))]
+    gx_h, gy_h = gx[pick].cpu().numpy(), gy[pick].cpu().numpy()
+    assert np.array_equal(rg_h[pick], orc.get_rnnt_prune_ranges(gx_h, gy_h, bd[pick], R))
+    o_grad, o_scores = orc.pruned_logits_grad(logits[pick].cpu().numpy(), sym[pick], rg_h[pick], term, bd[pick],
+                                              "regular", 0.0, -np.ones(len(pick)), np.float64, True)
+    assert_close(scores_h[pick], o_scores, LOSS_RTOL, 0, "c5 pruned scores")
+    assert_close(grad[pick].cpu().numpy(), o_grad, GRAD_RTOL, 2e-6, "c5 logits grad")
+    del logits, grad
+    # the bucketed schedule: same per-utterance losses as the padded batch
+    one = frn.pruned_rnnt_pipeline(lm, am, sym_d, term, bd_d, R, None, "regular", 0.0, "none", max_buckets=1,
+                                   return_ranges=True)
+    many = frn.pruned_rnnt_pipeline(lm, am, sym_d, term, bd_d, R, None, "regular", 0.0, "none", max_buckets=4,
+                                    return_ranges=True)
+    assert len(frn.make_buckets(bd_d, R, C, 4, 4)) > 1
+    assert_close(one[0].cpu().numpy(), loss.cpu().numpy(), LOSS_RTOL, 0, "simple loss, padded pipeline vs direct call")
+    assert_close(many[0].cpu().numpy(), one[0].cpu().numpy(), LOSS_RTOL, 0, "simple loss, bucketed vs padded")
+    r1, r4 = one[2].cpu().numpy(), many[2].cpu().numpy()
+    same = np.array([np.array_equal(r1[b, :bd[b, 3]], r4[b, :bd[b, 3]]) for b in range(B)])
+    assert same.sum() >= B - 3                # a near-tie of the arg-max may fall the other way (other kernel variant)
+    assert_close(many[1].cpu().numpy()[same], one[1].cpu().numpy()[same], LOSS_RTOL, 0, "pruned loss, bucketed vs padded")
+    assert_close(one[1].cpu().numpy(), -scores_h, LOSS_RTOL, 0, "pruned loss, padded pipeline vs direct calls")
+
+
 def test_c5_ragged_batch_sharded_sum():
     """configs[4]: ragged B=256 (T 200-1500, S 20-400), C=500, reduction=sum, sharded over 1/2/4/8 'ranks'
     (emulated on one GPU: the per-rank partial sums must add up to the unsharded sum)."""

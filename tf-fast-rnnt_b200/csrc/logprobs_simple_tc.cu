@@ -43,6 +43,13 @@
 #include "simple_params.cuh"
 
 namespace frn {
+#ifdef FRN_TC_TIMING
+// diagnostic build only: clock of block (1,0,0), thread 0 at the phase boundaries of the normaliser
+__device__ long long g_tc_timing[8];
+#define FRN_TCT(i) if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_tc_timing[(i) + 1] = clock64();
+#else
+#define FRN_TCT(i)
+#endif
 
 namespace tc {
 constexpr int TM = 128;   // frames per CTA  (MMA M)
@@ -168,6 +175,9 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
                           const __grid_constant__ CUtensorMap map_lmh, const __grid_constant__ CUtensorMap map_lml,
                           SimpleParams p) {
   using namespace tc;
+#ifdef FRN_TC_TIMING
+  if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_tc_timing[0] = clock64();
+#endif
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B operands need a 1024-byte aligned base; keep the arithmetic on the
   // __shared__ array so that accesses stay LDS/STS (a pointer rebuilt from an integer
@@ -278,6 +288,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
   if (w == 0) tmem_alloc(&sm.tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  FRN_TCT(0)
   tc_fence_after();
   const uint32_t tmem_d = sm.tmem;
 
@@ -362,6 +373,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
   }
   tc_fence_before();
   __syncthreads();                               // every warp has left the operand stages: the epilogue reuses them
+  FRN_TCT(1)
   tc_fence_after();
 
   if constexpr (!kXY) {
@@ -487,6 +499,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
         }
       }
       __syncthreads();
+      if (pass == 0) { FRN_TCT(2) }
       if (jb < n_rows) {
         const int rho = s0 + jb - s_begin, Delta = (t0 - t_begin) + kk * rho;
         const int ND = TM + kk * (ncols - 1), ngrp = (ncols + 1 + 31) / 32;
@@ -510,10 +523,12 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
         }
       }
       if (pass == 0) __syncthreads();
+      FRN_TCT(3 + pass)
     }
   }
   tc_fence_before();
   __syncthreads();
+  FRN_TCT(5)
   if (w == 0) tmem_dealloc(tmem_d, kTmemCols);
 }
 
@@ -583,3 +598,9 @@ int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
 }
 
 }  // namespace frn
+
+#ifdef FRN_TC_TIMING
+extern "C" int frn_debug_tc_timing(long long *host_out) {
+  return cudaMemcpyFromSymbol(host_out, frn::g_tc_timing, sizeof(frn::g_tc_timing)) == cudaSuccess ? 0 : 1;
+}
+#endif
