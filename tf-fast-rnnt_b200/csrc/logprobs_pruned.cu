@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(s) : "l"(ranges + row));
     s_ok = (s >= 0 && s <= S);
     if (s_ok) {
-      if (s < S) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(sym) : "l"(symbols + (size_t)blockIdx.y * S + s));
+      if (s < S) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(sym) : "l"(symbols + (size_t)(gridDim.y - 1 - blockIdx.y) * S + s));
       else sym = term;
     }
     return (sym < 0 || sym >= C) ? -1 : sym;
@@ -75,9 +75,13 @@ __global__ void __launch_bounds__(256) pruned_lse_kernel(const T *logits, const 
   // together; the two gathered logits are two more scalar loads issued as soon as their index is
   // known (they hit L2 behind the row itself), which keeps per-element work to max / ex2 / add.
   // grid: x = groups of 8 rows inside an utterance, y = utterance (no integer division by T*R)
-  const int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // Rows are taken LAST FIRST: the kernel that produced the logits (the joiner) wrote them first to last, so
+  // what is still in the 126 MB L2 is their tail; and this kernel then leaves the head there for the
+  // gradient kernel, which runs first to last (measured: 105.5 -> 103.6 us for the pruned loss at c2).
+  const int by = gridDim.y - 1 - blockIdx.y;
+  const int local = (gridDim.x - 1 - blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (local >= TR) return;
-  const int row = blockIdx.y * TR + local;
+  const int row = by * TR + local;
   const T *src = logits + (size_t)row * C;
   uint4 raw[kU];
   if (one_batch) load_batch(reinterpret_cast<const uint4 *>(src), 0, raw);
