@@ -50,7 +50,7 @@ enum frn_status {
 enum frn_rnnt_type { FRN_REGULAR = 0, FRN_MODIFIED = 1, FRN_CONSTRAINED = 2 };
 
 /* element type of the joiner logits handed to the pruned loss */
-enum frn_dtype { FRN_F32 = 0, FRN_BF16 = 1, FRN_F16 = 2 /* frn_cast_to_f32 only */ };
+enum frn_dtype { FRN_F32 = 0, FRN_BF16 = 1, FRN_F16 = 2 /* am / lm only (frn_cast_to_f32, *_lp) */ };
 
 /* reduction of the reference API (rnnt_loss.py:327-338) */
 enum frn_reduction { FRN_NONE = 0, FRN_MEAN = 1, FRN_SUM = 2 };
@@ -187,6 +187,25 @@ int frn_smoothed_loss_bwd_sharded(const float *lm, const float *am, const int32_
                                   const float *unigram_sums, float *du, int phase,
                                   float *am_grad, float *lm_grad, void *workspace,
                                   size_t workspace_bytes, void *stream);
+/*  The same two entry points for am / lm of element type `am_lm_dtype` (FRN_F32, FRN_BF16,
+ * FRN_F16), consumed as they are: the row-statistics kernel is the only kernel that reads them (it widens every
+ * element in registers and leaves the contraction's operands and the few gathered values the epilogue needs), so
+ * mixed-precision encoders / decoders save the widening pass and the float32 copies.  unigram_sums as in the
+ * *_sharded forms (NULL: this batch).  bf16 / fp16 need the tensor-core path (C % 4 == 0, 16-byte aligned bases):
+ * FRN_EUNSUPPORTED otherwise - widen with frn_cast_to_f32 then.  Everything else (px, py, scores, gradients) stays
+ * float32; the backward entry points take float32 am / lm. */
+int frn_simple_logprobs_lp(const void *lm, const void *am, int am_lm_dtype, const int32_t *symbols,
+                           const int32_t *boundary, int B, int S, int T, int C,
+                           int termination_symbol, int rnnt_type, int smoothed,
+                           float lm_only_scale, float am_only_scale, const float *unigram_sums,
+                           float *px, float *py, void *workspace, size_t workspace_bytes,
+                           void *stream);
+int frn_simple_loss_lp(const void *lm, const void *am, int am_lm_dtype, const int32_t *symbols,
+                       const int32_t *boundary, int B, int S, int T, int C,
+                       int termination_symbol, int rnnt_type, int smoothed,
+                       float lm_only_scale, float am_only_scale, const float *unigram_sums,
+                       float delay_penalty, int calc_gradients, float *scores, float *px_grad,
+                       float *py_grad, void *workspace, size_t workspace_bytes, void *stream);
 /* In-place sum all-reduce of n floats over an NCCL communicator the caller owns (ncclComm_t as void*), enqueued
  * on `stream` - the scalar of reduction='sum'|'mean' and the C+1 / C floats above.  libnccl.so.2 is bound lazily
  * with dlopen (no link-time dependency; the instance already loaded in the process is the one found);

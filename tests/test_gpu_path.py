@@ -532,27 +532,51 @@ def test_reduce_and_reduce_pair(reduction):
 @pytest.mark.debug_hooks
 @pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
 def test_half_precision_am_lm_inputs(dtype):
-    """ bf16 / fp16 am and lm on the device: widened by frn_cast_to_f32 and then the float32
-    path - identical to feeding the up-cast values."""
+    """ bf16 / fp16 am and lm on the device are consumed as they are (frn_simple_loss_lp /
+    frn_simple_logprobs_lp: the row-statistics kernel widens every element in registers) - bit-identical to feeding
+    the up-cast values, with NO extra kernel; shapes the tensor-core path cannot take (C % 4 != 0) are widened by
+    frn_cast_to_f32 (two more kernels) and then take the float32 path."""
     import torch
     import tf_fast_rnnt as frn
-    B, T, S, C = 2, 61, 17, 36
-    am, lm, sym, term, bd = make_inputs(12, B, T, S, C, ragged=True)
+    lib = frn._lib.lib
     td = getattr(torch, dtype)
+    for C, extra in ((36, 0), (35, 2)):
+        B, T, S = 2, 61, 17
+        am, lm, sym, term, bd = make_inputs(12, B, T, S, C, ragged=True)
+        am_h, lm_h = torch.from_numpy(am).cuda().to(td), torch.from_numpy(lm).cuda().to(td)
+        for kind in ("simple", "smoothed", "modified", "logprobs"):
+            def run(l, a):
+                if kind == "simple":
+                    loss, (gx, gy) = frn.rnnt_loss_simple(l, a, sym, term, bd, "regular", 0.1, "none", True)
+                elif kind == "smoothed":
+                    loss, (gx, gy) = frn.rnnt_loss_smoothed(l, a, sym, term, 0.2, 0.1, bd, "regular", 0.0, "none", True)
+                elif kind == "modified":
+                    loss, (gx, gy) = frn.rnnt_loss_simple(l, a, sym, term, bd, "modified", 0.0, "none", True)
+                else:
+                    gx, gy = frn.get_rnnt_logprobs(l, a, sym, term, "regular", bd)
+                    loss = gx[:, 0, 0]
+                return loss, gx, gy
+            n0 = lib.frn_kernel_launches()
+            loss_h, gx_h, gy_h = run(lm_h, am_h)
+            launched = lib.frn_kernel_launches() - n0
+            n1 = lib.frn_kernel_launches()
+            loss_f, gx_f, gy_f = run(lm_h.float(), am_h.float())
+            assert torch.equal(loss_h, loss_f) and torch.equal(gx_h, gx_f) and torch.equal(gy_h, gy_f), (C, kind)
+            assert launched == (lib.frn_kernel_launches() - n1) + extra, (C, kind)
+    # against the float64 oracle on the up-cast values ("upcast then reference math")
+    am, lm, sym, term, bd = make_inputs(12, 2, 61, 17, 36, ragged=True)
     am_h, lm_h = torch.from_numpy(am).cuda().to(td), torch.from_numpy(lm).cuda().to(td)
-    n0 = frn._lib.lib.frn_kernel_launches()
-    loss_h, (gx_h, gy_h) = frn.rnnt_loss_simple(lm_h, am_h, sym, term, bd, "regular", 0.0, "none", True)
-    launched = frn._lib.lib.frn_kernel_launches() - n0
-    loss_f, (gx_f, gy_f) = frn.rnnt_loss_simple(lm_h.float(), am_h.float(), sym, term, bd, "regular", 0.0, "none", True)
-    assert torch.equal(loss_h, loss_f) and torch.equal(gx_h, gx_f) and torch.equal(gy_h, gy_f)
-    n1 = frn._lib.lib.frn_kernel_launches()
-    frn.rnnt_loss_simple(lm_h.float(), am_h.float(), sym, term, bd, "regular", 0.0, "none", True)
-    assert launched == (frn._lib.lib.frn_kernel_launches() - n1) + 2      # the two cast kernels are the library's
-    # odd element counts take the scalar tail
+    loss, (gx, gy) = frn.rnnt_loss_simple(lm_h, am_h, sym, term, bd, "regular", 0.0, "none", True)
+    o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm_h.float().cpu().numpy(), am_h.float().cpu().numpy(), sym, term, bd,
+                                                "regular", 0.0, "none", True, dtype=np.float64)
+    assert_close(loss.cpu().numpy(), o_loss, LOSS_RTOL, 0, "loss of bf16 / fp16 inputs")
+    assert_close(gx.cpu().numpy(), o_gx, GRAD_RTOL, GRAD_ATOL, "px_grad of bf16 / fp16 inputs")
+    assert_close(gy.cpu().numpy(), o_gy, GRAD_RTOL, GRAD_ATOL, "py_grad of bf16 / fp16 inputs")
+    # odd element counts take the scalar tail of the widening kernel
     x = torch.randn(1003, device="cuda").to(td)
     y = torch.empty(1003, dtype=torch.float32, device="cuda")
-    frn._lib.check(frn._lib.lib.frn_cast_to_f32(x.data_ptr(), 1 if dtype == "bfloat16" else 2, 1003, y.data_ptr(),
-                                                torch.cuda.current_stream().cuda_stream), "cast")
+    frn._lib.check(lib.frn_cast_to_f32(x.data_ptr(), 1 if dtype == "bfloat16" else 2, 1003, y.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream), "cast")
     assert torch.equal(y, x.float())
 
 

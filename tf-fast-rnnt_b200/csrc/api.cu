@@ -248,14 +248,24 @@ int frn_simple_logprobs_sharded(const float *lm, const float *am, const int32_t 
                                 float lm_only_scale, float am_only_scale, const float *unigram_sums, float *px,
                                 float *py, void *workspace, size_t workspace_bytes, void *stream) {
   FRN_RANGE();
+  return frn_simple_logprobs_lp(lm, am, FRN_F32, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                lm_only_scale, am_only_scale, unigram_sums, px, py, workspace, workspace_bytes, stream);
+}
+
+int frn_simple_logprobs_lp(const void *lm, const void *am, int am_lm_dtype, const int32_t *symbols,
+                           const int32_t *boundary, int B, int S, int T, int C, int termination_symbol, int rnnt_type,
+                           int smoothed, float lm_only_scale, float am_only_scale, const float *unigram_sums, float *px,
+                           float *py, void *workspace, size_t workspace_bytes, void *stream) {
+  FRN_RANGE();
+  FRN_REQUIRE(am_lm_dtype == FRN_F32 || am_lm_dtype == FRN_BF16 || am_lm_dtype == FRN_F16);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
   FRN_REQUIRE(lm && am && symbols && boundary && px && py);
   FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
   FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
   if (!workspace || !aligned256(workspace) || workspace_bytes < simple_stats_bytes(B, S, T, C)) return FRN_EWORKSPACE;
-  return launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                lm_only_scale, am_only_scale, px, py, workspace, static_cast<cudaStream_t>(stream),
-                                nullptr, smoothed ? unigram_sums : nullptr);
+  return launch_simple_logprobs_any(lm, am, am_lm_dtype, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type,
+                                    smoothed, lm_only_scale, am_only_scale, px, py, workspace,
+                                    static_cast<cudaStream_t>(stream), nullptr, smoothed ? unigram_sums : nullptr);
 }
 
 // ------------------------------------------------------------------ A1/A2 + A3 + A4
@@ -300,6 +310,18 @@ int frn_simple_loss_sharded(const float *lm, const float *am, const int32_t *sym
                             int calc_gradients, float *scores, float *px_grad, float *py_grad, void *workspace,
                             size_t workspace_bytes, void *stream_) {
   FRN_RANGE();
+  return frn_simple_loss_lp(lm, am, FRN_F32, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                            lm_only_scale, am_only_scale, unigram_sums, delay_penalty, calc_gradients, scores, px_grad,
+                            py_grad, workspace, workspace_bytes, stream_);
+}
+
+int frn_simple_loss_lp(const void *lm, const void *am, int am_lm_dtype, const int32_t *symbols,
+                       const int32_t *boundary, int B, int S, int T, int C, int termination_symbol, int rnnt_type,
+                       int smoothed, float lm_only_scale, float am_only_scale, const float *unigram_sums,
+                       float delay_penalty, int calc_gradients, float *scores, float *px_grad, float *py_grad,
+                       void *workspace, size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
+  FRN_REQUIRE(am_lm_dtype == FRN_F32 || am_lm_dtype == FRN_BF16 || am_lm_dtype == FRN_F16);
   if (!smoothed) unigram_sums = nullptr;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1);
@@ -319,14 +341,16 @@ int frn_simple_loss_sharded(const float *lm, const float *am, const int32_t *sym
   if (!scan && simple_arc_plane_supported(lm, am, C, rnnt_type)) {
     // 4 launches: row statistics, normaliser (arcs straight into the recursion's plane), recursion, read-out
     const ArcPlaneOut arcs{dw.XY, g.P, g.Dn, g.k, dp};
-    FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                   lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs, unigram_sums));
+    FRN_TRY(launch_simple_logprobs_any(lm, am, am_lm_dtype, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type,
+                                       smoothed, lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs,
+                                       unigram_sums));
     FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
     return launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
                                  calc_gradients ? py_grad : nullptr, stream);
   }
-  FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
-                                 lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream, nullptr, unigram_sums));
+  FRN_TRY(launch_simple_logprobs_any(lm, am, am_lm_dtype, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type,
+                                     smoothed, lm_only_scale, am_only_scale, w.px, w.py, w.stats, stream, nullptr,
+                                     unigram_sums));
   if (scan)
     return launch_scan_dp(w.px, w.py, boundary, B, S, T, T1, dp, calc_gradients != 0, w.dp, scores, px_grad, py_grad,
                           stream);

@@ -39,12 +39,18 @@ int launch_allreduce_sum(float *buf, size_t n, void *comm, cudaStream_t stream);
 size_t simple_stats_bytes(int B, int S, int T, int C);
 // arcs != nullptr: the arcs go straight into the recursion's diagonal-major plane instead of px/py
 struct ArcPlaneOut { float4 *XY; int P, Dn, k; float delay_penalty; };
-bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnnt_type);
+bool simple_arc_plane_supported(const void *lm, const void *am, int C, int rnnt_type);
 int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
                            int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
                            float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
                            cudaStream_t stream, const ArcPlaneOut *arcs = nullptr,
                            const float *unigram_sums = nullptr);
+// the same for am / lm of element type `dtype` (frn_dtype); bf16 / fp16 need the tensor-core path (else FRN_EUNSUPPORTED)
+int launch_simple_logprobs_any(const void *lm, const void *am, int dtype, const int32_t *symbols,
+                               const int32_t *boundary, int B, int S, int T, int C, int term, int rnnt_type,
+                               int smoothed, float lm_only_scale, float am_only_scale, float *px, float *py,
+                               void *stats_ws, cudaStream_t stream, const ArcPlaneOut *arcs = nullptr,
+                               const float *unigram_sums = nullptr);
 int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T, int C, void *stats_ws,
                            cudaStream_t stream, const float *unigram_sums = nullptr);
 int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, float *sums, cudaStream_t stream);

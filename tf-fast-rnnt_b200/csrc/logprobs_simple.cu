@@ -9,9 +9,11 @@
 // products, the parity baseline).  The tcgen05/TMA split-precision version of
 // the contraction lives in logprobs_simple_tc.cu when enabled; both share the
 // row-statistics kernels and the epilogue below.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "launchers.h"
@@ -34,6 +36,46 @@ __device__ __forceinline__ float tiny_f32() { return __int_as_float(1); }
 // tensor cores contract, p = exp(x - rowmax) * 2^15 = h + l' * 2^-11 with h = fp16(p), l' = fp16((p - h) * 2^11)
 // (SplitPlanes; pitch Cp halves per row): every probability is exponentiated and split ONCE here instead of once
 // per 128 x 112 tile of the contraction (12 x for lm, 4 x for am at the c4 shape).
+// am / lm element types: float32 (the reference's), bfloat16 and float16 (consumed as they are -
+// the row-statistics kernel is the only kernel of the tensor-core path that reads am / lm at all).
+template <typename T> __device__ __forceinline__ float elem_to_f(T v);
+template <> __device__ __forceinline__ float elem_to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float elem_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float elem_to_f<__half>(__half v) { return __half2float(v); }
+// four consecutive elements (16-byte / 8-byte aligned), streamed
+template <typename T> __device__ __forceinline__ float4 load4_stream(const T *p);
+template <> __device__ __forceinline__ float4 load4_stream<float>(const float *p) {
+  return ld_stream_f4(reinterpret_cast<const float4 *>(p));
+}
+template <> __device__ __forceinline__ float4 load4_stream<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  uint32_t a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  return make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xFFFF0000u), __uint_as_float(b << 16),
+                     __uint_as_float(b & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 load4_stream<__half>(const __half *p) {
+  uint32_t a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&a));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&b));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <typename T> __device__ __forceinline__ float4 load4_cached(const T *p);
+template <> __device__ __forceinline__ float4 load4_cached<float>(const float *p) {
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+template <> __device__ __forceinline__ float4 load4_cached<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 load4_cached<__half>(const __half *p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __device__ __forceinline__ void split4(const float4 &x, float nmx, uint2 &h, uint2 &l) {
   const float p0 = ex2_approx(fmaf(x.x, kLog2e, nmx)), p1 = ex2_approx(fmaf(x.y, kLog2e, nmx));
   const float p2 = ex2_approx(fmaf(x.z, kLog2e, nmx)), p3 = ex2_approx(fmaf(x.w, kLog2e, nmx));
@@ -45,16 +87,20 @@ __device__ __forceinline__ void split4(const float4 &x, float nmx, uint2 &h, uin
   l = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
 }
 
-__global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
+// `gat` (tensor-core path): the three other values the normaliser's epilogue needs of am / lm - am[b,t,blank],
+// lm[b,s,blank], lm[b,s,symbols[b,s]] - so that kernel never touches am / lm itself.
+template <typename TE>
+__global__ void __launch_bounds__(256) rowstats_kernel(const TE *lm, int rows_lm, const TE *am, int rows_am,
                                                        int C, float *lmmax, float *lmsum, float *ammax,
                                                        const int32_t *symbols = nullptr, int S = 0, int T = 1,
-                                                       float *pxam_t = nullptr, SplitPlanes split = SplitPlanes()) {
+                                                       float *pxam_t = nullptr, SplitPlanes split = SplitPlanes(),
+                                                       RowGathers gat = RowGathers()) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows_lm + rows_am) return;
   const bool is_lm = row < rows_lm;
   if (!is_lm) row -= rows_lm;
-  const float *src = (is_lm ? lm : am) + (size_t)row * C;
+  const TE *src = (is_lm ? lm : am) + (size_t)row * C;
   // am[b,t,sym[b,s]] for the normaliser's epilogue (SimpleParams::pxam_t): the symbol indices are fetched first,
   // the gathers are issued right behind the row's own vector loads (same sectors, one memory round trip for
   // both) and stored at the end - a gather in front of the row loads was a second, dependent round trip.
@@ -73,22 +119,21 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
   auto issue_gathers = [&]() {
     if (gather) {
 #pragma unroll
-      for (int u = 0; u < kG; ++u) gval[u] = (gidx[u] >= 0 && gidx[u] < C) ? __ldg(src + gidx[u]) : 0.f;
+      for (int u = 0; u < kG; ++u) gval[u] = (gidx[u] >= 0 && gidx[u] < C) ? elem_to_f(src[gidx[u]]) : 0.f;
     }
   };
   float *rmax = is_lm ? lmmax : ammax;
   float *rsum = is_lm ? lmsum : nullptr;
   float m = -INFINITY;
-  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & (4 * sizeof(TE) - 1)) == 0);
   if (vec && C <= 4 * 32 * 8) {
     const int nv = C / 4;
-    const float4 *p = reinterpret_cast<const float4 *>(src);
     float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int c = u * 32 + lane;
       v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (c < nv) v[u] = ld_stream_f4(p + c);
+      if (c < nv) v[u] = load4_stream(src + 4 * c);
     }
     issue_gathers();
 #pragma unroll
@@ -120,16 +165,15 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
     // long rows (large vocabularies): three passes of 128-bit loads over a row that stays in L1 / L2
     issue_gathers();
     const int nv = C / 4;
-    const float4 *p = reinterpret_cast<const float4 *>(src);
     for (int c = lane; c < nv; c += 32) {
-      const float4 x = __ldg(p + c);
+      const float4 x = load4_cached(src + 4 * c);
       m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
     }
     m = warp_max(m);
     if (rsum) {
       float s = 0.f;
       for (int c = lane; c < nv; c += 32) {
-        const float4 x = __ldg(p + c);
+        const float4 x = load4_cached(src + 4 * c);
         s += (expf(x.x - m) + expf(x.y - m)) + (expf(x.z - m) + expf(x.w - m));
       }
       s = warp_sum(s);
@@ -141,17 +185,17 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
       const float nmx = fmaf(-m, kLog2e, 15.f);
       for (int c = lane; c < nv; c += 32) {
         uint2 h, l;
-        split4(__ldg(p + c), nmx, h, l);
+        split4(load4_cached(src + 4 * c), nmx, h, l);
         hrow[c] = h; lrow[c] = l;
       }
     }
   } else {
     issue_gathers();
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, elem_to_f(src[c]));
     m = warp_max(m);
     if (rsum) {
       float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += expf(src[c] - m);
+      for (int c = lane; c < C; c += 32) s += expf(elem_to_f(src[c]) - m);
       s = warp_sum(s);
       if (lane == 0) rsum[row] = s;
     }
@@ -164,7 +208,17 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
       if (lane + 32 * u < S) dst[lane + 32 * u] = gval[u];
     for (int s = lane + 32 * kG; s < S; s += 32) {      // long label sequences: the row is in L1 / L2 by now
       const int c = sym[s];
-      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+      dst[s] = (c >= 0 && c < C) ? elem_to_f(src[c]) : 0.f;
+    }
+  }
+  if (gat.am_term && lane == 0) {
+    if (is_lm) {
+      const int S1 = S + 1, b = row / S1, sl = row - b * S1;
+      gat.lm_term[row] = elem_to_f(src[gat.term]);
+      const int c = sl < S ? symbols[(size_t)b * S + sl] : -1;
+      gat.lm_sym[row] = (c >= 0 && c < C) ? elem_to_f(src[c]) : 0.f;
+    } else {
+      gat.am_term[row] = elem_to_f(src[gat.term]);
     }
   }
 }
@@ -174,7 +228,8 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float *lm, int rows
 // Batch sharded by utterance: the mean runs over the GLOBAL batch, so the column sums and the row
 // count are exposed (`sums_out` [C+1], frn_smoothed_unigram_sums), all-reduced by the caller and handed back
 // (`ext_sums`): then unigram = ext_sums[c] / ext_sums[C] + tiny and no row is read here.
-__global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const float *lmmax, const float *lmsum,
+template <typename TE>
+__global__ void __launch_bounds__(256) unigram_kernel(const TE *lm, const float *lmmax, const float *lmsum,
                                                       int rows, int C, const float *ext_sums, float *sums_out,
                                                       float *unigram, float *log_unigram) {
   __shared__ float part[8][32];
@@ -182,7 +237,7 @@ __global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const flo
   const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
   if (c < C && !ext_sums)
-    for (int r = w; r < rows; r += 8) acc += expf(lm[(size_t)r * C + c] - lmmax[r]) / lmsum[r];
+    for (int r = w; r < rows; r += 8) acc += expf(elem_to_f(lm[(size_t)r * C + c]) - lmmax[r]) / lmsum[r];
   part[w][lane] = acc;
   __syncthreads();
   if (w == 0 && c < C) {
@@ -201,15 +256,16 @@ __global__ void __launch_bounds__(256) unigram_kernel(const float *lm, const flo
 }
 
 // amonly[b,t] = log( sum_c exp(am-ammax) * unigram[c] ) + ammax  (rnnt_loss.py:1281-1286)
-__global__ void __launch_bounds__(256) amonly_kernel(const float *am, const float *ammax, const float *unigram,
+template <typename TE>
+__global__ void __launch_bounds__(256) amonly_kernel(const TE *am, const float *ammax, const float *unigram,
                                                      int rows, int C, float *amonly) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float *src = am + (size_t)row * C;
+  const TE *src = am + (size_t)row * C;
   const float m = ammax[row];
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += expf(src[c] - m) * unigram[c];
+  for (int c = lane; c < C; c += 32) s += expf(elem_to_f(src[c]) - m) * unigram[c];
   s = warp_sum(s);
   if (lane == 0) amonly[row] = logf(s) + m;
 }
@@ -336,24 +392,24 @@ __global__ void __launch_bounds__(256) constrained_fix_kernel(float *px, const f
 // per thread), so the row is read from memory once for the maximum, the sum and the float16 split.  With a warp
 // per row the three passes re-read 20 KB rows that ~10 k resident warps had long pushed out of L2 (the kernel
 // read am and lm twice from DRAM at the c4 shape).
-__global__ void __launch_bounds__(256) rowstats_long_kernel(const float *lm, int rows_lm, const float *am, int rows_am,
+template <typename TE>
+__global__ void __launch_bounds__(256) rowstats_long_kernel(const TE *lm, int rows_lm, const TE *am, int rows_am,
                                                             int C, float *lmmax, float *lmsum, float *ammax,
                                                             const int32_t *symbols, int S, int T, float *pxam_t,
-                                                            SplitPlanes split) {
+                                                            SplitPlanes split, RowGathers gat) {
   __shared__ float red[8];
   int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool is_lm = row < rows_lm;
   if (!is_lm) row -= rows_lm;
-  const float *src = (is_lm ? lm : am) + (size_t)row * C;
+  const TE *src = (is_lm ? lm : am) + (size_t)row * C;
   const int nv = C / 4;
-  const float4 *p = reinterpret_cast<const float4 *>(src);
   float4 v[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int c = u * 256 + tid;
     v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (c < nv) v[u] = ld_stream_f4(p + c);
+    if (c < nv) v[u] = load4_stream(src + 4 * c);
   }
   // am[b,t,sym[b,s]] (see rowstats_kernel): issued behind the row's loads
   const bool gather = !is_lm && pxam_t != nullptr;
@@ -362,7 +418,7 @@ __global__ void __launch_bounds__(256) rowstats_long_kernel(const float *lm, int
     float *dst = pxam_t + (size_t)row * S;
     for (int s = tid; s < S; s += 256) {
       const int c = sym[s];
-      dst[s] = (c >= 0 && c < C) ? __ldg(src + c) : 0.f;
+      dst[s] = (c >= 0 && c < C) ? elem_to_f(src[c]) : 0.f;
     }
   }
   float m = -INFINITY;
@@ -392,6 +448,16 @@ __global__ void __launch_bounds__(256) rowstats_long_kernel(const float *lm, int
     }
   }
   if (tid == 0) (is_lm ? lmmax : ammax)[row] = m;
+  if (gat.am_term && tid == 32) {
+    if (is_lm) {
+      const int S1 = S + 1, b = row / S1, sl = row - b * S1;
+      gat.lm_term[row] = elem_to_f(src[gat.term]);
+      const int c = sl < S ? symbols[(size_t)b * S + sl] : -1;
+      gat.lm_sym[row] = (c >= 0 && c < C) ? elem_to_f(src[c]) : 0.f;
+    } else {
+      gat.am_term[row] = elem_to_f(src[gat.term]);
+    }
+  }
   if (split.Cp) {
     uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
     uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
@@ -410,17 +476,20 @@ __global__ void __launch_bounds__(256) rowstats_long_kernel(const float *lm, int
 
 // row statistics of lm ([rows_lm][C]) and am ([rows_am][C]) in one launch: a warp per row, or a block per row for
 // long aligned rows
-static void launch_rowstats(const float *lm, int rows_lm, const float *am, int rows_am, int C, float *lmmax,
+template <typename TE>
+static void launch_rowstats(const TE *lm, int rows_lm, const TE *am, int rows_am, int C, float *lmmax,
                             float *lmsum, float *ammax, const int32_t *symbols, int S, int T, float *pxam_t,
-                            const SplitPlanes &split, cudaStream_t stream) {
-  const bool aligned = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0;
+                            const SplitPlanes &split, const RowGathers &gat, cudaStream_t stream) {
+  const uintptr_t mask = 4 * sizeof(TE) - 1;
+  const bool aligned = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & mask) == 0;
   if (aligned && C > 4 * 32 * 8 && C <= 4 * 256 * 8 && rows_lm + rows_am > 0) {
-    count_launch(), rowstats_long_kernel<<<rows_lm + rows_am, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C, lmmax, lmsum,
-                                                                                 ammax, symbols, S, T, pxam_t, split);
+    count_launch(), rowstats_long_kernel<TE><<<rows_lm + rows_am, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C, lmmax,
+                                                                                     lmsum, ammax, symbols, S, T, pxam_t,
+                                                                                     split, gat);
   } else {
-    count_launch(), rowstats_kernel<<<(rows_lm + rows_am + 7) / 8, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C, lmmax,
-                                                                                      lmsum, ammax, symbols, S, T, pxam_t,
-                                                                                      split);
+    count_launch(), rowstats_kernel<TE><<<(rows_lm + rows_am + 7) / 8, 256, 0, stream>>>(lm, rows_lm, am, rows_am, C,
+                                                                                          lmmax, lmsum, ammax, symbols, S,
+                                                                                          T, pxam_t, split, gat);
   }
 }
 
@@ -434,6 +503,8 @@ size_t simple_stats_bytes(int B, int S, int T, int C) {
   // two-term float16 operands of the tensor-core contraction (SplitPlanes): h and l planes of am and of lm
   const size_t Cp = (size_t)round_up(C, 8);
   n += 2 * round_up_sz((size_t)B * T * Cp * 2, 256) + 2 * round_up_sz((size_t)B * (S + 1) * Cp * 2, 256);
+  // am[b,t,blank], lm[b,s,blank], lm[b,s,symbol] (RowGathers)
+  n += round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256);
   return n;
 }
 
@@ -449,7 +520,7 @@ int launch_smoothing_stats(const float *lm, const float *am, int B, int S, int T
   float *amonly = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
   float *unigram = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *logu = reinterpret_cast<float *>(w);
-  launch_rowstats(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax, nullptr, 0, 1, nullptr, SplitPlanes(), stream);
+  launch_rowstats(lm, B * S1, am, B * T, C, lmmax, lmsum, ammax, nullptr, 0, 1, nullptr, SplitPlanes(), RowGathers(), stream);
   count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
                                                                  unigram, logu);
   count_launch(), amonly_kernel<<<(B * T + 7) / 8, 256, 0, stream>>>(am, ammax, unigram, B * T, C, amonly);
@@ -463,7 +534,7 @@ int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, fl
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
   float *lmsum = reinterpret_cast<float *>(w);
-  launch_rowstats(lm, B * S1, lm, 0, C, lmmax, lmsum, lmmax, nullptr, 0, 1, nullptr, SplitPlanes(), stream);
+  launch_rowstats(lm, B * S1, lm, 0, C, lmmax, lmsum, lmmax, nullptr, 0, 1, nullptr, SplitPlanes(), RowGathers(), stream);
   count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, nullptr, sums, nullptr,
                                                                  nullptr);
   return check_launch();
@@ -472,15 +543,17 @@ int launch_unigram_sums(const float *lm, int B, int S, int C, void *stats_ws, fl
 // One launcher for both outputs of the contraction: px/py in the reference layout (arcs == nullptr), or
 // the arcs of the dense-lattice recursion written straight into its diagonal-major plane (arcs != nullptr:
 // tensor-core kernel only, regular / modified; check simple_arc_plane_supported() first).
-bool simple_arc_plane_supported(const float *lm, const float *am, int C, int rnnt_type) {
+bool simple_arc_plane_supported(const void *lm, const void *am, int C, int rnnt_type) {
   if (debug_env_int("FRN_SIMPLE_SIMT", 0) == 1 || debug_env_int("FRN_SIMPLE_PXPY", 0) == 1) return false;
   return rnnt_type != FRN_CONSTRAINED && simple_logprobs_tc_applicable(lm, am, C);
 }
 
-int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
-                           int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
-                           float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
-                           cudaStream_t stream, const ArcPlaneOut *arcs, const float *unigram_sums) {
+template <typename TE>
+static int launch_simple_logprobs_t(const TE *lm, const TE *am, const int32_t *symbols, const int32_t *boundary,
+                                    int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
+                                    float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
+                                    cudaStream_t stream, const ArcPlaneOut *arcs, const float *unigram_sums) {
+  constexpr bool kF32 = std::is_same<TE, float>::value;
   const int S1 = S + 1;
   char *w = static_cast<char *>(stats_ws);
   float *lmmax = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
@@ -491,17 +564,23 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   float *logu = reinterpret_cast<float *>(w); w += round_up_sz((size_t)C * sizeof(float), 256);
   float *pxam_t = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * S * sizeof(float), 256);
   const bool tc = simple_logprobs_tc_applicable(lm, am, C) && debug_env_int("FRN_SIMPLE_SIMT", 0) != 1;
+  if (!tc && !kF32) return FRN_EUNSUPPORTED;      // bf16 / fp16 am, lm: tensor-core path only (the caller widens them)
   SplitPlanes split;
+  RowGathers gat;
   if (tc) {
     split.Cp = round_up(C, 8);
     const size_t am_plane = round_up_sz((size_t)B * T * split.Cp * 2, 256), lm_plane = round_up_sz((size_t)B * S1 * split.Cp * 2, 256);
     split.amh = reinterpret_cast<unsigned short *>(w); w += am_plane;
     split.aml = reinterpret_cast<unsigned short *>(w); w += am_plane;
     split.lmh = reinterpret_cast<unsigned short *>(w); w += lm_plane;
-    split.lml = reinterpret_cast<unsigned short *>(w);
+    split.lml = reinterpret_cast<unsigned short *>(w); w += lm_plane;
+    gat.am_term = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+    gat.lm_term = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+    gat.lm_sym = reinterpret_cast<float *>(w);
+    gat.term = term;
   }
   launch_rowstats(lm, B * S1, am, B * T, C, lmmax, smoothed ? lmsum : nullptr, ammax, symbols, S, T,
-                  tc ? pxam_t : nullptr, split, stream);
+                  tc ? pxam_t : nullptr, split, gat, stream);
   if (smoothed) {
     count_launch(), unigram_kernel<<<(C + 31) / 32, 256, 0, stream>>>(lm, lmmax, lmsum, B * S1, C, unigram_sums, nullptr,
                                                                    unigram, logu);
@@ -510,7 +589,10 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   int rc = check_launch();
   if (rc) return rc;
   SimpleParams sp;
-  sp.lm = lm; sp.am = am; sp.symbols = symbols; sp.boundary = boundary;
+  sp.lm = kF32 ? reinterpret_cast<const float *>(lm) : nullptr;      // read by the SIMT kernel only
+  sp.am = kF32 ? reinterpret_cast<const float *>(am) : nullptr;
+  sp.gat = gat;
+  sp.symbols = symbols; sp.boundary = boundary;
   sp.lmmax = lmmax; sp.ammax = ammax; sp.lmsum = lmsum; sp.amonly = amonly; sp.logu = logu;
   sp.px = px; sp.py = py; sp.pxam_t = tc ? pxam_t : nullptr; sp.split = split;
   sp.B = B; sp.S = S; sp.T = T; sp.T1 = (rnnt_type == FRN_REGULAR) ? T + 1 : T; sp.C = C; sp.term = term;
@@ -526,7 +608,7 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
   }
   // tensor-core path (tcgen05 + TMA); the exact-FP32 SIMT kernel serves shapes TMA cannot address (C % 4 != 0)
   rc = debug_env_int("FRN_SIMPLE_SIMT", 0) == 1 ? FRN_EUNSUPPORTED : launch_simple_logprobs_tc(sp, stream);
-  if (rc == FRN_EUNSUPPORTED) {
+  if (rc == FRN_EUNSUPPORTED && kF32) {
     dim3 grid((sp.T1 + kTile - 1) / kTile, (S1 + kTile - 1) / kTile, B);
     count_launch(), simple_logprobs_kernel<<<grid, 256, 0, stream>>>(sp);
     rc = check_launch();
@@ -538,6 +620,35 @@ int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symb
     rc = check_launch();
   }
   return rc;
+}
+
+int launch_simple_logprobs(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary,
+                           int B, int S, int T, int C, int term, int rnnt_type, int smoothed,
+                           float lm_only_scale, float am_only_scale, float *px, float *py, void *stats_ws,
+                           cudaStream_t stream, const ArcPlaneOut *arcs, const float *unigram_sums) {
+  return launch_simple_logprobs_t<float>(lm, am, symbols, boundary, B, S, T, C, term, rnnt_type, smoothed, lm_only_scale,
+                                         am_only_scale, px, py, stats_ws, stream, arcs, unigram_sums);
+}
+
+// am / lm of any supported element type (frn_dtype); float32 takes the path above
+int launch_simple_logprobs_any(const void *lm, const void *am, int dtype, const int32_t *symbols,
+                               const int32_t *boundary, int B, int S, int T, int C, int term, int rnnt_type,
+                               int smoothed, float lm_only_scale, float am_only_scale, float *px, float *py,
+                               void *stats_ws, cudaStream_t stream, const ArcPlaneOut *arcs, const float *unigram_sums) {
+  if (dtype == FRN_F32)
+    return launch_simple_logprobs(static_cast<const float *>(lm), static_cast<const float *>(am), symbols, boundary, B, S,
+                                  T, C, term, rnnt_type, smoothed, lm_only_scale, am_only_scale, px, py, stats_ws, stream,
+                                  arcs, unigram_sums);
+  if (dtype == FRN_BF16)
+    return launch_simple_logprobs_t<__nv_bfloat16>(static_cast<const __nv_bfloat16 *>(lm),
+                                                   static_cast<const __nv_bfloat16 *>(am), symbols, boundary, B, S, T, C,
+                                                   term, rnnt_type, smoothed, lm_only_scale, am_only_scale, px, py,
+                                                   stats_ws, stream, arcs, unigram_sums);
+  if (dtype == FRN_F16)
+    return launch_simple_logprobs_t<__half>(static_cast<const __half *>(lm), static_cast<const __half *>(am), symbols,
+                                            boundary, B, S, T, C, term, rnnt_type, smoothed, lm_only_scale, am_only_scale,
+                                            px, py, stats_ws, stream, arcs, unigram_sums);
+  return FRN_EINVAL;
 }
 
 }  // namespace frn

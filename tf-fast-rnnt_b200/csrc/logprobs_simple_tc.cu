@@ -246,8 +246,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
       }
     if (tile_dead) return;
   }
-  const float *lmb = p.lm + (size_t)b * S1 * C;
-  const float *amb = p.am + (size_t)b * p.T * C;
   if (tid < TM) {
     const int t = t0 + tid;
     const float mx = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
@@ -259,10 +257,10 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
     int sym = -1;
     if (s < S1) {
       lmmax = p.lmmax[(size_t)b * S1 + s];
-      pylm = lmb[(size_t)s * C + p.term];
+      pylm = p.gat.lm_term[(size_t)b * S1 + s];
       if (s < p.S) {
         sym = p.symbols[(size_t)b * p.S + s];
-        pxlm = lmb[(size_t)s * C + sym];
+        pxlm = p.gat.lm_sym[(size_t)b * S1 + s];
       }
       if (p.smoothed) {
         lmonly = logf(p.lmsum[(size_t)b * S1 + s]) + lmmax;
@@ -299,7 +297,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
   const int erow = q * 32 + lane, et = t0 + erow;
   const bool t_ok = et < p.T;
   const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
-  const float py_am = __ldg(amb + (size_t)(t_ok ? et : 0) * C + p.term);
+  const float py_am = __ldg(p.gat.am_term + (size_t)b * p.T + (t_ok ? et : 0));
   const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
   const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
   // am[b,t,sym_s] for this thread's frame: gathered by the row-statistics kernel while it had the row in flight
@@ -569,7 +567,7 @@ static bool make_map_3d(CUtensorMap *map, const unsigned short *base, int rows, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C) {
+bool simple_logprobs_tc_applicable(const void *lm, const void *am, int C) {
   // the row-statistics kernel builds the operands with 128-bit loads (C % 4 == 0, 16-byte aligned bases); the
   // contraction itself needs the driver's tensor-map encoder
   return C % 4 == 0 && ((reinterpret_cast<uintptr_t>(am) | reinterpret_cast<uintptr_t>(lm)) & 15u) == 0 &&
@@ -579,8 +577,8 @@ bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C) {
 // returns FRN_EUNSUPPORTED when the tensor-core path does not apply (caller falls back to the SIMT kernel):
 // C % 4 != 0 or misaligned bases.  sp.XY != nullptr selects the arc-plane output (regular / modified only).
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream) {
-  if (!simple_logprobs_tc_applicable(sp.lm, sp.am, sp.C) || sp.pxam_t == nullptr || sp.split.Cp == 0)
-    return FRN_EUNSUPPORTED;
+  if (sp.pxam_t == nullptr || sp.split.Cp == 0 || sp.gat.am_term == nullptr || get_encode_fn() == nullptr)
+    return FRN_EUNSUPPORTED;                      // the row-statistics kernel did not prepare the operands
   if (sp.XY != nullptr && sp.rnnt_type == FRN_CONSTRAINED) return FRN_EUNSUPPORTED;
   CUtensorMap map_amh, map_aml, map_lmh, map_lml;
   if (!make_map_3d(&map_amh, sp.split.amh, sp.T, sp.C, sp.split.Cp, sp.B, tc::TM) ||

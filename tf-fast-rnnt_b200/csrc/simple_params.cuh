@@ -11,13 +11,19 @@ struct SplitPlanes {
   unsigned short *amh = nullptr, *aml = nullptr, *lmh = nullptr, *lml = nullptr;
   int Cp = 0;                           // 0: not wanted
 };
+// am[b,t,blank] [B][T], lm[b,s,blank] and lm[b,s,symbols[b,s]] [B][S+1], gathered by the row-statistics kernel
+struct RowGathers {
+  float *am_term = nullptr, *lm_term = nullptr, *lm_sym = nullptr;
+  int term = 0;
+};
 struct SimpleParams {
-  const float *lm, *am;
+  const float *lm, *am;                 // float32 inputs (SIMT kernel); the tensor-core kernel never reads them
   const int32_t *symbols, *boundary;
   const float *lmmax, *ammax;           // row maxima
   const float *lmsum, *amonly, *logu;   // smoothed only (may be null)
   const float *pxam_t = nullptr;        // [B][T][S] am[b,t,symbols[b,s]], written by the row-statistics kernel
   SplitPlanes split;                    // tensor-core path: the contraction's operands
+  RowGathers gat;                       // tensor-core path: the other am / lm values of the epilogue
   float *px, *py;                       // reference layout
   int B, S, T, T1, C, term, rnnt_type, smoothed;
   float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
@@ -30,5 +36,5 @@ struct SimpleParams {
 };
 int launch_simple_logprobs_tc(const SimpleParams &sp, cudaStream_t stream);
 // true when the tensor-core kernel can take this problem (TMA needs C % 4 == 0 and 16-byte aligned bases)
-bool simple_logprobs_tc_applicable(const float *lm, const float *am, int C);
+bool simple_logprobs_tc_applicable(const void *lm, const void *am, int C);
 }  // namespace frn

@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get(
 
 FRN_OK = 0
 REGULAR, MODIFIED, CONSTRAINED = 0, 1, 2
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+EUNSUPPORTED = -4
 NONE, MEAN, SUM = 0, 1, 2
 RNNT_TYPES = {"regular": REGULAR, "modified": MODIFIED, "constrained": CONSTRAINED}
 REDUCTIONS = {"none": NONE, "mean": MEAN, "sum": SUM}
@@ -107,6 +108,10 @@ _SIGS = {
                                             c_float, _P, _P, _P, _P, c_size_t, _P]),
     "frn_simple_loss_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_float, _P, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_logprobs_lp": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_loss_lp": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                   c_float, _P, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "frn_smoothed_loss_bwd_sharded": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_float, c_float, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "frn_allreduce_sum": (c_int, [_P, c_size_t, _P, _P]),

@@ -91,6 +91,21 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_LP_CODES = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _low_precision_pair(lm, am):
+    """(lm, am, dtype code) when both are bf16 (or both fp16) CUDA tensors the library can consume as they are
+    (frn_simple_loss_lp / frn_simple_logprobs_lp - no widening pass, no float32 copies), else None."""
+    if not (isinstance(lm, torch.Tensor) and isinstance(am, torch.Tensor) and lm.is_cuda and am.is_cuda):
+        return None
+    if lm.dtype != am.dtype or lm.dtype not in _LP_CODES or lm.requires_grad or am.requires_grad:
+        return None
+    if lm.dim() != 3 or am.dim() != 3 or am.shape[2] % 4 != 0:
+        return None
+    return lm.contiguous(), am.contiguous(), _LP_CODES[lm.dtype]
+
+
 def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
@@ -255,8 +270,9 @@ def cummin(x: Tensor):
 def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, smoothed,
                      lm_only_scale, am_only_scale, usums=None):
     io = _Io(lm, am)
-    lm_d = io.dev_tensor(lm, torch.float32)
-    am_d = io.dev_tensor(am, torch.float32)
+    lp = _low_precision_pair(lm, am) if usums is None else None
+    lm_d = lp[0] if lp else io.dev_tensor(lm, torch.float32)
+    am_d = lp[1] if lp else io.dev_tensor(am, torch.float32)
     sym_d = io.dev_tensor(symbols, torch.int32)
     B, T, C = am_d.shape
     S = lm_d.shape[1] - 1
@@ -268,6 +284,15 @@ def _simple_logprobs(lm, am, symbols, termination_symbol, rnnt_type, boundary, s
     px = torch.empty((B, S, T1), dtype=torch.float32, device=io.dev)
     py = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev)
     ws = _workspace(lib.frn_simple_logprobs_workspace_bytes(B, S, T, C), io.dev)
+    if lp:
+        rc = lib.frn_simple_logprobs_lp(_ptr(lm_d), _ptr(am_d), lp[2], _ptr(sym_d), _ptr(bd), B, S, T, C,
+                                        int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                                        float(am_only_scale), None, _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
+                                        _stream(io.dev))
+        if rc != _lib.EUNSUPPORTED:
+            check(rc, "frn_simple_logprobs_lp")
+            return io.out(px), io.out(py)
+        lm_d, am_d = io.dev_tensor(lm, torch.float32), io.dev_tensor(am, torch.float32)    # widen, then the float32 path
     check(lib.frn_simple_logprobs_sharded(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
                                           int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
                                           float(am_only_scale), _ptr(usums), _ptr(px), _ptr(py), _ptr(ws), ws.numel(),
@@ -338,8 +363,11 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
         raise ValueError(
             f"reduction should be ('none' | 'mean' | 'sum'), given {reduction}")
     io = _Io(lm, am)
-    lm_d = io.dev_tensor(lm, torch.float32)
-    am_d = io.dev_tensor(am, torch.float32)
+    # bf16 / fp16 am, lm on the device are consumed as they are (the sharded smoothed loss widens them: its
+    # unigram sums are formed by a float32 entry point)
+    lp = _low_precision_pair(lm, am) if not (smoothed and group is not None) else None
+    lm_d = lp[0] if lp else io.dev_tensor(lm, torch.float32)
+    am_d = lp[1] if lp else io.dev_tensor(am, torch.float32)
     sym_d = io.dev_tensor(symbols, torch.int32)
     B, T, C = am_d.shape
     S = lm_d.shape[1] - 1
@@ -353,6 +381,16 @@ def _simple_loss(lm, am, symbols, termination_symbol, boundary, rnnt_type, delay
     gy = torch.empty((B, S + 1, T), dtype=torch.float32, device=io.dev) if calc_gradients else None
     ws = _workspace(lib.frn_simple_loss_workspace_bytes(B, S, T, C), io.dev)
     dp = float(delay_penalty) if delay_penalty > 0.0 else 0.0
+    if lp:
+        rc = lib.frn_simple_loss_lp(_ptr(lm_d), _ptr(am_d), lp[2], _ptr(sym_d), _ptr(bd), B, S, T, C,
+                                    int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
+                                    float(am_only_scale), None, dp, int(calc_gradients), _ptr(scores), _ptr(gx), _ptr(gy),
+                                    _ptr(ws), ws.numel(), _stream(io.dev))
+        if rc != _lib.EUNSUPPORTED:
+            check(rc, "frn_simple_loss_lp")
+            loss = io.out(_reduce(scores, reduction, group))
+            return (loss, (io.out(gx), io.out(gy))) if calc_gradients else loss
+        lm_d, am_d = io.dev_tensor(lm, torch.float32), io.dev_tensor(am, torch.float32)    # widen, then the float32 path
     usums = _unigram_sums(lm_d, group) if smoothed else None
     check(lib.frn_simple_loss_sharded(_ptr(lm_d), _ptr(am_d), _ptr(sym_d), _ptr(bd), B, S, T, C,
                                       int(termination_symbol), rt, int(smoothed), float(lm_only_scale),
