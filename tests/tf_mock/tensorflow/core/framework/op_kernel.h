@@ -13,6 +13,7 @@ namespace Eigen {
 struct GpuDevice {
   void *stream() const { return nullptr; }
 };
+struct half { uint16_t x; };
 }  // namespace Eigen
 
 namespace tensorflow {

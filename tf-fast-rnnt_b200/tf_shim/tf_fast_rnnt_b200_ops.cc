@@ -152,10 +152,11 @@ REGISTER_KERNEL_BUILDER(Name("Cummin").Device(tf::DEVICE_GPU), CumminOp);
 // (rnnt_loss.py:225-338, 1369-1494), reduction "none"; scores = -loss.
 // ---------------------------------------------------------------------------
 REGISTER_OP("FastRnntSimpleLoss")
-    .Input("lm: float32")
-    .Input("am: float32")
+    .Input("lm: T")
+    .Input("am: T")
     .Input("symbols: int32")
     .Input("boundary: int32")
+    .Attr("T: {float32, bfloat16, half} = DT_FLOAT")
     .Attr("termination_symbol: int")
     .Attr("rnnt_type: int = 0")
     .Attr("smoothed: bool = false")
@@ -173,6 +174,9 @@ REGISTER_OP("FastRnntSimpleLoss")
       return tf::OkStatus();
     });
 
+// lm / am of type T are consumed as they are (frn_simple_loss_lp: bf16 / fp16 need no tf.cast and no float32 copy;
+// the reference's op is float32-only, op.cc:28-34).  Scores and occupation counts are float32.
+template <typename DT>
 class FastRnntSimpleLossOp : public tf::OpKernel {
  public:
   explicit FastRnntSimpleLossOp(tf::OpKernelConstruction *ctx) : tf::OpKernel(ctx) {
@@ -195,12 +199,13 @@ class FastRnntSimpleLossOp : public tf::OpKernel {
     OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({B, S + 1, T}), &gy));
     const size_t bytes = frn_simple_loss_workspace_bytes(B, S, T, C);
     OP_REQUIRES_OK(ctx, Workspace(ctx, bytes, &ws));
-    OP_REQUIRES_OK(ctx, FromFrn(frn_simple_loss(lm.flat<float>().data(), am.flat<float>().data(),
-                                                sym.flat<tf::int32>().data(), bd.flat<tf::int32>().data(), B, S, T, C,
-                                                term_, type_, smoothed_ ? 1 : 0, lms_, ams_, dp_, calc_ ? 1 : 0,
-                                                scores->flat<float>().data(), gx->flat<float>().data(),
-                                                gy->flat<float>().data(), ws.flat<tf::uint8>().data(), bytes,
-                                                StreamOf(ctx)),
+    const int dtype = std::is_same<DT, float>::value ? FRN_F32 : (std::is_same<DT, tf::bfloat16>::value ? FRN_BF16 : FRN_F16);
+    OP_REQUIRES_OK(ctx, FromFrn(frn_simple_loss_lp(lm.flat<DT>().data(), am.flat<DT>().data(), dtype,
+                                                   sym.flat<tf::int32>().data(), bd.flat<tf::int32>().data(), B, S, T,
+                                                   C, term_, type_, smoothed_ ? 1 : 0, lms_, ams_, nullptr, dp_,
+                                                   calc_ ? 1 : 0, scores->flat<float>().data(),
+                                                   gx->flat<float>().data(), gy->flat<float>().data(),
+                                                   ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx)),
                                 "FastRnntSimpleLoss"));
   }
 
@@ -209,7 +214,12 @@ class FastRnntSimpleLossOp : public tf::OpKernel {
   bool smoothed_, calc_;
   float lms_, ams_, dp_;
 };
-REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLoss").Device(tf::DEVICE_GPU), FastRnntSimpleLossOp);
+REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLoss").Device(tf::DEVICE_GPU).TypeConstraint<float>("T"),
+                        FastRnntSimpleLossOp<float>);
+REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLoss").Device(tf::DEVICE_GPU).TypeConstraint<tf::bfloat16>("T"),
+                        FastRnntSimpleLossOp<tf::bfloat16>);
+REGISTER_KERNEL_BUILDER(Name("FastRnntSimpleLoss").Device(tf::DEVICE_GPU).TypeConstraint<Eigen::half>("T"),
+                        FastRnntSimpleLossOp<Eigen::half>);
 
 // gradient of FastRnntSimpleLoss w.r.t. lm and am (A9: what TF autodiff derives through
 // rnnt_loss.py:175-221 / 1266-1365 once _RNNTLossGrad, __init__.py:154-162, has supplied the

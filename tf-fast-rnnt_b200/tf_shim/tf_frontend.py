@@ -53,13 +53,16 @@ def _do_pruning_add_joiner_grad(op, g_am, g_lm, g_logits):
 @ops.RegisterGradient("FastRnntSimpleLoss")
 def _simple_loss_grad(op, g_scores, _g_px_grad, _g_py_grad):
     """A9: d scores / d (lm, am) from the occupation counts the forward op produced (it must have
-    run with calc_gradients=True)."""
+    run with calc_gradients=True).  The forward op takes bf16 / fp16 lm, am as they are; the gradient op is
+    float32: low-precision inputs are widened here and the gradients returned in the inputs' type."""
+    in_type = op.inputs[0].dtype
     lm_g, am_g = _ops.fast_rnnt_simple_loss_grad(
-        op.inputs[0], op.inputs[1], op.inputs[2], op.inputs[3], op.outputs[1], op.outputs[2], g_scores,
+        tf.cast(op.inputs[0], tf.float32), tf.cast(op.inputs[1], tf.float32), op.inputs[2], op.inputs[3],
+        op.outputs[1], op.outputs[2], g_scores,
         termination_symbol=op.get_attr("termination_symbol"), rnnt_type=op.get_attr("rnnt_type"),
         smoothed=op.get_attr("smoothed"), lm_only_scale=op.get_attr("lm_only_scale"),
         am_only_scale=op.get_attr("am_only_scale"))
-    return [lm_g, am_g, None, None]
+    return [tf.cast(lm_g, in_type), tf.cast(am_g, in_type), None, None]
 
 
 @ops.RegisterGradient("FastRnntSimpleLogprobs")
