@@ -79,6 +79,10 @@ __device__ void block_rev_cummin(int32_t *x, int T, int32_t *warp_carry) {
 }
 
 constexpr int kArgmaxThreads = 128;   // maximum columns (t) per block; blockDim.x = columns actually used
+#ifndef FRN_ARGMAX_TILE_KB
+#define FRN_ARGMAX_TILE_KB 112        // 2 x 112 KB still fit one SM
+#endif
+constexpr size_t kArgmaxTileBytes = (size_t)FRN_ARGMAX_TILE_KB * 1024;
 
 // The [S+1] x 128 tile of py_grad and the [S] x 128 tile of px_grad are brought into shared memory
 // with 4-byte cp.async (fire and forget: every load of the tile is in flight at once, one memory
@@ -521,6 +525,8 @@ int launch_prune_ranges(const float *px_grad, const float *py_grad, const int32_
   // columns per block: as many as keep the tile under ~100 KB (two blocks per SM)
   int cols = kArgmaxThreads;
   while (cols > 8 && (size_t)(2 * S + 1) * cols * sizeof(float) > 100 * 1024) cols >>= 1;
+  // a full warp of columns (128-byte rows) if 2 x kArgmaxTileBytes still fit an SM: S = 400 (c4, c5) gets 32, not 16
+  if (cols < 32 && (size_t)(2 * S + 1) * 32 * sizeof(float) <= kArgmaxTileBytes) cols = 32;
   const size_t tile_bytes = (size_t)(2 * S + 1) * cols * sizeof(float);
   if (tile_bytes > 200 * 1024) return FRN_EUNSUPPORTED;
   dim3 grid((T + cols - 1) / cols, B);
