@@ -316,7 +316,7 @@ class Pipeline:
         self._reduce()
 
 
-def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=5):
+def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=50):
     """The reference's OWN CUDA op (oracle/_ref/libref_mi.so = mutual_information_cuda.cu compiled
     unmodified for sm_100, driven like tf_fast_rnnt_op.cc:66-113 incl. its memsets, H2D copy and
     stream sync) timed on this GPU beside frn_mi_fwd_bwd on the SAME px/py — a reported baseline
@@ -363,7 +363,7 @@ def reference_gpu_op_leg(pipe, am, lm, sym, bd, reps=5):
                                ws.numel(), st), "mi_fwd_bwd")
 
     out = {"what": "reference FastRNNTLoss op (its own kernels, sm_100 build, op.cc launch sequence incl. sync) vs "
-                   "frn_mi_fwd_bwd on the same dense px/py; host wall clock per call, ms"}
+                   "frn_mi_fwd_bwd on the same dense px/py; host wall clock per call over %d back-to-back calls, ms" % reps}
     # lattice of the simple loss
     chk(lib.frn_simple_logprobs(ptr(lm), ptr(am), ptr(sym), ptr(bd), B, S, T, C, C - 1, 0, 0, 0.0, 0.0, ptr(px),
                                 ptr(py), ptr(ws), ws.numel(), st), "simple_logprobs")
