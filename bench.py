@@ -1184,7 +1184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--buckets", type=int, default=4, help="c5: length buckets per rank (1 = pad the shard to its maxima)")
+    ap.add_argument("--buckets", type=int, default=8, help="c5: length buckets per rank (1 = pad the shard to its maxima; 4+: the planner may also split by label length)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--c5-streams", type=int, default=1, help="c5: 1 = every length bucket on its own CUDA stream (default), 0 = one stream")
     ap.add_argument("--streams", type=int, default=1,

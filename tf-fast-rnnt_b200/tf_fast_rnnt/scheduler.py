@@ -54,7 +54,7 @@ class Bucket:
         raise ValueError(kind)
 
 
-def make_buckets(boundary, s_range: int, vocab: int, max_buckets: int = 4, min_bucket: int = 4,
+def make_buckets(boundary, s_range: int, vocab: int, max_buckets: int = 8, min_bucket: int = 4,
                  device=None) -> List[Bucket]:
     """Length buckets of a batch from its boundary rows [s_begin, t_begin, s_end, t_end] (host copy needed:
     the plan is made on the CPU).  s_end / t_end bound what a bucket is trimmed to."""
@@ -76,7 +76,7 @@ def _additive_joiner(am, lm, ranges):
 def pruned_rnnt_pipeline(lm: torch.Tensor, am: torch.Tensor, symbols: torch.Tensor, termination_symbol: int,
                          boundary: torch.Tensor, s_range: int, joiner: Optional[Callable] = None,
                          rnnt_type: str = "regular", delay_penalty: float = 0.0, reduction: Optional[str] = "sum",
-                         max_buckets: int = 4, min_bucket: int = 4, lm_only_scale: float = 0.0,
+                         max_buckets: int = 8, min_bucket: int = 4, lm_only_scale: float = 0.0,
                          am_only_scale: float = 0.0, group=None, return_ranges: bool = False):
     """The full pruned RNN-T step on a ragged batch, per length bucket.
 

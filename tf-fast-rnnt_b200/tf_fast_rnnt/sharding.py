@@ -45,33 +45,30 @@ def shard_max_shapes(boundary: np.ndarray, idx: Sequence[int]):
     return int(b[:, 2].max()), int(b[:, 3].max())
 
 
-def plan_buckets(boundary: np.ndarray, s_range: int, vocab: int, max_buckets: int = 4,
-                 min_bucket: int = 4):
-    """Batch scheduler for ragged shards (SURVEY.md §8f-4): split a shard into at most
-    ``max_buckets`` length buckets so that the bandwidth-bound kernels do not stream
-    padding.  The lattice recursions already stop at each utterance's own (S_b, T_b); what
-    padding costs is bytes: ``do_rnnt_pruning``, the joiner and the pruned log-softmax touch
-    ``T_max * s_range * vocab`` elements per utterance whatever T_b is.
+def _bucket_cost(n_utt: int, t_max: int, s_max: int, s_range: int, vocab: int) -> float:
+    """Modelled bytes a bucket streams, padding included: the pruned path touches 20 bytes per [t, i, c] element
+    (pruning + joiner + log-softmax + logits gradient); the simple loss touches every cell of the
+    padded (S_max + 1) x T_max lattice (arcs, recursion planes, occupation counts: ~60 bytes) and contracts
+    2 * 3 * vocab flops per cell there (~vocab / 25 byte-equivalents at this part's flop : byte ratio)."""
+    return float(n_utt) * t_max * (20.0 * s_range * vocab + (s_max + 1) * (60.0 + vocab / 25.0))
 
-    Utterances are sorted by T_b and cut by dynamic programming into contiguous groups that
-    minimise  sum_g |g| * T_max(g)  (the padded frame count, proportional to the bytes of
-    those kernels), subject to ``len(g) >= min_bucket`` (each bucket is one more set of kernel
-    launches; tiny buckets cannot fill the GPU).  Returns a list of dicts
-    ``{"idx", "S_max", "T_max", "padded_frames", "bytes"}`` ordered by decreasing T_max;
-    ``bytes`` estimates the pruned-path traffic of the bucket (SURVEY.md §8d:
-    20 bytes per [t, i, c] element for pruning + joiner + log-softmax + logits gradient)."""
-    b = np.asarray(boundary, dtype=np.int64)
-    n = len(b)
-    if n == 0:
-        return []
-    order = np.argsort(-b[:, 3], kind="stable")             # decreasing T_b: a group's T_max is its first element
+
+def _plan_by_t(b: np.ndarray, members: np.ndarray, s_range: int, vocab: int, max_buckets: int, min_bucket: int):
+    """Cut `members` (indices into b), sorted by decreasing T_b, into at most max_buckets contiguous groups that
+    minimise the modelled cost (dynamic programming)."""
+    n = len(members)
+    order = members[np.argsort(-b[members, 3], kind="stable")]      # a group's T_max is its first element
     T_sorted = b[order, 3]
+    # S_max of order[i:j] for the cost: running maxima from every start (n is a few hundred at most)
     k_max = max(1, min(max_buckets, n // max(min_bucket, 1) or 1))
     INF = float("inf")
-    # cost[k][j] = minimal padded frames covering the first j utterances with k groups
     cost = np.full((k_max + 1, n + 1), INF)
     back = np.zeros((k_max + 1, n + 1), dtype=np.int64)
     cost[0, 0] = 0.0
+    S_sorted = b[order, 2]
+    smax = np.zeros((n, n + 1), dtype=np.int64)
+    for i in range(n):
+        smax[i, i + 1:] = np.maximum.accumulate(S_sorted[i:])
     for k in range(1, k_max + 1):
         for j in range(1, n + 1):
             for i in range(0, j):
@@ -79,7 +76,7 @@ def plan_buckets(boundary: np.ndarray, s_range: int, vocab: int, max_buckets: in
                     continue
                 if cost[k - 1, i] == INF:
                     continue
-                c = cost[k - 1, i] + (j - i) * T_sorted[i]
+                c = cost[k - 1, i] + _bucket_cost(j - i, int(T_sorted[i]), int(smax[i, j]), s_range, vocab)
                 if c < cost[k, j]:
                     cost[k, j] = c
                     back[k, j] = i
@@ -89,13 +86,47 @@ def plan_buckets(boundary: np.ndarray, s_range: int, vocab: int, max_buckets: in
         i = int(back[k, j])
         cuts.append((i, j))
         j = i
+    return [order[i:j] for i, j in reversed(cuts)], float(cost[k_best, n])
+
+
+def plan_buckets(boundary: np.ndarray, s_range: int, vocab: int, max_buckets: int = 8,
+                 min_bucket: int = 4):
+    """Batch scheduler for ragged shards (SURVEY.md §8f-4): split a shard into at most
+    ``max_buckets`` length buckets so that the kernels do not work on padding.  What padding
+    costs: ``do_rnnt_pruning``, the joiner and the pruned log-softmax touch
+    ``T_max * s_range * vocab`` elements per utterance whatever T_b is, and the normaliser and
+    the read-out of the simple loss work on the padded ``(S_max + 1) x T_max`` lattice
+    (``_bucket_cost``).
+
+    Two plans are made and the cheaper (modelled) one is returned: (a) utterances sorted by T_b
+    and cut by dynamic programming into contiguous groups; (b) the shard first halved at the
+    median S_b - label lengths are nearly independent of frame counts, so sorting by T alone
+    leaves S_max ~ the shard maximum in every bucket - and each half cut the same way with half
+    the bucket budget.  Every group has ``len(g) >= min_bucket`` (each bucket is one more set of
+    kernel launches; tiny buckets cannot fill the GPU).  Returns a list of dicts
+    ``{"idx", "S_max", "T_max", "padded_frames", "bytes"}`` ordered by decreasing T_max;
+    ``bytes`` estimates the pruned-path traffic of the bucket (SURVEY.md §8d:
+    20 bytes per [t, i, c] element for pruning + joiner + log-softmax + logits gradient)."""
+    b = np.asarray(boundary, dtype=np.int64)
+    n = len(b)
+    if n == 0:
+        return []
+    everyone = np.arange(n)
+    groups, best = _plan_by_t(b, everyone, s_range, vocab, max_buckets, min_bucket)
+    if max_buckets >= 4 and n >= 4 * max(min_bucket, 1):
+        by_s = np.argsort(b[:, 2], kind="stable")
+        lo, hi = by_s[: n // 2], by_s[n // 2:]
+        g_lo, c_lo = _plan_by_t(b, lo, s_range, vocab, max_buckets // 2, min_bucket)
+        g_hi, c_hi = _plan_by_t(b, hi, s_range, vocab, max_buckets - max_buckets // 2, min_bucket)
+        if c_lo + c_hi < best:
+            groups = g_lo + g_hi
     out = []
-    for i, j in reversed(cuts):
-        idx = order[i:j]
+    for idx in groups:
         t_max, s_max = int(b[idx, 3].max()), int(b[idx, 2].max())
         frames = int(len(idx) * t_max)
         out.append({"idx": np.sort(idx), "S_max": s_max, "T_max": t_max, "padded_frames": frames,
                     "bytes": int(20 * frames * s_range * vocab)})
+    out.sort(key=lambda g: (-g["T_max"], -g["S_max"]))
     return out
 
 

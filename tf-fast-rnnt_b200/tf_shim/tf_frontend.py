@@ -219,7 +219,7 @@ def get_rnnt_logprobs_joint(logits, symbols, termination_symbol, boundary=None, 
 
 
 def pruned_rnnt_pipeline(lm, am, symbols, termination_symbol, boundary, s_range, joiner=None, rnnt_type="regular",
-                         delay_penalty=0.0, reduction="sum", max_buckets=4, min_bucket=4, lm_only_scale=0.0,
+                         delay_penalty=0.0, reduction="sum", max_buckets=8, min_bucket=4, lm_only_scale=0.0,
                          am_only_scale=0.0):
     """(extension) The full pruned RNN-T step on a ragged batch, per length bucket: the batch is
     cut into at most ``max_buckets`` buckets by frame count (``sharding.plan_buckets``: the plan is made on the
