@@ -231,6 +231,12 @@ int frn_prune_ranges(const float *px_grad, const float *py_grad,
 int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int B,
                    int S, int T, int R, int C, float *am_pruned,
                    float *lm_pruned, void *stream);
+/*  The same for am / lm of element type `am_lm_dtype` (FRN_F32, FRN_BF16, FRN_F16); am_pruned /
+ * lm_pruned have that type too, like the reference's broadcast_to / gather (rnnt_loss.py:802-811), which keep the
+ * dtype of their inputs.  2-byte types need an even C (FRN_EUNSUPPORTED otherwise). */
+int frn_do_pruning_lp(const void *am, const void *lm, int am_lm_dtype, const int32_t *ranges,
+                      int B, int S, int T, int R, int C, void *am_pruned, void *lm_pruned,
+                      void *stream);
 int frn_do_pruning_bwd(const float *am_pruned_grad, const float *lm_pruned_grad,
                        const int32_t *ranges, int B, int S, int T, int R, int C,
                        float *am_grad, float *lm_grad, void *stream);

@@ -572,6 +572,16 @@ def test_half_precision_am_lm_inputs(dtype):
     assert_close(loss.cpu().numpy(), o_loss, LOSS_RTOL, 0, "loss of bf16 / fp16 inputs")
     assert_close(gx.cpu().numpy(), o_gx, GRAD_RTOL, GRAD_ATOL, "px_grad of bf16 / fp16 inputs")
     assert_close(gy.cpu().numpy(), o_gy, GRAD_RTOL, GRAD_ATOL, "py_grad of bf16 / fp16 inputs")
+    # do_rnnt_pruning keeps the type of bf16 / fp16 inputs (rnnt_loss.py:802-811 are a broadcast and a gather)
+    rng = np.random.default_rng(3)
+    for C in (36, 34):
+        am, lm, sym, term, bd = make_inputs(12, 2, 61, 17, C, ragged=True)
+        am_h, lm_h = torch.from_numpy(am).cuda().to(td), torch.from_numpy(lm).cuda().to(td)
+        rg = torch.from_numpy(np.sort(rng.integers(0, 14, (2, 61, 1)), axis=1).astype(np.int32) + np.arange(4, dtype=np.int32)).cuda()
+        am_p, lm_p = frn.do_rnnt_pruning(am_h, lm_h, rg)
+        assert am_p.dtype == td and lm_p.dtype == td
+        ref_a, ref_l = frn.do_rnnt_pruning(am_h.float(), lm_h.float(), rg)
+        assert torch.equal(am_p.float(), ref_a) and torch.equal(lm_p.float(), ref_l)
     # odd element counts take the scalar tail of the widening kernel
     x = torch.randn(1003, device="cuda").to(td)
     y = torch.empty(1003, dtype=torch.float32, device="cuda")

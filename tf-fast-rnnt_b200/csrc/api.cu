@@ -180,6 +180,24 @@ int frn_do_pruning(const float *am, const float *lm, const int32_t *ranges, int 
   return launch_do_pruning(am, lm, ranges, B, S, T, R, C, am_pruned, lm_pruned, static_cast<cudaStream_t>(stream));
 }
 
+// am / lm of a 2-byte element type: the gather is a copy of whole rows, so pairs of elements travel as one 32-bit
+// word through the same kernels (C must be even; the 128-bit path then needs C % 8 == 0)
+int frn_do_pruning_lp(const void *am, const void *lm, int am_lm_dtype, const int32_t *ranges, int B, int S, int T, int R,
+                      int C, void *am_pruned, void *lm_pruned, void *stream) {
+  FRN_RANGE();
+  FRN_REQUIRE(am_lm_dtype == FRN_F32 || am_lm_dtype == FRN_BF16 || am_lm_dtype == FRN_F16);
+  if (am_lm_dtype == FRN_F32)
+    return frn_do_pruning(static_cast<const float *>(am), static_cast<const float *>(lm), ranges, B, S, T, R, C,
+                          static_cast<float *>(am_pruned), static_cast<float *>(lm_pruned), stream);
+  FRN_REQUIRE(B > 0 && S >= 0 && T > 0 && R > 0 && C > 0);
+  FRN_REQUIRE(am_pruned || lm_pruned);
+  FRN_REQUIRE((!am_pruned || am) && (!lm_pruned || (lm && ranges)));
+  if (C % 2 != 0) return FRN_EUNSUPPORTED;
+  return launch_do_pruning(static_cast<const float *>(am), static_cast<const float *>(lm), ranges, B, S, T, R, C / 2,
+                           static_cast<float *>(am_pruned), static_cast<float *>(lm_pruned),
+                           static_cast<cudaStream_t>(stream));
+}
+
 int frn_do_pruning_add_joiner(const float *am, const float *lm, const int32_t *ranges, int B, int S, int T, int R,
                               int C, float *am_pruned, float *lm_pruned, float *logits, void *stream) {
   FRN_RANGE();

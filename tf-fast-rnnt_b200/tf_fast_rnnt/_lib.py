@@ -95,6 +95,7 @@ _SIGS = {
     "frn_prune_ranges_workspace_bytes": (c_size_t, [c_int, c_int]),
     "frn_prune_ranges": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "frn_do_pruning": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "frn_do_pruning_lp": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "frn_do_pruning_add_joiner": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "frn_broadcast_am_pruned": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "frn_do_pruning_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),

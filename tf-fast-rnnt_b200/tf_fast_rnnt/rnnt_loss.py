@@ -94,14 +94,14 @@ def _ptr(t: Optional[torch.Tensor]):
 _LP_CODES = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
 
-def _low_precision_pair(lm, am):
+def _low_precision_pair(lm, am, multiple=4):
     """(lm, am, dtype code) when both are bf16 (or both fp16) CUDA tensors the library can consume as they are
     (frn_simple_loss_lp / frn_simple_logprobs_lp - no widening pass, no float32 copies), else None."""
     if not (isinstance(lm, torch.Tensor) and isinstance(am, torch.Tensor) and lm.is_cuda and am.is_cuda):
         return None
     if lm.dtype != am.dtype or lm.dtype not in _LP_CODES or lm.requires_grad or am.requires_grad:
         return None
-    if lm.dim() != 3 or am.dim() != 3 or am.shape[2] % 4 != 0:
+    if lm.dim() != 3 or am.dim() != 3 or am.shape[2] % multiple != 0:
         return None
     return lm.contiguous(), am.contiguous(), _LP_CODES[lm.dtype]
 
@@ -606,16 +606,22 @@ def do_rnnt_pruning(am: Tensor, lm: Tensor, ranges: Tensor):
         return _PruningFn.apply(io.dev_tensor(am, torch.float32), io.dev_tensor(lm, torch.float32),
                                 io.dev_tensor(ranges, torch.int32), False)
     io = _Io(am, lm)
-    am_d = io.dev_tensor(am, torch.float32)
-    lm_d = io.dev_tensor(lm, torch.float32)
+    # bf16 / fp16 am, lm on the device keep their type, like the reference's broadcast_to / gather (an even C)
+    lp = _low_precision_pair(lm, am, multiple=2)
+    lm_d = lp[0] if lp else io.dev_tensor(lm, torch.float32)
+    am_d = lp[1] if lp else io.dev_tensor(am, torch.float32)
     rg = io.dev_tensor(ranges, torch.int32)
     B, T, C = am_d.shape
     S = lm_d.shape[1] - 1
     R = rg.shape[2]
     if tuple(rg.shape) != (B, T, R) or tuple(lm_d.shape) != (B, S + 1, C):
         raise ValueError("am [B,T,C], lm [B,S+1,C], ranges [B,T,s_range] expected")
-    am_p = torch.empty((B, T, R, C), dtype=torch.float32, device=io.dev)
-    lm_p = torch.empty((B, T, R, C), dtype=torch.float32, device=io.dev)
+    am_p = torch.empty((B, T, R, C), dtype=am_d.dtype, device=io.dev)
+    lm_p = torch.empty((B, T, R, C), dtype=am_d.dtype, device=io.dev)
+    if lp:
+        check(lib.frn_do_pruning_lp(_ptr(am_d), _ptr(lm_d), lp[2], _ptr(rg), B, S, T, R, C, _ptr(am_p), _ptr(lm_p),
+                                    _stream(io.dev)), "frn_do_pruning_lp")
+        return am_p, lm_p
     check(lib.frn_do_pruning(_ptr(am_d), _ptr(lm_d), _ptr(rg), B, S, T, R, C, _ptr(am_p), _ptr(lm_p),
                              _stream(io.dev)), "frn_do_pruning")
     return io.out(am_p), io.out(lm_p)
