@@ -954,7 +954,7 @@ def run_c5(args):
     B, C, R = 256, 500, 5
     bd_all = c5_boundaries(B)
     mine = partition_batch(bd_all, world)[rank]
-    buckets = plan_buckets(bd_all[mine], R, C, max_buckets=args.buckets)
+    buckets = plan_buckets(bd_all[mine], R, C, max_buckets=args.buckets, min_bucket=args.min_bucket)
     nb = len(buckets)
 
     # one contiguous block holds every bucket's (am, lm, symbols, boundary): the end-to-end leg moves a step's
@@ -1184,7 +1184,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--buckets", type=int, default=8, help="c5: length buckets per rank (1 = pad the shard to its maxima; 4+: the planner may also split by label length)")
+    ap.add_argument("--buckets", type=int, default=16, help="c5: length buckets per rank (1 = pad the shard to its maxima; 4+: the planner may also split by label length)")
+    ap.add_argument("--min-bucket", type=int, default=2, help="c5: fewest utterances a length bucket may hold")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--c5-streams", type=int, default=1, help="c5: 1 = every length bucket on its own CUDA stream (default), 0 = one stream")
     ap.add_argument("--streams", type=int, default=1,
