@@ -54,7 +54,7 @@ __device__ long long g_tc_timing[8];
 namespace tc {
 constexpr int TM = 128;   // frames per CTA  (MMA M)
 constexpr int TN = 112;   // symbols per CTA (MMA N, multiple of 16)
-constexpr int KC = 64;    // vocabulary slice per stage = one 128-byte swizzle row of bf16
+constexpr int KC = 64;    // vocabulary slice per stage = one 128-byte swizzle row of float16
 constexpr int kEpiWarps = 16;   // drain / epilogue warps: 4 per TMEM lane quarter, 28 symbol columns each
 constexpr int kThreads = (kEpiWarps + 2) * 32;   // + the TMA producer warp + the MMA issuer warp
 constexpr int kStages = 3;
@@ -81,7 +81,6 @@ constexpr float kLog2eLo = 1.92596299112661746e-8f;   // log2(e) - (float)log2(e
 struct Small {                                        // per-CTA row / column constants
   double sm_x[TN], sm_y[TN];                          // smoothed: lm_scale * log2e * (lm[s,sym|blank] - lmonly[s])
   uint64_t bars[2 * kStages + 4];                     // full[kStages], empty[kStages], accfull[2], accfree[2]
-  float amneg[TM], lmneg[TN];                         // -max * log2e (-inf: row masked)
   float ammax[TM], lmmax[TN];
   float pxlm[TN], pylm[TN], lmonly[TN], logusym[TN];
   int sym[TN];
@@ -250,7 +249,6 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
     const int t = t0 + tid;
     const float mx = (t < p.T) ? p.ammax[(size_t)b * p.T + t] : 0.f;
     sm.ammax[tid] = mx;
-    sm.amneg[tid] = (t < p.T) ? -mx * kLog2e : -INFINITY;   // exp2(x*log2e - inf) = 0 for masked rows
   } else if (tid < TM + TN) {
     const int j = tid - TM, s = s0 + j;
     float lmmax = 0.f, pxlm = 0.f, pylm = 0.f, lmonly = 0.f, logus = 0.f;
@@ -267,7 +265,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
         logus = (sym >= 0) ? p.logu[sym] : 0.f;
       }
     }
-    sm.lmmax[j] = lmmax; sm.lmneg[j] = (s < S1) ? -lmmax * kLog2e : -INFINITY;
+    sm.lmmax[j] = lmmax;
     sm.pxlm[j] = pxlm; sm.pylm[j] = pylm; sm.lmonly[j] = lmonly; sm.logusym[j] = logus; sm.sym[j] = sym;
     if constexpr (kXY) {
       // shifted lm scores in log2 units, integer + fraction (formed once per column in float64)
