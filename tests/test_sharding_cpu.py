@@ -71,6 +71,38 @@ def test_bucket_plan_covers_the_shard_and_cuts_padding():
     assert plan_buckets(np.zeros((0, 4), np.int32), 5, 500) == []
 
 
+def test_bucket_plan_over_frames_and_labels():
+    """With enough buckets the planner may first halve the shard at the median label length (label lengths are
+    nearly independent of frame counts): exact cover, bucket size floor, and never a higher modelled cost than the
+    frames-only plan."""
+    from tf_fast_rnnt.sharding import _bucket_cost, _plan_by_t, plan_buckets
+    rng = np.random.default_rng(7)
+    B, R, C = 128, 5, 500
+    bd = np.zeros((B, 4), np.int32)
+    bd[:, 3] = rng.integers(200, 1501, B)
+    bd[:, 2] = np.minimum(rng.integers(20, 401, B), bd[:, 3])
+    plan = plan_buckets(bd, R, C, max_buckets=8, min_bucket=4)
+    assert 1 <= len(plan) <= 8
+    assert sorted(np.concatenate([g["idx"] for g in plan]).tolist()) == list(range(B))
+    cost = 0.0
+    for g in plan:
+        assert len(g["idx"]) >= 4
+        assert g["T_max"] == bd[g["idx"], 3].max() and g["S_max"] == bd[g["idx"], 2].max()
+        cost += _bucket_cost(len(g["idx"]), g["T_max"], g["S_max"], R, C)
+    _, frames_only = _plan_by_t(bd.astype(np.int64), np.arange(B), R, C, 8, 4)
+    assert cost <= frames_only * (1 + 1e-12)
+    # uniform, independent S_b: the two-way plan wins, and half of the buckets hold the short label sequences only
+    med = np.median(bd[:, 2])
+    assert sum(g["S_max"] <= med for g in plan) >= len(plan) // 2 - 1
+    assert cost < 0.97 * frames_only
+    # a shard whose label length follows its frame count gains nothing from the split: frames-only plan
+    tied = bd.copy()
+    tied[:, 2] = tied[:, 3] // 4
+    plan2 = plan_buckets(tied, R, C, max_buckets=8, min_bucket=4)
+    for a, b in zip(plan2, plan2[1:]):
+        assert tied[a["idx"], 3].min() >= tied[b["idx"], 3].max()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -46,11 +46,14 @@ def shard_max_shapes(boundary: np.ndarray, idx: Sequence[int]):
 
 
 def _bucket_cost(n_utt: int, t_max: int, s_max: int, s_range: int, vocab: int) -> float:
-    """Modelled bytes a bucket streams, padding included: the pruned path touches 20 bytes per [t, i, c] element
-    (pruning + joiner + log-softmax + logits gradient); the simple loss touches every cell of the
-    padded (S_max + 1) x T_max lattice (arcs, recursion planes, occupation counts: ~60 bytes) and contracts
-    2 * 3 * vocab flops per cell there (~vocab / 25 byte-equivalents at this part's flop : byte ratio)."""
-    return float(n_utt) * t_max * (20.0 * s_range * vocab + (s_max + 1) * (60.0 + vocab / 25.0))
+    """Modelled cost of a bucket in byte-equivalents, padding included: the pruned path touches 20 bytes per
+    [t, i, c] element (pruning + joiner + log-softmax + logits gradient); the simple loss works on
+    every cell of the padded (S_max + 1) x T_max lattice - arcs, recursion planes, occupation counts, prune-range
+    arg-max, and the contraction's 2 * 3 * vocab flops per cell.  The per-cell weight is calibrated on the kernel
+    shares of the ragged c5 batch (profiles/r02ai_c5_launches_summary.txt: lattice kernels 56 %, pruned-path
+    kernels 41 % of the step at S_max ~ 400, vocab 500: ~170 byte-equivalents per cell; the recursion is latency
+    bound, so its cost per cell is well above its bytes)."""
+    return float(n_utt) * t_max * (20.0 * s_range * vocab + (s_max + 1) * (130.0 + vocab / 12.0))
 
 
 def _plan_by_t(b: np.ndarray, members: np.ndarray, s_range: int, vocab: int, max_buckets: int, min_bucket: int):
