@@ -353,7 +353,7 @@ def test_fuzz_band_recursion_equals_dense_recursions(monkeypatch):
 
 
 def test_fuzz_tensor_core_normaliser_equals_simt(monkeypatch):
-    """Fuzz: the tcgen05 normaliser (3 x bf16 split) against the exact-FP32 SIMT kernel of the same op on
+    """Fuzz: the tcgen05 normaliser (two-term float16 split) against the exact-FP32 SIMT kernel of the same op on
     random shapes (C % 4 == 0 so that both paths exist), simple and smoothed, all rnnt types."""
     import tf_fast_rnnt as frn
     rng = np.random.default_rng(78)
@@ -373,6 +373,46 @@ def test_fuzz_tensor_core_normaliser_equals_simt(monkeypatch):
         tag = f"case {case}: {rnnt_type} B={B} S={S} T={T} C={C} smoothed={case % 2}"
         assert_close(out[0][0], out[1][0], 2e-6, 2e-6, tag + " px")
         assert_close(out[0][1], out[1][1], 2e-6, 2e-6, tag + " py")
+
+
+@pytest.mark.parametrize("scale", [8.0, 14.0])
+def test_normaliser_on_peaky_distributions(scale):
+    """The two-term float16 operands of the tensor-core normaliser on the inputs they are weakest on: peaky am / lm
+    rows (probabilities down to e^-100 relative to the row maximum), row maxima far from zero, am and lm peaking
+    at DIFFERENT classes (Z = sum_c p_am p_lm is then made of small products only), against the float64 oracle."""
+    import tf_fast_rnnt as frn
+    rng = np.random.default_rng(int(scale))
+    B, T, S, C = 2, 150, 40, 256
+    am = (scale * rng.standard_normal((B, T, C))).astype(np.float32)
+    lm = (scale * rng.standard_normal((B, S + 1, C))).astype(np.float32)
+    am += rng.uniform(-30, 30, (B, T, 1)).astype(np.float32)            # row offsets cancel in px / py
+    lm += rng.uniform(-30, 30, (B, S + 1, 1)).astype(np.float32)
+    am[0, :, 7] += 4 * scale                                           # utterance 0: am peaks at class 7 ...
+    lm[0, :, 11] += 4 * scale                                          # ... lm at class 11
+    sym = rng.integers(0, C - 1, (B, S)).astype(np.int32)
+    term = C - 1
+    bd = np.tile(np.array([0, 0, S, T], np.int32), (B, 1))
+    px, py = frn.get_rnnt_logprobs(lm, am, sym, term, "regular", bd)
+    o_px, o_py = orc.get_rnnt_logprobs(lm, am, sym, term, "regular", bd, dtype=np.float64)
+    # px = am[sym] + lm[sym] - log Z - ammax - lmmax in float32: a few ulp of the largest operand, + the 2^-21 of Z
+    atol = 4e-7 * float(np.abs(am).max() + np.abs(lm).max())
+    # the float32 reference saturates at log(0 + tiny) = -103.3 once Z underflows (rnnt_loss.py:181), and within
+    # e^10 of the underflow edge the terms of Z themselves flush to zero one by one; compare where Z and its leading
+    # terms are representable in float32 (log Z > -70) - at the larger scale some cells of utterance 0 are not
+    lm64, am64 = lm.astype(np.float64), am.astype(np.float64)
+    z = np.einsum("bsc,btc->bst", np.exp(lm64 - lm64.max(2, keepdims=True)), np.exp(am64 - am64.max(2, keepdims=True)))
+    ok = np.log(z) > -70.0
+    assert ok.mean() > 0.6 and (np.log(z[0]) < -25.0).mean() > 0.5       # the hard regime is what is being tested
+    assert_close(np.where(ok[:, :S, :], px[:, :, :T], 0), np.where(ok[:, :S, :], o_px[:, :, :T], 0), 3e-7, atol,
+                 f"px, scale {scale}")
+    assert_close(np.where(ok, py, 0), np.where(ok, o_py, 0), 3e-7, atol, f"py, scale {scale}")
+    if not ok.all():
+        return                                   # a saturated cell changes the float32 reference's loss: nothing to compare
+    loss, (gx, gy) = frn.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True)
+    o_loss, (o_gx, o_gy) = orc.rnnt_loss_simple(lm, am, sym, term, bd, "regular", 0.0, "none", True, dtype=np.float64)
+    assert_close(loss, o_loss, LOSS_RTOL, 0, f"loss, scale {scale}")
+    assert_close(gx, o_gx, GRAD_RTOL, GRAD_ATOL, f"px_grad, scale {scale}")
+    assert_close(gy, o_gy, GRAD_RTOL, GRAD_ATOL, f"py_grad, scale {scale}")
 
 
 def test_fuzz_pipeline_against_float64_oracle(monkeypatch):

@@ -76,7 +76,7 @@ template <> __device__ __forceinline__ float4 load4_cached<__half>(const __half 
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__device__ __forceinline__ void split4(const float4 &x, float nmx, uint2 &h, uint2 &l) {
+__device__ __forceinline__ float split4(const float4 &x, float nmx, uint2 &h, uint2 &l) {
   const float p0 = ex2_approx(fmaf(x.x, kLog2e, nmx)), p1 = ex2_approx(fmaf(x.y, kLog2e, nmx));
   const float p2 = ex2_approx(fmaf(x.z, kLog2e, nmx)), p3 = ex2_approx(fmaf(x.w, kLog2e, nmx));
   const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
@@ -85,6 +85,7 @@ __device__ __forceinline__ void split4(const float4 &x, float nmx, uint2 &h, uin
   const __half2 l23 = __floats2half2_rn((p2 - f23.x) * 2048.f, (p3 - f23.y) * 2048.f);
   h = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
   l = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+  return (p0 + p1) + (p2 + p3);                 // 2^15 * sum of the four probabilities (accuracy guard of the normaliser)
 }
 
 // `gat` (tensor-core path): the three other values the normaliser's epilogue needs of am / lm - am[b,t,blank],
@@ -151,15 +152,18 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const TE *lm, int rows_lm
       uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
       uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
       const float nmx = fmaf(-m, kLog2e, 15.f);
+      float psum = 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int c = u * 32 + lane;
         if (c < nv) {
           uint2 h, l;
-          split4(v[u], nmx, h, l);
+          psum += split4(v[u], nmx, h, l);
           hrow[c] = h; lrow[c] = l;
         }
       }
+      psum = warp_sum(psum);
+      if (lane == 0 && gat.am_sum) (is_lm ? gat.lm_sum : gat.am_sum)[row] = psum * 0x1p-15f;
     }
   } else if (vec) {
     // long rows (large vocabularies): three passes of 128-bit loads over a row that stays in L1 / L2
@@ -183,11 +187,14 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const TE *lm, int rows_lm
       uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
       uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
       const float nmx = fmaf(-m, kLog2e, 15.f);
+      float psum = 0.f;
       for (int c = lane; c < nv; c += 32) {
         uint2 h, l;
-        split4(load4_cached(src + 4 * c), nmx, h, l);
+        psum += split4(load4_cached(src + 4 * c), nmx, h, l);
         hrow[c] = h; lrow[c] = l;
       }
+      psum = warp_sum(psum);
+      if (lane == 0 && gat.am_sum) (is_lm ? gat.lm_sum : gat.am_sum)[row] = psum * 0x1p-15f;
     }
   } else {
     issue_gathers();
@@ -462,13 +469,26 @@ __global__ void __launch_bounds__(256) rowstats_long_kernel(const TE *lm, int ro
     uint2 *hrow = reinterpret_cast<uint2 *>((is_lm ? split.lmh : split.amh) + (size_t)row * split.Cp);
     uint2 *lrow = reinterpret_cast<uint2 *>((is_lm ? split.lml : split.aml) + (size_t)row * split.Cp);
     const float nmx = fmaf(-m, kLog2e, 15.f);
+    float psum = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int c = u * 256 + tid;
       if (c < nv) {
         uint2 h, l;
-        split4(v[u], nmx, h, l);
+        psum += split4(v[u], nmx, h, l);
         hrow[c] = h; lrow[c] = l;
+      }
+    }
+    if (gat.am_sum) {                            // block-uniform
+      psum = warp_sum(psum);
+      __syncthreads();
+      if (lane == 0) red[w] = psum;
+      __syncthreads();
+      if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        (is_lm ? gat.lm_sum : gat.am_sum)[row] = t * 0x1p-15f;
       }
     }
   }
@@ -503,8 +523,8 @@ size_t simple_stats_bytes(int B, int S, int T, int C) {
   // two-term float16 operands of the tensor-core contraction (SplitPlanes): h and l planes of am and of lm
   const size_t Cp = (size_t)round_up(C, 8);
   n += 2 * round_up_sz((size_t)B * T * Cp * 2, 256) + 2 * round_up_sz((size_t)B * (S + 1) * Cp * 2, 256);
-  // am[b,t,blank], lm[b,s,blank], lm[b,s,symbol] (RowGathers)
-  n += round_up_sz((size_t)B * T * sizeof(float), 256) + 2 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256);
+  // am[b,t,blank], lm[b,s,blank], lm[b,s,symbol], and the row sums of exp(x - max) (RowGathers)
+  n += 2 * round_up_sz((size_t)B * T * sizeof(float), 256) + 3 * round_up_sz((size_t)B * (S + 1) * sizeof(float), 256);
   return n;
 }
 
@@ -576,7 +596,9 @@ static int launch_simple_logprobs_t(const TE *lm, const TE *am, const int32_t *s
     split.lml = reinterpret_cast<unsigned short *>(w); w += lm_plane;
     gat.am_term = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
     gat.lm_term = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
-    gat.lm_sym = reinterpret_cast<float *>(w);
+    gat.lm_sym = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * S1 * sizeof(float), 256);
+    gat.am_sum = reinterpret_cast<float *>(w); w += round_up_sz((size_t)B * T * sizeof(float), 256);
+    gat.lm_sum = reinterpret_cast<float *>(w);
     gat.term = term;
   }
   launch_rowstats(lm, B * S1, am, B * T, C, lmmax, smoothed ? lmsum : nullptr, ammax, symbols, S, T,
@@ -592,6 +614,8 @@ static int launch_simple_logprobs_t(const TE *lm, const TE *am, const int32_t *s
   sp.lm = kF32 ? reinterpret_cast<const float *>(lm) : nullptr;      // read by the SIMT kernel only
   sp.am = kF32 ? reinterpret_cast<const float *>(am) : nullptr;
   sp.gat = gat;
+  sp.am_raw = am; sp.lm_raw = lm;
+  sp.raw_dtype = kF32 ? FRN_F32 : (std::is_same<TE, __nv_bfloat16>::value ? FRN_BF16 : FRN_F16);
   sp.symbols = symbols; sp.boundary = boundary;
   sp.lmmax = lmmax; sp.ammax = ammax; sp.lmsum = lmsum; sp.amonly = amonly; sp.logu = logu;
   sp.px = px; sp.py = py; sp.pxam_t = tc ? pxam_t : nullptr; sp.split = split;

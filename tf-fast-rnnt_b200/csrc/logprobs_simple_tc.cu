@@ -36,6 +36,7 @@
 // float32-accurate by construction (the occupation counts downstream need ~2^-21
 // on the normaliser, which rules out plain bf16/tf32: DESIGN.md "numerics").
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -82,6 +83,7 @@ struct Small {                                        // per-CTA row / column co
   double sm_x[TN], sm_y[TN];                          // smoothed: lm_scale * log2e * (lm[s,sym|blank] - lmonly[s])
   uint64_t bars[2 * kStages + 4];                     // full[kStages], empty[kStages], accfull[2], accfree[2]
   float ammax[TM], lmmax[TN];
+  float lmsum_g[TN];                                  // sum_c exp(lm - lmmax) of the column's row (accuracy guard)
   float pxlm[TN], pylm[TN], lmonly[TN], logusym[TN];
   int sym[TN];
   // arc-plane epilogue: (lm[s,sym] - lmmax) * log2e and (lm[s,blank] - lmmax) * log2e as integer + fraction in [0,1)
@@ -266,6 +268,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
       }
     }
     sm.lmmax[j] = lmmax;
+    sm.lmsum_g[j] = (s < S1) ? p.gat.lm_sum[(size_t)b * S1 + s] : 0.f;
     sm.pxlm[j] = pxlm; sm.pylm[j] = pylm; sm.lmonly[j] = lmonly; sm.logusym[j] = logus; sm.sym[j] = sym;
     if constexpr (kXY) {
       // shifted lm scores in log2 units, integer + fraction (formed once per column in float64)
@@ -296,6 +299,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
   const bool t_ok = et < p.T;
   const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
   const float py_am = __ldg(p.gat.am_term + (size_t)b * p.T + (t_ok ? et : 0));
+  const float sa = t_ok ? __ldg(p.gat.am_sum + (size_t)b * p.T + et) : 0.f;   // accuracy guard (after the k loop)
   const float amonly = (p.smoothed && t_ok) ? p.amonly[(size_t)b * p.T + et] : 0.f;
   const float logu_term = p.smoothed ? p.logu[p.term] : 0.f;
   // am[b,t,sym_s] for this thread's frame: gathered by the row-statistics kernel while it had the row in flight
@@ -303,6 +307,17 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
   float accr[kColsPerHalf];                     // float32 sum of the per-slice tensor-core partial sums
 #pragma unroll
   for (int i = 0; i < kColsPerHalf; ++i) accr[i] = 0.f;
+  // run-time indexed access for the guard's rare path (a select chain: accr stays in registers)
+  auto accr_at = [&](int i) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kColsPerHalf; ++k) v = (k == i) ? accr[k] : v;
+    return v;
+  };
+  auto accr_set = [&](int i, float v) {
+#pragma unroll
+    for (int k = 0; k < kColsPerHalf; ++k) accr[k] = (k == i) ? v : accr[k];
+  };
   // TMEM columns [col, col + 112) of this thread's lane -> registers: all loads issued, one wait
   auto drain_accumulator = [&](uint32_t col, auto &&fold) {
     uint32_t part[kColsPerHalf / 4][4];
@@ -366,6 +381,56 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
     }
     // every MMA has completed (the last commit covers all earlier ones): add the cross terms, undo the 2^15 x 2^15
     drain_accumulator((uint32_t)kCrossCol, [](float &a, float v) { a = fmaf(v, 0x1p-11f, a) * 0x1p-30f; });
+
+    // ---- accuracy guard.  A float16 operand carries its probability to 2^-22 relative only down to 2^-29 of the
+    //      row maximum and to 2^-51 absolute below that (h underflows, the pre-scaled low term lives on), so the
+    //      sum is off by at most 2^-51 (sum_c p_am + sum_c p_lm) absolutely: negligible unless Z itself is tiny -
+    //      am and lm rows whose mass sits on DIFFERENT classes, tens of nats apart (the float32 reference keeps
+    //      such a Z down to e^-87).  Cells with Z < 2^-27 (sum p_am + sum p_lm) (4 x the bound at 2^-22 relative)
+    //      are recomputed exactly: the warp walks the two rows of the cell together, float32 products. ----
+    {
+      const float my_amneg = -sm.ammax[erow] * kLog2e;
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < kColsPerHalf; ++i) {
+        const int j = col_of(half, i);
+        any |= t_ok && j < n_rows && s0 + j < S1 && accr[i] < (sa + sm.lmsum_g[j]) * 0x1p-27f;
+      }
+      if (__any_sync(0xffffffffu, any)) {        // never on ordinary data: one vote per warp is all the guard costs
+#pragma unroll 1
+      for (int i = 0; i < kColsPerHalf; ++i) {
+        const int j = col_of(half, i), s = s0 + j;
+        const bool cell = t_ok && j < n_rows && s < S1;
+        unsigned need = __ballot_sync(0xffffffffu, cell && accr_at(i) < (sa + sm.lmsum_g[j]) * 0x1p-27f);
+        while (need) {                           // warp-uniform
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int tt = t0 + q * 32 + src;
+          const float amneg = __shfl_sync(0xffffffffu, my_amneg, src);
+          const float lmneg = -sm.lmmax[j] * kLog2e;
+          float acc = 0.f;
+          for (int c = lane; c < C; c += 32) {
+            float xa, xl;
+            const size_t ia = ((size_t)b * p.T + tt) * C + c, il = ((size_t)b * S1 + s) * C + c;
+            if (p.raw_dtype == FRN_F32) {
+              xa = static_cast<const float *>(p.am_raw)[ia]; xl = static_cast<const float *>(p.lm_raw)[il];
+            } else if (p.raw_dtype == FRN_BF16) {
+              xa = __uint_as_float((uint32_t)static_cast<const unsigned short *>(p.am_raw)[ia] << 16);
+              xl = __uint_as_float((uint32_t)static_cast<const unsigned short *>(p.lm_raw)[il] << 16);
+            } else {
+              xa = __half2float(static_cast<const __half *>(p.am_raw)[ia]);
+              xl = __half2float(static_cast<const __half *>(p.lm_raw)[il]);
+            }
+            // exp(am - ammax) * exp(lm - lmmax) as ONE exponential: no intermediate underflow
+            acc += ex2_approx(fmaf(xa, kLog2e, amneg) + fmaf(xl, kLog2e, lmneg));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == src) accr_set(i, acc);
+        }
+      }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();                               // every warp has left the operand stages: the epilogue reuses them

@@ -14,6 +14,7 @@ struct SplitPlanes {
 // am[b,t,blank] [B][T], lm[b,s,blank] and lm[b,s,symbols[b,s]] [B][S+1], gathered by the row-statistics kernel
 struct RowGathers {
   float *am_term = nullptr, *lm_term = nullptr, *lm_sym = nullptr;
+  float *am_sum = nullptr, *lm_sum = nullptr;    // sum_c exp(x - rowmax) per am / lm row: the normaliser's accuracy guard
   int term = 0;
 };
 struct SimpleParams {
@@ -24,6 +25,8 @@ struct SimpleParams {
   const float *pxam_t = nullptr;        // [B][T][S] am[b,t,symbols[b,s]], written by the row-statistics kernel
   SplitPlanes split;                    // tensor-core path: the contraction's operands
   RowGathers gat;                       // tensor-core path: the other am / lm values of the epilogue
+  const void *am_raw = nullptr, *lm_raw = nullptr;   // am / lm as given (element type raw_dtype, frn_dtype): read only
+  int raw_dtype = 0;                                  // by the guard's exact recomputation of a cell
   float *px, *py;                       // reference layout
   int B, S, T, T1, C, term, rnnt_type, smoothed;
   float comb, lm_scale, am_scale;       // 1-lm-am; scales with the 1e-20 substitution (rnnt_loss.py:1342-1349)
