@@ -235,8 +235,15 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
     const int Dfill = bd_ok ? min(p.Dn, round_up(Tb + p.k * Sb + 1, kChunk)) : 0;
     const int dlo = (int)((long long)Dfill * lt / ntile), dhi = (int)((long long)Dfill * (lt + 1) / ntile);
     const float4 dead4 = make_float4(dead2.x, dead2.y, dead2.x, dead2.y);
-    for (int d = dlo + w; d < dhi; d += kThreads / 32)
-      for (int r = lane; r < p.P; r += 32) {
+    for (int d = dlo + w; d < dhi; d += kThreads / 32) {
+      // Rows whose two arcs are both live need nothing here, and for a fixed diagonal they form ONE interval
+      // [lo, hi] (k = 1: 0 <= d-1-r and d-r < Tb with 1 <= r <= Sb; k = 0: all of 1..Sb or none): the lanes walk
+      // the other rows only - a third of the plane at the c2 shape.
+      const int lo = p.k ? max(d - Tb + 1, 1) : 1;
+      const int hi = p.k ? min(d - 1, Sb) : ((d - 1 >= 0 && d - 1 < Tb) ? Sb : 0);
+      const int len = max(hi - lo + 1, 0);
+      for (int idx = lane; idx < p.P - len; idx += 32) {
+        const int r = (len > 0 && idx >= lo) ? idx + len : idx;
         const int ty = d - 1 - p.k * r, tx = ty + p.k;
         const bool xa = r >= 1 && r <= Sb && tx >= 0 && tx < Tb;
         const bool ya = r <= Sb && ty >= 0 && ty < Tb;
@@ -245,6 +252,7 @@ simple_logprobs_tc_kernel(const __grid_constant__ CUtensorMap map_amh, const __g
         else if (!xa) *reinterpret_cast<float2 *>(dst) = dead2;
         else if (!ya) *(reinterpret_cast<float2 *>(dst) + 1) = dead2;
       }
+    }
     if (tile_dead) return;
   }
   if (tid < TM) {
