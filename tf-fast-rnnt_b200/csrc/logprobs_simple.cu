@@ -117,10 +117,22 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const TE *lm, int rows_lm
       gidx[u] = s < S ? sym[s] : -1;
     }
   }
+  // the blank / symbol values of the row for the normaliser's epilogue (RowGathers): requested with the other
+  // gathers, stored at the end (a load at the end of the warp's life was one more exposed memory round trip)
+  int sym_c = -1;
+  if (gat.am_term && is_lm) {
+    const int S1 = S + 1, b = row / S1, sl = row - b * S1;
+    sym_c = sl < S ? symbols[(size_t)b * S + sl] : -1;
+  }
+  float term_v = 0.f, sym_v = 0.f;
   auto issue_gathers = [&]() {
     if (gather) {
 #pragma unroll
       for (int u = 0; u < kG; ++u) gval[u] = (gidx[u] >= 0 && gidx[u] < C) ? elem_to_f(src[gidx[u]]) : 0.f;
+    }
+    if (gat.am_term) {
+      term_v = elem_to_f(src[gat.term]);
+      sym_v = (sym_c >= 0 && sym_c < C) ? elem_to_f(src[sym_c]) : 0.f;
     }
   };
   float *rmax = is_lm ? lmmax : ammax;
@@ -220,12 +232,10 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const TE *lm, int rows_lm
   }
   if (gat.am_term && lane == 0) {
     if (is_lm) {
-      const int S1 = S + 1, b = row / S1, sl = row - b * S1;
-      gat.lm_term[row] = elem_to_f(src[gat.term]);
-      const int c = sl < S ? symbols[(size_t)b * S + sl] : -1;
-      gat.lm_sym[row] = (c >= 0 && c < C) ? elem_to_f(src[c]) : 0.f;
+      gat.lm_term[row] = term_v;
+      gat.lm_sym[row] = sym_v;
     } else {
-      gat.am_term[row] = elem_to_f(src[gat.term]);
+      gat.am_term[row] = term_v;
     }
   }
 }
