@@ -144,7 +144,7 @@ class Pipeline:
     sub-batch (lattice recursions, normaliser) overlap the bandwidth-bound kernels of another.
     Same calls, same results; the two loss sums are reduced over the whole batch at the end."""
 
-    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True, am_side=0, logits_bf16=False,
+    def __init__(self, B, T, S, C, R, dev, nsplit=1, overlap=False, fuse_add=True, am_side=0, am_side_at="start", logits_bf16=False,
                  training=False):
         import torch
         from tf_fast_rnnt import _lib
@@ -181,7 +181,14 @@ class Pipeline:
         # normaliser's / recursion's big CTAs on the other SMs; frn_do_pruning_add_joiner then writes
         # lm_pruned and the logits only.
         self.am_side = am_side if fuse_add else 0
+        self.am_side_at = am_side_at          # "start": beside the whole simple loss; "chain": forked behind the normaliser
         self.side = torch.cuda.Stream(dev) if (overlap or self.am_side) else None
+        self.fork_ev = self.join_ev = None
+        if self.am_side and am_side_at == "chain":
+            # two caller-owned events for frn_simple_loss_bcast (created by their first record)
+            self.fork_ev, self.join_ev = torch.cuda.Event(), torch.cuda.Event()
+            self.fork_ev.record(); self.join_ev.record()
+            torch.cuda.synchronize(dev)
         self.full = self._part(0, B)
         self.ws_pruned = self.full["ws_pruned"]
         nsplit = max(1, min(nsplit, B))
@@ -256,10 +263,17 @@ class Pipeline:
         if self.fuse_add:
             # do_rnnt_pruning and the additive joiner in ONE pass (frn_do_pruning_add_joiner): am_pruned,
             # lm_pruned and logits are all written, the two pruned tensors are not read back for the sum
-            out[2:4] = [("do_pruning+add_joiner", 4 * B * (T * C + (S + 1) * C + T * R) + 12 * n_logits,
-                         lambda: chk(lib.frn_do_pruning_add_joiner(p(am), p(lm), p(self.ranges), B, S, T, R, C,
-                                                                   p(self.am_p), p(self.lm_p), p(self.logits), st()),
-                                     "do_pruning_add_joiner"))]
+            if self.am_side and part is self.full:
+                # am_pruned comes from frn_broadcast_am_pruned (beside the recursion): lm_pruned and the logits here
+                out[2:4] = [("do_pruning+add_joiner(lm,logits)", 4 * B * (T * C + (S + 1) * C + T * R) + 8 * n_logits,
+                             lambda: chk(lib.frn_do_pruning_add_joiner(p(am), p(lm), p(self.ranges), B, S, T, R, C, 0,
+                                                                       p(self.lm_p), p(self.logits), st()),
+                                         "do_pruning_add_joiner(lm, logits)"))]
+            else:
+                out[2:4] = [("do_pruning+add_joiner", 4 * B * (T * C + (S + 1) * C + T * R) + 12 * n_logits,
+                             lambda: chk(lib.frn_do_pruning_add_joiner(p(am), p(lm), p(self.ranges), B, S, T, R, C,
+                                                                       p(self.am_p), p(self.lm_p), p(self.logits), st()),
+                                         "do_pruning_add_joiner"))]
         return out
 
     def _reduce(self):
@@ -274,16 +288,23 @@ class Pipeline:
             lib, chk, B, S, T, R, C = self.lib, self._lib.check, self.B, self.S, self.T, self.R, self.C
             st = self.stages(am, lm, sym, bd)
             main = torch.cuda.current_stream(self.dev)
-            self.side.wait_stream(main)
-            with torch.cuda.stream(self.side):
-                chk(lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, C, self.am_p.data_ptr(), self.am_side,
-                                                self.side.cuda_stream), "broadcast_am_pruned")
-            st[0][2](); st[1][2]()                                   # simple loss, prune ranges
-            main.wait_stream(self.side)
-            chk(lib.frn_do_pruning_add_joiner(am.data_ptr(), lm.data_ptr(), self.ranges.data_ptr(), B, S, T, R, C, 0,
-                                              self.lm_p.data_ptr(), self.logits.data_ptr(), main.cuda_stream),
-                "do_pruning_add_joiner(lm, logits)")
-            for _, _, fn in st[3:]:                                  # pruned loss, reductions
+            if self.am_side_at == "chain":
+                # one call: the broadcast is forked behind the normaliser and runs beside the recursion only
+                ws_s = self.full["ws_simple"]
+                chk(lib.frn_simple_loss_bcast(lm.data_ptr(), am.data_ptr(), sym.data_ptr(), bd.data_ptr(), B, S, T, C,
+                                              C - 1, 0, 0, 0.0, 0.0, 0.0, 1, self.scores.data_ptr(), self.gx.data_ptr(),
+                                              self.gy.data_ptr(), R, self.am_p.data_ptr(), self.am_side,
+                                              self.side.cuda_stream, self.fork_ev.cuda_event, self.join_ev.cuda_event,
+                                              ws_s.data_ptr(), ws_s.numel(), main.cuda_stream), "simple_loss_bcast")
+                st[1][2]()                                           # prune ranges
+            else:
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    chk(lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, C, self.am_p.data_ptr(), self.am_side,
+                                                    self.side.cuda_stream), "broadcast_am_pruned")
+                st[0][2](); st[1][2]()                               # simple loss, prune ranges
+                main.wait_stream(self.side)
+            for _, _, fn in st[2:]:                                  # lm_pruned + logits, pruned loss, reductions
                 fn()
             return
         if not self.parts and self.overlap:
@@ -499,7 +520,7 @@ def run_gpu_arm(args):
     B, T, S, C, R = WORKLOADS[args.workload]
     logits_bf16 = args.workload == "c4" and not args.fp32_logits     # BASELINE.json configs[3]: bf16 joiner logits
     pipe = Pipeline(B, T, S, C, R, dev, nsplit=args.streams, overlap=args.overlap and args.streams <= 1, fuse_add=not args.no_fuse_add and not args.overlap,
-                    am_side=args.am_side, logits_bf16=logits_bf16, training=args.profile_training)
+                    am_side=args.am_side, am_side_at=args.am_side_at, logits_bf16=logits_bf16, training=args.profile_training)
 
     # rotating input sets: 4 x (am+lm) = 154 MB > 126 MB L2, and the step itself
     # streams ~1.1 GB of intermediates, so no iteration finds its inputs in L2
@@ -831,6 +852,7 @@ def run_gpu_arm(args):
     # dependency-chain bound and are reported in `stages_ms` / `lattice_cells_per_s` instead).
     kernel_of_stage = {"do_pruning": "do_pruning_vec_kernel<8, 1, 1, 0>", "add_joiner": "add_kernel",
                        "do_pruning+add_joiner": "do_pruning_vec_kernel<8, 1, 1, 1>",
+                       "do_pruning+add_joiner(lm,logits)": "do_pruning_vec_kernel<8, 0, 1, 1>",
                        "add_joiner(bf16)": "pruned_add_joiner_vec_bf16_kernel<8>"}
     hbm_stages = {k: v for k, v in stage_ms.items() if k in kernel_of_stage}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k][0])
@@ -858,7 +880,10 @@ def run_gpu_arm(args):
             "launch": "cuda_graph" if use_graph else "direct",
             "streams": f"{max(1, len(pipe.parts))} sub-batch stream(s) per step"
                        + ("; am half of do_rnnt_pruning on a second stream beside the simple loss" if pipe.overlap and not pipe.parts else "")
-                       + (f"; am_pruned broadcast by {pipe.am_side} copy-engine CTAs on a second stream beside the simple loss"
+                       + ((f"; am_pruned (the half of do_rnnt_pruning that does not depend on the ranges) broadcast by "
+                           f"{pipe.am_side} copy-engine CTAs on a second stream, "
+                           + ("forked behind the normaliser: beside the lattice recursion (frn_simple_loss_bcast)"
+                              if pipe.am_side_at == "chain" else "beside the whole simple loss"))
                           if pipe.am_side and not pipe.parts else ""),
             "l2": f"{NSETS} rotating input sets ({NSETS * h2d / 1e6:.0f} MB) + ~1.1 GB of streamed intermediates per step (> 126 MB L2)",
             "sharding": ("utterances sharded across ranks, one 2-float NCCL all-reduce per step; rank 0 bound to NUMA "
@@ -1193,9 +1218,12 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="run the am half of do_rnnt_pruning on a second stream beside the simple loss (measured: "
                          "0.380 ms/step against 0.372 without - the copy slows the latency-bound kernels it overlaps)")
-    ap.add_argument("--am-side", type=int, default=0,
+    ap.add_argument("--am-side", type=int, default=64,
                     help="G > 0: am half of do_rnnt_pruning by frn_broadcast_am_pruned (G persistent copy-engine CTAs) on a "
                          "second stream beside the simple loss")
+    ap.add_argument("--am-side-at", default="chain", choices=["start", "chain"],
+                    help="--am-side: start the broadcast with the step (beside the whole simple loss) or fork it behind "
+                         "the normaliser so that it runs beside the lattice recursion only (frn_simple_loss_bcast)")
     ap.add_argument("--no-fuse-add", action="store_true",
                     help="do_rnnt_pruning and the additive joiner as two passes (frn_do_pruning, frn_add_joiner) "
                          "instead of the one-pass frn_do_pruning_add_joiner")

@@ -127,6 +127,22 @@ int frn_simple_loss(const float *lm, const float *am, const int32_t *symbols,
                     float *px_grad, float *py_grad, void *workspace,
                     size_t workspace_bytes, void *stream);
 
+/* frn_simple_loss plus the am half of do_rnnt_pruning (am_pruned [B][T][R][C] = am broadcast over R,
+ * rnnt_loss.py:802-806: it does not depend on the prune ranges) on `side_stream` BESIDE the lattice recursion:
+ * forked behind the normaliser (fork_event) and joined back into `stream` after the read-out (join_event).
+ * The recursion occupies 2 B of the 148 SMs; the copy's persistent CTAs (at most max_ctas, <= 0: 20) take others.
+ * side_stream, fork_event, join_event: a second stream and two cudaEvent_t the caller owns; capturable in a CUDA
+ * graph.  Then pass am_pruned = NULL to frn_do_pruning_add_joiner.  Shapes the fused path does not take (long
+ * lattices on the row-scan kernel, C % 4 != 0) run the two calls one after the other on `stream`. */
+int frn_simple_loss_bcast(const float *lm, const float *am, const int32_t *symbols,
+                          const int32_t *boundary, int B, int S, int T, int C,
+                          int termination_symbol, int rnnt_type, int smoothed,
+                          float lm_only_scale, float am_only_scale, float delay_penalty,
+                          int calc_gradients, float *scores, float *px_grad, float *py_grad,
+                          int R, float *am_pruned, int max_ctas, void *side_stream,
+                          void *fork_event, void *join_event, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
 /* A9. Gradient of sum_b scores_grad[b]*scores[b] w.r.t. am [B][T][C] and lm
  * [B][S+1][C] given the occupation counts returned by frn_simple_loss with the
  * same arguments (what TensorFlow autodiff + _RNNTLossGrad, __init__.py:154-162,

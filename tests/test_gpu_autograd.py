@@ -145,6 +145,58 @@ def test_broadcast_am_pruned_and_joiner_without_am_output():
     assert lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, 63, ref[0].data_ptr(), 4, st) == -4   # C % 4 != 0
 
 
+@pytest.mark.parametrize("shape", [(3, 70, 20, 64), (2, 150, 100, 128), (2, 600, 40, 36)])
+def test_simple_loss_with_the_am_broadcast_beside_the_recursion(shape):
+    """frn_simple_loss_bcast (the am half of do_rnnt_pruning forked onto a second stream behind the normaliser, joined
+    after the read-out) == frn_simple_loss followed by frn_broadcast_am_pruned, bit for bit - on the fused arc-plane
+    path (first two shapes) and on the sequential fall-back (third: long lattice on the row-scan kernel); also
+    captured in a CUDA graph."""
+    import torch
+    import tf_fast_rnnt as frn
+    lib, chk = frn._lib.lib, frn._lib.check
+    B, T, S, C = shape
+    R = 5
+    am_h, lm_h, sym_h, term, bd_h = make_inputs(5, B, T, S, C, ragged=True)
+    am, lm = torch.from_numpy(am_h).cuda(), torch.from_numpy(lm_h).cuda()
+    sym, bd = torch.from_numpy(sym_h).cuda(), torch.from_numpy(bd_h).cuda()
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    fork, join = torch.cuda.Event(), torch.cuda.Event()
+    fork.record(); join.record()
+    torch.cuda.synchronize()
+    ws = torch.empty(int(lib.frn_simple_loss_workspace_bytes(B, S, T, C)), dtype=torch.uint8, device="cuda")
+
+    def outputs():
+        return (torch.full((B,), float("nan"), device="cuda"), torch.full((B, S, T + 1), float("nan"), device="cuda"),
+                torch.full((B, S + 1, T), float("nan"), device="cuda"), torch.full((B, T, R, C), float("nan"), device="cuda"))
+
+    ref = outputs()
+    chk(lib.frn_simple_loss(lm.data_ptr(), am.data_ptr(), sym.data_ptr(), bd.data_ptr(), B, S, T, C, term, 0, 0, 0.0, 0.0,
+                            0.1, 1, ref[0].data_ptr(), ref[1].data_ptr(), ref[2].data_ptr(), ws.data_ptr(), ws.numel(),
+                            main.cuda_stream), "simple_loss")
+    chk(lib.frn_broadcast_am_pruned(am.data_ptr(), B, T, R, C, ref[3].data_ptr(), 8, main.cuda_stream), "broadcast")
+
+    def fused(out):
+        chk(lib.frn_simple_loss_bcast(lm.data_ptr(), am.data_ptr(), sym.data_ptr(), bd.data_ptr(), B, S, T, C, term, 0, 0,
+                                      0.0, 0.0, 0.1, 1, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), R,
+                                      out[3].data_ptr(), 8, side.cuda_stream, fork.cuda_event, join.cuda_event,
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+            "simple_loss_bcast")
+
+    out = outputs()
+    fused(out)
+    torch.cuda.synchronize()
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    out2 = outputs()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fused(out2)
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(out2, ref):
+        assert torch.equal(a, b)
+
+
 def test_pruning_backward_with_arbitrary_index_patterns():
     """frn_do_pruning_bwd's lm side is a scatter-add over ranges: any index pattern, also non-consecutive and
     repeated indices (hand-made ranges); wide bands take the per-element path."""

@@ -379,6 +379,59 @@ int frn_simple_loss_lp(const void *lm, const void *am, int am_lm_dtype, const in
   return FRN_OK;
 }
 
+// frn_simple_loss with the am half of do_rnnt_pruning (am_pruned[b,t,i,:] = am[b,t,:], independent of the prune
+// ranges) running on `side_stream` BESIDE the lattice recursion: forked behind the normaliser - the row statistics
+// and the normaliser want the whole GPU, the recursion occupies 2 B of its 148 SMs - and joined back into `stream`
+// after the read-out.  The copy's persistent single-warp CTAs ask for enough shared memory not to share an SM with a
+// recursion CTA.  fork_event / join_event: two caller-owned cudaEvent_t (no timing needed); everything stays
+// stream-ordered and capturable in a CUDA graph.  Shapes the fused arc-plane path does not take run the two calls
+// one after the other on `stream`.
+int frn_simple_loss_bcast(const float *lm, const float *am, const int32_t *symbols, const int32_t *boundary, int B,
+                          int S, int T, int C, int termination_symbol, int rnnt_type, int smoothed,
+                          float lm_only_scale, float am_only_scale, float delay_penalty, int calc_gradients,
+                          float *scores, float *px_grad, float *py_grad, int R, float *am_pruned, int max_ctas,
+                          void *side_stream, void *fork_event, void *join_event, void *workspace,
+                          size_t workspace_bytes, void *stream_) {
+  FRN_RANGE();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_), side = static_cast<cudaStream_t>(side_stream);
+  FRN_REQUIRE(B > 0 && S >= 1 && T >= 1 && C >= 1 && R >= 1);
+  FRN_REQUIRE(lm && am && symbols && boundary && scores && am_pruned);
+  FRN_REQUIRE(termination_symbol >= 0 && termination_symbol < C);
+  FRN_REQUIRE(rnnt_type >= FRN_REGULAR && rnnt_type <= FRN_CONSTRAINED);
+  FRN_REQUIRE(!calc_gradients || (px_grad && py_grad));
+  const int T1 = type_t1(T, rnnt_type);
+  DpGeom g = make_geom(B, S, T, T1);
+  const bool fused = side && fork_event && join_event && side != stream && !dense_dp_uses_scan(g) &&
+                     g.P <= kMaxRowsDp && simple_arc_plane_supported(lm, am, C, rnnt_type) && C % 4 == 0;
+  if (!fused) {
+    int rc = frn_simple_loss(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                             lm_only_scale, am_only_scale, delay_penalty, calc_gradients, scores, px_grad, py_grad,
+                             workspace, workspace_bytes, stream_);
+    if (rc) return rc;
+    return frn_broadcast_am_pruned(am, B, T, R, C, am_pruned, 0, stream_);
+  }
+  if (!workspace || !aligned256(workspace) || workspace_bytes < carve_simple_loss(nullptr, B, S, T, T1, C).bytes)
+    return FRN_EWORKSPACE;
+  SimpleLossWs w = carve_simple_loss(workspace, B, S, T, T1, C);
+  DpWorkspace dw = carve_dp(w.dp, g);
+  const float dp = delay_penalty > 0.f ? delay_penalty : 0.f;
+  const ArcPlaneOut arcs{dw.XY, g.P, g.Dn, g.k, dp};
+  FRN_TRY(launch_simple_logprobs(lm, am, symbols, boundary, B, S, T, C, termination_symbol, rnnt_type, smoothed,
+                                 lm_only_scale, am_only_scale, nullptr, nullptr, w.stats, stream, &arcs, nullptr));
+  cudaEvent_t fork = static_cast<cudaEvent_t>(fork_event), join = static_cast<cudaEvent_t>(join_event);
+  cudaError_t e = cudaEventRecord(fork, stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fork, 0);
+  if (e != cudaSuccess) return note_cuda_error(e);
+  FRN_TRY(launch_broadcast_am(am, B, T, R, C, am_pruned, max_ctas, side));
+  e = cudaEventRecord(join, side);
+  if (e != cudaSuccess) return note_cuda_error(e);
+  FRN_TRY(launch_chain(boundary, g, dw, calc_gradients != 0, stream));
+  FRN_TRY(launch_finalize_dense(boundary, g, dw, scores, calc_gradients ? px_grad : nullptr,
+                                calc_gradients ? py_grad : nullptr, stream));
+  e = cudaStreamWaitEvent(stream, join, 0);
+  return e == cudaSuccess ? FRN_OK : note_cuda_error(e);
+}
+
 size_t frn_simple_loss_bwd_workspace_bytes(int B, int S, int T, int C) {
   if (B <= 0 || S < 0 || T <= 0 || C <= 0) return 0;
   return simple_bwd_workspace_bytes(B, S, T, C);

@@ -427,12 +427,17 @@ __global__ void __launch_bounds__(32) broadcast_am_kernel(const float *am, float
                                                           int rows_per_chunk) {
   extern __shared__ __align__(128) unsigned char bc_smem[];
   __shared__ uint64_t bars[kBcStages];
-  if (threadIdx.x != 0) return;
+  const int lane = threadIdx.x;
   const uint32_t row_bytes = (uint32_t)C * sizeof(float);
   const int nchunk_all = (BT + rows_per_chunk - 1) / rows_per_chunk;
   const int n = (nchunk_all - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // chunks of this CTA
-  for (int s = 0; s < kBcStages; ++s) mbar_init(&bars[s], 1);
-  mbar_fence_init();
+  if (lane == 0) {
+    for (int s = 0; s < kBcStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  // lane 0 requests the chunks; ALL lanes issue the R x rows stores of a chunk (one thread issuing them was the
+  // limit: 58 GB/s per CTA) - bulk async-groups are per thread, so every lane commits and waits for its own
   auto load = [&](int j) {
     const int chunk = blockIdx.x + j * gridDim.x, row0 = chunk * rows_per_chunk;
     const uint32_t bytes = (uint32_t)min(rows_per_chunk, BT - row0) * row_bytes;
@@ -440,23 +445,26 @@ __global__ void __launch_bounds__(32) broadcast_am_kernel(const float *am, float
     mbar_arrive_expect_tx(&bars[s], bytes);
     bulk_g2s(bc_smem + (size_t)s * kBcStageBytes, am + (size_t)row0 * C, bytes, &bars[s]);
   };
-  for (int j = 0; j < kBcLook && j < n; ++j) load(j);
+  if (lane == 0)
+    for (int j = 0; j < kBcLook && j < n; ++j) load(j);
   for (int k = 0; k < n; ++k) {
     const int j = k + kBcLook;
-    if (j < n) {
+    if (j < n) {                                  // warp-uniform
       // stage j % kBcStages was last read by the stores of chunk j - kBcStages: at most
-      // kBcStages - kBcLook - 1 younger store groups may still be reading
+      // kBcStages - kBcLook - 1 younger store groups (of any lane) may still be reading
       asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBcStages - kBcLook - 1) : "memory");
-      load(j);
+      __syncwarp();
+      if (lane == 0) load(j);
     }
     const int s = k % kBcStages;
     mbar_wait(&bars[s], (uint32_t)((k / kBcStages) & 1));
     const int chunk = blockIdx.x + k * gridDim.x, row0 = chunk * rows_per_chunk;
     const int rows = min(rows_per_chunk, BT - row0);
     const unsigned char *src = bc_smem + (size_t)s * kBcStageBytes;
-    for (int r = 0; r < rows; ++r)
-      for (int i = 0; i < R; ++i)
-        bulk_s2g(am_p + ((size_t)(row0 + r) * R + i) * C, src + (size_t)r * row_bytes, row_bytes);
+    for (int q = lane; q < rows * R; q += 32) {
+      const int r = q / R, i = q - r * R;
+      bulk_s2g(am_p + ((size_t)(row0 + r) * R + i) * C, src + (size_t)r * row_bytes, row_bytes);
+    }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -84,6 +84,9 @@ _SIGS = {
     "frn_simple_loss_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_simple_loss": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_float, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "frn_simple_loss_bcast": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_float, c_float, c_float, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P,
+                                      c_size_t, _P]),
     "frn_simple_loss_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
     "frn_simple_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _P, _P, _P, c_size_t, _P]),
