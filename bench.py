@@ -180,7 +180,7 @@ class Pipeline:
         # single-warp CTAs doing nothing but bulk copies, with a shared-memory footprint that keeps the
         # normaliser's / recursion's big CTAs on the other SMs; frn_do_pruning_add_joiner then writes
         # lm_pruned and the logits only.
-        self.am_side = am_side if fuse_add else 0
+        self.am_side = am_side if self.fuse_add else 0     # (bf16 logits take the two-pass form: no am-side copy)
         self.am_side_at = am_side_at          # "start": beside the whole simple loss; "chain": forked behind the normaliser
         self.side = torch.cuda.Stream(dev) if (overlap or self.am_side) else None
         self.fork_ev = self.join_ev = None

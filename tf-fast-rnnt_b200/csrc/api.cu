@@ -408,7 +408,7 @@ int frn_simple_loss_bcast(const float *lm, const float *am, const int32_t *symbo
                              lm_only_scale, am_only_scale, delay_penalty, calc_gradients, scores, px_grad, py_grad,
                              workspace, workspace_bytes, stream_);
     if (rc) return rc;
-    return frn_broadcast_am_pruned(am, B, T, R, C, am_pruned, 0, stream_);
+    return frn_broadcast_am_pruned(am, B, T, R, C, am_pruned, 296, stream_);     // alone on the GPU: all SMs
   }
   if (!workspace || !aligned256(workspace) || workspace_bytes < carve_simple_loss(nullptr, B, S, T, T1, C).bytes)
     return FRN_EWORKSPACE;
